@@ -1,0 +1,213 @@
+/*
+ * pdeb200.h — C ABI of the B200-native utility-evaluation path of PDE-Controller.
+ *
+ * One call evaluates a BATCH of independent samples.  One sample = one 1D heat
+ * or 1D wave finite-element forward simulation (femformal style: two-material
+ * rod, Dirichlet at x=0, controlled flux/force at x=L) plus the quantitative
+ * robustness of one STL specification over the simulated field.
+ *
+ * What each entry point replaces in the reference (paths relative to the
+ * reference tree):
+ *
+ *   pdeb_eval_batch          the per-sample chain
+ *                              eval_robustness_helper  test/PDEcontrol/evaluation/eval/eval_script.py:43-79
+ *                              -> wrapper main         test/PDEcontrol/evaluation/eval/eval_robustness_wrapper.py:13-21
+ *                              -> control.femformal.eval_robustness.eval_robustness   (call site wrapper:16)
+ *                            fanned out one process per sample by
+ *                              evaluate_future         test/PDEcontrol/evaluation/infer/simulate_gt.py:62-89
+ *   PdebBatch                the femformal program dialect that chain receives as text
+ *                              heatlinfem.heatlinfem_mix(xpart, rho, E, g, f_nodal, dt)
+ *                              mechlinfem.mechlinfem(xpart, rho, E, g, f_nodal, dt)
+ *                              logic.APCont([x_lo,x_hi], rel, p, dp), cregions, cspec
+ *                            (call sites: utils/few_shot_prompts/examples/one_d_heat/examples.jsonl:1-3,
+ *                             one_d_wave/examples.jsonl:1-3), already parsed to numbers.
+ *   robustness_out/status    the {"robustness": r, "runtime": t} line of wrapper:18-21 and the
+ *                            -100 failure label of simulate_gt.py:55-59.
+ *
+ * All pointers are caller-owned.  Nothing is retained after a call returns
+ * (except inside an explicit PdebResident handle).  No torch types.
+ *
+ * Layout: structure of arrays.  Per-sample scalars are arrays of length n.
+ * Per-sample lists (control knots, predicates, formula-tree nodes) are
+ * PLANE-MAJOR: element j of sample s lives at  base[j*stride + s]  so that
+ * consecutive samples are consecutive in memory (coalesced on the device).
+ */
+#ifndef PDEB200_H
+#define PDEB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDEB_ABI_VERSION 1
+
+/* kind */
+#define PDEB_KIND_HEAT 0   /* rho*c u_t = (E u_x)_x   first order,  heatlinfem_mix */
+#define PDEB_KIND_WAVE 1   /* rho u_tt  = (E u_x)_x   second order, mechlinfem     */
+
+/* pred_rel */
+#define PDEB_REL_GT 0      /* u(x) - (m x + b) > 0 */
+#define PDEB_REL_LT 1      /* u(x) - (m x + b) < 0 */
+#define PDEB_REL_EQ 2      /* u(x) - (m x + b) = 0 */
+
+/* pred_top (temporal operator of the clause) */
+#define PDEB_TOP_G 0       /* always   : min over the window */
+#define PDEB_TOP_F 1       /* eventually: max over the window */
+
+/* tree_op; nodes are stored children-before-parent, root = node n_tree-1 */
+#define PDEB_TREE_LEAF 0   /* lhs = predicate (clause) index */
+#define PDEB_TREE_AND  1   /* min(lhs, rhs), operands are earlier tree nodes */
+#define PDEB_TREE_OR   2   /* max(lhs, rhs) */
+
+/* status_out */
+#define PDEB_OK            0
+#define PDEB_ST_PARSE      1   /* set by the host front-end only (program text not understood) */
+#define PDEB_ST_NONFINITE  2   /* simulation or robustness produced inf/nan */
+#define PDEB_ST_BADPARAM   3   /* mesh / material / step parameters out of the supported range */
+
+#define PDEB_FAILED_ROBUSTNESS (-100.0)  /* simulate_gt.py:59 */
+
+/* limits of this build */
+#define PDEB_MAX_PRED   8
+#define PDEB_MAX_TREE   (2 * PDEB_MAX_PRED - 1)
+#define PDEB_MAX_ELEM   1055          /* 32 lanes x 32 rows + 31 separators */
+#define PDEB_MAX_STEPS  (1 << 22)
+
+/* return codes */
+#define PDEB_E_OK        0
+#define PDEB_E_ARG      -1
+#define PDEB_E_CUDA     -2
+#define PDEB_E_NOMEM    -3
+#define PDEB_E_NODEVICE -4
+
+/*
+ * Convention flags.  The reference's femformal source
+ * is not public in the snapshot, so every choice that moves the result is an
+ * explicit parameter.  pdeb_default_conventions() fills the "v0" defaults.
+ */
+typedef struct PdebConventions {
+    int32_t material_sampling; /* C1: 0 element midpoint (v0), 1 left node, 2 right node */
+    int32_t mass_heat;         /* C2: 0 consistent (v0), 1 lumped */
+    int32_t mass_wave;         /* C2: 0 consistent, 1 lumped (v0) */
+    int32_t steps_rule;        /* C6: 0 ceil(T/dt - 1e-9) (v0), 1 round, 2 floor(T/dt + 1e-9) */
+    int32_t window_rule;       /* C7: 0 [ceil, floor] inclusive (v0), 1 int() truncation of both ends */
+    int32_t region_rule;       /* C8: 0 nodes inside, end-point interpolation only if none (v0);
+                                      1 nodes inside plus both interpolated end points */
+    int32_t eq_rule;           /* C9: 0 -|u-p| (v0), 1 band: min(u-(p-eps), (p+eps)-u) */
+    int32_t reserved0;
+    double  eq_eps;            /* C9 band half width, used when eq_rule == 1 */
+    double  theta;             /* C4: heat generalised-trapezoidal parameter, v0 = 0.5 */
+    double  newmark_beta;      /* C5: v0 = 0.25 */
+    double  newmark_gamma;     /* C5: v0 = 0.5  */
+} PdebConventions;
+
+typedef struct PdebBatch {
+    int64_t n;        /* number of samples */
+    int64_t stride;   /* plane stride of the 2-D arrays, >= n */
+    int32_t kmax;     /* planes in knot_t / knot_y */
+    int32_t pmax;     /* planes in pred_*  (<= PDEB_MAX_PRED) */
+    int32_t tmax;     /* planes in tree_*  (<= PDEB_MAX_TREE) */
+    int32_t reserved0;
+
+    /* optional: if all arrays below live in one contiguous host block, give it
+       here and the library moves it with a single copy; else NULL / 0 */
+    const void* slab_base;
+    int64_t     slab_bytes;
+
+    const uint8_t* kind;     /* [n] PDEB_KIND_* */
+    const int32_t* n_elem;   /* [n] N: elements; nodes x_i = i L/N, i = 0..N  (xpart = linspace(0,L,N+1)) */
+    const double*  L;        /* [n] rod length */
+    const double*  dt;       /* [n] time step */
+    const double*  T;        /* [n] horizon */
+    const double*  g0;       /* [n] Dirichlet value at x = 0   (g = [g0, None]) */
+    const double*  x_a;      /* [n] inner segment is x_a <= x <= x_b, outer is x < x_a or x > x_b */
+    const double*  x_b;
+    const double*  rho_in;   /* [n] rho(x) on the inner segment (heat: rho*c product) */
+    const double*  rho_out;
+    const double*  E_in;
+    const double*  E_out;
+
+    const int32_t* n_knots;  /* [n] 0 = zero input */
+    const double*  knot_t;   /* [kmax][stride] ascending knot times of the PWL input at x = L */
+    const double*  knot_y;   /* [kmax][stride] knot values (heat: flux, wave: force), added to F[N] */
+
+    const int32_t* n_pred;   /* [n] clauses, 1..pmax */
+    const double*  pred_xlo; /* [pmax][stride] APCont interval */
+    const double*  pred_xhi;
+    const double*  pred_m;   /* profile p(x) = m x + b */
+    const double*  pred_b;
+    const double*  pred_tlo; /* temporal window of the clause */
+    const double*  pred_thi;
+    const uint8_t* pred_rel; /* PDEB_REL_* */
+    const uint8_t* pred_top; /* PDEB_TOP_* */
+
+    const int32_t* n_tree;   /* [n] nodes, 1..tmax */
+    const uint8_t* tree_op;  /* [tmax][stride] */
+    const int8_t*  tree_lhs;
+    const int8_t*  tree_rhs;
+} PdebBatch;
+
+/* timing detail of one call, all in milliseconds, filled when non-NULL */
+typedef struct PdebTiming {
+    float h2d_ms;
+    float kernel_ms;     /* CUDA events around the kernel launches only */
+    float d2h_ms;
+    float total_ms;      /* events around h2d + kernels + d2h */
+    int32_t launches;    /* kernels launched by this call */
+    int32_t reserved0;
+} PdebTiming;
+
+int  pdeb_version(void);
+int  pdeb_device_count(void);
+const char* pdeb_last_error(void);       /* thread-local, valid until the next call on this thread */
+void pdeb_default_conventions(PdebConventions* out);
+
+/*
+ * Evaluate a host batch on one device: H2D, kernels, D2H.
+ *   precision       64 or 32 (arithmetic of the time loop; inputs/outputs stay f64)
+ *   conv            NULL = v0 defaults
+ *   robustness_out  [n]          formula robustness, PDEB_FAILED_ROBUSTNESS where status != 0
+ *   clause_out      [pmax][stride] per-clause robustness, or NULL
+ *   status_out      [n] or NULL
+ *   stream          cudaStream_t or NULL (default stream); the call synchronises it before returning
+ */
+int pdeb_eval_batch(const PdebBatch* in, int device, int precision, const PdebConventions* conv,
+                    double* robustness_out, double* clause_out, int32_t* status_out,
+                    void* stream, PdebTiming* timing);
+
+/*
+ * Same over several devices of one box: contiguous shards [floor(r n/R), floor((r+1) n/R)),
+ * one host thread and one stream per device, no inter-device traffic.
+ * devices == NULL means 0..ndev-1.
+ */
+int pdeb_eval_batch_multi(const PdebBatch* in, int ndev, const int* devices, int precision,
+                          const PdebConventions* conv, double* robustness_out, double* clause_out,
+                          int32_t* status_out, PdebTiming* timing_per_device);
+
+/*
+ * Resident form: upload once, evaluate many times (used to time the kernels with
+ * inputs already in HBM, and by the many-controls search that rewrites only the knots).
+ */
+typedef struct PdebResident PdebResident;
+
+int  pdeb_resident_create(const PdebBatch* in, int device, void* stream, PdebResident** out);
+int  pdeb_resident_eval(PdebResident* r, int precision, const PdebConventions* conv,
+                        void* stream, PdebTiming* timing);   /* asynchronous on stream unless timing != NULL */
+int  pdeb_resident_set_knots(PdebResident* r, const double* knot_t, const double* knot_y,
+                             const int32_t* n_knots, void* stream);      /* host planes, same kmax/stride */
+int  pdeb_resident_fetch(PdebResident* r, double* robustness_out, double* clause_out,
+                         int32_t* status_out, void* stream);
+/* device pointers of the results (f64[n], f64[pmax][stride], i32[n]) for zero-copy consumers */
+int  pdeb_resident_device_ptrs(PdebResident* r, void** robustness_dev, void** clause_dev, void** status_dev);
+void pdeb_resident_destroy(PdebResident* r);
+
+/* pinned host memory for batches that are uploaded every step */
+void* pdeb_host_alloc(int64_t bytes);
+void  pdeb_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDEB200_H */

@@ -1,0 +1,132 @@
+"""ctypes mirror of include/pdeb200.h (data layout only, no behaviour)."""
+import ctypes as C
+
+ABI_VERSION = 1
+
+KIND_HEAT, KIND_WAVE = 0, 1
+REL_GT, REL_LT, REL_EQ = 0, 1, 2
+TOP_G, TOP_F = 0, 1
+TREE_LEAF, TREE_AND, TREE_OR = 0, 1, 2
+OK, ST_PARSE, ST_NONFINITE, ST_BADPARAM = 0, 1, 2, 3
+FAILED_ROBUSTNESS = -100.0
+MAX_PRED = 8
+MAX_TREE = 2 * MAX_PRED - 1
+MAX_ELEM = 1055
+MAX_STEPS = 1 << 22
+
+REL_CODE = {">": REL_GT, "<": REL_LT, "=": REL_EQ}
+REL_TEXT = {v: k for k, v in REL_CODE.items()}
+TOP_CODE = {"G": TOP_G, "F": TOP_F}
+TOP_TEXT = {v: k for k, v in TOP_CODE.items()}
+
+
+class PdebConventions(C.Structure):
+    _fields_ = [
+        ("material_sampling", C.c_int32),
+        ("mass_heat", C.c_int32),
+        ("mass_wave", C.c_int32),
+        ("steps_rule", C.c_int32),
+        ("window_rule", C.c_int32),
+        ("region_rule", C.c_int32),
+        ("eq_rule", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("eq_eps", C.c_double),
+        ("theta", C.c_double),
+        ("newmark_beta", C.c_double),
+        ("newmark_gamma", C.c_double),
+    ]
+
+
+def default_conventions(**overrides):
+    """The "v0" convention set of SURVEY.md §8c."""
+    c = PdebConventions()
+    c.material_sampling = 0
+    c.mass_heat = 0
+    c.mass_wave = 1
+    c.steps_rule = 0
+    c.window_rule = 0
+    c.region_rule = 0
+    c.eq_rule = 0
+    c.eq_eps = 0.0
+    c.theta = 0.5
+    c.newmark_beta = 0.25
+    c.newmark_gamma = 0.5
+    for k, v in overrides.items():
+        if not hasattr(c, k):
+            raise AttributeError(f"unknown convention flag {k!r}")
+        setattr(c, k, v)
+    return c
+
+
+_P = C.c_void_p
+
+
+class PdebBatch(C.Structure):
+    _fields_ = [
+        ("n", C.c_int64),
+        ("stride", C.c_int64),
+        ("kmax", C.c_int32),
+        ("pmax", C.c_int32),
+        ("tmax", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("slab_base", _P),
+        ("slab_bytes", C.c_int64),
+        ("kind", _P),
+        ("n_elem", _P),
+        ("L", _P),
+        ("dt", _P),
+        ("T", _P),
+        ("g0", _P),
+        ("x_a", _P),
+        ("x_b", _P),
+        ("rho_in", _P),
+        ("rho_out", _P),
+        ("E_in", _P),
+        ("E_out", _P),
+        ("n_knots", _P),
+        ("knot_t", _P),
+        ("knot_y", _P),
+        ("n_pred", _P),
+        ("pred_xlo", _P),
+        ("pred_xhi", _P),
+        ("pred_m", _P),
+        ("pred_b", _P),
+        ("pred_tlo", _P),
+        ("pred_thi", _P),
+        ("pred_rel", _P),
+        ("pred_top", _P),
+        ("n_tree", _P),
+        ("tree_op", _P),
+        ("tree_lhs", _P),
+        ("tree_rhs", _P),
+    ]
+
+
+class PdebTiming(C.Structure):
+    _fields_ = [
+        ("h2d_ms", C.c_float),
+        ("kernel_ms", C.c_float),
+        ("d2h_ms", C.c_float),
+        ("total_ms", C.c_float),
+        ("launches", C.c_int32),
+        ("reserved0", C.c_int32),
+    ]
+
+
+# every symbol include/pdeb200.h declares (checked by tests/test_abi_symbols.py)
+EXPORTS = [
+    "pdeb_version",
+    "pdeb_device_count",
+    "pdeb_last_error",
+    "pdeb_default_conventions",
+    "pdeb_eval_batch",
+    "pdeb_eval_batch_multi",
+    "pdeb_resident_create",
+    "pdeb_resident_eval",
+    "pdeb_resident_set_knots",
+    "pdeb_resident_fetch",
+    "pdeb_resident_device_ptrs",
+    "pdeb_resident_destroy",
+    "pdeb_host_alloc",
+    "pdeb_host_free",
+]

@@ -1,0 +1,276 @@
+"""Problem IR of the utility-evaluation path and its packed batch form.
+
+A `Problem` is what one femformal-dialect program describes (call
+sites utils/few_shot_prompts/examples/one_d_heat/examples.jsonl:1-3 and
+one_d_wave/examples.jsonl:1-3 of the reference): PDE kind, uniform mesh, two-material rod,
+Dirichlet value, step, horizon, APCont predicates and the cspec formula tree.  The control
+input (piecewise linear in time, applied at x = L) is a separate argument because the
+reference synthesises it inside femformal; here it is given.
+
+`ProblemBatch` packs many problems into the structure-of-arrays layout of
+include/pdeb200.h inside ONE contiguous host block, so the library can move it with a
+single copy.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import abi
+
+
+@dataclass
+class Predicate:
+    """One clause: TOP_[t_lo,t_hi] ( forall x in [x_lo,x_hi]: u(x) - (m x + b) REL 0 )."""
+    x_lo: float
+    x_hi: float
+    rel: str          # ">", "<", "="
+    m: float
+    b: float
+    top: str = "G"    # "G" or "F"
+    t_lo: float = 0.0
+    t_hi: float = 0.0
+    label: str = ""
+
+
+@dataclass
+class Problem:
+    kind: str                      # "heat" | "wave"
+    n_elem: int
+    L: float
+    dt: float
+    T: float
+    g0: float
+    x_a: float
+    x_b: float
+    rho_in: float
+    rho_out: float
+    E_in: float
+    E_out: float
+    predicates: List[Predicate] = field(default_factory=list)
+    # children-before-parent list of (op, lhs, rhs); op in {"leaf","and","or"}; root is last
+    tree: List[Tuple[str, int, int]] = field(default_factory=list)
+
+    def default_tree(self):
+        """Left-associated conjunction of all clauses (the only shape in the 14 in-tree records)."""
+        out = [("leaf", 0, 0)]
+        acc = 0
+        for j in range(1, len(self.predicates)):
+            out.append(("leaf", j, 0))
+            leaf = len(out) - 1
+            out.append(("and", acc, leaf))
+            acc = len(out) - 1
+        return out
+
+
+def default_knot_times(p: Problem) -> np.ndarray:
+    """C11: uniform knots linspace(0, T, K); K = round(T)+1 for heat, 5 for wave."""
+    k = int(round(p.T)) + 1 if p.kind == "heat" else 5
+    k = max(k, 2)
+    return np.linspace(0.0, p.T, k)
+
+
+_F64 = ["L", "dt", "T", "g0", "x_a", "x_b", "rho_in", "rho_out", "E_in", "E_out"]
+_PRED_F64 = ["pred_xlo", "pred_xhi", "pred_m", "pred_b", "pred_tlo", "pred_thi"]
+_PLANAR = set(["knot_t", "knot_y", "pred_rel", "pred_top", "tree_op", "tree_lhs", "tree_rhs"] + _PRED_F64)
+_TREE_OPS = {"leaf": abi.TREE_LEAF, "and": abi.TREE_AND, "or": abi.TREE_OR}
+
+
+def _align(x, a=64):
+    return (x + a - 1) // a * a
+
+
+class ProblemBatch:
+    """SoA batch in one host slab.  Arrays are numpy views; 2-D arrays are [plane, sample]."""
+
+    def __init__(self, n: int, kmax: int, pmax: int, tmax: Optional[int] = None, buffer=None):
+        if tmax is None:
+            tmax = 2 * pmax - 1
+        if not (1 <= pmax <= abi.MAX_PRED) or not (1 <= tmax <= abi.MAX_TREE) or kmax < 1:
+            raise ValueError("kmax/pmax/tmax out of range")
+        self.n, self.kmax, self.pmax, self.tmax = int(n), int(kmax), int(pmax), int(tmax)
+        self.stride = self.n
+        layout = []
+        off = 0
+
+        def add(name, dtype, planes):
+            nonlocal off
+            nbytes = np.dtype(dtype).itemsize * max(self.n, 1) * planes
+            layout.append((name, dtype, planes, off))
+            off = _align(off + nbytes)
+
+        for f in _F64:
+            add(f, np.float64, 1)
+        add("knot_t", np.float64, kmax)
+        add("knot_y", np.float64, kmax)
+        for f in _PRED_F64:
+            add(f, np.float64, pmax)
+        for f in ("n_elem", "n_knots", "n_pred", "n_tree"):
+            add(f, np.int32, 1)
+        add("kind", np.uint8, 1)
+        add("pred_rel", np.uint8, pmax)
+        add("pred_top", np.uint8, pmax)
+        add("tree_op", np.uint8, tmax)
+        add("tree_lhs", np.int8, tmax)
+        add("tree_rhs", np.int8, tmax)
+        self.slab_bytes = off
+        if buffer is None:
+            buffer = np.zeros(off, dtype=np.uint8)
+        else:
+            buffer = np.frombuffer(buffer, dtype=np.uint8, count=off)
+            buffer[:] = 0
+        self.slab = buffer
+        self._names = []
+        for name, dtype, planes, o in layout:
+            cnt = self.n * planes
+            arr = np.frombuffer(self.slab, dtype=dtype, count=cnt, offset=o) if cnt else np.zeros(0, dtype)
+            if name in _PLANAR:
+                arr = arr.reshape(planes, self.n)
+            setattr(self, name, arr)
+            self._names.append(name)
+        self._parent = None  # set on slices to keep the slab alive
+
+    # ---- construction -----------------------------------------------------
+    @staticmethod
+    def nbytes_for(n, kmax, pmax, tmax=None):
+        """Slab size of a batch, e.g. to allocate it in pinned memory first."""
+        if tmax is None:
+            tmax = 2 * pmax - 1
+        off = 0
+        n1 = max(n, 1)
+        for planes, isz in ([(1, 8)] * len(_F64) + [(kmax, 8)] * 2 + [(pmax, 8)] * len(_PRED_F64)
+                            + [(1, 4)] * 4 + [(1, 1), (pmax, 1), (pmax, 1), (tmax, 1), (tmax, 1), (tmax, 1)]):
+            off = _align(off + isz * n1 * planes)
+        return off
+
+    @classmethod
+    def from_problems(cls, problems: Sequence[Problem], controls: Optional[Sequence] = None,
+                      kmax: Optional[int] = None, pmax: Optional[int] = None) -> "ProblemBatch":
+        n = len(problems)
+        if controls is None:
+            controls = [None] * n
+        if len(controls) != n:
+            raise ValueError("controls must have one entry per problem")
+        ctrl = []
+        for c in controls:
+            if c is None:
+                ctrl.append((np.zeros(0), np.zeros(0)))
+            else:
+                t, y = c
+                t = np.asarray(t, dtype=np.float64).ravel()
+                y = np.asarray(y, dtype=np.float64).ravel()
+                if t.shape != y.shape:
+                    raise ValueError("control knot times and values differ in length")
+                ctrl.append((t, y))
+        if kmax is None:
+            kmax = max([len(t) for t, _ in ctrl] + [1])
+        if pmax is None:
+            pmax = max([len(p.predicates) for p in problems] + [1])
+        tmax = max([len(p.tree) if p.tree else 2 * len(p.predicates) - 1 for p in problems] + [1])
+        tmax = max(tmax, 2 * pmax - 1)
+        b = cls(n, kmax, pmax, tmax)
+        for s, p in enumerate(problems):
+            b.set_problem(s, p, ctrl[s])
+        return b
+
+    def set_problem(self, s: int, p: Problem, control=None):
+        self.kind[s] = abi.KIND_HEAT if p.kind == "heat" else abi.KIND_WAVE
+        self.n_elem[s] = p.n_elem
+        for f in _F64:
+            getattr(self, f)[s] = getattr(p, f)
+        np_ = len(p.predicates)
+        if np_ > self.pmax:
+            raise ValueError("too many predicates for this batch")
+        self.n_pred[s] = np_
+        for j, q in enumerate(p.predicates):
+            self.pred_xlo[j, s] = q.x_lo
+            self.pred_xhi[j, s] = q.x_hi
+            self.pred_m[j, s] = q.m
+            self.pred_b[j, s] = q.b
+            self.pred_tlo[j, s] = q.t_lo
+            self.pred_thi[j, s] = q.t_hi
+            self.pred_rel[j, s] = abi.REL_CODE[q.rel]
+            self.pred_top[j, s] = abi.TOP_CODE[q.top]
+        tree = p.tree if p.tree else p.default_tree()
+        if len(tree) > self.tmax:
+            raise ValueError("formula tree too large for this batch")
+        self.n_tree[s] = len(tree)
+        for j, (op, l, r) in enumerate(tree):
+            self.tree_op[j, s] = _TREE_OPS[op]
+            self.tree_lhs[j, s] = l
+            self.tree_rhs[j, s] = r
+        if control is not None:
+            t, y = control
+            if len(t) > self.kmax:
+                raise ValueError("too many control knots for this batch")
+            self.n_knots[s] = len(t)
+            self.knot_t[: len(t), s] = t
+            self.knot_y[: len(t), s] = y
+        else:
+            self.n_knots[s] = 0
+
+    def get_problem(self, s: int):
+        """Inverse of set_problem: -> (Problem, control or None)."""
+        preds = []
+        for j in range(int(self.n_pred[s])):
+            preds.append(Predicate(float(self.pred_xlo[j, s]), float(self.pred_xhi[j, s]),
+                                   abi.REL_TEXT[int(self.pred_rel[j, s])], float(self.pred_m[j, s]),
+                                   float(self.pred_b[j, s]), abi.TOP_TEXT[int(self.pred_top[j, s])],
+                                   float(self.pred_tlo[j, s]), float(self.pred_thi[j, s]), chr(ord("A") + j)))
+        names = {v: k for k, v in _TREE_OPS.items()}
+        tree = [(names[int(self.tree_op[j, s])], int(self.tree_lhs[j, s]), int(self.tree_rhs[j, s]))
+                for j in range(int(self.n_tree[s]))]
+        p = Problem("heat" if self.kind[s] == abi.KIND_HEAT else "wave", int(self.n_elem[s]),
+                    *[float(getattr(self, f)[s]) for f in _F64], predicates=preds, tree=tree)
+        k = int(self.n_knots[s])
+        control = (self.knot_t[:k, s].copy(), self.knot_y[:k, s].copy()) if k else None
+        return p, control
+
+    # ---- views ------------------------------------------------------------
+    def shard(self, lo: int, hi: int) -> "ProblemBatch":
+        """Zero-copy view of samples [lo, hi) (same plane stride; no slab fast path)."""
+        v = object.__new__(ProblemBatch)
+        v.n, v.kmax, v.pmax, v.tmax = hi - lo, self.kmax, self.pmax, self.tmax
+        v.stride = self.stride
+        v.slab, v.slab_bytes = None, 0
+        v._names = list(self._names)
+        for name in self._names:
+            a = getattr(self, name)
+            setattr(v, name, a[..., lo:hi])
+        v._parent = self
+        return v
+
+    def as_c(self) -> abi.PdebBatch:
+        c = abi.PdebBatch()
+        c.n, c.stride = self.n, self.stride
+        c.kmax, c.pmax, c.tmax = self.kmax, self.pmax, self.tmax
+        if self.slab is not None and self.n > 0:
+            c.slab_base = self.slab.ctypes.data
+            c.slab_bytes = self.slab_bytes
+        else:
+            c.slab_base, c.slab_bytes = None, 0
+        for name in self._names:
+            a = getattr(self, name)
+            setattr(c, name, a.ctypes.data if a.size else None)
+        c._keepalive = self
+        return c
+
+    def steps(self, steps_rule: int = 0) -> np.ndarray:
+        """C6 step count per sample (host-side helper for sharding by cost and for sorting)."""
+        q = self.T / self.dt
+        if steps_rule == 1:
+            s = np.floor(q + 0.5)
+        elif steps_rule == 2:
+            s = np.floor(q + 1e-9)
+        else:
+            s = np.ceil(q - 1e-9)
+        return np.maximum(s, 1).astype(np.int64)
+
+    def algorithmic_bytes(self) -> int:
+        """105 + 16 K + 50 P + 3 (2P-1) bytes per evaluation, summed over the batch."""
+        k = self.n_knots.astype(np.int64)
+        p = self.n_pred.astype(np.int64)
+        return int(np.sum(105 + 16 * k + 50 * p + 3 * (2 * p - 1)))

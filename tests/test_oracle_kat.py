@@ -1,0 +1,219 @@
+"""Analytical known-answer tests that pin the oracle (the reference ships none: SURVEY.md §4).
+
+Every expected value below comes from a closed form of the DISCRETE scheme (exact up to
+rounding), not from another run of the code under test.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from pde_controller_b200 import Predicate, Problem, ProblemBatch, default_conventions
+from oracle import pde_oracle_np as onp
+
+
+def heat_problem(N=30, L=100.0, dt=0.05, T=4.0, g0=300.0, x_a=30.0, x_b=60.0, rho_in=1710.0, rho_out=1864.0,
+                 E_in=1.5e6, E_out=8e5, preds=None):
+    preds = preds or [Predicate(0.0, L, ">", 0.0, 0.0, "G", 0.0, T)]
+    return Problem("heat", N, L, dt, T, g0, x_a, x_b, rho_in, rho_out, E_in, E_out, preds)
+
+
+def wave_problem(N=20, L=1e5, dt=0.0025, T=1.0, x_a=3e4, x_b=6e4, rho_in=8.5e-6, rho_out=8e-6, E_in=1e8,
+                 E_out=2e8, preds=None):
+    preds = preds or [Predicate(0.0, L, ">", 0.0, 0.0, "G", 0.0, T)]
+    return Problem("wave", N, L, dt, T, 0.0, x_a, x_b, rho_in, rho_out, E_in, E_out, preds)
+
+
+def traj_of(oracle_lib, p, control=None, conv=None, vel=False):
+    b = ProblemBatch.from_problems([p], [control])
+    return oracle_lib.trajectory(b, 0, conv, want_velocity=vel)
+
+
+def const_control(p, y):
+    return (np.array([0.0, p.T]), np.array([y, y]))
+
+
+# (i) steady state under a constant flux: u_i = g0 + q * sum_{e<i} h/E_e, exact at the nodes
+def test_heat_steady_state_constant_flux(oracle_lib):
+    p = heat_problem(T=2000.0, dt=5.0)
+    q = 4.0e5
+    conv = default_conventions(theta=1.0)   # backward Euler: monotone decay to the steady state
+    traj, rob, cl, st = traj_of(oracle_lib, p, const_control(p, q), conv)
+    assert st == 0
+    h = p.L / p.n_elem
+    E = np.array([p.E_out if ((e + .5) * h < p.x_a or (e + .5) * h > p.x_b) else p.E_in for e in range(p.n_elem)])
+    expect = p.g0 + q * np.concatenate([[0.0], np.cumsum(h / E)])
+    np.testing.assert_allclose(traj[-1], expect, rtol=1e-12)
+
+
+def _modes(N):
+    th = (2 * np.arange(1, N + 1) - 1) * math.pi / (2 * N)
+    i = np.arange(1, N + 1)
+    return th, np.sin(np.outer(i, th))       # phi[i-1, j]
+
+
+# (ii) single material, step flux: modal closed form with the theta-method amplification factor
+#      rho_j = (1 - (1-th) dt lam_j) / (1 + th dt lam_j), lam_j the DISCRETE eigenvalue
+@pytest.mark.parametrize("theta", [0.5, 1.0])
+def test_heat_modal_amplification(oracle_lib, theta):
+    N, L, rho, E, q = 30, 120.0, 2000.0, 1.0e6, 3.0e5
+    p = heat_problem(N=N, L=L, T=6.0, rho_in=rho, rho_out=rho, E_in=E, E_out=E)
+    traj, _, _, st = traj_of(oracle_lib, p, const_control(p, q), default_conventions(theta=theta))
+    assert st == 0
+    h = L / N
+    th, phi = _modes(N)
+    lam = 6 * E / (rho * h * h) * (1 - np.cos(th)) / (2 + np.cos(th))
+    # consistent mass on the free dofs
+    M = np.zeros((N, N))
+    for i in range(N):
+        M[i, i] = rho * h * (2 / 3 if i < N - 1 else 1 / 3)
+        if i + 1 < N:
+            M[i, i + 1] = M[i + 1, i] = rho * h / 6
+    mj = np.einsum("ij,ik,kj->j", phi, M, phi)
+    css = q * phi[-1] / (mj * lam)
+    amp = (1 - (1 - theta) * p.dt * lam) / (1 + theta * p.dt * lam)
+    S = traj.shape[0] - 1
+    for k in (0, 1, 7, S // 2, S):
+        expect = p.g0 + phi @ (css * (1 - amp ** k))
+        np.testing.assert_allclose(traj[k, 1:], expect, rtol=0, atol=1e-9 * np.abs(expect).max())
+
+
+# (iii) Newmark beta=1/4, gamma=1/2, lumped mass, step force: each mode follows
+#       c_k = c_ss (1 - cos(k phi_j)),  tan(phi_j / 2) = w_j dt / 2   (period elongation formula)
+def test_wave_modal_period_elongation(oracle_lib):
+    N, L, rho, E, F = 20, 1.0e5, 8e-6, 2e8, 3000.0
+    p = wave_problem(N=N, L=L, T=1.0, rho_in=rho, rho_out=rho, E_in=E, E_out=E)
+    traj, _, _, st = traj_of(oracle_lib, p, const_control(p, F))
+    assert st == 0
+    h = L / N
+    th, phi = _modes(N)
+    lam = 2 * E / (rho * h * h) * (1 - np.cos(th))
+    w = np.sqrt(lam)
+    m = np.full(N, rho * h)
+    m[-1] *= 0.5
+    mj = (phi * phi * m[:, None]).sum(0)
+    css = F * phi[-1] / (mj * lam)
+    ang = 2 * np.arctan(w * p.dt / 2)
+    S = traj.shape[0] - 1
+    for k in (0, 1, 13, S // 2, S):
+        expect = phi @ (css * (1 - np.cos(k * ang)))
+        np.testing.assert_allclose(traj[k, 1:], expect, rtol=0, atol=1e-9 * np.abs(traj).max())
+
+
+# (iii) energy is conserved exactly once the force is back to zero
+def test_wave_energy_conservation(oracle_lib):
+    p = wave_problem(T=1.5)
+    ctrl = (np.array([0.0, 0.2, 0.4, 1.5]), np.array([0.0, 4000.0, 0.0, 0.0]))
+    traj, _, _, st, vel = traj_of(oracle_lib, p, ctrl, vel=True)
+    assert st == 0
+    M, K, h = onp.assemble(p, onp.V0)
+    k0 = int(round(0.4 / p.dt)) + 1
+    en = np.array([0.5 * v @ M @ v + 0.5 * d @ K @ d for d, v in zip(traj[k0:], vel[k0:])])
+    assert en.min() > 0
+    assert (en.max() - en.min()) / en.mean() < 1e-10
+
+
+# (iii) static limit: a slowly ramped force ends near u(L) = F * sum h/E_e
+def test_wave_static_limit(oracle_lib):
+    p = wave_problem(T=40.0, dt=0.01)
+    F = 2000.0
+    traj, _, _, st = traj_of(oracle_lib, p, (np.array([0.0, 39.0, 40.0]), np.array([0.0, F, F])))
+    assert st == 0
+    h = p.L / p.n_elem
+    E = np.array([p.E_out if ((e + .5) * h < p.x_a or (e + .5) * h > p.x_b) else p.E_in for e in range(p.n_elem)])
+    assert traj[-1, -1] == pytest.approx(F * np.sum(h / E), rel=2e-2)
+
+
+# (iv) STL semantics on the oracle's own trajectory, recomputed by hand with slices
+def test_stl_semantics_hand_computed(oracle_lib):
+    L, T, dt = 100.0, 4.0, 0.05
+    preds = [
+        Predicate(10.0, 50.0, ">", 0.1, 295.0, "G", 0.5, 1.5),     # nodes 3..15
+        Predicate(60.0, 100.0, "<", -0.05, 330.0, "F", 2.0, 4.0),  # nodes 18..30, window ends at the horizon
+        Predicate(20.0, 40.0, "=", 0.0, 305.0, "F", 1.0, 3.0),     # nodes 6..12
+    ]
+    p = heat_problem(L=L, T=T, dt=dt, preds=preds)
+    p.tree = [("leaf", 0, 0), ("leaf", 1, 0), ("or", 0, 1), ("leaf", 2, 0), ("and", 2, 3)]
+    traj, rob, cl, st = traj_of(oracle_lib, p, (np.array([0.0, 4.0]), np.array([0.0, 8e5])))
+    assert st == 0
+    x = np.arange(31) * (L / 30)
+    m0 = (traj[10:31, 3:16] - (0.1 * x[3:16] + 295.0)).min(axis=1).min()
+    m1 = ((-0.05 * x[18:31] + 330.0) - traj[40:81, 18:31]).min(axis=1).max()
+    m2 = (-np.abs(traj[20:61, 6:13] - 305.0)).min(axis=1).max()
+    assert cl[0] == m0 and cl[1] == m1 and cl[2] == m2
+    assert rob == min(max(m0, m1), m2)
+
+
+def test_stl_window_edge_cases(oracle_lib):
+    L, T, dt = 100.0, 2.0, 0.05
+    preds = [
+        Predicate(0.0, 100.0, ">", 0.0, 299.0, "G", 1.0, 1.0),      # degenerate window on a step: k = 20
+        Predicate(0.0, 100.0, ">", 0.0, 299.0, "G", 1.06, 1.08),    # between steps: nearest step (1.07/0.05 = 21.4 -> k = 21)
+        Predicate(12.0, 12.0, ">", 0.0, 299.0, "G", 0.0, 2.0),      # no node inside: interpolate at x = 12
+        Predicate(0.0, 100.0, ">", 0.0, 299.0, "F", 1.95, 7.0),     # window clipped at the horizon
+    ]
+    p = heat_problem(L=L, T=T, dt=dt, preds=preds)
+    p.tree = [("leaf", 0, 0)]
+    traj, rob, cl, st = traj_of(oracle_lib, p, (np.array([0.0, 2.0]), np.array([0.0, -8e5])))
+    assert st == 0
+    assert cl[0] == (traj[20] - 299.0).min()
+    assert cl[1] == (traj[21] - 299.0).min()
+    h = L / 30
+    xi = (12.0 - 3 * h) / h
+    u12 = traj[:, 3] + xi * (traj[:, 4] - traj[:, 3])
+    assert cl[2] == pytest.approx((u12 - 299.0).min(), rel=1e-14)
+    assert cl[3] == (traj[39:41] - 299.0).min(axis=1).max()
+
+
+# (v) second-order convergence in h of the end-point value
+def test_mesh_refinement_order_two(oracle_lib):
+    errs = []
+    ref = None
+    for N in (1024, 16, 32, 64):
+        p = heat_problem(N=N, x_a=25.0, x_b=62.5, T=4.0, dt=0.02)   # interfaces on element edges for every N
+        traj, _, _, st = traj_of(oracle_lib, p, (np.array([0.0, 4.0]), np.array([0.0, 5e5])))
+        assert st == 0
+        if ref is None:
+            ref = traj[-1, -1]
+        else:
+            errs.append(abs(traj[-1, -1] - ref))
+    assert 3.5 < errs[0] / errs[1] < 4.5 and 3.5 < errs[1] / errs[2] < 4.5
+
+
+def test_c_oracle_matches_numpy_restatement(oracle_lib):
+    from pde_controller_b200 import synth
+    for wl in ("heat", "wave"):
+        b = synth.make_batch(24, wl, seed=3)
+        rob, st, cl = oracle_lib.eval_batch(b, want_clauses=True)
+        assert (st == 0).all()
+        for s in range(b.n):
+            p, c = b.get_problem(s)
+            r, clause = onp.evaluate(p, c)
+            scale = max(abs(r), 1e-3 * (abs(p.g0) + 1.0))
+            assert abs(rob[s] - r) <= 1e-10 * scale
+            np.testing.assert_allclose(cl[: len(clause), s], clause, rtol=0, atol=1e-10 * max(scale, np.abs(clause).max()))
+
+
+def test_conventions_change_results(oracle_lib):
+    """Each declared convention flag is live (moves the result) and is honoured by both restatements."""
+    from pde_controller_b200 import synth
+    b = synth.make_batch(8, "heat", seed=5)
+    base, _ = oracle_lib.eval_batch(b)
+    for kw in (dict(mass_heat=1), dict(material_sampling=1), dict(theta=1.0), dict(region_rule=1), dict(eq_rule=1, eq_eps=0.5)):
+        rob, st = oracle_lib.eval_batch(b, default_conventions(**kw))
+        assert (st == 0).all()
+        assert np.any(np.abs(rob - base) > 1e-9), kw
+        p, c = b.get_problem(0)
+        r, _ = onp.evaluate(p, c, kw)
+        assert abs(rob[0] - r) <= 1e-10 * max(abs(r), 1.0), kw
+
+
+def test_bad_parameters_are_flagged_not_raised(oracle_lib):
+    from pde_controller_b200 import synth
+    b = synth.make_batch(4, "heat", seed=1)
+    b.dt[1] = 0.0
+    b.n_elem[2] = 0
+    b.knot_y[0, 3] = np.inf
+    rob, st = oracle_lib.eval_batch(b)
+    assert st[0] == 0 and st[1] == 3 and st[2] == 3 and st[3] == 2
+    assert rob[1] == -100.0 and rob[2] == -100.0 and rob[3] == -100.0
