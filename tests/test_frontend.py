@@ -1,0 +1,125 @@
+"""Front-end: dialect text -> Problem, no exec (Appendix A for the grammar)."""
+import numpy as np
+import pytest
+
+from pde_controller_b200 import Predicate, Problem, ProblemBatch, synth
+from pde_controller_b200.frontend import ParseError, parse_cspec, parse_program, render_program
+
+HEAT = '''
+from femformal.core.fem import heatlinfem as heatlinfem
+
+N = 30
+L = 140
+rho = lambda x: 4.2e-06*455000000 if x < 21 or x > 77 else 5.1e-06*401000000
+E = lambda x: 905000 if x < 21 or x > 77 else 1420000
+xpart = np.linspace(0, L, N + 1)
+g = [305, None]
+f_nodal = np.zeros(N + 1)
+dt = .05
+
+T = 9
+fosys = heatlinfem.heatlinfem_mix(xpart, rho, E, g, f_nodal, dt)
+
+apc0 = logic.APCont([11, 40], "=", lambda x: 0.25 * x + 290.5, lambda x: 0.25)
+apc1 = logic.APCont([90.0, 121.0], "<", lambda x: -0.031 * x + -2.5e+2 + 560, lambda x: -0.031)
+cregions = {"A" : apc0, "B" : apc1}
+cspec = "((F_[0.5, 2.25] (A)) & (G_[4.125, 7.5] (B)))"
+'''
+
+
+def test_parse_canonical_heat_program():
+    p = parse_program(HEAT)
+    assert (p.kind, p.n_elem, p.L, p.dt, p.T, p.g0) == ("heat", 30, 140.0, 0.05, 9.0, 305.0)
+    assert (p.x_a, p.x_b) == (21.0, 77.0)
+    assert p.rho_out == 4.2e-06 * 455000000 and p.rho_in == 5.1e-06 * 401000000
+    assert (p.E_out, p.E_in) == (905000.0, 1420000.0)
+    a, b = p.predicates
+    assert (a.x_lo, a.x_hi, a.rel, a.m, a.b, a.top, a.t_lo, a.t_hi) == (11.0, 40.0, "=", 0.25, 290.5, "F", 0.5, 2.25)
+    assert (b.rel, b.top) == ("<", "G") and b.m == pytest.approx(-0.031) and b.b == pytest.approx(310.0)
+    assert p.tree == [("leaf", 0, 0), ("leaf", 1, 0), ("and", 0, 1)]
+
+
+def test_wave_and_or_tree():
+    txt = HEAT.replace("heatlinfem as heatlinfem", "mechlinfem as mechlinfem") \
+              .replace("fosys = heatlinfem.heatlinfem_mix", "sosys = mechlinfem.mechlinfem") \
+              .replace('cspec = "((F_[0.5, 2.25] (A)) & (G_[4.125, 7.5] (B)))"',
+                       'cspec = "(((G_[0.5, 2.25] (A)) & (G_[1, 2] (B))) | (F_[4.125, 7.5] (B)))"')
+    p = parse_program(txt)
+    assert p.kind == "wave" and len(p.predicates) == 3
+    assert p.tree == [("leaf", 0, 0), ("leaf", 1, 0), ("and", 0, 1), ("leaf", 2, 0), ("or", 2, 3)]
+    assert [q.label for q in p.predicates] == ["A", "B", "B"]
+
+
+def test_render_round_trip_on_synthetic_samples():
+    for wl in ("heat", "wave"):
+        b = synth.make_batch(64, wl, seed=4)
+        for s in range(b.n):
+            p, _ = b.get_problem(s)
+            q = parse_program(render_program(p))
+            for pq in q.predicates:
+                pq.label = ""
+            for pp in p.predicates:
+                pp.label = ""
+            assert q == p
+
+
+def test_general_material_callables_are_fitted():
+    txt = HEAT.replace("rho = lambda x: 4.2e-06*455000000 if x < 21 or x > 77 else 5.1e-06*401000000", "rho = lambda x: 2000.0") \
+              .replace("E = lambda x: 905000 if x < 21 or x > 77 else 1420000", "E = lambda x: 1e6 if x <= 70 else 2e6")
+    p = parse_program(txt)
+    assert p.rho_in == p.rho_out == 2000.0
+    assert (p.E_out, p.E_in) == (1e6, 2e6) and p.x_a == pytest.approx(70.0) and p.x_b == 140.0
+
+
+@pytest.mark.parametrize("mutate", [
+    lambda t: t.replace("T = 9", "T = __import__('os').getpid()"),
+    lambda t: t.replace("T = 9", "T = open('/etc/passwd').read()"),
+    lambda t: t.replace("g = [305, None]", "g = [305, 300]"),
+    lambda t: t.replace("f_nodal = np.zeros(N + 1)", "f_nodal = np.ones(N + 1)"),
+    lambda t: t.replace('"="', '">="'),
+    lambda t: t.replace("lambda x: 0.25 * x + 290.5,", "lambda x: 0.25 * x * x + 290.5,"),
+    lambda t: t.replace("(A)) &", "(Z)) &"),
+    lambda t: t.replace("T = 9", ""),
+    lambda t: t.replace("dt = .05", "dt = 0"),
+    lambda t: t.replace("xpart = np.linspace(0, L, N + 1)", "xpart = np.array([0, 1, 5, 140])"),
+    lambda t: t[: len(t) // 2],
+    lambda t: "this is not a program",
+    lambda t: t.replace("E = lambda x: 905000 if x < 21 or x > 77 else 1420000",
+                        "E = lambda x: 1e6 if x < 20 else (2e6 if x < 60 else 3e6)"),
+    lambda t: t.replace("N = 30", "N = 30\nwhile True: pass"),
+    lambda t: t.replace("N = 30", "N = 10**9"),
+])
+def test_malformed_or_hostile_programs_raise_parse_error(mutate):
+    with pytest.raises(ParseError):
+        parse_program(mutate(HEAT))
+
+
+def test_stray_statements_are_never_executed(tmp_path):
+    """Expression statements (prints, stray calls) are skipped, not run: the text is never exec'd."""
+    marker = tmp_path / "pwned"
+    p = parse_program(HEAT.replace("N = 30", f"N = 30\nimport os\nos.system('touch {marker}')\nprint('hi')"))
+    assert p.n_elem == 30 and not marker.exists()
+
+
+def test_cspec_grammar():
+    cl, tr = parse_cspec("((G_[0.1, 0.2] (A)))")
+    assert cl == [("G", 0.1, 0.2, "A")] and tr == [("leaf", 0, 0)]
+    cl, tr = parse_cspec("G_[0,1] ((A) & (B))")          # G distributes over & exactly
+    assert [c[3] for c in cl] == ["A", "B"] and tr[-1] == ("and", 0, 1)
+    cl, tr = parse_cspec("(A) & F_[1e-1, 2.5E0] (B)")
+    assert cl[0] == ("G", 0.0, 0.0, "A") and cl[1] == ("F", 0.1, 2.5, "B")
+    for bad in ("G_[0,1] ((A) | (B))", "G_[0,1] (F_[0,1] (A))", "", "((A)", "G_[1,0] (A)", "A & & B", "G_[a,b] (A)"):
+        with pytest.raises(ParseError):
+            parse_cspec(bad)
+
+
+def test_batch_packing_round_trip():
+    p = parse_program(HEAT)
+    ctrl = (np.linspace(0, 9, 10), np.arange(10.0))
+    b = ProblemBatch.from_problems([p, p], [ctrl, None])
+    q, c = b.get_problem(0)
+    for a in q.predicates + p.predicates:
+        a.label = ""
+    assert q == p and np.array_equal(c[0], ctrl[0]) and np.array_equal(c[1], ctrl[1])
+    assert b.get_problem(1)[1] is None
+    assert b.algorithmic_bytes() == (105 + 16 * 10 + 50 * 2 + 9) + (105 + 0 + 50 * 2 + 9)
