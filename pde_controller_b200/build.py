@@ -16,18 +16,20 @@ def _newest(paths):
     return max(os.path.getmtime(p) for p in paths)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: build an experimental variant (tools/variant_bench.py) next to the default library."""
+    global_so = SO if out is None else out
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
     deps = srcs + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
-    if not force and os.path.exists(SO) and os.path.getmtime(SO) >= _newest(deps):
-        return SO
+    if not force and os.path.exists(global_so) and os.path.getmtime(global_so) >= _newest(deps):
+        return global_so
     nvcc = os.environ.get("NVCC", "nvcc")
     objs = []
     procs = []
     for s in srcs:
-        o = os.path.splitext(s)[0] + ".o"
+        o = os.path.splitext(s)[0] + (".o" if out is None else "." + os.path.basename(out) + ".o")
         objs.append(o)
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:
         out, _ = p.communicate()
@@ -35,9 +37,9 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    link = [nvcc, "-shared", "-o", SO] + objs + ["-lcudart"]
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", global_so] + objs + ["-lcudart"]
     subprocess.run(link, check=True)
-    return SO
+    return global_so
 
 
 if __name__ == "__main__":

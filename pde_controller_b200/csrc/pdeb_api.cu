@@ -91,6 +91,10 @@ struct PdebResident {
     PdebDevOut out{};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool host_slab = false;          /* device slab mirrors the caller's host slab byte for byte */
+    unsigned char* plan = nullptr;   /* keys | order | hist | vstart_count */
+    PdebPlanBuffers pb{};
+    int32_t* vsc_host = nullptr;     /* pinned copy of vstart_count */
+    int plan_launches = 0;
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -117,6 +121,8 @@ extern "C" void pdeb_resident_destroy(PdebResident* r) {
     for (auto& e : r->ev) if (e) cudaEventDestroy(e);
     if (r->slab) cudaFree(r->slab);
     if (r->outs) cudaFree(r->outs);
+    if (r->plan) cudaFree(r->plan);
+    if (r->vsc_host) cudaFreeHost(r->vsc_host);
     delete r;
 }
 
@@ -168,6 +174,23 @@ static int upload(PdebResident* r, const PdebBatch* in, cudaStream_t stream, boo
     CK(copy(d.tree_op, in->tree_op, 1, r->tmax));
     CK(copy(d.tree_lhs, in->tree_lhs, 1, r->tmax));
     CK(copy(d.tree_rhs, in->tree_rhs, 1, r->tmax));
+    return 0;
+}
+
+/*
+ * Order the resident samples by kernel variant and step count (device side, 3 launches) and bring
+ * the per-variant counts back: this is the one host synchronisation of an upload.
+ */
+static int plan_resident(PdebResident* r, cudaStream_t stream) {
+    if (r->n == 0) return 0;
+    PdebConventions cv;
+    pdeb_default_conventions(&cv);
+    int nl = 0;
+    int rc = pdeb_plan(r->dev, cv, r->out, r->pb, stream, &nl);
+    if (rc) return fail(PDEB_E_CUDA, "plan launch", (cudaError_t)rc);
+    r->plan_launches = nl;
+    CK(cudaMemcpyAsync(r->vsc_host, r->pb.vstart_count, sizeof(int32_t) * 2 * PDEB_NUM_VARIANTS, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
     return 0;
 }
 
@@ -226,6 +249,18 @@ static int resident_alloc(const PdebBatch* in, int device, PdebResident** outp) 
     const size_t out_total = align_up(out_status + 4 * (size_t)(n > 0 ? n : 1), 256);
     cudaError_t ce = cudaMalloc((void**)&r->slab, total > 0 ? total : 256);
     if (ce == cudaSuccess) ce = cudaMalloc((void**)&r->outs, out_total);
+    const size_t n1 = (size_t)(n > 0 ? n : 1);
+    const size_t plan_keys = 0, plan_order = align_up(4 * n1, 256), plan_hist = plan_order + align_up(4 * n1, 256);
+    const size_t plan_vsc = plan_hist + sizeof(int32_t) * PDEB_PLAN_BINS;
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&r->plan, plan_vsc + 256);
+    if (ce == cudaSuccess) ce = cudaHostAlloc((void**)&r->vsc_host, sizeof(int32_t) * 2 * PDEB_NUM_VARIANTS, cudaHostAllocDefault);
+    if (ce == cudaSuccess) {
+        r->pb.keys = (int32_t*)(r->plan + plan_keys);
+        r->pb.order = (int32_t*)(r->plan + plan_order);
+        r->pb.hist = (int32_t*)(r->plan + plan_hist);
+        r->pb.vstart_count = (int32_t*)(r->plan + plan_vsc);
+        memset(r->vsc_host, 0, sizeof(int32_t) * 2 * PDEB_NUM_VARIANTS);
+    }
     for (int i = 0; i < 4 && ce == cudaSuccess; ++i) ce = cudaEventCreate(&r->ev[i]);
     if (ce != cudaSuccess) {
         pdeb_resident_destroy(r);
@@ -260,6 +295,7 @@ extern "C" int pdeb_resident_create(const PdebBatch* in, int device, void* strea
     if (rc) return rc;
     DeviceGuard g(device);
     rc = upload(r, in, (cudaStream_t)stream_, false);
+    if (rc == 0) rc = plan_resident(r, (cudaStream_t)stream_);
     if (rc) { pdeb_resident_destroy(r); return rc; }
     *outp = r;
     return 0;
@@ -275,7 +311,9 @@ extern "C" int pdeb_resident_upload(PdebResident* r, const PdebBatch* in, void* 
     if (slab != r->host_slab || (slab && (size_t)in->slab_bytes != r->slab_bytes))
         return fail(PDEB_E_ARG, "batch slab layout differs from the resident image");
     DeviceGuard g(r->device);
-    return upload(r, in, (cudaStream_t)stream_, false);
+    rc = upload(r, in, (cudaStream_t)stream_, false);
+    if (rc == 0) rc = plan_resident(r, (cudaStream_t)stream_);
+    return rc;
 }
 
 extern "C" int pdeb_resident_set_knots(PdebResident* r, const double* knot_t, const double* knot_y,
@@ -299,7 +337,7 @@ extern "C" int pdeb_resident_eval(PdebResident* r, int precision, const PdebConv
     if (conv) cv = *conv; else pdeb_default_conventions(&cv);
     int launches = 0;
     if (timing) CK(cudaEventRecord(r->ev[0], stream));
-    int rc = pdeb_launch_all(r->dev, cv, r->out, precision, stream, &launches);
+    int rc = pdeb_launch_all(r->dev, cv, r->out, r->pb, r->vsc_host, precision, stream, &launches);
     if (rc) return fail(PDEB_E_CUDA, "kernel launch", (cudaError_t)rc);
     if (timing) {
         CK(cudaEventRecord(r->ev[1], stream));
@@ -360,8 +398,11 @@ extern "C" int pdeb_eval_batch(const PdebBatch* in, int device, int precision, c
     if (ce == cudaSuccess) { rc = upload(r, in, stream, false); if (rc) { pdeb_resident_destroy(r); return rc; } }
     if (ce == cudaSuccess && timing) ce = cudaEventRecord(r->ev[1], stream);
     if (ce == cudaSuccess) {
-        int lrc = pdeb_launch_all(r->dev, cv, r->out, precision, stream, &launches);
+        rc = plan_resident(r, stream);
+        if (rc) { pdeb_resident_destroy(r); return rc; }
+        int lrc = pdeb_launch_all(r->dev, cv, r->out, r->pb, r->vsc_host, precision, stream, &launches);
         if (lrc) ce = (cudaError_t)lrc;
+        launches += r->plan_launches;
     }
     if (ce == cudaSuccess && timing) ce = cudaEventRecord(r->ev[2], stream);
     if (ce != cudaSuccess) { pdeb_resident_destroy(r); return fail(PDEB_E_CUDA, "launch", ce); }

@@ -10,41 +10,116 @@
 #include "pdeb_core.h"
 #include "pdeb_launch.h"
 
+#ifdef PDEB_REG_MAXNREG
+#define PDEB_REG_BOUNDS __maxnreg__(PDEB_REG_MAXNREG)
+#else
+#define PDEB_REG_BOUNDS __launch_bounds__(PDEB_REG_THREADS, PDEB_REG_MINBLOCKS)
+#endif
+
 template <int KIND, int N, typename real>
-__global__ void __launch_bounds__(PDEB_REG_THREADS)
+__global__ void PDEB_REG_BOUNDS
 pdeb_reg_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant__ PdebConventions cv,
                 const __grid_constant__ PdebDevOut out, const int32_t* __restrict__ order, int64_t first, int64_t count) {
     extern __shared__ __align__(16) unsigned char pdeb_smem[];
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool live = t < count;
-    int64_t s = 0;
-    if (live) {
-        s = order ? (int64_t)order[first + t] : first + t;
-        /* a sample belongs to exactly one kernel variant; the others skip it */
-        if (b.kind[s] != KIND || b.n_elem[s] != N) live = false;
-    }
-    if (!__any_sync(0xffffffffu, live)) return;
-    PdebClauseSlots<real> slots = pdeb_clause_slots<real>(pdeb_smem, blockDim.x, b.pmax, threadIdx.x);
-    pdeb_run_reg<KIND, N, real>(b, cv, out, s, slots, live);
+    const bool live = t < count;                      /* padding lanes of the last warp idle through the loop */
+    const int64_t s = live ? (int64_t)order[first + t] : 0;
+    typedef typename PdebVec2<real>::type real2;
+    real2* table = reinterpret_cast<real2*>(pdeb_smem) + threadIdx.x;
+    PdebClauseSlots<real> slots = pdeb_clause_slots<real>(pdeb_smem + pdeb_table_smem_bytes<real>(blockDim.x, N),
+                                                          blockDim.x, b.pmax, threadIdx.x);
+    pdeb_run_reg<KIND, N, real>(b, cv, out, s, table, blockDim.x, slots, live);
 }
 
-/* samples no compute variant of this build covers: flag them, never drop them silently */
-__global__ void pdeb_unsupported_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant__ PdebDevOut out) {
+/*
+ * Plan: order the samples so that every warp gets trajectories of the same kernel variant and
+ * (nearly) the same number of time steps, longest first.  Three tiny kernels: keys + histogram,
+ * exclusive scan of the PDEB_PLAN_BINS bins, scatter.  Samples no variant of this build covers
+ * are flagged here (status BADPARAM, robustness -100), never dropped silently.
+ */
+__device__ __forceinline__ int pdeb_plan_key(const PdebDevBatch& b, const PdebConventions& cv, int64_t s) {
+    const int kind = b.kind[s], N = b.n_elem[s];
+    const int v = pdeb_variant_of(kind, N);
+    if (v < 0) return -1;
+    const double T = b.T[s], dt = b.dt[s];
+    int64_t S = 1;
+    if (T > 0 && dt > 0 && isfinite(T) && isfinite(dt)) S = pdeb_step_count(T, dt, cv.steps_rule);
+    if (S > PDEB_PLAN_SBINS - 1) S = PDEB_PLAN_SBINS - 1;
+    return v * PDEB_PLAN_SBINS + (PDEB_PLAN_SBINS - 1 - (int)S);     /* descending in S inside a variant */
+}
+
+__global__ void pdeb_plan_keys_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant__ PdebConventions cv,
+                                      const __grid_constant__ PdebDevOut out, int32_t* __restrict__ keys,
+                                      int32_t* __restrict__ hist) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= b.n) return;
-    const int kind = b.kind[s], N = b.n_elem[s];
-    if (pdeb_variant_of(kind, N) >= 0) return;
+    const int key = pdeb_plan_key(b, cv, s);
+    keys[s] = key;
+    if (key >= 0) { atomicAdd(&hist[key], 1); return; }
     out.robustness[s] = PDEB_FAILED_ROBUSTNESS;
     if (out.status) out.status[s] = PDEB_ST_BADPARAM;
     if (out.clause)
         for (int j = 0; j < b.pmax; ++j) out.clause[(int64_t)j * b.stride + s] = PDEB_FAILED_ROBUSTNESS;
 }
 
+/* one block: hist -> exclusive offsets (in place), per-variant start / count */
+__global__ void pdeb_plan_scan_kernel(int32_t* __restrict__ hist, int32_t* __restrict__ vstart_count) {
+    __shared__ int32_t part[1024];
+    constexpr int PER = PDEB_PLAN_BINS / 1024;
+    const int t = threadIdx.x;
+    int32_t loc[PER];
+    int32_t sum = 0;
+    for (int q = 0; q < PER; ++q) { loc[q] = hist[t * PER + q]; sum += loc[q]; }
+    part[t] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        int32_t v = (t >= off) ? part[t - off] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    int32_t run = part[t] - sum;
+    for (int q = 0; q < PER; ++q) { hist[t * PER + q] = run; run += loc[q]; }
+    __syncthreads();
+    if (t < PDEB_NUM_VARIANTS) {
+        const int first_bin = t * PDEB_PLAN_SBINS, last_bin = (t + 1) * PDEB_PLAN_SBINS - 1;
+        const int tf = first_bin / PER, tl = last_bin / PER;
+        /* inclusive sums are in part[]; bins of a variant are whole multiples of PER */
+        const int32_t start = (tf == 0) ? 0 : part[tf - 1];
+        vstart_count[2 * t] = start;
+        vstart_count[2 * t + 1] = part[tl] - start;
+    }
+}
+
+__global__ void pdeb_plan_scatter_kernel(int64_t n, const int32_t* __restrict__ keys, int32_t* __restrict__ cursor,
+                                         int32_t* __restrict__ order) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int key = keys[s];
+    if (key < 0) return;
+    order[atomicAdd(&cursor[key], 1)] = (int32_t)s;
+}
+
+int pdeb_plan(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out, const PdebPlanBuffers& pb,
+              cudaStream_t stream, int* launches) {
+    if (b.n <= 0) { if (launches) *launches = 0; return 0; }
+    cudaError_t e = cudaMemsetAsync(pb.hist, 0, sizeof(int32_t) * PDEB_PLAN_BINS, stream);
+    if (e != cudaSuccess) return (int)e;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((b.n + threads - 1) / threads);
+    pdeb_plan_keys_kernel<<<blocks, threads, 0, stream>>>(b, cv, out, pb.keys, pb.hist);
+    pdeb_plan_scan_kernel<<<1, 1024, 0, stream>>>(pb.hist, pb.vstart_count);
+    pdeb_plan_scatter_kernel<<<blocks, threads, 0, stream>>>(b.n, pb.keys, pb.hist, pb.order);
+    if (launches) *launches = 3;
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
 template <int KIND, int N, typename real>
 static cudaError_t launch_reg(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out,
                               const int32_t* order, int64_t first, int64_t count, cudaStream_t stream) {
     if (count <= 0) return cudaSuccess;
-    const size_t smem = pdeb_clause_smem_bytes<real>(PDEB_REG_THREADS, b.pmax);
+    const size_t smem = pdeb_table_smem_bytes<real>(PDEB_REG_THREADS, N) + pdeb_clause_smem_bytes<real>(PDEB_REG_THREADS, b.pmax);
     auto kern = pdeb_reg_kernel<KIND, N, real>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -55,26 +130,26 @@ static cudaError_t launch_reg(const PdebDevBatch& b, const PdebConventions& cv, 
     return cudaGetLastError();
 }
 
-int pdeb_launch_all(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out, int precision,
-                    cudaStream_t stream, int* launches) {
+int pdeb_launch_all(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out, const PdebPlanBuffers& pb,
+                    const int32_t* vstart_count_host, int precision, cudaStream_t stream, int* launches) {
     cudaError_t e = cudaSuccess;
     int nl = 0;
-    if (b.n <= 0) { if (launches) *launches = 0; return 0; }
-    {
-        const int threads = 256;
-        pdeb_unsupported_kernel<<<(unsigned)((b.n + threads - 1) / threads), threads, 0, stream>>>(b, out);
-        e = cudaGetLastError();
+    for (int v = 0; v < PDEB_NUM_VARIANTS && e == cudaSuccess; ++v) {
+        const int64_t first = vstart_count_host[2 * v], count = vstart_count_host[2 * v + 1];
+        if (count <= 0) continue;
         ++nl;
-    }
-    if (e == cudaSuccess) {
-        if (precision == 32) e = launch_reg<PDEB_KIND_HEAT, 30, float>(b, cv, out, nullptr, 0, b.n, stream);
-        else e = launch_reg<PDEB_KIND_HEAT, 30, double>(b, cv, out, nullptr, 0, b.n, stream);
-        ++nl;
-    }
-    if (e == cudaSuccess) {
-        if (precision == 32) e = launch_reg<PDEB_KIND_WAVE, 20, float>(b, cv, out, nullptr, 0, b.n, stream);
-        else e = launch_reg<PDEB_KIND_WAVE, 20, double>(b, cv, out, nullptr, 0, b.n, stream);
-        ++nl;
+        switch (v) {
+        case 0:
+            e = (precision == 32) ? launch_reg<PDEB_KIND_HEAT, 30, float>(b, cv, out, pb.order, first, count, stream)
+                                  : launch_reg<PDEB_KIND_HEAT, 30, double>(b, cv, out, pb.order, first, count, stream);
+            break;
+        case 1:
+            e = (precision == 32) ? launch_reg<PDEB_KIND_WAVE, 20, float>(b, cv, out, pb.order, first, count, stream)
+                                  : launch_reg<PDEB_KIND_WAVE, 20, double>(b, cv, out, pb.order, first, count, stream);
+            break;
+        default:
+            break;
+        }
     }
     if (launches) *launches = nl;
     return e == cudaSuccess ? 0 : (int)e;

@@ -15,7 +15,8 @@ from . import abi
 from .problem import ProblemBatch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libpdeb200.so")
+# PDEB_LIB lets the kernel-variant experiments in tools/ load an alternative build of the same ABI
+SO_PATH = os.environ.get("PDEB_LIB") or os.path.join(_HERE, "libpdeb200.so")
 _lib = None
 
 

@@ -8,7 +8,7 @@ scale (0.3 K for heat at 300 K, 1e-3 mm for waves) instead of against itself.
 import numpy as np
 
 TOL_FP64 = 1e-9
-TOL_FP32 = {"heat": 2e-3, "wave": 2e-2}   # FP32 mode is reported separately at its own tolerance
+TOL_FP32 = {"heat": 2e-3, "wave": 5e-2}   # FP32 mode is reported separately at its own tolerance
 
 
 def scale_of(ref, batch):

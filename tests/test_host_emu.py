@@ -56,7 +56,7 @@ def test_device_code_matches_oracle(emu, oracle_lib, wl, kw):
 def test_device_code_fp32_mode(emu, oracle_lib):
     from parity import rel_err
     conv = default_conventions()
-    for wl, tol in (("heat", 2e-3), ("wave", 2e-2)):
+    for wl, tol in (("heat", 2e-3), ("wave", 5e-2)):
         b = synth.make_batch(256, wl, seed=22)
         ref, ref_st = oracle_lib.eval_batch(b, conv)
         rob, st, _ = run_emu(emu, b, conv, 32)

@@ -1,0 +1,77 @@
+"""Time alternative builds of libpdeb200.so against each other on the GPU box (development tool).
+
+  python tools/variant_bench.py build  NAME=DEFINE[,DEFINE...] ...   # here (nvcc cross-compiles)
+  python tools/variant_bench.py run [--workloads heat,wave] [--batch 65536]   # under gpurun
+
+`run` loads every pde_controller_b200/variants/lib*.so in a fresh process, checks parity on a
+4096-sample batch against the oracle, then times the resident eval with CUDA events.
+"""
+import glob
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+VDIR = os.path.join(ROOT, "pde_controller_b200", "variants")
+
+
+def do_build(specs):
+    from pde_controller_b200 import build
+    os.makedirs(VDIR, exist_ok=True)
+    for spec in specs:
+        name, _, defs = spec.partition("=")
+        defines = [d for d in defs.split(",") if d]
+        out = os.path.join(VDIR, f"lib{name}.so")
+        build.build(force=True, defines=defines, out=out)
+        print("built", out, defines)
+
+
+def one(workloads, batch, precision):
+    import numpy as np
+    import oracle
+    from pde_controller_b200 import native, synth
+    res = {}
+    for wl in workloads:
+        small = synth.make_batch(4096, wl, seed=5)
+        got = native.evaluate_batch(small, precision=precision)
+        ref, st = oracle.eval_batch(small)
+        scale = np.maximum(np.abs(ref), 1e-3 * (np.abs(small.g0) + 1))
+        err = float((np.abs(got["robustness"] - ref) / scale).max())
+        b = synth.make_batch(batch, wl, seed=0)
+        r = native.ResidentBatch(b)
+        for _ in range(3):
+            r.eval(precision, timing=True)
+        ms = sorted(r.eval(precision, timing=True).kernel_ms for _ in range(15))
+        res[wl] = {"ms_median": ms[len(ms) // 2], "ms_min": ms[0], "evals_per_s": batch / (ms[len(ms) // 2] * 1e-3),
+                   "max_rel_err": err, "status_ok": bool((got["status"] == st).all())}
+        r.close()
+    print(json.dumps(res))
+
+
+def do_run(argv):
+    workloads, batch, precision = "heat,wave", 65536, 64
+    for i, a in enumerate(argv):
+        if a == "--workloads":
+            workloads = argv[i + 1]
+        if a == "--batch":
+            batch = int(argv[i + 1])
+        if a == "--precision":
+            precision = int(argv[i + 1])
+    libs = [os.path.join(ROOT, "pde_controller_b200", "libpdeb200.so")] + sorted(glob.glob(os.path.join(VDIR, "lib*.so")))
+    for lib in libs:
+        env = dict(os.environ, PDEB_LIB=lib)
+        p = subprocess.run([sys.executable, __file__, "one", workloads, str(batch), str(precision)], env=env,
+                           capture_output=True, text=True, timeout=600)
+        line = p.stdout.strip().splitlines()[-1] if p.stdout.strip() else p.stderr[-400:]
+        print(os.path.basename(lib), line, flush=True)
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "build":
+        do_build(sys.argv[2:])
+    elif sys.argv[1] == "run":
+        do_run(sys.argv[2:])
+    elif sys.argv[1] == "one":
+        one(sys.argv[2].split(","), int(sys.argv[3]), int(sys.argv[4]))
