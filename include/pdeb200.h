@@ -72,7 +72,7 @@ extern "C" {
 /* limits of this build */
 #define PDEB_MAX_PRED   8
 #define PDEB_MAX_TREE   (2 * PDEB_MAX_PRED - 1)
-#define PDEB_MAX_ELEM   1055          /* 32 lanes x 32 rows + 31 separators */
+#define PDEB_MAX_ELEM   1054          /* heat; 32 lanes x 32 rows + 31 separators - the Dirichlet node (waves: 542) */
 #define PDEB_MAX_STEPS  (1 << 22)
 
 /* return codes */

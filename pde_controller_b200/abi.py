@@ -11,7 +11,7 @@ OK, ST_PARSE, ST_NONFINITE, ST_BADPARAM = 0, 1, 2, 3
 FAILED_ROBUSTNESS = -100.0
 MAX_PRED = 8
 MAX_TREE = 2 * MAX_PRED - 1
-MAX_ELEM = 1055
+MAX_ELEM = 1054
 MAX_STEPS = 1 << 22
 
 REL_CODE = {">": REL_GT, "<": REL_LT, "=": REL_EQ}

@@ -63,28 +63,25 @@ __global__ void pdeb_plan_keys_kernel(const __grid_constant__ PdebDevBatch b, co
 }
 
 /* one block: hist -> exclusive offsets (in place), per-variant start / count */
-__global__ void pdeb_plan_scan_kernel(int32_t* __restrict__ hist, int32_t* __restrict__ vstart_count) {
+__global__ void __launch_bounds__(1024) pdeb_plan_scan_kernel(int32_t* __restrict__ hist, int32_t* __restrict__ vstart_count) {
     __shared__ int32_t part[1024];
     constexpr int PER = PDEB_PLAN_BINS / 1024;
     const int t = threadIdx.x;
-    int32_t loc[PER];
     int32_t sum = 0;
-    for (int q = 0; q < PER; ++q) { loc[q] = hist[t * PER + q]; sum += loc[q]; }
+    for (int q = 0; q < PER; ++q) sum += hist[t * PER + q];
     part[t] = sum;
     __syncthreads();
     for (int off = 1; off < 1024; off <<= 1) {
-        int32_t v = (t >= off) ? part[t - off] : 0;
+        const int32_t v = (t >= off) ? part[t - off] : 0;
         __syncthreads();
         part[t] += v;
         __syncthreads();
     }
     int32_t run = part[t] - sum;
-    for (int q = 0; q < PER; ++q) { hist[t * PER + q] = run; run += loc[q]; }
-    __syncthreads();
+    for (int q = 0; q < PER; ++q) { const int32_t c = hist[t * PER + q]; hist[t * PER + q] = run; run += c; }
     if (t < PDEB_NUM_VARIANTS) {
-        const int first_bin = t * PDEB_PLAN_SBINS, last_bin = (t + 1) * PDEB_PLAN_SBINS - 1;
-        const int tf = first_bin / PER, tl = last_bin / PER;
-        /* inclusive sums are in part[]; bins of a variant are whole multiples of PER */
+        /* the bins of a variant are whole multiples of PER, so its range is a range of threads */
+        const int tf = t * PDEB_PLAN_SBINS / PER, tl = ((t + 1) * PDEB_PLAN_SBINS - 1) / PER;
         const int32_t start = (tf == 0) ? 0 : part[tf - 1];
         vstart_count[2 * t] = start;
         vstart_count[2 * t + 1] = part[tl] - start;
@@ -148,6 +145,8 @@ int pdeb_launch_all(const PdebDevBatch& b, const PdebConventions& cv, const Pdeb
                                   : launch_reg<PDEB_KIND_WAVE, 20, double>(b, cv, out, pb.order, first, count, stream);
             break;
         default:
+            if (v >= 2 && v <= 7) e = pdeb_launch_chunk_heat(1 << (v - 2), b, cv, out, pb.order, first, count, stream);
+            else if (v >= 8 && v <= 12) e = pdeb_launch_chunk_wave(1 << (v - 8), b, cv, out, pb.order, first, count, stream);
             break;
         }
     }

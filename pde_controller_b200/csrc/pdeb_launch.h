@@ -13,16 +13,35 @@
 #define PDEB_REG_MINBLOCKS 2   /* resident blocks per SM the register family is compiled for */
 #endif
 
-/* which kernel variant owns a (kind, mesh) pair; -1 = none in this build */
+/*
+ * Kernel variants.  0: heat N=30 and 1: wave N=20 are the register family (thread per trajectory);
+ * 2..7: chunk family heat with R = 1,2,4,8,16,32 rows per lane; 8..12: chunk family wave, R = 1..16.
+ * A mesh of N elements needs 32 R + 30 >= N.
+ */
+#define PDEB_NUM_VARIANTS 13
+#define PDEB_VARIANT_SLOTS 16
 PDEB_HD int pdeb_variant_of(int kind, int n_elem) {
-    if (kind == PDEB_KIND_HEAT && n_elem == 30) return 0;
-    if (kind == PDEB_KIND_WAVE && n_elem == 20) return 1;
+    if (n_elem < 1) return -1;
+    if (kind == PDEB_KIND_HEAT) {
+        if (n_elem == 30) return 0;
+        for (int q = 0; q < 6; ++q) if (n_elem <= 32 * (1 << q) + 30) return 2 + q;
+        return -1;
+    }
+    if (kind == PDEB_KIND_WAVE) {
+        if (n_elem == 20) return 1;
+        for (int q = 0; q < 5; ++q) if (n_elem <= 32 * (1 << q) + 30) return 8 + q;
+        return -1;
+    }
     return -1;
 }
 
-#define PDEB_NUM_VARIANTS 2
-#define PDEB_PLAN_SBINS 4096                                   /* step-count bins per variant */
-#define PDEB_PLAN_BINS (PDEB_NUM_VARIANTS * PDEB_PLAN_SBINS)   /* multiple of 1024 */
+#define PDEB_PLAN_SBINS 4096                                    /* step-count bins per variant */
+#define PDEB_PLAN_BINS (PDEB_VARIANT_SLOTS * PDEB_PLAN_SBINS)   /* multiple of 1024 */
+
+cudaError_t pdeb_launch_chunk_heat(int R, const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out,
+                                   const int32_t* order, int64_t first, int64_t count, cudaStream_t stream);
+cudaError_t pdeb_launch_chunk_wave(int R, const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out,
+                                   const int32_t* order, int64_t first, int64_t count, cudaStream_t stream);
 
 /* device scratch of the plan (owned by the resident batch) */
 struct PdebPlanBuffers {
