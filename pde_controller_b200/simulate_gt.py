@@ -1,0 +1,108 @@
+"""Batched ground-truth labelling: the reference's simulate_gt.py driver with ONE GPU call instead of a process pool.
+
+Mirrors test/PDEcontrol/evaluation/infer/simulate_gt.py:92-191 of the reference: same CLI flags (the ones that
+concern this path), same sampling (`random.seed(42)`, `random.sample`), same output files
+(`{data_dir}_{max_num_examples}/test.jsonl` with `robustness` and `time` added, `metrics.json` with the
+three rates).  `evaluate_future` (simulate_gt.py:62-89: one future per sample, 300 s timeout) is replaced by
+`eval_robustness_batch`.  A sample whose program cannot be evaluated is labelled -100, exactly what
+simulate_gt.py:55-59 / :144-147 count as "failed"; there are no timeouts any more.
+
+Controls: the reference's labels are the robustness under the MILP-synthesised input (out of scope here).  This driver
+evaluates under the control given per record in the optional `control_key` field ({"t": [...], "y": [...]}), else zero
+input.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import random
+
+from .eval_script import eval_robustness_batch
+
+
+def evaluate_future(eval_fn, tasks, _timeout=300, python_key="python", nl_key="nl", control_key="control"):
+    """Drop-in for simulate_gt.evaluate_future: -> (robustness tuple, time tuple, timeout_cnt).
+
+    `eval_fn` is accepted for signature compatibility and ignored: the whole task list goes to the GPU at once.
+    """
+    controls = []
+    for t in tasks:
+        c = t.get(control_key)
+        controls.append((c["t"], c["y"]) if isinstance(c, dict) and "t" in c and "y" in c else None)
+    rob, rt = eval_robustness_batch([t[python_key] for t in tasks], [t.get(nl_key, "") for t in tasks], controls)
+    return tuple(rob), tuple(rt), 0
+
+
+def main(args):
+    random.seed(42)
+    test_data = []
+    fname = "validation.jsonl" if args.infer_on_train_set else "test.jsonl"
+    with open(os.path.join(args.data_dir, fname)) as fin:
+        for line in fin:
+            example = json.loads(line)
+            example["python"] = example[args.python_key].strip()
+            example["sstl"] = example.get(args.stl_key)
+            example["nl"] = example.get(args.nl_key, "")
+            robustness = example.get(args.robustness_key, None)
+            if robustness is not None:
+                example["robustness"] = robustness
+            test_data.append(example)
+    if args.max_num_examples and len(test_data) > args.max_num_examples:
+        test_data = random.sample(test_data, args.max_num_examples)
+    if not test_data:
+        print("Ending. There was no data to test.")
+        return None
+    args.save_dir = os.path.join(args.data_dir + "_" + str(args.max_num_examples))
+    os.makedirs(args.save_dir, exist_ok=True)
+
+    metrics = {"n_samples": len(test_data)}
+    if args.eval_robustness:
+        rob, times, timeouts = evaluate_future(None, test_data, control_key=args.control_key)
+        for item, r, t in zip(test_data, rob, times):
+            if "robustness" not in item:
+                item["robustness"] = r
+                item["time"] = t
+        pos = sum(1 for it in test_data if it["robustness"] > 0)
+        failed = sum(1 for it in test_data if it["robustness"] == -100)
+        neg = sum(1 for it in test_data if it["robustness"] < 0 and it["robustness"] != -100)
+        if pos + neg + failed != len(test_data):
+            bad = [it["robustness"] for it in test_data if it["robustness"] == 0]
+            raise ValueError(f"gt_r = {bad[0] if bad else 'nan'}")       # simulate_gt.py:148-149: exact 0 is an error
+        metrics["gt positive robustness rate"] = pos / len(test_data)
+        metrics["gt negative robustness rate"] = neg / len(test_data)
+        metrics["gt failed robustness rate"] = failed / len(test_data)
+        print(f"Timeout count >>> output eval robustness = {timeouts}", flush=True)
+
+    with open(os.path.join(args.save_dir, fname), "w") as fout:
+        for item in test_data:
+            for key in ("sstl", "python", "robustness", "time"):       # same key order as simulate_gt.py:167-178
+                if key in item:
+                    item[key] = item.pop(key)
+            json.dump(item, fout, ensure_ascii=True)
+            fout.write("\n")
+    with open(os.path.join(args.save_dir, "metrics.json"), "w") as fout:
+        json.dump(metrics, fout, indent=4)
+    return metrics
+
+
+def build_parser():
+    p = argparse.ArgumentParser()
+    p.add_argument("--data_dir", type=str, required=True)
+    p.add_argument("--python_key", type=str, default="python")
+    p.add_argument("--stl_key", type=str, default="sstl")
+    p.add_argument("--nl_key", type=str, default="nl")
+    p.add_argument("--robustness_key", type=str, default="robustness")
+    p.add_argument("--control_key", type=str, default="control")
+    p.add_argument("--max_num_examples", type=int, default=None)
+    p.add_argument("--infer_on_train_set", action="store_true")
+    p.add_argument("--eval_robustness", action="store_true")
+    p.add_argument("--gpus", type=str, default=None)
+    return p
+
+
+if __name__ == "__main__":
+    a, _ = build_parser().parse_known_args()
+    if a.gpus is not None:
+        os.environ["CUDA_VISIBLE_DEVICES"] = a.gpus
+    main(a)
