@@ -157,6 +157,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--gather", action="store_true", help="NCCL all_gather of the per-sample results after each step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-block", type=int, default=65536, help="samples per block of the end-to-end pipeline")
     args = ap.parse_args()
     if args.batch is None:
         args.batch = DEFAULT_BATCH[args.workload]
@@ -189,7 +190,8 @@ def main():
     host.slab[:] = src.slab
     res = native.ResidentBatch(host, device=dev, stream=stream)
     rob_dev, _, st_dev = res.device_ptrs()
-    out_host = {"robustness": np.empty(host.n), "status": np.empty(host.n, np.int32)}
+    pin_rob, pin_st = native.PinnedBuffer(8 * host.n), native.PinnedBuffer(4 * host.n)      # page-locked result buffers
+    out_host = {"robustness": pin_rob.array.view(np.float64), "status": pin_st.array.view(np.int32)}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     class _Dev:  # zero-copy view of the library's result buffer for the optional NCCL gather
@@ -231,21 +233,42 @@ def main():
     total_ms = float(t_dev.item())
     value = total * args.steps / (total_ms * 1e-3)
 
-    # ---- end to end through the C ABI with host buffers ("e2e") ----
-    for _ in range(2):
-        res.upload(host, stream=stream); res.eval(args.precision, stream=stream); res.fetch(stream=stream, out=out_host)
-    barrier()
-    e0 = time.perf_counter()
-    for _ in range(args.steps):
-        res.upload(host, stream=stream)            # H2D of this step's inputs (pinned slab, one copy)
-        res.eval(args.precision, stream=stream)
-        res.fetch(stream=stream, out=out_host)     # D2H of robustness + status, synchronises
-    torch.cuda.synchronize()
-    e1 = time.perf_counter()
-    t_e2e = torch.tensor([e1 - e0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = total * args.steps / float(t_e2e.item())
+    # ---- end to end through the public API with HOST buffers ("e2e") ----
+    # every step: the whole batch goes pinned host -> H2D -> plan -> kernels -> D2H (robustness + status) as
+    # args.e2e_block-sample blocks double-buffered on two streams (native.BlockPipeline); run() returns after the
+    # last byte of the results is back in host memory
+    pipe = native.BlockPipeline(src.n, src.kmax, src.pmax, src.tmax, block=args.e2e_block, device=dev, depth=2)
+    for g in range(2):
+        pipe.fill(src, g)
+
+    def e2e_loop(depth):
+        """K steps; depth 1 = wait for every step before the next, depth 2 = step i+1 is enqueued while step i runs
+        (its buffers are the other generation), which is how a sweep over many batches uses the API."""
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            g = i % depth
+            if i >= depth:
+                pipe.wait(g)                      # results of step i-depth are in host memory: they are read here
+            pipe.submit(g, args.precision)
+        for g in range(depth):
+            pipe.wait(g)
+        torch.cuda.synchronize()
+        dt_ = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt_, op=dist.ReduceOp.MAX)
+        return total * args.steps / float(dt_.item())
+
+    for _ in range(3):
+        pipe.run(args.precision)
+    e2e_sync = e2e_loop(1)
+    e2e_value = e2e_loop(2)
+    res.eval(args.precision, stream=stream)
+    res.fetch(stream=stream, out=out_host)
+    if not (np.array_equal(pipe.robustness[0], out_host["robustness"]) and np.array_equal(pipe.robustness[1], out_host["robustness"])):
+        raise SystemExit("bench: pipelined end-to-end results differ from the resident evaluation")
+    h2d_bytes = pipe.h2d_bytes
+    pipe.close()
 
     st = out_host["status"]
     n_fail = int((st != 0).sum())
@@ -261,9 +284,9 @@ def main():
             "dtype": "f64" if args.precision == 64 else "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_TEXT[args.workload], "batch_per_gpu": args.batch, "global_batch": total,
                        "precision": args.precision, "seed": args.seed, "l2": "flushed (256 MiB write) between timed steps",
-                       "gather": bool(rob_t is not None), "failed_samples": n_fail,
+                       "gather": bool(rob_t is not None), "failed_samples": n_fail, "e2e_block": args.e2e_block, "e2e_pipeline_depth": 2, "e2e_value_depth1": e2e_sync,
                        "wall_s_timed_region": wall1 - wall0},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host.slab_bytes),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(12 * host.n)},
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,

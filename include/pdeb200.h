@@ -194,12 +194,23 @@ typedef struct PdebResident PdebResident;
 
 int  pdeb_resident_create(const PdebBatch* in, int device, void* stream, PdebResident** out);
 int  pdeb_resident_upload(PdebResident* r, const PdebBatch* in, void* stream);  /* same shape: refill the image */
+/* upload + evaluate + fetch of a batch of the resident shape in one pipelined pass (H2D / kernels / D2H of
+   successive chunks overlap on two internal streams); synchronises before returning */
+int  pdeb_resident_run(PdebResident* r, const PdebBatch* in, int precision, const PdebConventions* conv,
+                       double* robustness_out, double* clause_out, int32_t* status_out, void* stream, PdebTiming* timing);
 int  pdeb_resident_eval(PdebResident* r, int precision, const PdebConventions* conv,
                         void* stream, PdebTiming* timing);   /* asynchronous on stream unless timing != NULL */
 int  pdeb_resident_set_knots(PdebResident* r, const double* knot_t, const double* knot_y,
                              const int32_t* n_knots, void* stream);      /* host planes, same kmax/stride */
 int  pdeb_resident_fetch(PdebResident* r, double* robustness_out, double* clause_out,
                          int32_t* status_out, void* stream);
+/* the same copies without the final synchronisation (pair with pdeb_stream_sync) */
+int  pdeb_resident_fetch_async(PdebResident* r, double* robustness_out, double* clause_out,
+                               int32_t* status_out, void* stream);
+/* library-owned non-blocking streams, for callers that do not bring their own (native.BlockPipeline) */
+void* pdeb_stream_create(int device);
+void  pdeb_stream_destroy(void* stream);
+int   pdeb_stream_sync(void* stream);
 /* device pointers of the results (f64[n], f64[pmax][stride], i32[n]) for zero-copy consumers */
 int  pdeb_resident_device_ptrs(PdebResident* r, void** robustness_dev, void** clause_dev, void** status_dev);
 void pdeb_resident_destroy(PdebResident* r);

@@ -123,9 +123,14 @@ EXPORTS = [
     "pdeb_eval_batch_multi",
     "pdeb_resident_create",
     "pdeb_resident_upload",
+    "pdeb_resident_run",
     "pdeb_resident_eval",
     "pdeb_resident_set_knots",
     "pdeb_resident_fetch",
+    "pdeb_resident_fetch_async",
+    "pdeb_stream_create",
+    "pdeb_stream_destroy",
+    "pdeb_stream_sync",
     "pdeb_resident_device_ptrs",
     "pdeb_resident_destroy",
     "pdeb_host_alloc",

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -79,6 +80,8 @@ extern "C" void* pdeb_host_alloc(int64_t bytes) {
 extern "C" void pdeb_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 /* ---- resident batch ------------------------------------------------------ */
+struct PdebResident;
+static int fetch_range_fwd(PdebResident* r, double* robustness_out, double* clause_out, int32_t* status_out, cudaStream_t stream);
 
 struct PdebResident {
     int device = 0;
@@ -91,11 +94,17 @@ struct PdebResident {
     PdebDevOut out{};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool host_slab = false;          /* device slab mirrors the caller's host slab byte for byte */
-    unsigned char* plan = nullptr;   /* keys | order | hist | vstart_count */
-    PdebPlanBuffers pb{};
-    int32_t* vsc_host = nullptr;     /* pinned copy of vstart_count */
+    unsigned char* plan = nullptr;   /* keys | order | PDEB_MAX_CHUNKS x (hist | vstart_count) */
+    PdebPlanBuffers pb{};            /* of the whole batch (chunk 0's histogram) */
+    int32_t* hist[4] = {nullptr, nullptr, nullptr, nullptr};
+    int32_t vsc_host[2 * PDEB_NUM_VARIANTS] = {0};   /* first index / count of each variant inside `order` (whole batch) */
     int plan_launches = 0;
+    bool plan_stale = false;         /* the last run planned chunk by chunk: whole-batch order must be rebuilt */
+    cudaStream_t pipe[2] = {nullptr, nullptr};        /* internal streams of the pipelined run */
+    cudaEvent_t pev[3] = {nullptr, nullptr, nullptr};
 };
+#define PDEB_MAX_CHUNKS 4
+#define PDEB_PIPELINE_MIN 16384     /* samples per chunk below which splitting stops paying */
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -122,15 +131,18 @@ extern "C" void pdeb_resident_destroy(PdebResident* r) {
     if (r->slab) cudaFree(r->slab);
     if (r->outs) cudaFree(r->outs);
     if (r->plan) cudaFree(r->plan);
-    if (r->vsc_host) cudaFreeHost(r->vsc_host);
+    for (auto& st : r->pipe) if (st) cudaStreamDestroy(st);
+    for (auto& e : r->pev) if (e) cudaEventDestroy(e);
     delete r;
 }
 
-static int upload(PdebResident* r, const PdebBatch* in, cudaStream_t stream, bool knots_only) {
-    const int64_t n = r->n;
-    if (n == 0) return 0;
+/* host -> device copy of samples [lo, hi) of every input array (or of the knot arrays only) */
+static int upload(PdebResident* r, const PdebBatch* in, int64_t lo, int64_t hi, cudaStream_t stream, bool knots_only) {
+    const int64_t n = hi - lo;
+    if (n <= 0) return 0;
     PdebDevBatch& d = r->dev;
-    const bool fast = !knots_only && r->host_slab && in->slab_base && in->slab_bytes > 0 && in->stride == n &&
+    const bool whole = lo == 0 && hi == r->n;
+    const bool fast = whole && !knots_only && r->host_slab && in->slab_base && in->slab_bytes > 0 && in->stride == r->n &&
                       (size_t)in->slab_bytes == r->slab_bytes &&
                       (const unsigned char*)in->L - (const unsigned char*)in->slab_base ==
                           (const unsigned char*)r->dev.L - r->slab;
@@ -139,11 +151,12 @@ static int upload(PdebResident* r, const PdebBatch* in, cudaStream_t stream, boo
         return 0;
     }
     auto copy = [&](const void* dst, const void* src, size_t elem, int planes) -> cudaError_t {
-        if (planes == 1 || in->stride == r->stride)
-            return cudaMemcpyAsync((void*)dst, src, elem * (size_t)(planes == 1 ? n : r->stride * (int64_t)planes - (r->stride - n)),
-                                   cudaMemcpyHostToDevice, stream);
-        return cudaMemcpy2DAsync((void*)dst, elem * r->stride, src, elem * in->stride, elem * n, planes,
-                                 cudaMemcpyHostToDevice, stream);
+        unsigned char* dp = (unsigned char*)dst + elem * (size_t)lo;
+        const unsigned char* sp = (const unsigned char*)src + elem * (size_t)lo;
+        if (planes == 1) return cudaMemcpyAsync(dp, sp, elem * (size_t)n, cudaMemcpyHostToDevice, stream);
+        if (whole && in->stride == r->stride && r->stride == r->n)
+            return cudaMemcpyAsync(dp, sp, elem * (size_t)n * planes, cudaMemcpyHostToDevice, stream);
+        return cudaMemcpy2DAsync(dp, elem * r->stride, sp, elem * in->stride, elem * n, planes, cudaMemcpyHostToDevice, stream);
     };
     CK(copy(d.n_knots, in->n_knots, 4, 1));
     CK(copy(d.knot_t, in->knot_t, 8, r->kmax));
@@ -177,20 +190,58 @@ static int upload(PdebResident* r, const PdebBatch* in, cudaStream_t stream, boo
     return 0;
 }
 
+/* a contiguous range of the resident batch seen as a batch of its own (pointer offsets, same plane stride) */
+struct RangeView {
+    PdebDevBatch dev;
+    PdebDevOut out;
+    PdebPlanBuffers pb;
+    int32_t vsc[2 * PDEB_NUM_VARIANTS];
+};
+
+static RangeView view_of(const PdebResident* r, int64_t lo, int64_t hi, int chunk) {
+    RangeView v;
+    v.dev = r->dev;
+    v.dev.n = hi - lo;
+#define OFF(f) v.dev.f = r->dev.f + lo
+    OFF(kind); OFF(n_elem); OFF(L); OFF(dt); OFF(T); OFF(g0); OFF(x_a); OFF(x_b); OFF(rho_in); OFF(rho_out); OFF(E_in);
+    OFF(E_out); OFF(n_knots); OFF(knot_t); OFF(knot_y); OFF(n_pred); OFF(pred_xlo); OFF(pred_xhi); OFF(pred_m); OFF(pred_b);
+    OFF(pred_tlo); OFF(pred_thi); OFF(pred_rel); OFF(pred_top); OFF(n_tree); OFF(tree_op); OFF(tree_lhs); OFF(tree_rhs);
+#undef OFF
+    v.out.robustness = r->out.robustness + lo;
+    v.out.clause = r->out.clause + lo;
+    v.out.status = r->out.status + lo;
+    v.pb.keys = r->pb.keys + lo;
+    v.pb.order = r->pb.order + lo;
+    v.pb.hist = r->hist[chunk];
+    v.pb.vstart_count = r->hist[chunk] + PDEB_PLAN_BINS;
+    memset(v.vsc, 0, sizeof v.vsc);
+    return v;
+}
+
 /*
- * Order the resident samples by kernel variant and step count (device side, 3 launches) and bring
- * the per-variant counts back: this is the one host synchronisation of an upload.
+ * Which kernel variants samples [lo, hi) need and how many of each: a pass over two small HOST arrays.
+ * The device-side plan orders the samples; because the variant of a sample depends on (kind, mesh) only,
+ * the host knows every variant's place inside that order without reading anything back.
  */
-static int plan_resident(PdebResident* r, cudaStream_t stream) {
-    if (r->n == 0) return 0;
+static void host_variant_counts(const PdebBatch* in, int64_t lo, int64_t hi, int32_t* vsc) {
+    int32_t cnt[PDEB_NUM_VARIANTS] = {0};
+    for (int64_t s = lo; s < hi; ++s) {
+        const int v = pdeb_variant_of(in->kind[s], in->n_elem[s]);
+        if (v >= 0) ++cnt[v];
+    }
+    int32_t run = 0;
+    for (int v = 0; v < PDEB_NUM_VARIANTS; ++v) { vsc[2 * v] = run; vsc[2 * v + 1] = cnt[v]; run += cnt[v]; }
+}
+
+/* order a range by kernel variant and step count (device side, 3 launches, asynchronous) */
+static int plan_view(PdebResident* r, const RangeView& v, cudaStream_t stream) {
+    if (v.dev.n == 0) return 0;
     PdebConventions cv;
     pdeb_default_conventions(&cv);
     int nl = 0;
-    int rc = pdeb_plan(r->dev, cv, r->out, r->pb, stream, &nl);
+    int rc = pdeb_plan(v.dev, cv, v.out, v.pb, stream, &nl);
     if (rc) return fail(PDEB_E_CUDA, "plan launch", (cudaError_t)rc);
     r->plan_launches = nl;
-    CK(cudaMemcpyAsync(r->vsc_host, r->pb.vstart_count, sizeof(int32_t) * 2 * PDEB_NUM_VARIANTS, cudaMemcpyDeviceToHost, stream));
-    CK(cudaStreamSynchronize(stream));
     return 0;
 }
 
@@ -251,15 +302,16 @@ static int resident_alloc(const PdebBatch* in, int device, PdebResident** outp) 
     if (ce == cudaSuccess) ce = cudaMalloc((void**)&r->outs, out_total);
     const size_t n1 = (size_t)(n > 0 ? n : 1);
     const size_t plan_keys = 0, plan_order = align_up(4 * n1, 256), plan_hist = plan_order + align_up(4 * n1, 256);
-    const size_t plan_vsc = plan_hist + sizeof(int32_t) * PDEB_PLAN_BINS;
-    if (ce == cudaSuccess) ce = cudaMalloc((void**)&r->plan, plan_vsc + 256);
-    if (ce == cudaSuccess) ce = cudaHostAlloc((void**)&r->vsc_host, sizeof(int32_t) * 2 * PDEB_NUM_VARIANTS, cudaHostAllocDefault);
+    const size_t hist_bytes = align_up(sizeof(int32_t) * (PDEB_PLAN_BINS + 2 * PDEB_VARIANT_SLOTS), 256);
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&r->plan, plan_hist + PDEB_MAX_CHUNKS * hist_bytes);
+    for (int i = 0; i < 2 && ce == cudaSuccess; ++i) ce = cudaStreamCreateWithFlags(&r->pipe[i], cudaStreamNonBlocking);
+    for (int i = 0; i < 3 && ce == cudaSuccess; ++i) ce = cudaEventCreateWithFlags(&r->pev[i], cudaEventDisableTiming);
     if (ce == cudaSuccess) {
         r->pb.keys = (int32_t*)(r->plan + plan_keys);
         r->pb.order = (int32_t*)(r->plan + plan_order);
-        r->pb.hist = (int32_t*)(r->plan + plan_hist);
-        r->pb.vstart_count = (int32_t*)(r->plan + plan_vsc);
-        memset(r->vsc_host, 0, sizeof(int32_t) * 2 * PDEB_NUM_VARIANTS);
+        for (int c = 0; c < PDEB_MAX_CHUNKS; ++c) r->hist[c] = (int32_t*)(r->plan + plan_hist + c * hist_bytes);
+        r->pb.hist = r->hist[0];
+        r->pb.vstart_count = r->hist[0] + PDEB_PLAN_BINS;
     }
     for (int i = 0; i < 4 && ce == cudaSuccess; ++i) ce = cudaEventCreate(&r->ev[i]);
     if (ce != cudaSuccess) {
@@ -294,8 +346,8 @@ extern "C" int pdeb_resident_create(const PdebBatch* in, int device, void* strea
     int rc = resident_alloc(in, device, &r);
     if (rc) return rc;
     DeviceGuard g(device);
-    rc = upload(r, in, (cudaStream_t)stream_, false);
-    if (rc == 0) rc = plan_resident(r, (cudaStream_t)stream_);
+    rc = upload(r, in, 0, r->n, (cudaStream_t)stream_, false);
+    if (rc == 0) { host_variant_counts(in, 0, r->n, r->vsc_host); rc = plan_view(r, view_of(r, 0, r->n, 0), (cudaStream_t)stream_); }
     if (rc) { pdeb_resident_destroy(r); return rc; }
     *outp = r;
     return 0;
@@ -311,8 +363,8 @@ extern "C" int pdeb_resident_upload(PdebResident* r, const PdebBatch* in, void* 
     if (slab != r->host_slab || (slab && (size_t)in->slab_bytes != r->slab_bytes))
         return fail(PDEB_E_ARG, "batch slab layout differs from the resident image");
     DeviceGuard g(r->device);
-    rc = upload(r, in, (cudaStream_t)stream_, false);
-    if (rc == 0) rc = plan_resident(r, (cudaStream_t)stream_);
+    rc = upload(r, in, 0, r->n, (cudaStream_t)stream_, false);
+    if (rc == 0) { host_variant_counts(in, 0, r->n, r->vsc_host); rc = plan_view(r, view_of(r, 0, r->n, 0), (cudaStream_t)stream_); }
     return rc;
 }
 
@@ -323,7 +375,7 @@ extern "C" int pdeb_resident_set_knots(PdebResident* r, const double* knot_t, co
     PdebBatch in{};
     in.n = r->n; in.stride = r->host_stride; in.kmax = r->kmax; in.pmax = r->pmax; in.tmax = r->tmax;
     in.knot_t = knot_t; in.knot_y = knot_y; in.n_knots = n_knots;
-    return upload(r, &in, (cudaStream_t)stream_, true);
+    return upload(r, &in, 0, r->n, (cudaStream_t)stream_, true);
 }
 
 extern "C" int pdeb_resident_eval(PdebResident* r, int precision, const PdebConventions* conv, void* stream_,
@@ -336,6 +388,11 @@ extern "C" int pdeb_resident_eval(PdebResident* r, int precision, const PdebConv
     PdebConventions cv;
     if (conv) cv = *conv; else pdeb_default_conventions(&cv);
     int launches = 0;
+    if (r->plan_stale) {
+        int prc = plan_view(r, view_of(r, 0, r->n, 0), stream);
+        if (prc) return prc;
+        r->plan_stale = false;
+    }
     if (timing) CK(cudaEventRecord(r->ev[0], stream));
     int rc = pdeb_launch_all(r->dev, cv, r->out, r->pb, r->vsc_host, precision, stream, &launches);
     if (rc) return fail(PDEB_E_CUDA, "kernel launch", (cudaError_t)rc);
@@ -369,11 +426,116 @@ extern "C" int pdeb_resident_fetch(PdebResident* r, double* robustness_out, doub
     return 0;
 }
 
+extern "C" int pdeb_resident_fetch_async(PdebResident* r, double* robustness_out, double* clause_out, int32_t* status_out,
+                                         void* stream_) {
+    if (!r || !robustness_out) return fail(PDEB_E_ARG, "NULL argument");
+    DeviceGuard g(r->device);
+    return fetch_range_fwd(r, robustness_out, clause_out, status_out, (cudaStream_t)stream_);
+}
+
+extern "C" void* pdeb_stream_create(int device) {
+    DeviceGuard g(device);
+    cudaStream_t st = nullptr;
+    if (!g.ok || cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return (void*)st;
+}
+extern "C" void pdeb_stream_destroy(void* stream) { if (stream) cudaStreamDestroy((cudaStream_t)stream); }
+extern "C" int pdeb_stream_sync(void* stream) {
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int pdeb_resident_device_ptrs(PdebResident* r, void** robustness_dev, void** clause_dev, void** status_dev) {
     if (!r) return fail(PDEB_E_ARG, "resident is NULL");
     if (robustness_dev) *robustness_dev = r->out.robustness;
     if (clause_dev) *clause_dev = r->out.clause;
     if (status_dev) *status_dev = r->out.status;
+    return 0;
+}
+
+/* ---- upload + evaluate + fetch, pipelined ---------------------------------- */
+
+static int fetch_range(PdebResident* r, int64_t lo, int64_t hi, double* robustness_out, double* clause_out,
+                       int32_t* status_out, cudaStream_t stream) {
+    const int64_t n = hi - lo;
+    if (n <= 0) return 0;
+    CK(cudaMemcpyAsync(robustness_out + lo, r->out.robustness + lo, 8 * (size_t)n, cudaMemcpyDeviceToHost, stream));
+    if (status_out) CK(cudaMemcpyAsync(status_out + lo, r->out.status + lo, 4 * (size_t)n, cudaMemcpyDeviceToHost, stream));
+    if (clause_out)
+        CK(cudaMemcpy2DAsync(clause_out + lo, 8 * (size_t)r->host_stride, r->out.clause + lo, 8 * (size_t)r->stride,
+                             8 * (size_t)n, r->pmax, cudaMemcpyDeviceToHost, stream));
+    return 0;
+}
+
+static int fetch_range_fwd(PdebResident* r, double* robustness_out, double* clause_out, int32_t* status_out, cudaStream_t stream) {
+    return fetch_range(r, 0, r->n, robustness_out, clause_out, status_out, stream);
+}
+
+/*
+ * One pass over a host batch through an existing resident image: the batch is cut into up to
+ * PDEB_MAX_CHUNKS contiguous chunks that alternate between two internal streams, so the H2D copy of one
+ * chunk overlaps the kernels of the previous one and the D2H of the one before.  Synchronises before returning.
+ */
+extern "C" int pdeb_resident_run(PdebResident* r, const PdebBatch* in, int precision, const PdebConventions* conv,
+                                 double* robustness_out, double* clause_out, int32_t* status_out, void* stream_,
+                                 PdebTiming* timing) {
+    if (!r || !robustness_out) return fail(PDEB_E_ARG, "NULL argument");
+    if (precision != 64 && precision != 32) return fail(PDEB_E_ARG, "precision must be 64 or 32");
+    int rc = check_batch(in);
+    if (rc) return rc;
+    if (in->n != r->n || in->kmax != r->kmax || in->pmax != r->pmax || in->tmax != r->tmax || in->stride != r->host_stride)
+        return fail(PDEB_E_ARG, "batch shape differs from the resident image");
+    DeviceGuard g(r->device);
+    if (!g.ok) return fail(PDEB_E_NODEVICE, "cudaSetDevice failed");
+    cudaStream_t user = (cudaStream_t)stream_;
+    PdebConventions cv;
+    if (conv) cv = *conv; else pdeb_default_conventions(&cv);
+    const int64_t n = r->n;
+    /* Chunking inside one call pays only when the per-field copies are not the bottleneck: a batch that lives in
+       one host slab moves fastest as ONE copy (measured on B200: 28 strided copies per chunk cost more CPU time than
+       the overlap wins), so the default is a single chunk; PDEB_CHUNKS=2..4 turns the in-call pipeline on.
+       Overlap across batches is what native.BlockPipeline is for. */
+    static const int env_chunks = [] { const char* e = getenv("PDEB_CHUNKS"); return e ? atoi(e) : 1; }();
+    int nch = env_chunks;
+    if (nch > (int)(n / PDEB_PIPELINE_MIN)) nch = (int)(n / PDEB_PIPELINE_MIN);
+    if (nch < 1) nch = 1;
+    if (nch > PDEB_MAX_CHUNKS) nch = PDEB_MAX_CHUNKS;
+    int launches = 0;
+    if (timing) CK(cudaEventRecord(r->ev[0], user));
+    CK(cudaEventRecord(r->pev[0], user));
+    for (int i = 0; i < 2; ++i) CK(cudaStreamWaitEvent(r->pipe[i], r->pev[0], 0));
+    for (int c = 0; c < nch; ++c) {
+        const int64_t lo = n * c / nch, hi = n * (c + 1) / nch;
+        cudaStream_t st = r->pipe[c & 1];
+        rc = upload(r, in, lo, hi, st, false);
+        if (rc) return rc;
+        RangeView v = view_of(r, lo, hi, c);
+        host_variant_counts(in, lo, hi, v.vsc);
+        rc = plan_view(r, v, st);
+        if (rc) return rc;
+        int nl = 0;
+        const int lrc = pdeb_launch_all(v.dev, cv, v.out, v.pb, v.vsc, precision, st, &nl);
+        if (lrc) return fail(PDEB_E_CUDA, "kernel launch", (cudaError_t)lrc);
+        launches += nl + r->plan_launches;
+        rc = fetch_range(r, lo, hi, robustness_out, clause_out, status_out, st);
+        if (rc) return rc;
+    }
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaEventRecord(r->pev[1 + i], r->pipe[i]));
+        CK(cudaStreamWaitEvent(user, r->pev[1 + i], 0));
+    }
+    if (timing) CK(cudaEventRecord(r->ev[3], user));
+    CK(cudaStreamSynchronize(user));
+    CK(cudaGetLastError());
+    /* the whole-batch order and counts are stale now (each chunk was planned on its own): rebuild lazily */
+    host_variant_counts(in, 0, n, r->vsc_host);
+    r->plan_stale = nch > 1;
+    if (timing) {
+        memset(timing, 0, sizeof *timing);
+        CK(cudaEventElapsedTime(&timing->total_ms, r->ev[0], r->ev[3]));
+        timing->launches = launches;
+    }
     return 0;
 }
 
@@ -387,37 +549,7 @@ extern "C" int pdeb_eval_batch(const PdebBatch* in, int device, int precision, c
     PdebResident* r = nullptr;
     int rc = resident_alloc(in, device, &r);
     if (rc) return rc;
-    DeviceGuard g(device);
-    cudaStream_t stream = (cudaStream_t)stream_;
-    PdebConventions cv;
-    if (conv) cv = *conv; else pdeb_default_conventions(&cv);
-    int launches = 0;
-    cudaError_t ce = cudaSuccess;
-    /* ev0 .. h2d .. ev1 .. kernels .. ev2 .. d2h .. ev3 */
-    if (timing) ce = cudaEventRecord(r->ev[0], stream);
-    if (ce == cudaSuccess) { rc = upload(r, in, stream, false); if (rc) { pdeb_resident_destroy(r); return rc; } }
-    if (ce == cudaSuccess && timing) ce = cudaEventRecord(r->ev[1], stream);
-    if (ce == cudaSuccess) {
-        rc = plan_resident(r, stream);
-        if (rc) { pdeb_resident_destroy(r); return rc; }
-        int lrc = pdeb_launch_all(r->dev, cv, r->out, r->pb, r->vsc_host, precision, stream, &launches);
-        if (lrc) ce = (cudaError_t)lrc;
-        launches += r->plan_launches;
-    }
-    if (ce == cudaSuccess && timing) ce = cudaEventRecord(r->ev[2], stream);
-    if (ce != cudaSuccess) { pdeb_resident_destroy(r); return fail(PDEB_E_CUDA, "launch", ce); }
-    rc = pdeb_resident_fetch(r, robustness_out, clause_out, status_out, stream_);
-    if (rc == 0 && timing) {
-        memset(timing, 0, sizeof *timing);
-        ce = cudaEventRecord(r->ev[3], stream);
-        if (ce == cudaSuccess) ce = cudaEventSynchronize(r->ev[3]);
-        if (ce == cudaSuccess) ce = cudaEventElapsedTime(&timing->h2d_ms, r->ev[0], r->ev[1]);
-        if (ce == cudaSuccess) ce = cudaEventElapsedTime(&timing->kernel_ms, r->ev[1], r->ev[2]);
-        if (ce == cudaSuccess) ce = cudaEventElapsedTime(&timing->d2h_ms, r->ev[2], r->ev[3]);
-        if (ce == cudaSuccess) ce = cudaEventElapsedTime(&timing->total_ms, r->ev[0], r->ev[3]);
-        timing->launches = launches;
-        if (ce != cudaSuccess) rc = fail(PDEB_E_CUDA, "timing", ce);
-    }
+    rc = pdeb_resident_run(r, in, precision, conv, robustness_out, clause_out, status_out, stream_, timing);
     pdeb_resident_destroy(r);
     return rc;
 }

@@ -48,12 +48,22 @@ def lib():
         L.pdeb_resident_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.pdeb_resident_upload.restype = C.c_int
         L.pdeb_resident_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pdeb_resident_run.restype = C.c_int
+        L.pdeb_resident_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]
         L.pdeb_resident_eval.restype = C.c_int
         L.pdeb_resident_eval.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pdeb_resident_set_knots.restype = C.c_int
         L.pdeb_resident_set_knots.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pdeb_resident_fetch.restype = C.c_int
         L.pdeb_resident_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pdeb_resident_fetch_async.restype = C.c_int
+        L.pdeb_resident_fetch_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pdeb_stream_create.restype = C.c_void_p
+        L.pdeb_stream_create.argtypes = [C.c_int]
+        L.pdeb_stream_destroy.argtypes = [C.c_void_p]
+        L.pdeb_stream_sync.restype = C.c_int
+        L.pdeb_stream_sync.argtypes = [C.c_void_p]
         L.pdeb_resident_device_ptrs.restype = C.c_int
         L.pdeb_resident_device_ptrs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pdeb_resident_destroy.argtypes = [C.c_void_p]
@@ -166,6 +176,24 @@ class ResidentBatch:
         cb = (batch or self.batch).as_c()
         _check(self._L.pdeb_resident_upload(self._h, C.addressof(cb), stream or None), "pdeb_resident_upload")
 
+    def run(self, batch: Optional[ProblemBatch] = None, precision: int = 64, conv=None, want_clauses: bool = False,
+            stream: int = 0, out=None, timing: bool = False):
+        """Upload + evaluate + fetch in one pipelined pass (the end-to-end path for a fresh batch of this shape)."""
+        b = batch or self.batch
+        cb = b.as_c()
+        rob = out["robustness"] if out else np.empty(b.n, dtype=np.float64)
+        st = out["status"] if out else np.empty(b.n, dtype=np.int32)
+        cl = np.empty((b.pmax, b.stride), dtype=np.float64) if want_clauses else None
+        tm = abi.PdebTiming() if timing else None
+        _check(self._L.pdeb_resident_run(self._h, C.addressof(cb), precision, _conv_ptr(conv), _ptr(rob), _ptr(cl), _ptr(st),
+                                         stream or None, C.addressof(tm) if tm is not None else None), "pdeb_resident_run")
+        res = {"robustness": rob, "status": st}
+        if want_clauses:
+            res["clause"] = cl[:, : b.n]
+        if timing:
+            res["timing"] = tm
+        return res
+
     def eval(self, precision: int = 64, conv=None, stream: int = 0, timing: bool = False):
         tm = abi.PdebTiming() if timing else None
         _check(self._L.pdeb_resident_eval(self._h, precision, _conv_ptr(conv), stream or None,
@@ -187,6 +215,11 @@ class ResidentBatch:
             res["clause"] = cl[:, : b.n]
         return res
 
+    def fetch_async(self, out, stream: int = 0):
+        """Enqueue the D2H copies of robustness + status into `out` (page-locked arrays); no synchronisation."""
+        _check(self._L.pdeb_resident_fetch_async(self._h, _ptr(out["robustness"]), None, _ptr(out["status"]), stream or None),
+               "pdeb_resident_fetch_async")
+
     def device_ptrs(self):
         r, c, s = C.c_void_p(), C.c_void_p(), C.c_void_p()
         _check(self._L.pdeb_resident_device_ptrs(self._h, C.addressof(r), C.addressof(c), C.addressof(s)),
@@ -197,6 +230,90 @@ class ResidentBatch:
         if self._h:
             self._L.pdeb_resident_destroy(self._h)
             self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BlockPipeline:
+    """Streams batches through the GPU as fixed-size blocks, double-buffered on two streams.
+
+    Every block has its own page-locked host slab (one H2D copy), its own resident image and its own slice of
+    page-locked result arrays; the upload of one block overlaps the kernels of the previous one and the download
+    of the one before.  `depth` generations of buffers let consecutive batches overlap as well: submit(g) enqueues
+    generation g and returns at once, wait(g) blocks until its results are in host memory.  This is the end-to-end
+    route for the 2M-sample sweep: fill(batch, g), submit(g), ..., wait(g), read robustness[g] / status[g].
+    """
+
+    def __init__(self, n: int, kmax: int, pmax: int, tmax=None, block: int = 65536, device: int = 0, depth: int = 2):
+        self._L = lib()
+        self.n, self.device, self.depth = int(n), device, int(depth)
+        self.bounds = [(lo, min(lo + block, n)) for lo in range(0, n, block)]
+        self.streams = [self._L.pdeb_stream_create(device), self._L.pdeb_stream_create(device)]
+        if not all(self.streams):
+            raise NativeError("stream creation failed")
+        self.blocks, self.residents, self.robustness, self.status, self._outs, self._pins = [], [], [], [], [], []
+        slot = 0
+        for g in range(self.depth):
+            rob, st = PinnedBuffer(8 * max(n, 1)), PinnedBuffer(4 * max(n, 1))
+            self._pins += [rob, st]
+            self.robustness.append(rob.array.view(np.float64)[:n])
+            self.status.append(st.array.view(np.int32)[:n])
+            blks = [pinned_batch(hi - lo, kmax, pmax, tmax) for lo, hi in self.bounds]
+            self.blocks.append(blks)
+            self._outs.append([{"robustness": self.robustness[g][lo:hi], "status": self.status[g][lo:hi]}
+                               for lo, hi in self.bounds])
+            res = []
+            for b in blks:
+                res.append((ResidentBatch(b, device=device, stream=self.streams[slot & 1]), slot & 1))
+                slot += 1
+            self.residents.append(res)
+        self._sync_all()
+
+    def fill(self, batch: ProblemBatch, gen: int = 0):
+        """Copy a whole batch into the blocks of one generation (host side)."""
+        for (lo, hi), blk in zip(self.bounds, self.blocks[gen]):
+            for name in blk._names:
+                getattr(blk, name)[...] = getattr(batch, name)[..., lo:hi]
+
+    def submit(self, gen: int = 0, precision: int = 64, conv=None):
+        """Enqueue upload + plan + kernels + download of every block of generation `gen`; does not wait."""
+        for blk, (res, si), out in zip(self.blocks[gen], self.residents[gen], self._outs[gen]):
+            st = self.streams[si]
+            res.upload(blk, stream=st)
+            res.eval(precision, conv, stream=st)
+            res.fetch_async(out, stream=st)
+
+    def wait(self, gen: int = 0):
+        """Block until generation `gen` is back in host memory (stream order: everything submitted before it too)."""
+        for si in sorted({si for _, si in self.residents[gen]}):
+            _check(self._L.pdeb_stream_sync(self.streams[si]), "pdeb_stream_sync")
+        return self.robustness[gen], self.status[gen]
+
+    def run(self, precision: int = 64, conv=None, gen: int = 0):
+        self.submit(gen, precision, conv)
+        return self.wait(gen)
+
+    def _sync_all(self):
+        for st in self.streams:
+            _check(self._L.pdeb_stream_sync(st), "pdeb_stream_sync")
+
+    @property
+    def h2d_bytes(self):
+        return sum(b.slab_bytes for b in self.blocks[0])
+
+    def close(self):
+        for gen in self.residents:
+            for r, _ in gen:
+                r.close()
+        self.residents = []
+        for st in self.streams:
+            if st:
+                self._L.pdeb_stream_destroy(st)
+        self.streams = []
 
     def __del__(self):
         try:

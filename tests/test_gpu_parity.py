@@ -166,3 +166,21 @@ def test_hand_written_problem(oracle_lib):
     b = ProblemBatch.from_problems([p, p], [None, ctrl])
     got, ref = check(b, oracle_lib)
     assert got["robustness"][0] == pytest.approx(321.0 - (0.0771 * 97 + 326.154) if False else ref[0], rel=1e-9)
+
+
+def test_pipelined_run_equals_resident_eval(oracle_lib):
+    """pdeb_resident_run cuts the batch into chunks on two streams; results must not depend on the cut."""
+    for wl, n in (("mixed", 70001), ("heat", 16384 * 4), ("wave", 100)):
+        b = synth.make_batch(n, wl, seed=17)
+        r = native.ResidentBatch(b)
+        r.eval()
+        whole = r.fetch(want_clauses=True)
+        piped = r.run(b, want_clauses=True, timing=True)
+        assert np.array_equal(piped["robustness"], whole["robustness"])
+        assert np.array_equal(piped["status"], whole["status"])
+        assert np.array_equal(piped["clause"], whole["clause"])
+        assert piped["timing"].launches >= 4
+        r.eval()                                   # whole-batch order is rebuilt after a chunked run
+        again = r.fetch()
+        assert np.array_equal(again["robustness"], whole["robustness"])
+        r.close()
