@@ -35,6 +35,8 @@
  *   wave      Newmark a-form: a0 = M^-1 (F0 - K d0);
  *             dp = d + dt v + (1-2b)/2 dt^2 a;  vp = v + (1-g) dt a;
  *             (M + b dt^2 K) a' = F' - K dp;  d' = dp + b dt^2 a';  v' = vp + g dt a'
+ *   horizon   only states up to the last step any clause observes can influence the result; a blow-up after that
+ *             step is not an error (status NONFINITE means a non-finite OBSERVED value)
  *   STL       clause = G|F over [t_lo,t_hi] of  forall x in [x_lo,x_hi]: u(x) - (m x + b) REL 0
  *             margin(>) = u-p, margin(<) = p-u, margin(=) = -|u-p|;  forall x = min over nodes
  *             in the interval; G = min over window steps, F = max; & = min, | = max.
@@ -337,7 +339,6 @@ static int eval_one(const Sample* p, const PdebConventions* c, double* rob_out, 
     }
     double rob = val[p->nt - 1];
     if (!isfinite(rob)) status = PDEB_ST_NONFINITE;
-    for (int i = 1; i <= N; ++i) if (!isfinite(d[i])) status = PDEB_ST_NONFINITE;   /* the simulation itself blew up */
     for (int j = 0; j < p->np; ++j) if (!isfinite(acc[j])) status = PDEB_ST_NONFINITE;
     if (clause) for (int j = 0; j < p->np; ++j) clause[j] = acc[j];
     *rob_out = (status == PDEB_OK) ? rob : PDEB_FAILED_ROBUSTNESS;

@@ -340,7 +340,10 @@ pdeb_chunk_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant_
         c_info = rel | (top << 2) | (endp << 3);
     }
 
-    const int32_t S32 = (int32_t)S;
+    /* simulate only up to the last step any clause observes */
+    int32_t S32 = (lane < np) ? c_khi : 0;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) { const int32_t other = __shfl_xor_sync(PDEB_FULL, S32, o); S32 = other > S32 ? other : S32; }
     const double eq_eps = (cv.eq_rule == 1) ? cv.eq_eps : 0.0;
 
     for (int32_t k = 0;; ++k) {
@@ -484,11 +487,6 @@ pdeb_chunk_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant_
     }
 
     /* ---- formula tree and outputs (lane 0) ---- */
-    double chk = 0.0;
-#pragma unroll
-    for (int l = 0; l < R; ++l) chk = fma(x[l], 0.0, chk);
-    chk = fma(xs, 0.0, chk);
-    if (__any_sync(PDEB_FULL, !(chk == 0.0)) && status == PDEB_OK) status = PDEB_ST_NONFINITE;
     double val[PDEB_MAX_TREE];
     double rob = PDEB_FAILED_ROBUSTNESS;
     if (status == PDEB_OK) {

@@ -415,7 +415,7 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
     int status = PDEB_OK;
     double dt = 1;
     int np = 0;
-    int32_t S32 = 0;
+    int32_t S32 = 0;          /* steps actually simulated: up to the last observed one */
     PdebTrajReg<KIND, N, real> tr;
     tr.tab = table;
     tr.tstride = table_stride;
@@ -496,7 +496,7 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
             }
         }
         if (status != PDEB_OK) { S = 0; np = 0; }
-        S32 = (int32_t)S;
+        int32_t k_end = 0;         /* last step any clause observes: nothing after it can change the result */
         /* clause slots */
         for (int j = 0; j < np; ++j) {
             const double m = b.pred_m[(int64_t)j * st + s], bb = b.pred_b[(int64_t)j * st + s];
@@ -531,7 +531,9 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
             slots.W(j, 1) = (uint32_t)(int32_t)a1;
             slots.W(j, 2) = nm;
             slots.W(j, 3) = rel | (top << 2) | (endp << 3);
+            if ((int32_t)a1 > k_end) k_end = (int32_t)a1;
         }
+        S32 = k_end;
     }
 
     real f_prev = in.eval(0.0, kt, ky, st);
@@ -548,13 +550,6 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
                 if (k >= a0 && k <= a1) { open |= (1u << j); if (a1 + 1 < next_ev) next_ev = a1 + 1; }
                 else if (k < a0 && a0 < next_ev) next_ev = a0;
             }
-        }
-        if (k == S32 && status == PDEB_OK) {
-            /* the trajectory ends here: the simulation must still be finite (inf/nan poison a 0 * x sum) */
-            real chk = 0;
-            PDEB_UNROLL
-            for (int i = 1; i <= N; ++i) chk = fma(tr.w[i], (real)0, chk);
-            if (!(chk == (real)0)) status = PDEB_ST_NONFINITE;
         }
         /* ---- (1) reduce the open clauses on the state of step k ---- */
         uint32_t todo = on ? open : 0u;

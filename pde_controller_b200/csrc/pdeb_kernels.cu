@@ -43,7 +43,19 @@ __device__ __forceinline__ int pdeb_plan_key(const PdebDevBatch& b, const PdebCo
     if (v < 0) return -1;
     const double T = b.T[s], dt = b.dt[s];
     int64_t S = 1;
-    if (T > 0 && dt > 0 && isfinite(T) && isfinite(dt)) S = pdeb_step_count(T, dt, cv.steps_rule);
+    if (T > 0 && dt > 0 && isfinite(T) && isfinite(dt)) {
+        S = pdeb_step_count(T, dt, cv.steps_rule);
+        /* the kernels stop at the last observed step: order by that */
+        const int np = b.n_pred[s];
+        double last = 0.0;
+        for (int j = 0; j < np && j < b.pmax; ++j) {
+            const double q = b.pred_thi[(int64_t)j * b.stride + s] / dt;
+            const double a1 = (cv.window_rule == 1) ? trunc(q) : floor(q + PDEB_EPS);
+            if (a1 > last) last = a1;
+        }
+        if (last < (double)S) S = (int64_t)last;
+        if (S < 1) S = 1;
+    }
     if (S > PDEB_PLAN_SBINS - 1) S = PDEB_PLAN_SBINS - 1;
     return v * PDEB_PLAN_SBINS + (PDEB_PLAN_SBINS - 1 - (int)S);     /* descending in S inside a variant */
 }
