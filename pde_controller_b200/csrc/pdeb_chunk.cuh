@@ -170,7 +170,7 @@ pdeb_chunk_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant_
             const double wdev = -g0;
             const double m_o = rho_out * h, m_i = rho_in * h;
             double f0;
-            { PdebPwl<double> p0; p0.init(kt, ky, nk); f0 = p0.eval(0.0, kt, ky, st); }
+            { PdebPwl<double> p0; p0.init(kt, ky, nk, st); f0 = p0.eval(0.0, kt, ky, st); }
             double* scr_r = tab;                       /* rhs / solution by position */
             double* scr_c = tab + (G::CAP + 1);        /* Thomas multipliers by position */
             /* every lane: r_g = (R w0)_g (+ f0 at row N) for its R interior rows and its separator */
@@ -302,7 +302,7 @@ pdeb_chunk_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant_
     }
 
     PdebPwl<double> in;
-    in.init(kt, ky, (status == PDEB_OK) ? nk : 0);
+    in.init(kt, ky, (status == PDEB_OK) ? nk : 0, st);
     double f_prev = in.eval(0.0, kt, ky, st);
 
     /* clause data: lane j keeps clause j */

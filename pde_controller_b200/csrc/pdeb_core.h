@@ -125,30 +125,34 @@ PDEB_HD bool pdeb_params_ok(int kind, int N, double L, double dt, double T, doub
 
 /*
  * Running piecewise-linear input (C11): value held before the first and after the last knot.
- * Only the current segment lives in registers: y0 + slope (t - t0) until t reaches t1.
+ * Only the current segment lives in registers: y0 + slope (t - t0) until t reaches t1.  The knot BEHIND the
+ * current segment is fetched one segment ahead, so that crossing a knot never waits for memory: lanes of a warp
+ * cross their knots at different steps, which makes the warp take this path in most steps.
  */
 template <typename real>
 struct PdebPwl {
-    double t1;            /* end of the current segment (+inf on the last) */
-    real t0, y0, slope;
-    int nk, j;            /* j: index of the current knot segment, -1 before the first knot */
+    double t1, tn;        /* end of the current segment (+inf on the last); time of the knot after it (+inf: none) */
+    real t0, y0, slope;   /* current segment */
+    real y1, yn;          /* values at t1 and tn */
+    int nk, j;            /* j: index of the knot at t1 */
 
-    PDEB_HD void init(const double* kt, const double* ky, int nk_) {
-        nk = nk_; j = -1;
-        t0 = 0; slope = 0; y0 = 0; t1 = INFINITY;
-        if (nk >= 1) { y0 = (real)ky[0]; t1 = kt[0]; }
+    PDEB_HD void init(const double* kt, const double* ky, int nk_, int64_t stride) {
+        nk = nk_; j = 0;
+        t0 = 0; slope = 0; y0 = 0; y1 = 0; yn = 0; t1 = INFINITY; tn = INFINITY;
+        if (nk >= 1) { y0 = y1 = (real)ky[0]; t1 = kt[0]; }
+        if (nk >= 2) { tn = kt[stride]; yn = (real)ky[stride]; }
     }
     /* kt, ky already point at this sample's first knot; stride = plane stride */
     PDEB_HD real eval(double t, const double* kt, const double* ky, int64_t stride) {
         while (t >= t1) {
-            ++j;
-            if (j + 1 < nk) {
-                const double a = kt[(int64_t)j * stride], b = kt[(int64_t)(j + 1) * stride];
-                const double ya = ky[(int64_t)j * stride], yb = ky[(int64_t)(j + 1) * stride];
-                t0 = (real)a; y0 = (real)ya; slope = (real)((yb - ya) / (b - a)); t1 = b;
-            } else {
-                y0 = (real)ky[(int64_t)(nk - 1) * stride]; slope = 0; t1 = INFINITY;
-            }
+            t0 = (real)t1; y0 = y1;
+            if (tn < INFINITY) {
+                slope = (real)(((double)yn - (double)y1) / (tn - t1));
+                t1 = tn; y1 = yn;
+                ++j;
+                if (j + 1 < nk) { tn = kt[(int64_t)(j + 1) * stride]; yn = (real)ky[(int64_t)(j + 1) * stride]; }
+                else tn = INFINITY;
+            } else { slope = 0; t1 = INFINITY; }
         }
         return fma(slope, (real)(t - (double)t0), y0);
     }
@@ -420,7 +424,7 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
     tr.tab = table;
     tr.tstride = table_stride;
     PdebPwl<real> in;
-    in.init(nullptr, nullptr, 0);
+    in.init(nullptr, nullptr, 0, 0);
     const double* kt = b.knot_t + (live ? s : 0);
     const double* ky = b.knot_y + (live ? s : 0);
     PDEB_UNROLL
@@ -458,7 +462,7 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
             const double cR = (1.0 - cv.theta) * dt;
             const bool ok = tr.setup(L, x_a, x_b, rho_in, rho_out, E_in, E_out, lumped, cv.material_sampling, cA, cR);
             if (!ok) status = PDEB_ST_NONFINITE;
-            in.init(kt, ky, nk);
+            in.init(kt, ky, nk, st);
             if (KIND == PDEB_KIND_WAVE) {
                 /* wave initial state: d = 0 on the free nodes (deviation -g0), v = 0, a0 = M^-1 (f0 e_N - K w0) */
                 PDEB_UNROLL

@@ -10,6 +10,18 @@
 #include "pdeb_core.h"
 #include "pdeb_launch.h"
 
+/*
+ * PDEB_USE_PAIR=1 builds the default meshes on the pair family (pdeb_pair.cuh: two lanes per trajectory) instead of
+ * the one-thread register family.  Measured on B200 (profiles/README.md): same speed for heat (+2 %), 9 % slower for
+ * waves, so the register family stays the default; the variant is kept buildable for tools/variant_bench.py.
+ */
+#ifndef PDEB_USE_PAIR
+#define PDEB_USE_PAIR 0
+#endif
+#if PDEB_USE_PAIR
+#include "pdeb_pair.cuh"
+#endif
+
 #ifdef PDEB_REG_MAXNREG
 #define PDEB_REG_BOUNDS __maxnreg__(PDEB_REG_MAXNREG)
 #else
@@ -139,6 +151,24 @@ static cudaError_t launch_reg(const PdebDevBatch& b, const PdebConventions& cv, 
     return cudaGetLastError();
 }
 
+#if PDEB_USE_PAIR
+template <int KIND, int N, typename real>
+static cudaError_t launch_pair(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out,
+                               const int32_t* order, int64_t first, int64_t count, cudaStream_t stream) {
+    if (count <= 0) return cudaSuccess;
+    const size_t smem = pdeb_pair_smem_bytes<KIND, N, real>(b.pmax);
+    auto kern = pdeb_pair_kernel<KIND, N, real>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    const int64_t blocks = (2 * count + PDEB_PAIR_THREADS - 1) / PDEB_PAIR_THREADS;
+    kern<<<(unsigned)blocks, PDEB_PAIR_THREADS, smem, stream>>>(b, cv, out, order, first, count);
+    return cudaGetLastError();
+}
+
+#endif /* PDEB_USE_PAIR */
+
 int pdeb_launch_all(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out, const PdebPlanBuffers& pb,
                     const int32_t* vstart_count_host, int precision, cudaStream_t stream, int* launches) {
     cudaError_t e = cudaSuccess;
@@ -149,12 +179,22 @@ int pdeb_launch_all(const PdebDevBatch& b, const PdebConventions& cv, const Pdeb
         ++nl;
         switch (v) {
         case 0:
+#if PDEB_USE_PAIR
+            e = (precision == 32) ? launch_pair<PDEB_KIND_HEAT, 30, float>(b, cv, out, pb.order, first, count, stream)
+                                  : launch_pair<PDEB_KIND_HEAT, 30, double>(b, cv, out, pb.order, first, count, stream);
+#else
             e = (precision == 32) ? launch_reg<PDEB_KIND_HEAT, 30, float>(b, cv, out, pb.order, first, count, stream)
                                   : launch_reg<PDEB_KIND_HEAT, 30, double>(b, cv, out, pb.order, first, count, stream);
+#endif
             break;
         case 1:
+#if PDEB_USE_PAIR
+            e = (precision == 32) ? launch_pair<PDEB_KIND_WAVE, 20, float>(b, cv, out, pb.order, first, count, stream)
+                                  : launch_pair<PDEB_KIND_WAVE, 20, double>(b, cv, out, pb.order, first, count, stream);
+#else
             e = (precision == 32) ? launch_reg<PDEB_KIND_WAVE, 20, float>(b, cv, out, pb.order, first, count, stream)
                                   : launch_reg<PDEB_KIND_WAVE, 20, double>(b, cv, out, pb.order, first, count, stream);
+#endif
             break;
         default:
             if (v >= 2 && v <= 7) e = pdeb_launch_chunk_heat(1 << (v - 2), b, cv, out, pb.order, first, count, stream);
