@@ -32,7 +32,7 @@
 #include "pdeb_core.h"
 
 #define PDEB_CHUNK_NCLS 8      /* lane classes per trajectory: outer, inner, padding, <= 5 special */
-#define PDEB_CHUNK_NVEC 6      /* table vectors per class: c, dinv, v, w, rd, ror */
+#define PDEB_CHUNK_NVEC 6      /* table values per row and class, as three 16-byte pairs: {e, dinv} {v, w} {rd, ror} */
 #define PDEB_CHUNK_WARPS 4     /* warps (trajectories) per block */
 #define PDEB_FULL 0xffffffffu
 
@@ -70,7 +70,8 @@ struct PdebRowCoef {
 template <int R>
 struct PdebChunkGeom {
     static constexpr int CAP = 32 * R + 31;                   /* positions */
-    static constexpr int CLS_STRIDE = PDEB_CHUNK_NVEC * R + 1;  /* reals; the +1 staggers the banks of the classes */
+    static constexpr int CLS_STRIDE = PDEB_CHUNK_NVEC * R + 2;  /* reals; the +2 staggers the banks of the classes, keeps 16-byte alignment */
+    static constexpr int M = R / 2;                           /* twist row of the interior block */
     static constexpr int TAB_REALS = PDEB_CHUNK_NCLS * CLS_STRIDE;
     static constexpr int SCR_REALS = 2 * (CAP + 1);               /* two position-indexed scratch vectors (set-up) */
     static constexpr int WARP_REALS = TAB_REALS > SCR_REALS ? TAB_REALS : SCR_REALS;
@@ -220,61 +221,110 @@ pdeb_chunk_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant_
             __syncwarp();
         }
     }
-    double* tc = tab + cls * G::CLS_STRIDE;       /* this lane's class table: [vec][l] */
+    /* this lane's class table: three arrays of 16-byte pairs indexed by the local row */
+    PdebD2* t_ed = reinterpret_cast<PdebD2*>(tab + cls * G::CLS_STRIDE);      /* { e_l : multiplier of edge (l, l+1), 1/pivot_l } */
+    PdebD2* t_vw = t_ed + R;                                                   /* { v_l, w_l } spikes */
+    PdebD2* t_rr = t_ed + 2 * R;                                               /* { R_ll, R_l,l+1 } */
+    constexpr int M = G::M;
+    /*
+     * In-place TWISTED solve of the interior block with the factors in t_ed, run with run-time loops over shared
+     * memory (set-up only).  sel = 0 works on the v slots, 1 on the w slots; on entry they hold the right-hand side.
+     */
+    auto smem_solve = [&](int sel) {
+        double* yv = reinterpret_cast<double*>(t_vw) + sel;          /* element l at yv[2 l] */
+        double z = 0.0, zt = 0.0, zb = 0.0;
+        for (int l = 0; l < M; ++l) {                                 /* top chain */
+            z = yv[2 * l] - ((l > 0) ? t_ed[l - 1].x * zt : 0.0);
+            zt = z;
+            yv[2 * l] = z * t_ed[l].y;
+        }
+        for (int l = R - 1; l > M; --l) {                             /* bottom chain */
+            z = yv[2 * l] - ((l < R - 1) ? t_ed[l].x * zb : 0.0);
+            zb = z;
+            yv[2 * l] = z * t_ed[l].y;
+        }
+        z = yv[2 * M] - ((M > 0) ? t_ed[M - 1].x * zt : 0.0) - ((M < R - 1) ? t_ed[M].x * zb : 0.0);
+        yv[2 * M] = z * t_ed[M].y;
+        for (int l = M - 1; l >= 0; --l) yv[2 * l] = yv[2 * l] - t_ed[l].x * yv[2 * (l + 1)];
+        for (int l = M + 1; l < R; ++l) yv[2 * l] = yv[2 * l] - t_ed[l - 1].x * yv[2 * (l - 1)];
+    };
     {
         const int g_first = base + 1 - shift;
-        /* pass 1: L D L^T of the interior block, R-operator rows */
-        double dprev = 0.0, ao_prev = 0.0;
+        /* pass 1: twisted L D L^T of the interior block (top sweep, bottom sweep, twist row M), R-operator rows */
         bool ok = true;
+        double dprev = 0.0, ao_prev = 0.0, a_first = 0.0;
         for (int l = 0; l < R; ++l) {
             double Ad, Ao, Rd, Ro;
             rc.row(g_first + l, Ad, Ao, Rd, Ro);
-            double c = 0.0, piv = Ad;
-            if (l > 0) { c = ao_prev * dprev; piv -= c * ao_prev; }
-            if (!(piv > 0.0)) ok = false;
-            dprev = 1.0 / piv;
-            tc[0 * R + l] = c;
-            tc[1 * R + l] = dprev;
-            tc[4 * R + l] = Rd;
-            tc[5 * R + l] = Ro;
-            ao_prev = Ao;
+            PdebD2 rr; rr.x = Rd; rr.y = Ro;
+            t_rr[l] = rr;
             if (l == R - 1) { a_last = Ao; rs_l = Ro; }
         }
-        if (!isfinite(dprev)) ok = false;
+        for (int l = 0; l < M; ++l) {                                 /* top sweep */
+            double Ad, Ao, Rd, Ro;
+            rc.row(g_first + l, Ad, Ao, Rd, Ro);
+            double piv = Ad;
+            if (l > 0) piv -= (ao_prev * dprev) * ao_prev;
+            if (!(piv > 0.0)) ok = false;
+            dprev = 1.0 / piv;
+            PdebD2 ed; ed.x = Ao * dprev; ed.y = dprev;               /* edge (l, l+1) eliminated downwards */
+            t_ed[l] = ed;
+            ao_prev = Ao;
+        }
+        const double dtop = dprev, aotop = ao_prev;
+        dprev = 0.0;
+        double ao_this = 0.0;
+        for (int l = R - 1; l > M; --l) {                             /* bottom sweep */
+            double Ad, Ao, Rd, Ro;
+            rc.row(g_first + l, Ad, Ao, Rd, Ro);
+            double piv = Ad;
+            if (l < R - 1) piv -= (Ao * dprev) * Ao;                  /* edge (l, l+1) eliminated upwards */
+            if (!(piv > 0.0)) ok = false;
+            const double e_up = (l < R - 1) ? Ao * dprev : 0.0;
+            dprev = 1.0 / piv;
+            PdebD2 ed; ed.x = e_up; ed.y = dprev;
+            t_ed[l] = ed;
+            ao_this = Ao;
+        }
+        (void)ao_this;
+        {
+            double Ad, Ao, Rd, Ro;
+            rc.row(g_first + M, Ad, Ao, Rd, Ro);                      /* twist row; Ao couples M with M+1 */
+            const double e_dn = (M > 0) ? aotop * dtop : 0.0;         /* already stored in t_ed[M-1].x */
+            const double e_up = (M < R - 1) ? Ao * dprev : 0.0;
+            const double piv = Ad - ((M > 0) ? e_dn * aotop : 0.0) - ((M < R - 1) ? e_up * Ao : 0.0);
+            if (!(piv > 0.0)) ok = false;
+            const double dm = 1.0 / piv;
+            if (!isfinite(dm) || !isfinite(dtop) || !isfinite(dprev)) ok = false;
+            PdebD2 ed; ed.x = e_up; ed.y = dm;
+            t_ed[M] = ed;
+        }
         /* couplings to the previous separator (row g_first - 1) */
-        double Adp, a_first, Rdp, rfirst;
-        rc.row(g_first - 1, Adp, a_first, Rdp, rfirst);
-        if (lane == 0) { a_first = 0.0; rfirst = 0.0; }
-        rol0 = rfirst;
+        {
+            double Adp, Rdp, rfirst;
+            rc.row(g_first - 1, Adp, a_first, Rdp, rfirst);
+            if (lane == 0) { a_first = 0.0; rfirst = 0.0; }
+            rol0 = rfirst;
+        }
         __syncwarp();
         /* pass 2: spikes v = A_loc^-1 (a_first e_0), w = A_loc^-1 (a_last e_{R-1}) */
-        {
-            double z = a_first;
-            for (int l = 0; l < R; ++l) {
-                if (l > 0) z = -tc[0 * R + l] * z;
-                tc[2 * R + l] = z * tc[1 * R + l];
-            }
-            __syncwarp();
-            double nxt = tc[2 * R + R - 1];
-            for (int l = R - 2; l >= 0; --l) {
-                nxt = tc[2 * R + l] - tc[0 * R + l + 1] * nxt;
-                tc[2 * R + l] = nxt;
-            }
-            double wv = a_last * tc[1 * R + R - 1];
-            tc[3 * R + R - 1] = wv;
-            for (int l = R - 2; l >= 0; --l) {
-                wv = -tc[0 * R + l + 1] * wv;
-                tc[3 * R + l] = wv;
-            }
+        for (int l = 0; l < R; ++l) {
+            PdebD2 vw; vw.x = (l == 0) ? a_first : 0.0; vw.y = (l == R - 1) ? a_last : 0.0;
+            t_vw[l] = vw;
         }
+        __syncwarp();
+        smem_solve(0);
+        __syncwarp();
+        smem_solve(1);
+        if (__any_sync(PDEB_FULL, !ok) && status == PDEB_OK) { status = PDEB_ST_NONFINITE; S = 0; np = 0; }
         __syncwarp();
         /* separator row and Schur complement */
         double As, Ao_s;
         rc.row(base + R + 1 - shift, As, Ao_s, rs_d, rs_r);
         if (lane == 31) { As = 1.0; Ao_s = 0.0; rs_d = 0.0; rs_r = 0.0; rs_l = 0.0; a_last = 0.0; }
         a_first_next = Ao_s;
-        const double v_last = tc[2 * R + R - 1], w_last = tc[3 * R + R - 1];
-        const double v0 = tc[2 * R + 0], w0 = tc[3 * R + 0];
+        const double v_last = t_vw[R - 1].x, w_last = t_vw[R - 1].y;
+        const double v0 = t_vw[0].x, w0 = t_vw[0].y;
         const double v0_n = pdeb_shfl_dn1(v0, lane), w0_n = pdeb_shfl_dn1(w0, lane);
         double Sdi = As - a_last * w_last - a_first_next * v0_n;
         double Slo = (lane == 0) ? 0.0 : -a_last * v_last;
@@ -439,21 +489,47 @@ pdeb_chunk_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant_
         f_prev = f_next;
         {
             const double xs_prev = pdeb_shfl_up1(xs, lane), x_nf = pdeb_shfl_dn1(x[0], lane);
-            /* right-hand side R x and forward elimination of the interior block */
-            double ror_prev = rol0, z = 0.0;
+            /* right-hand side R x of the interior block (all rows independent) */
+            double ror_prev = rol0;
 #pragma unroll
             for (int l = 0; l < R; ++l) {
-                const double rd = tc[4 * R + l], ror = tc[5 * R + l];
+                const PdebD2 rr = t_rr[l];
                 const double xl = (l == 0) ? xs_prev : x[l - 1], xr = (l == R - 1) ? xs : x[l + 1];
-                double r = fma(rd, x[l], fma(ror_prev, xl, ror * xr));
+                double r = fma(rr.x, x[l], fma(ror_prev, xl, rr.y * xr));
                 if (l == R - 1) r += (lane == 31) ? fN : 0.0;
-                if (l > 0) r = fma(-tc[0 * R + l], z, r);
-                z = r;
-                y[l] = r * tc[1 * R + l];
-                ror_prev = ror;
+                y[l] = r;
+                ror_prev = rr.y;
             }
+            /* twisted solve: two independent elimination chains meet at row M, two independent back-substitutions leave it */
+            {
+                double zt = 0.0, zb = 0.0, e_top = 0.0;
 #pragma unroll
-            for (int l = R - 2; l >= 0; --l) y[l] = fma(-tc[0 * R + l + 1], y[l + 1], y[l]);
+                for (int l = 0; l < M; ++l) {
+                    const PdebD2 ed = t_ed[l];
+                    const double z = (l > 0) ? fma(-e_top, zt, y[l]) : y[l];
+                    zt = z;
+                    y[l] = z * ed.y;
+                    e_top = ed.x;
+                }
+#pragma unroll
+                for (int l = R - 1; l > M; --l) {
+                    const PdebD2 ed = t_ed[l];
+                    const double z = (l < R - 1) ? fma(-ed.x, zb, y[l]) : y[l];
+                    zb = z;
+                    y[l] = z * ed.y;
+                }
+                {
+                    const PdebD2 ed = t_ed[M];
+                    double z = y[M];
+                    if (M > 0) z = fma(-e_top, zt, z);
+                    if (M < R - 1) z = fma(-ed.x, zb, z);
+                    y[M] = z * ed.y;
+                }
+#pragma unroll
+                for (int l = M - 1; l >= 0; --l) y[l] = fma(-t_ed[l].x, y[l + 1], y[l]);
+#pragma unroll
+                for (int l = M + 1; l < R; ++l) y[l] = fma(-t_ed[l - 1].x, y[l - 1], y[l]);
+            }
             /* Schur right-hand side and PCR across the lanes */
             const double rsep = fma(rs_d, xs, fma(rs_l, x[R - 1], rs_r * x_nf));
             const double y_nf = pdeb_shfl_dn1(y[0], lane);
@@ -468,13 +544,14 @@ pdeb_chunk_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant_
             const double xs_new_prev = pdeb_shfl_up1(xs_new, lane);
             if (KIND == PDEB_KIND_HEAT) {
 #pragma unroll
-                for (int l = 0; l < R; ++l) x[l] = fma(-tc[2 * R + l], xs_new_prev, fma(-tc[3 * R + l], xs_new, y[l]));
+                for (int l = 0; l < R; ++l) { const PdebD2 vw = t_vw[l]; x[l] = fma(-vw.x, xs_new_prev, fma(-vw.y, xs_new, y[l])); }
                 xs = xs_new;
             } else {
                 const double cw4 = cv.newmark_beta * dt * dt, cw5 = cv.newmark_gamma * dt;
 #pragma unroll
                 for (int l = 0; l < R; ++l) {
-                    const double an = fma(-tc[2 * R + l], xs_new_prev, fma(-tc[3 * R + l], xs_new, y[l]));
+                    const PdebD2 vw = t_vw[l];
+                    const double an = fma(-vw.x, xs_new_prev, fma(-vw.y, xs_new, y[l]));
                     aa[l] = an;
                     x[l] = fma(cw4, an, x[l]);
                     vv[l] = fma(cw5, an, vv[l]);
