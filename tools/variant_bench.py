@@ -37,7 +37,7 @@ def one(workloads, batch, precision):
         small = synth.make_batch(4096, wl, seed=5)
         got = native.evaluate_batch(small, precision=precision)
         ref, st = oracle.eval_batch(small)
-        scale = np.maximum(np.abs(ref), 1e-3 * (np.abs(small.g0) + 1))
+        scale = np.maximum(np.abs(ref), 1e-3 * (np.abs(small.g0) + 1 + np.abs(small.knot_y).max(axis=0) * small.L / np.minimum(small.E_in, small.E_out)))
         err = float((np.abs(got["robustness"] - ref) / scale).max())
         b = synth.make_batch(batch, wl, seed=0)
         r = native.ResidentBatch(b)
@@ -50,9 +50,48 @@ def one(workloads, batch, precision):
     print(json.dumps(res))
 
 
+def decomp(workloads, batch, precision):
+    """Cost split of the fused kernel on uniform synthetic inputs (all trajectories the same length):
+    solve only / + piecewise-linear input / + one clause pass per step / + two."""
+    import numpy as np
+    from pde_controller_b200 import abi, native, synth
+    res = {}
+    for wl in workloads:
+        out = {}
+        for case in ("solve", "solve+pwl", "solve+pwl+1clause", "solve+pwl+2clauses"):
+            b = synth.make_batch(batch, wl, seed=0)
+            T = 10.0 if wl == "heat" else 1.5
+            b.T[:] = T
+            nk = int(b.n_knots.max())
+            b.n_knots[:] = 1 if case == "solve" else nk
+            b.knot_t[:nk, :] = (np.arange(nk)[:, None] * (T / (nk - 1)))
+            npred = 2 if case.endswith("2clauses") else 1
+            b.n_pred[:] = npred
+            b.pred_tlo[:, :] = T if "clause" not in case else 0.0
+            b.pred_thi[:, :] = T
+            b.n_tree[:] = 2 * npred - 1
+            b.tree_op[0, :] = abi.TREE_LEAF; b.tree_lhs[0, :] = 0
+            if npred == 2:
+                b.tree_op[1, :] = abi.TREE_LEAF; b.tree_lhs[1, :] = 1
+                b.tree_op[2, :] = abi.TREE_AND; b.tree_lhs[2, :] = 0; b.tree_rhs[2, :] = 1
+            r = native.ResidentBatch(b)
+            for _ in range(3):
+                r.eval(precision, timing=True)
+            ms = sorted(r.eval(precision, timing=True).kernel_ms for _ in range(9))
+            steps = T / float(b.dt[0])
+            # SMSP-cycles per warp-step at 1965 MHz, 592 SMSPs
+            out[case] = {"ms": round(ms[len(ms) // 2], 4),
+                         "smsp_cycles_per_warp_step": round(ms[len(ms) // 2] * 1e-3 * 1.965e9 * 592 / (batch / 32 * steps), 1)}
+            r.close()
+        res[wl] = out
+    print(json.dumps(res))
+
+
 def do_run(argv):
-    workloads, batch, precision = "heat,wave", 65536, 64
+    workloads, batch, precision, mode = "heat,wave", 65536, 64, "one"
     for i, a in enumerate(argv):
+        if a == "--decomp":
+            mode = "decomp"
         if a == "--workloads":
             workloads = argv[i + 1]
         if a == "--batch":
@@ -62,7 +101,7 @@ def do_run(argv):
     libs = [os.path.join(ROOT, "pde_controller_b200", "libpdeb200.so")] + sorted(glob.glob(os.path.join(VDIR, "lib*.so")))
     for lib in libs:
         env = dict(os.environ, PDEB_LIB=lib)
-        p = subprocess.run([sys.executable, __file__, "one", workloads, str(batch), str(precision)], env=env,
+        p = subprocess.run([sys.executable, __file__, mode, workloads, str(batch), str(precision)], env=env,
                            capture_output=True, text=True, timeout=600)
         line = p.stdout.strip().splitlines()[-1] if p.stdout.strip() else p.stderr[-400:]
         print(os.path.basename(lib), line, flush=True)
@@ -73,5 +112,7 @@ if __name__ == "__main__":
         do_build(sys.argv[2:])
     elif sys.argv[1] == "run":
         do_run(sys.argv[2:])
+    elif sys.argv[1] == "decomp":
+        decomp(sys.argv[2].split(","), int(sys.argv[3]), int(sys.argv[4]))
     elif sys.argv[1] == "one":
         one(sys.argv[2].split(","), int(sys.argv[3]), int(sys.argv[4]))
