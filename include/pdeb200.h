@@ -215,6 +215,23 @@ int   pdeb_stream_sync(void* stream);
 int  pdeb_resident_device_ptrs(PdebResident* r, void** robustness_dev, void** clause_dev, void** status_dev);
 void pdeb_resident_destroy(PdebResident* r);
 
+/*
+ * Many candidate controls for ONE specification (north star "many candidate controls per spec").
+ * In the reference the boundary input is synthesised by Gurobi inside control.femformal
+ * (eval_robustness_wrapper.py:16); that MILP is out of scope, and this is its sampling surrogate: the robustness
+ * of every one of m piecewise-linear inputs for sample `sample` of `spec`, and the arg-max.
+ *   knot_t   [n_knots] knot times shared by all candidates (C11), ascending; the spec's own knots are ignored
+ *   knot_y   host [n_knots][m], plane-major: value j of candidate i at knot_y[j*m + i]; NULL = values already there
+ *   outputs  robustness [m], clause [n_pred][m], status [m], best index / value: all optional (NULL)
+ * Default meshes only (heat N=30, wave N=20), FP64; other meshes go through pdeb_eval_batch with a replicated spec.
+ */
+typedef struct PdebControls PdebControls;
+int  pdeb_controls_create(const PdebBatch* spec, int64_t sample, int64_t capacity, int32_t n_knots, const double* knot_t,
+                          int device, const PdebConventions* conv, PdebControls** out);
+int  pdeb_controls_eval(PdebControls* h, int64_t m, const double* knot_y, double* robustness_out, double* clause_out,
+                        int32_t* status_out, int64_t* best_index, double* best_value, void* stream, PdebTiming* timing);
+void pdeb_controls_destroy(PdebControls* h);
+
 /* pinned host memory for batches that are uploaded every step */
 void* pdeb_host_alloc(int64_t bytes);
 void  pdeb_host_free(void* p);

@@ -126,6 +126,9 @@ EXPORTS = [
     "pdeb_resident_run",
     "pdeb_resident_eval",
     "pdeb_resident_set_knots",
+    "pdeb_controls_create",
+    "pdeb_controls_eval",
+    "pdeb_controls_destroy",
     "pdeb_resident_fetch",
     "pdeb_resident_fetch_async",
     "pdeb_stream_create",

@@ -45,6 +45,8 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+void pdeb_set_last_error(const char* msg) { g_err = msg ? msg : ""; }
+
 extern "C" int pdeb_version(void) { return PDEB_ABI_VERSION; }
 
 extern "C" int pdeb_device_count(void) {

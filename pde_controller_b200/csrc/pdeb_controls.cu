@@ -1,0 +1,500 @@
+/*
+ * pdeb_controls.cu — "controls family": ONE specification evaluated against MANY candidate controls
+ * (north star: "many candidate controls per spec").  In the reference the boundary input is
+ * chosen by the Gurobi MILP inside control.femformal (call site eval_robustness_wrapper.py:16); that synthesis is
+ * out of scope, and this family is the sampling surrogate for it: the robustness of 10^3..10^6 piecewise-linear
+ * inputs for one program, plus the arg-max, in one call.
+ *
+ * Because mesh, materials, windows and intervals are the same for every thread,
+ *   - the scaled step-matrix factors, R~ diagonal, node scales and clause data are computed ONCE on the host (the
+ *     same PDEB_HD set-up code the batch kernels run per thread) and passed in the kernel-parameter bank: FP64
+ *     instructions take them as constant-bank operands, so the time loop has no table loads at all;
+ *   - every branch on windows, intervals and relations is warp-uniform: clause passes only run while a window is
+ *     open and only over the groups of four nodes their interval touches;
+ *   - a thread keeps nothing but its state in registers, so many more warps are resident than in the batch kernels.
+ * One thread = one candidate control.  Knot TIMES are shared (C11: uniform knots), knot VALUES are per candidate,
+ * plane-major [knot][candidate] like every list of the batch layout.
+ */
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pdeb200.h"
+#include "pdeb_core.h"
+#include "pdeb_launch.h"
+
+#define PDEB_CTL_THREADS 128
+#define PDEB_CTL_KMAX 32
+
+template <int N>
+struct PdebSpecConst {
+    double rd[N + 1], rl[N + 1], dinv[N + 1], c[N + 1], s[N + 1];   /* index = node 1..N; rl: low part of R~_ii (waves) */
+    double w0[N + 1], a0_base[N + 1], a0_unit[N + 1];             /* waves: scaled initial state, a0 = base + f0 unit */
+    double knot_t[PDEB_CTL_KMAX];
+    PdebClauseData cl[PDEB_MAX_PRED];
+    double sN, dt, th_dt, eq_eps;
+    double cw1, cw2, cw3, cw4, cw5;
+    int32_t nk, np, nt, k_end;
+    uint8_t tree_op[PDEB_MAX_TREE];
+    int8_t tree_lhs[PDEB_MAX_TREE], tree_rhs[PDEB_MAX_TREE];
+};
+
+struct PdebCtlOut {
+    double* robustness;   /* [m] */
+    double* clause;       /* [pmax][stride] or NULL */
+    int32_t* status;      /* [m] or NULL */
+};
+
+/* masked max over four consecutive nodes starting at node B (uniform mask, per-thread values) */
+template <int N, int B>
+__device__ __forceinline__ void pdeb_ctl_group(const PdebSpecConst<N>& sp, const double* w, double mh, double c0, uint32_t nmask,
+                                               uint32_t and_mask, uint32_t xor_mask, double* hi) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        constexpr int dummy = 0; (void)dummy;
+        const int i = B + q;
+        if (i <= N) {
+            const double qv = fma(-mh, (double)i, -c0);
+            const double d = (i == 0) ? qv : fma(sp.s[i == 0 ? 1 : i], w[i], qv);
+            const double g = pdeb_signop(d, and_mask, xor_mask);
+            /* B + q is a compile-time constant after unrolling; the template form of the masked max needs it as one */
+            switch (q) {
+            case 0: pdeb_masked_max<(B + 0) & 31>(hi[0], g, nmask); break;
+            case 1: pdeb_masked_max<(B + 1) & 31>(hi[1], g, nmask); break;
+            case 2: pdeb_masked_max<(B + 2) & 31>(hi[2], g, nmask); break;
+            default: pdeb_masked_max<(B + 3) & 31>(hi[3], g, nmask); break;
+            }
+        }
+    }
+}
+
+template <int N, int B>
+struct PdebCtlGroups {
+    static __device__ __forceinline__ void run(const PdebSpecConst<N>& sp, const double* w, double mh, double c0, uint32_t nmask,
+                                               uint32_t and_mask, uint32_t xor_mask, double* hi) {
+        if (nmask & (0xFu << B)) pdeb_ctl_group<N, B>(sp, w, mh, c0, nmask, and_mask, xor_mask, hi);   /* warp-uniform */
+        PdebCtlGroups<N, B + 4>::run(sp, w, mh, c0, nmask, and_mask, xor_mask, hi);
+    }
+};
+template <int N>
+struct PdebCtlGroups<N, 32> {
+    static __device__ __forceinline__ void run(const PdebSpecConst<N>&, const double*, double, double, uint32_t, uint32_t, uint32_t,
+                                               double*) {}
+};
+
+/* z[1..N] <- A~^-1 (R~ x + fNs e_N): the twisted solve of pdeb_core.h with every factor a constant-bank operand */
+template <int KIND, int N>
+__device__ __forceinline__ void pdeb_ctl_solve(const PdebSpecConst<N>& sp, const double* x, double fNs, double* z) {
+    constexpr int M = (N + 1) / 2;
+    double zt = 0, zb = 0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const int it = 1 + j, ib = N - j;
+        if (it < M) {
+            double r = x[it - 1] + x[it + 1];
+            if (KIND == PDEB_KIND_WAVE) r = fma(sp.rl[it], x[it], r);
+            r = fma(sp.rd[it], x[it], r);
+            if (it > 1) r = fma(-sp.c[it - 1], zt, r);
+            zt = r;
+            z[it] = r * sp.dinv[it];
+        }
+        if (ib > M) {
+            double r = x[ib - 1] + ((ib == N) ? fNs : x[ib + 1]);
+            if (KIND == PDEB_KIND_WAVE) r = fma(sp.rl[ib], x[ib], r);
+            r = fma(sp.rd[ib], x[ib], r);
+            if (ib < N) r = fma(-sp.c[ib], zb, r);
+            zb = r;
+            z[ib] = r * sp.dinv[ib];
+        }
+    }
+    {
+        double r = x[M - 1] + x[M + 1];
+        if (KIND == PDEB_KIND_WAVE) r = fma(sp.rl[M], x[M], r);
+        r = fma(sp.rd[M], x[M], r);
+        r = fma(-sp.c[M - 1], zt, r);
+        r = fma(-sp.c[M], zb, r);
+        z[M] = r * sp.dinv[M];
+    }
+#pragma unroll
+    for (int j = 1; j < N; ++j) {
+        const int it = M - j, ib = M + j;
+        if (it >= 1) z[it] = fma(-sp.c[it], z[it + 1], z[it]);
+        if (ib <= N) z[ib] = fma(-sp.c[ib - 1], z[ib - 1], z[ib]);
+    }
+}
+
+template <int KIND, int N, int PMAX>
+__global__ void __launch_bounds__(PDEB_CTL_THREADS)
+pdeb_controls_kernel(const __grid_constant__ PdebSpecConst<N> sp, const double* __restrict__ ky, int64_t stride, int64_t m,
+                     const __grid_constant__ PdebCtlOut out) {
+    const int64_t t = (int64_t)blockIdx.x * PDEB_CTL_THREADS + threadIdx.x;
+    const bool live = t < m;
+    const double* y = ky + (live ? t : 0);
+
+    double w[N + 2];
+    double v[KIND == PDEB_KIND_WAVE ? N + 2 : 1], a[KIND == PDEB_KIND_WAVE ? N + 2 : 1];
+    double acc[PMAX];
+#pragma unroll
+    for (int i = 0; i <= N + 1; ++i) w[i] = 0;
+#pragma unroll
+    for (int j = 0; j < PMAX; ++j)
+        acc[j] = (j < sp.np && (((sp.cl[j].info >> 2) & 1u) == PDEB_TOP_F)) ? -INFINITY : INFINITY;
+
+    /* piecewise-linear input: knot times are uniform, values per thread; same arithmetic as PdebPwl */
+    const int nk = sp.nk;
+    int jn = 0;                        /* index of the knot at t1 */
+    double t0 = 0, y0 = 0, slope = 0, y1 = 0, t1 = INFINITY;
+    if (nk >= 1) { y0 = y1 = y[0]; t1 = sp.knot_t[0]; }
+    auto input = [&](double tt) {
+        while (tt >= t1) {             /* warp-uniform */
+            t0 = t1; y0 = y1;
+            if (jn + 1 < nk) {
+                const double tn = sp.knot_t[jn + 1], yn = y[(int64_t)(jn + 1) * stride];
+                slope = (yn - y1) / (tn - t1);
+                t1 = tn; y1 = yn;
+                ++jn;
+            } else { slope = 0; t1 = INFINITY; }
+        }
+        return fma(slope, tt - t0, y0);
+    };
+    double f_prev = input(0.0);
+    if (KIND == PDEB_KIND_WAVE) {
+#pragma unroll
+        for (int i = 0; i <= N + 1; ++i) { v[i] = 0; a[i] = 0; }
+#pragma unroll
+        for (int i = 1; i <= N; ++i) { w[i] = sp.w0[i]; a[i] = fma(f_prev, sp.a0_unit[i], sp.a0_base[i]); }
+    }
+
+    const int32_t k_end = sp.k_end;
+    for (int32_t k = 0;; ++k) {
+        /* ---- clauses whose window contains step k (uniform) ---- */
+#pragma unroll
+        for (int j = 0; j < PMAX; ++j) {
+            if (j < sp.np && k >= sp.cl[j].klo && k <= sp.cl[j].khi) {
+                const PdebClauseData& cd = sp.cl[j];
+                const uint32_t rel = cd.info & 3u;
+                const uint32_t and_mask = (rel == PDEB_REL_EQ) ? 0x7fffffffu : 0xffffffffu;
+                const uint32_t xor_mask = (rel == PDEB_REL_GT) ? 0x80000000u : 0u;
+                double hi[4] = { -INFINITY, -INFINITY, -INFINITY, -INFINITY };
+                PdebCtlGroups<N, 0>::run(sp, w, cd.mh, cd.c0, cd.nmask, and_mask, xor_mask, hi);
+                const double h01 = hi[0] > hi[1] ? hi[0] : hi[1], h23 = hi[2] > hi[3] ? hi[2] : hi[3];
+                double gmax = h01 > h23 ? h01 : h23;
+                if (cd.info & 8u) {
+                    /* interpolated end points (C8): uniform elements, so the two node values are picked by a uniform scan */
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int e = (int)((cd.info >> (4 + 5 * q)) & 31u);
+                        double we = 0, wf = 0, se = 0, sf = 0;
+#pragma unroll
+                        for (int i = 0; i <= N; ++i) {
+                            if (i == e) { we = (i == 0) ? 0.0 : w[i]; se = (i == 0) ? 0.0 : sp.s[i == 0 ? 1 : i]; }
+                            if (i == e + 1) { wf = w[i]; sf = sp.s[i == 0 ? 1 : i]; }
+                        }
+                        const double de = fma(se, we, fma(-cd.mh, (double)e, -cd.c0));
+                        const double df = fma(sf, wf, fma(-cd.mh, (double)(e + 1), -cd.c0));
+                        const double gq = pdeb_signop(fma(cd.xi[q], df - de, de), and_mask, xor_mask);
+                        if (gq > gmax) gmax = gq;
+                    }
+                }
+                const double r = (rel == PDEB_REL_EQ) ? sp.eq_eps - gmax : -gmax;
+                const bool take = (((cd.info >> 2) & 1u) == PDEB_TOP_G) ? (r < acc[j]) : (r > acc[j]);
+                if (take || r != r) acc[j] = r;
+            }
+        }
+        if (k >= k_end) break;
+        /* ---- advance to step k+1 ---- */
+        const double f_next = input((double)(k + 1) * sp.dt);
+        if (KIND == PDEB_KIND_HEAT) {
+            const double fb = fma(sp.dt - sp.th_dt, f_prev, sp.th_dt * f_next);
+            double z[N + 2];
+            z[0] = 0; z[N + 1] = 0;
+            pdeb_ctl_solve<KIND, N>(sp, w, sp.sN * fb, z);
+#pragma unroll
+            for (int i = 1; i <= N; ++i) w[i] = z[i];
+        } else {
+#pragma unroll
+            for (int i = 1; i <= N; ++i) {
+                w[i] = fma(sp.cw2, a[i], fma(sp.cw1, v[i], w[i]));
+                v[i] = fma(sp.cw3, a[i], v[i]);
+            }
+            pdeb_ctl_solve<KIND, N>(sp, w, sp.sN * f_next, a);
+#pragma unroll
+            for (int i = 1; i <= N; ++i) {
+                w[i] = fma(sp.cw4, a[i], w[i]);
+                v[i] = fma(sp.cw5, a[i], v[i]);
+            }
+        }
+        f_prev = f_next;
+    }
+
+    if (!live) return;
+    /* ---- formula tree ---- */
+    double val[PDEB_MAX_TREE];
+    int status = PDEB_OK;
+#pragma unroll
+    for (int q = 0; q < 2 * PMAX - 1; ++q) {
+        if (q < sp.nt) {
+            const int op = sp.tree_op[q], lh = sp.tree_lhs[q], rh = sp.tree_rhs[q];
+            double x = NAN;
+            if (op == PDEB_TREE_LEAF) {
+#pragma unroll
+                for (int j = 0; j < PMAX; ++j) if (j == lh) x = acc[j];
+            } else {
+                double a0 = NAN, a1 = NAN;
+#pragma unroll
+                for (int u = 0; u < 2 * PMAX - 1; ++u) { if (u == lh && u < q) a0 = val[u]; if (u == rh && u < q) a1 = val[u]; }
+                if (a0 != a0 || a1 != a1) x = NAN;
+                else if (op == PDEB_TREE_AND) x = a0 < a1 ? a0 : a1;
+                else x = a0 > a1 ? a0 : a1;
+            }
+            val[q] = x;
+        } else val[q] = NAN;
+    }
+    double rob = NAN;
+#pragma unroll
+    for (int q = 0; q < 2 * PMAX - 1; ++q) if (q == sp.nt - 1) rob = val[q];
+    if (!isfinite(rob)) status = PDEB_ST_NONFINITE;
+#pragma unroll
+    for (int j = 0; j < PMAX; ++j) if (j < sp.np && !isfinite(acc[j])) status = PDEB_ST_NONFINITE;
+    out.robustness[t] = (status == PDEB_OK) ? rob : PDEB_FAILED_ROBUSTNESS;
+    if (out.status) out.status[t] = status;
+    if (out.clause) {
+#pragma unroll
+        for (int j = 0; j < PMAX; ++j)
+            if (j < sp.np) out.clause[(int64_t)j * stride + t] = (status == PDEB_OK) ? acc[j] : PDEB_FAILED_ROBUSTNESS;
+    }
+}
+
+/* ---- arg-max of the robustness over the candidates (two tiny launches) ---- */
+__global__ void pdeb_argmax_partial_kernel(const double* __restrict__ r, const int32_t* __restrict__ status, int64_t m,
+                                           double* __restrict__ pv, int64_t* __restrict__ pi) {
+    double bv = -INFINITY;
+    int64_t bi = -1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool ok = status ? (status[i] == PDEB_OK) : true;
+        const double x = r[i];
+        if (ok && (bi < 0 || x > bv)) { bv = x; bi = i; }      /* ascending i: the first of equal values wins */
+    }
+    __shared__ double sv[256];
+    __shared__ int64_t si[256];
+    sv[threadIdx.x] = bv; si[threadIdx.x] = bi;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o >= 1; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            const double ov = sv[threadIdx.x + o]; const int64_t oi = si[threadIdx.x + o];
+            const double mv = sv[threadIdx.x]; const int64_t mi = si[threadIdx.x];
+            if (oi >= 0 && (mi < 0 || ov > mv || (ov == mv && oi < mi))) { sv[threadIdx.x] = ov; si[threadIdx.x] = oi; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { pv[blockIdx.x] = sv[0]; pi[blockIdx.x] = si[0]; }
+}
+
+/* ---- host side ------------------------------------------------------------------------------------------------ */
+static int cfail(int code, const char* what, cudaError_t ce = cudaSuccess) {
+    char buf[512];
+    if (ce != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(ce));
+    else snprintf(buf, sizeof buf, "%s", what);
+    pdeb_set_last_error(buf);          /* read back through pdeb_last_error() */
+    return code;
+}
+#define CCK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return cfail(PDEB_E_CUDA, #call, _e); } while (0)
+
+struct PdebControls {
+    int device = 0, kind = 0, n_elem = 0, pmax = 0, nk = 0;
+    int64_t capacity = 0;
+    int spec_status = PDEB_OK;
+    PdebSpecConst<30> heat{};
+    PdebSpecConst<20> wave{};
+    double* d_y = nullptr;        /* [nk][capacity] */
+    double* d_rob = nullptr;      /* [capacity] */
+    double* d_clause = nullptr;   /* [pmax][capacity] */
+    int32_t* d_status = nullptr;  /* [capacity] */
+    double* d_pv = nullptr;       /* arg-max partials */
+    int64_t* d_pi = nullptr;
+    double* h_pv = nullptr;       /* pinned */
+    int64_t* h_pi = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+};
+#define PDEB_ARGMAX_BLOCKS 128
+
+/* the per-thread set-up of the batch kernels, run once on the host for the one specification */
+template <int KIND, int N>
+static int build_spec(const PdebBatch* in, int64_t s, const PdebConventions& cv, int nk, const double* knot_t, PdebSpecConst<N>& sp) {
+    memset(&sp, 0, sizeof sp);
+    const int64_t st = in->stride;
+    const double L = in->L[s], dt = in->dt[s], T = in->T[s], g0 = in->g0[s];
+    const double rho_in = in->rho_in[s], rho_out = in->rho_out[s], E_in = in->E_in[s], E_out = in->E_out[s];
+    const int np = in->n_pred[s], nt = in->n_tree[s];
+    if (!pdeb_params_ok(KIND, N, L, dt, T, g0, rho_in, rho_out, E_in, E_out)) return PDEB_ST_BADPARAM;
+    if (np < 1 || np > in->pmax || np > PDEB_MAX_PRED || nt < 1 || nt > in->tmax || nt > PDEB_MAX_TREE) return PDEB_ST_BADPARAM;
+    if (nk < 0 || nk > PDEB_CTL_KMAX) return PDEB_ST_BADPARAM;
+    for (int j = 1; j < nk; ++j) if (!(knot_t[j] > knot_t[j - 1])) return PDEB_ST_BADPARAM;
+    for (int j = 0; j < np; ++j)
+        if (in->pred_rel[(int64_t)j * st + s] > 2 || in->pred_top[(int64_t)j * st + s] > 1) return PDEB_ST_BADPARAM;
+    const int64_t S = pdeb_step_count(T, dt, cv.steps_rule);
+    if (S > PDEB_MAX_STEPS) return PDEB_ST_BADPARAM;
+    const double h = L / N;
+    const int lumped = (KIND == PDEB_KIND_HEAT) ? cv.mass_heat : cv.mass_wave;
+    const double cA = (KIND == PDEB_KIND_HEAT) ? cv.theta * dt : cv.newmark_beta * dt * dt;
+    const double cR = (1.0 - cv.theta) * dt;
+
+    PdebTrajReg<KIND, N, double, 1> tr;
+    PdebD2 tab[N + 1];
+    double stab[N + 1], ltab[N + 1];
+#if PDEB_C_SMEM
+    double ctab[N + 1];
+    tr.ctab = ctab;
+#endif
+    memset(ltab, 0, sizeof ltab);
+    tr.tab = tab; tr.stab = stab; tr.ltab = ltab; tr.sN = 0;
+    for (int i = 0; i <= N + 1; ++i) tr.w[i] = 0;
+    if (!tr.setup(L, in->x_a[s], in->x_b[s], rho_in, rho_out, E_in, E_out, lumped, cv.material_sampling, cA, cR)) return PDEB_ST_NONFINITE;
+    for (int i = 1; i <= N; ++i) {
+        sp.rd[i] = tab[i - 1].x; sp.dinv[i] = tab[i - 1].y; sp.s[i] = stab[i - 1]; sp.rl[i] = ltab[i - 1];
+        sp.c[i] = (i < N) ? tr.getc(i) : 0.0;
+    }
+    if constexpr (KIND == PDEB_KIND_WAVE) {
+        /* a0 is affine in the initial load f0: evaluate the set-up at f0 = 0 and f0 = 1 */
+        tr.wave_init(h, g0, 0.0, rho_in, rho_out, E_in, E_out, lumped);
+        for (int i = 1; i <= N; ++i) { sp.w0[i] = tr.w[i]; sp.a0_base[i] = tr.a[i]; }
+        tr.wave_init(h, g0, 1.0, rho_in, rho_out, E_in, E_out, lumped);
+        for (int i = 1; i <= N; ++i) sp.a0_unit[i] = tr.a[i] - sp.a0_base[i];
+    }
+    sp.sN = tr.sN; sp.dt = dt; sp.th_dt = cv.theta * dt; sp.eq_eps = (cv.eq_rule == 1) ? cv.eq_eps : 0.0;
+    sp.cw1 = dt; sp.cw2 = 0.5 * (1.0 - 2.0 * cv.newmark_beta) * dt * dt; sp.cw3 = (1.0 - cv.newmark_gamma) * dt;
+    sp.cw4 = cv.newmark_beta * dt * dt; sp.cw5 = cv.newmark_gamma * dt;
+    sp.nk = nk; sp.np = np; sp.nt = nt;
+    for (int j = 0; j < nk; ++j) sp.knot_t[j] = knot_t[j];
+    int32_t k_end = 0;
+    for (int j = 0; j < np; ++j) {
+        sp.cl[j] = pdeb_clause_data<N>(in->pred_m[(int64_t)j * st + s], in->pred_b[(int64_t)j * st + s],
+                                       in->pred_xlo[(int64_t)j * st + s], in->pred_xhi[(int64_t)j * st + s],
+                                       in->pred_tlo[(int64_t)j * st + s], in->pred_thi[(int64_t)j * st + s],
+                                       in->pred_rel[(int64_t)j * st + s], in->pred_top[(int64_t)j * st + s], L, h, dt, g0, S, cv);
+        if (sp.cl[j].khi > k_end) k_end = sp.cl[j].khi;
+    }
+    sp.k_end = k_end;
+    for (int q = 0; q < nt; ++q) {
+        const int op = in->tree_op[(int64_t)q * st + s], lh = in->tree_lhs[(int64_t)q * st + s], rh = in->tree_rhs[(int64_t)q * st + s];
+        if (op == PDEB_TREE_LEAF) { if (lh < 0 || lh >= np) return PDEB_ST_BADPARAM; }
+        else if (op == PDEB_TREE_AND || op == PDEB_TREE_OR) { if (lh < 0 || lh >= q || rh < 0 || rh >= q) return PDEB_ST_BADPARAM; }
+        else return PDEB_ST_BADPARAM;
+        sp.tree_op[q] = (uint8_t)op; sp.tree_lhs[q] = (int8_t)lh; sp.tree_rhs[q] = (int8_t)rh;
+    }
+    return PDEB_OK;
+}
+
+extern "C" void pdeb_controls_destroy(PdebControls* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_y); cudaFree(h->d_rob); cudaFree(h->d_clause); cudaFree(h->d_status); cudaFree(h->d_pv); cudaFree(h->d_pi);
+    if (h->h_pv) cudaFreeHost(h->h_pv);
+    if (h->h_pi) cudaFreeHost(h->h_pi);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    delete h;
+}
+
+extern "C" int pdeb_controls_create(const PdebBatch* spec, int64_t sample, int64_t capacity, int32_t n_knots, const double* knot_t,
+                                    int device, const PdebConventions* conv, PdebControls** out) {
+    if (!spec || !out || sample < 0 || sample >= spec->n || capacity < 1 || (n_knots > 0 && !knot_t))
+        return cfail(PDEB_E_ARG, "pdeb_controls_create: bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return cfail(PDEB_E_NODEVICE, "no CUDA device (this library has no CPU path)"); }
+    if (device < 0 || device >= ndev) return cfail(PDEB_E_ARG, "bad device");
+    PdebConventions cv;
+    if (conv) cv = *conv; else pdeb_default_conventions(&cv);
+    const int kind = spec->kind[sample], N = spec->n_elem[sample];
+    if (!((kind == PDEB_KIND_HEAT && N == 30) || (kind == PDEB_KIND_WAVE && N == 20)))
+        return cfail(PDEB_E_ARG, "controls family covers the default meshes (heat N=30, wave N=20); use the batch path for other meshes");
+    PdebControls* h = new PdebControls;
+    h->device = device; h->kind = kind; h->n_elem = N; h->capacity = capacity; h->nk = n_knots; h->pmax = spec->n_pred[sample];
+    h->spec_status = (kind == PDEB_KIND_HEAT) ? build_spec<PDEB_KIND_HEAT, 30>(spec, sample, cv, n_knots, knot_t, h->heat)
+                                              : build_spec<PDEB_KIND_WAVE, 20>(spec, sample, cv, n_knots, knot_t, h->wave);
+    if (h->pmax < 1 || h->pmax > PDEB_MAX_PRED) h->pmax = 1;
+    cudaError_t e = cudaSetDevice(device);
+    const int nkp = n_knots > 0 ? n_knots : 1;
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_y, sizeof(double) * (size_t)nkp * capacity);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_rob, sizeof(double) * (size_t)capacity);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_clause, sizeof(double) * (size_t)h->pmax * capacity);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_status, sizeof(int32_t) * (size_t)capacity);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_pv, sizeof(double) * PDEB_ARGMAX_BLOCKS);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_pi, sizeof(int64_t) * PDEB_ARGMAX_BLOCKS);
+    if (e == cudaSuccess) e = cudaHostAlloc(&h->h_pv, sizeof(double) * PDEB_ARGMAX_BLOCKS, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc(&h->h_pi, sizeof(int64_t) * PDEB_ARGMAX_BLOCKS, cudaHostAllocDefault);
+    for (auto& ev : h->ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
+    if (e != cudaSuccess) { pdeb_controls_destroy(h); return cfail(PDEB_E_CUDA, "pdeb_controls_create", e); }
+    *out = h;
+    return PDEB_E_OK;
+}
+
+template <int KIND, int N>
+static cudaError_t launch_controls(const PdebSpecConst<N>& sp, int pmax, const double* ky, int64_t stride, int64_t m,
+                                   const PdebCtlOut& out, cudaStream_t stream) {
+    const unsigned blocks = (unsigned)((m + PDEB_CTL_THREADS - 1) / PDEB_CTL_THREADS);
+    if (pmax <= 3) pdeb_controls_kernel<KIND, N, 3><<<blocks, PDEB_CTL_THREADS, 0, stream>>>(sp, ky, stride, m, out);
+    else pdeb_controls_kernel<KIND, N, PDEB_MAX_PRED><<<blocks, PDEB_CTL_THREADS, 0, stream>>>(sp, ky, stride, m, out);
+    return cudaGetLastError();
+}
+
+/*
+ * Evaluate m <= capacity candidate controls.  knot_y: host [n_knots][m] plane-major, or NULL to re-evaluate the values
+ * already on the device.  Outputs (all optional): robustness [m], clause [pmax][m], status [m], best index / value
+ * (largest robustness among the candidates with status 0; index -1 if none).  Synchronises `stream` before returning.
+ */
+extern "C" int pdeb_controls_eval(PdebControls* h, int64_t m, const double* knot_y, double* robustness_out, double* clause_out,
+                                  int32_t* status_out, int64_t* best_index, double* best_value, void* stream_, PdebTiming* timing) {
+    if (!h || m < 1 || m > h->capacity) return cfail(PDEB_E_ARG, "pdeb_controls_eval: bad arguments");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CCK(cudaSetDevice(h->device));
+    if (h->spec_status != PDEB_OK) {
+        /* the specification itself is unusable: every candidate fails the same way (never raises per sample) */
+        for (int64_t i = 0; i < m; ++i) {
+            if (robustness_out) robustness_out[i] = PDEB_FAILED_ROBUSTNESS;
+            if (status_out) status_out[i] = h->spec_status;
+        }
+        if (clause_out) for (int64_t i = 0; i < (int64_t)h->pmax * m; ++i) clause_out[i] = PDEB_FAILED_ROBUSTNESS;
+        if (best_index) *best_index = -1;
+        if (best_value) *best_value = PDEB_FAILED_ROBUSTNESS;
+        if (timing) memset(timing, 0, sizeof *timing);
+        return PDEB_E_OK;
+    }
+    if (knot_y && h->nk > 0) CCK(cudaMemcpyAsync(h->d_y, knot_y, sizeof(double) * (size_t)h->nk * m, cudaMemcpyHostToDevice, stream));
+    PdebCtlOut out{h->d_rob, h->d_clause, h->d_status};
+    CCK(cudaEventRecord(h->ev[0], stream));
+    cudaError_t e = (h->kind == PDEB_KIND_HEAT) ? launch_controls<PDEB_KIND_HEAT, 30>(h->heat, h->pmax, h->d_y, m, m, out, stream)
+                                                : launch_controls<PDEB_KIND_WAVE, 20>(h->wave, h->pmax, h->d_y, m, m, out, stream);
+    if (e != cudaSuccess) return cfail(PDEB_E_CUDA, "controls kernel launch", e);
+    int launches = 1;
+    if (best_index || best_value) {
+        pdeb_argmax_partial_kernel<<<PDEB_ARGMAX_BLOCKS, 256, 0, stream>>>(h->d_rob, h->d_status, m, h->d_pv, h->d_pi);
+        CCK(cudaGetLastError());
+        ++launches;
+    }
+    CCK(cudaEventRecord(h->ev[1], stream));
+    if (best_index || best_value) {
+        CCK(cudaMemcpyAsync(h->h_pv, h->d_pv, sizeof(double) * PDEB_ARGMAX_BLOCKS, cudaMemcpyDeviceToHost, stream));
+        CCK(cudaMemcpyAsync(h->h_pi, h->d_pi, sizeof(int64_t) * PDEB_ARGMAX_BLOCKS, cudaMemcpyDeviceToHost, stream));
+    }
+    if (robustness_out) CCK(cudaMemcpyAsync(robustness_out, h->d_rob, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost, stream));
+    if (status_out) CCK(cudaMemcpyAsync(status_out, h->d_status, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, stream));
+    if (clause_out) CCK(cudaMemcpyAsync(clause_out, h->d_clause, sizeof(double) * (size_t)h->pmax * m, cudaMemcpyDeviceToHost, stream));
+    CCK(cudaStreamSynchronize(stream));
+    if (best_index || best_value) {
+        double bv = -INFINITY; int64_t bi = -1;
+        for (int q = 0; q < PDEB_ARGMAX_BLOCKS; ++q)
+            if (h->h_pi[q] >= 0 && (bi < 0 || h->h_pv[q] > bv || (h->h_pv[q] == bv && h->h_pi[q] < bi))) { bv = h->h_pv[q]; bi = h->h_pi[q]; }
+        if (best_index) *best_index = bi;
+        if (best_value) *best_value = (bi >= 0) ? bv : PDEB_FAILED_ROBUSTNESS;
+    }
+    if (timing) {
+        memset(timing, 0, sizeof *timing);
+        float ms = 0;
+        CCK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+        timing->kernel_ms = ms; timing->total_ms = ms; timing->launches = launches;
+    }
+    return PDEB_E_OK;
+}

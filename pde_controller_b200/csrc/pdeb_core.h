@@ -556,6 +556,66 @@ PDEB_HD real pdeb_endpoint_gmax(const real* w, const real* stab, real mh, real c
 }
 
 /*
+ * Discrete form of one clause  TOP_[t_lo,t_hi] ( forall x in [x_lo,x_hi]: u(x) - (m x + b) REL 0 )  on a mesh of N
+ * elements of size h with S steps of size dt (conventions C7, C8): window steps, node mask, profile per node
+ * index, and for intervals that need interpolated end points their elements and local coordinates.
+ */
+struct PdebClauseData {
+    double mh, c0;        /* profile per node index: p(x_i) - g0 = mh i + c0 */
+    double xi[2];         /* local coordinate of each interval end inside its element (info bit 3) */
+    int32_t klo, khi;     /* window, in steps */
+    uint32_t nmask;       /* bit i: node i inside the interval */
+    uint32_t info;        /* bits 0-1 rel, bit 2 top, bit 3 end points needed, bits 4-8 / 9-13 their elements */
+};
+template <int N>
+PDEB_HD PdebClauseData pdeb_clause_data(double m, double bb, double xlo, double xhi, double tlo, double thi, uint32_t rel,
+                                        uint32_t top, double L, double h, double dt, double g0, int64_t S,
+                                        const PdebConventions& cv) {
+    PdebClauseData cd;
+    const double qlo = tlo / dt, qhi = thi / dt;
+    double a0, a1;
+    if (cv.window_rule == 1) { a0 = trunc(qlo); a1 = trunc(qhi); }
+    else { a0 = ceil(qlo - PDEB_EPS); a1 = floor(qhi + PDEB_EPS); }
+    if (!(a0 >= 0.0)) a0 = 0.0;
+    if (!(a1 <= (double)S)) a1 = (double)S;
+    if (a0 > a1) {
+        double k = floor(0.5 * (tlo + thi) / dt + 0.5);
+        if (!(k >= 0.0)) k = 0.0;
+        if (k > (double)S) k = (double)S;
+        a0 = a1 = k;
+    }
+    double ilo = ceil(xlo / h - PDEB_EPS), ihi = floor(xhi / h + PDEB_EPS);
+    if (!(ilo >= 0.0)) ilo = 0.0;
+    if (!(ihi <= (double)N)) ihi = (double)N;
+    uint32_t nm = 0;
+    if (ilo <= ihi) {
+        const int i0 = (int)ilo, i1 = (int)ihi;
+        nm = (i1 >= 31 ? 0xffffffffu : ((1u << (i1 + 1)) - 1u)) & ~((1u << i0) - 1u);
+    }
+    const uint32_t endp = (nm == 0 || cv.region_rule == 1) ? 1u : 0u;
+    uint32_t ebits = 0;
+    cd.xi[0] = 0.0; cd.xi[1] = 0.0;
+    if (endp) {
+        const double xe[2] = { xlo, xhi };
+        for (int q = 0; q < 2; ++q) {
+            const double xx = xe[q] < 0 ? 0 : (xe[q] > L ? L : xe[q]);
+            int e = (int)floor(xx / h);
+            if (e < 0) e = 0;
+            if (e > N - 1) e = N - 1;
+            cd.xi[q] = (xx - e * h) / h;
+            ebits |= (uint32_t)e << (4 + 5 * q);
+        }
+    }
+    cd.mh = m * h;
+    cd.c0 = bb - g0;
+    cd.klo = (int32_t)a0;
+    cd.khi = (int32_t)a1;
+    cd.nmask = nm;
+    cd.info = rel | (top << 2) | (endp << 3) | ebits;
+    return cd;
+}
+
+/*
  * Whole trajectory of sample s.  `slots` is this thread's clause column in shared memory,
  * `table` its row table.  Writes robustness / clause / status.
  *
@@ -635,48 +695,19 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
             const double m = b.pred_m[(int64_t)j * st + s], bb = b.pred_b[(int64_t)j * st + s];
             const double xlo = b.pred_xlo[(int64_t)j * st + s], xhi = b.pred_xhi[(int64_t)j * st + s];
             const double tlo = b.pred_tlo[(int64_t)j * st + s], thi = b.pred_thi[(int64_t)j * st + s];
-            const double qlo = tlo / dt, qhi = thi / dt;
-            double a0, a1;
-            if (cv.window_rule == 1) { a0 = trunc(qlo); a1 = trunc(qhi); }
-            else { a0 = ceil(qlo - PDEB_EPS); a1 = floor(qhi + PDEB_EPS); }
-            if (!(a0 >= 0.0)) a0 = 0.0;
-            if (!(a1 <= (double)S)) a1 = (double)S;
-            if (a0 > a1) {
-                double k = floor(0.5 * (tlo + thi) / dt + 0.5);
-                if (!(k >= 0.0)) k = 0.0;
-                if (k > (double)S) k = (double)S;
-                a0 = a1 = k;
-            }
-            double ilo = ceil(xlo / h - PDEB_EPS), ihi = floor(xhi / h + PDEB_EPS);
-            if (!(ilo >= 0.0)) ilo = 0.0;
-            if (!(ihi <= (double)N)) ihi = (double)N;
-            uint32_t nm = 0;
-            if (ilo <= ihi) {
-                const int i0 = (int)ilo, i1 = (int)ihi;
-                nm = (i1 >= 31 ? 0xffffffffu : ((1u << (i1 + 1)) - 1u)) & ~((1u << i0) - 1u);
-            }
-            const uint32_t top = b.pred_top[(int64_t)j * st + s], rel = b.pred_rel[(int64_t)j * st + s];
-            const uint32_t endp = (nm == 0 || cv.region_rule == 1) ? 1u : 0u;
-            uint32_t ebits = 0;
-            if (endp) {
-                const double xe[2] = { xlo, xhi };
-                for (int q = 0; q < 2; ++q) {
-                    const double xx = xe[q] < 0 ? 0 : (xe[q] > L ? L : xe[q]);
-                    int e = (int)floor(xx / h);
-                    if (e < 0) e = 0;
-                    if (e > N - 1) e = N - 1;
-                    slots.R(j, 3 + q) = (real)((xx - e * h) / h);
-                    ebits |= (uint32_t)e << (4 + 5 * q);
-                }
-            }
-            slots.R(j, 0) = (real)(m * h);
-            slots.R(j, 1) = (real)(bb - g0);
-            slots.R(j, 2) = (top == PDEB_TOP_G) ? (real)INFINITY : (real)(-INFINITY);
-            slots.W(j, 0) = (uint32_t)(int32_t)a0;
-            slots.W(j, 1) = (uint32_t)(int32_t)a1;
-            slots.W(j, 2) = nm;
-            slots.W(j, 3) = rel | (top << 2) | (endp << 3) | ebits;
-            if ((int32_t)a1 > k_end) k_end = (int32_t)a1;
+            const PdebClauseData cd = pdeb_clause_data<N>(m, bb, xlo, xhi, tlo, thi, b.pred_rel[(int64_t)j * st + s],
+                                                          b.pred_top[(int64_t)j * st + s], L, h, dt, g0, S, cv);
+            slots.R(j, 0) = (real)cd.mh;
+            slots.R(j, 1) = (real)cd.c0;
+            slots.R(j, 2) = (((cd.info >> 2) & 1u) == PDEB_TOP_G) ? (real)INFINITY : (real)(-INFINITY);
+            slots.R(j, 3) = (real)cd.xi[0];
+            slots.R(j, 4) = (real)cd.xi[1];
+            slots.W(j, 0) = (uint32_t)cd.klo;
+            slots.W(j, 1) = (uint32_t)cd.khi;
+            slots.W(j, 2) = cd.nmask;
+            slots.W(j, 3) = cd.info;
+            const int32_t a1 = cd.khi;
+            if (a1 > k_end) k_end = a1;
         }
         S32 = k_end;
     }

@@ -8,9 +8,17 @@
 
 #ifndef PDEB_REG_THREADS
 #define PDEB_REG_THREADS 128
+
+/* sets the thread-local message pdeb_last_error() returns (pdeb_api.cu) */
+void pdeb_set_last_error(const char* msg);
+
 #endif
 #ifndef PDEB_REG_MINBLOCKS
 #define PDEB_REG_MINBLOCKS 2   /* resident blocks per SM the register family is compiled for */
+
+/* sets the thread-local message pdeb_last_error() returns (pdeb_api.cu) */
+void pdeb_set_last_error(const char* msg);
+
 #endif
 
 /*
@@ -58,5 +66,9 @@ int pdeb_plan(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut
 /* enqueue the compute kernels of every non-empty variant; returns 0 or a cudaError_t value */
 int pdeb_launch_all(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out, const PdebPlanBuffers& pb,
                     const int32_t* vstart_count_host, int precision, cudaStream_t stream, int* launches);
+
+
+/* sets the thread-local message pdeb_last_error() returns (pdeb_api.cu) */
+void pdeb_set_last_error(const char* msg);
 
 #endif

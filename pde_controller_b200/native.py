@@ -67,6 +67,12 @@ def lib():
         L.pdeb_resident_device_ptrs.restype = C.c_int
         L.pdeb_resident_device_ptrs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pdeb_resident_destroy.argtypes = [C.c_void_p]
+        L.pdeb_controls_create.restype = C.c_int
+        L.pdeb_controls_create.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.pdeb_controls_eval.restype = C.c_int
+        L.pdeb_controls_eval.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pdeb_controls_destroy.argtypes = [C.c_void_p]
         if L.pdeb_version() != abi.ABI_VERSION:
             raise NativeError("libpdeb200.so ABI version mismatch: rebuild it")
         _lib = L
@@ -320,3 +326,56 @@ class BlockPipeline:
             self.close()
         except Exception:
             pass
+
+
+class ControlsEvaluator:
+    """One specification against many candidate controls (pdeb_controls_*).
+
+    `batch`/`sample` name the specification (its own knots are ignored), `knot_t` the knot times every candidate
+    shares, `capacity` the largest number of candidates of one eval() call."""
+
+    def __init__(self, batch: ProblemBatch, knot_t, capacity: int, sample: int = 0, device: int = 0, conv=None):
+        self._L = lib()
+        self.knot_t = np.ascontiguousarray(knot_t, dtype=np.float64).ravel()
+        self.nk = int(self.knot_t.size)
+        self.capacity = int(capacity)
+        self.n_pred = int(batch.n_pred[sample])
+        self._h = C.c_void_p()
+        cb = batch.as_c()
+        _check(self._L.pdeb_controls_create(C.addressof(cb), sample, self.capacity, self.nk, _ptr(self.knot_t), device,
+                                            _conv_ptr(conv), C.addressof(self._h)), "pdeb_controls_create")
+
+    def eval(self, knot_y: Optional[np.ndarray], m: Optional[int] = None, want_robustness: bool = True,
+             want_clauses: bool = False, stream: int = 0):
+        """knot_y: [n_knots, m] (plane-major, C-contiguous) or None to re-evaluate the values already on the device.
+        Returns dict(robustness, status, [clause], best_index, best_value, kernel_ms, launches)."""
+        if knot_y is not None:
+            knot_y = np.ascontiguousarray(knot_y, dtype=np.float64)
+            if knot_y.ndim != 2 or knot_y.shape[0] != self.nk:
+                raise ValueError(f"knot_y must be [n_knots={self.nk}, m]")
+            m = knot_y.shape[1]
+        if m is None or not (1 <= m <= self.capacity):
+            raise ValueError("number of candidates out of range")
+        rob = np.empty(m, dtype=np.float64) if want_robustness else None
+        st = np.empty(m, dtype=np.int32) if want_robustness else None
+        cl = np.empty((self.n_pred, m), dtype=np.float64) if want_clauses else None
+        bi, bv, tm = C.c_int64(-1), C.c_double(0.0), abi.PdebTiming()
+        _check(self._L.pdeb_controls_eval(self._h, m, _ptr(knot_y), _ptr(rob), _ptr(cl), _ptr(st), C.addressof(bi),
+                                          C.addressof(bv), stream or None, C.addressof(tm)), "pdeb_controls_eval")
+        res = {"robustness": rob, "status": st, "best_index": int(bi.value), "best_value": float(bv.value),
+               "kernel_ms": float(tm.kernel_ms), "launches": int(tm.launches)}
+        if want_clauses:
+            res["clause"] = cl
+        return res
+
+    def close(self):
+        if self._h:
+            self._L.pdeb_controls_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+

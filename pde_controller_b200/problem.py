@@ -274,3 +274,30 @@ class ProblemBatch:
         k = self.n_knots.astype(np.int64)
         p = self.n_pred.astype(np.int64)
         return int(np.sum(105 + 16 * k + 50 * p + 3 * (2 * p - 1)))
+
+    def algorithmic_flops(self, executed_only: bool = True) -> int:
+        """SURVEY.md §8(d) counting convention (FMA = 2), summed over the batch:
+        heat S (15 n + 3 sum_p n_p), wave S (21 n + 3 sum_p n_p), plus 20 n one-off for assembly and factorisation;
+        n = free dofs, n_p = nodes inside predicate p's interval, counted on the steps of p's window only.
+        executed_only: S = steps up to the last observed one (what the kernels simulate) instead of the horizon."""
+        n = self.n_elem.astype(np.float64)
+        dt = self.dt
+        S = self.steps().astype(np.float64)
+        P = self.n_pred.astype(np.int64)
+        h = self.L / n
+        clause = np.zeros(self.n)
+        last = np.zeros(self.n)
+        for j in range(self.pmax):
+            live = j < P
+            ilo = np.clip(np.ceil(self.pred_xlo[j] / h - 1e-9), 0, n)
+            ihi = np.clip(np.floor(self.pred_xhi[j] / h + 1e-9), 0, n)
+            nodes = np.maximum(ihi - ilo + 1, 2)           # an interval without a node costs its two end points
+            a0 = np.clip(np.ceil(self.pred_tlo[j] / dt - 1e-9), 0, S)
+            a1 = np.clip(np.floor(self.pred_thi[j] / dt + 1e-9), 0, S)
+            steps = np.maximum(a1 - a0 + 1, 1)
+            clause += np.where(live, 3.0 * nodes * steps, 0.0)
+            last = np.maximum(last, np.where(live, a1, 0.0))
+        S_run = np.maximum(last, 1.0) if executed_only else S
+        per_step = np.where(self.kind == abi.KIND_HEAT, 15.0, 21.0) * n
+        return int(np.sum(S_run * per_step + clause + 20.0 * n))
+

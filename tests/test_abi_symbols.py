@@ -54,3 +54,6 @@ def test_no_cpu_fallback_without_device():
     b = synth.make_batch(4, "heat")
     with pytest.raises(native.NativeError):
         native.evaluate_batch(b)
+    with pytest.raises(native.NativeError):
+        native.ControlsEvaluator(b, [0.0, 1.0], capacity=8)
+

@@ -6,6 +6,7 @@
  */
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 #include <cuda_runtime.h>
 #include "pdeb_core.h"
 
@@ -93,9 +94,10 @@ __global__ void __launch_bounds__(THREADS, 2) probe(double* out, const double* p
 #pragma unroll
     for (int i = 0; i <= N + 1; ++i) { w[i] = 0; z[i] = 0; }
     double fN = par[7];
+    double* stab0 = reinterpret_cast<double*>(smem + sizeof(PdebD2) * THREADS * N) + threadIdx.x;
     if (VAR == 0) {
         PdebTrajReg<PDEB_KIND_HEAT, N, double, THREADS> tr;
-        tr.tab = table;
+        tr.tab = table; tr.stab = stab0; tr.ltab = stab0;
         tr.setup(L, x_a, x_b, par[3], par[4], par[5], par[6], 0, 0, 0.025, 0.025);
         for (int k = 0; k < steps; k += 2) {
             tr.step_solve(w, fN, z);
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(THREADS, 2) probe(double* out, const double* p
     } else {
         /* the scaled variants only need plausible SPD factors: reuse the real set-up, then treat R as unit off-diagonal */
         PdebTrajReg<PDEB_KIND_HEAT, N, double, THREADS> tr;
-        tr.tab = table;
+        tr.tab = table; tr.stab = stab0; tr.ltab = stab0;
         tr.setup(L, x_a, x_b, par[3], par[4], par[5], par[6], 0, 0, 0.025, 0.025);
         typename std::conditional<VAR == 1, V1, V2>::type v;
         v.tab = table;
@@ -127,9 +129,64 @@ __global__ void __launch_bounds__(THREADS, 2) probe(double* out, const double* p
     out[t] = s;
 }
 
+/* solve + one clause pass per step through the real device functions (scaled state, PTX masked max) */
+template <int PASSES>
+__global__ void __launch_bounds__(THREADS, 2) probe_clause(double* out, const double* par, int steps) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    PdebD2* table = reinterpret_cast<PdebD2*>(smem) + threadIdx.x;
+    double* stab = reinterpret_cast<double*>(smem + sizeof(PdebD2) * THREADS * N) + threadIdx.x;
+    const int t = blockIdx.x * THREADS + threadIdx.x;
+    const double L = par[0] + (t & 63), x_a = par[1] + (t & 15), x_b = par[2] + (t & 31);
+    PdebTrajReg<PDEB_KIND_HEAT, N, double, THREADS> tr;
+    tr.tab = table; tr.stab = stab; tr.ltab = stab;
+#pragma unroll
+    for (int i = 0; i <= N + 1; ++i) tr.w[i] = 0;
+    tr.setup(L, x_a, x_b, par[3], par[4], par[5], par[6], 0, 0, 0.025, 0.025);
+    double fN = par[7] * tr.sN;
+    const double mh = par[1] * 1e-3, c0 = par[2] * 1e-2;
+    const uint32_t nm = 0x00ffff00u >> (t & 7), rel = t % 3;
+    const uint32_t and_mask = (rel == PDEB_REL_EQ) ? 0x7fffffffu : 0xffffffffu;
+    const uint32_t xor_mask = (rel == PDEB_REL_GT) ? 0x80000000u : 0u;
+    double acc = INFINITY;
+    double z[N + 2];
+    z[0] = 0; z[N + 1] = 0;
+    for (int k = 0; k < steps; ++k) {
+#pragma unroll
+        for (int q = 0; q < PASSES; ++q) {
+            const double g = pdeb_clause_gmax<N, double, THREADS>(tr.w, tr.stab, mh + q, c0, nm, and_mask, xor_mask);
+            const double r = -g;
+            if (r < acc) acc = r;
+        }
+        tr.step_solve(tr.w, fN, z);
+#pragma unroll
+        for (int i = 1; i <= N; ++i) tr.w[i] = z[i];
+        fN += 1e-3;
+    }
+    out[t] = acc;
+}
+
+template <int PASSES>
+static void run_clause(const char* name, int sms, double* dout, double* dpar, int clock_khz) {
+    const size_t smem = (sizeof(PdebD2) + sizeof(double)) * THREADS * N;
+    CK(cudaFuncSetAttribute(probe_clause<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int steps = 2000, blocks = sms * 2;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    probe_clause<PASSES><<<blocks, THREADS, smem>>>(dout, dpar, steps);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    probe_clause<PASSES><<<blocks, THREADS, smem>>>(dout, dpar, steps);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double cycles = ms * 1e-3 * clock_khz * 1e3;
+    printf("%-28s %8.3f ms   %7.1f SMSP-cycles per warp-step\n", name, ms, cycles / steps / 2.0);
+}
+
 template <int VAR>
 static void run(const char* name, int sms, double* dout, double* dpar, int clock_khz) {
-    const size_t smem = sizeof(PdebD2) * THREADS * N;
+    const size_t smem = (sizeof(PdebD2) + sizeof(double)) * THREADS * N;
     CK(cudaFuncSetAttribute(probe<VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int steps = 2000, blocks = sms * 2;
     cudaEvent_t e0, e1;
@@ -154,8 +211,11 @@ int main() {
     double *dpar, *dout;
     CK(cudaMalloc(&dpar, sizeof h)); CK(cudaMemcpy(dpar, h, sizeof h, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&dout, sizeof(double) * p.multiProcessorCount * 2 * THREADS));
-    run<0>("v0 current step_solve", p.multiProcessorCount, dout, dpar, p.clockRate);
+    run<0>("v0 library step_solve", p.multiProcessorCount, dout, dpar, p.clockRate);
     run<1>("v1 unit off-diagonal", p.multiProcessorCount, dout, dpar, p.clockRate);
     run<2>("v2 unit, rhs batch first", p.multiProcessorCount, dout, dpar, p.clockRate);
+    run_clause<0>("real solve, 0 clause passes", p.multiProcessorCount, dout, dpar, p.clockRate);
+    run_clause<1>("real solve + 1 clause pass", p.multiProcessorCount, dout, dpar, p.clockRate);
+    run_clause<2>("real solve + 2 clause passes", p.multiProcessorCount, dout, dpar, p.clockRate);
     return 0;
 }

@@ -87,11 +87,36 @@ def decomp(workloads, batch, precision):
     print(json.dumps(res))
 
 
+def controls(workloads, m, precision):
+    """Controls family: one specification, m candidate controls; kernel time from the library's CUDA events."""
+    import numpy as np
+    from pde_controller_b200 import native, synth
+    res = {}
+    for wl in workloads:
+        spec = synth.make_batch(8, wl, seed=0)
+        s = 3
+        T = float(spec.T[s])
+        nk = int(spec.n_knots[s])
+        knot_t = np.linspace(0.0, T, nk)
+        lo, hi = (0.0, 1e6) if wl == "heat" else (-5e3, 5e3)
+        y = np.random.Generator(np.random.PCG64(0)).uniform(lo, hi, size=(nk, m))
+        ev = native.ControlsEvaluator(spec, knot_t, capacity=m, sample=s)
+        ev.eval(y, want_robustness=False)
+        ms = sorted(ev.eval(None, m=m, want_robustness=False)["kernel_ms"] for _ in range(7))
+        ev.close()
+        steps = T / float(spec.dt[s])
+        res[wl] = {"m": m, "ms": round(ms[len(ms) // 2], 4), "evals_per_s": m / (ms[len(ms) // 2] * 1e-3), "steps": steps,
+                   "n_pred": int(spec.n_pred[s])}
+    print(json.dumps(res))
+
+
 def do_run(argv):
     workloads, batch, precision, mode = "heat,wave", 65536, 64, "one"
     for i, a in enumerate(argv):
         if a == "--decomp":
             mode = "decomp"
+        if a == "--controls":
+            mode = "controls"
         if a == "--workloads":
             workloads = argv[i + 1]
         if a == "--batch":
@@ -112,6 +137,8 @@ if __name__ == "__main__":
         do_build(sys.argv[2:])
     elif sys.argv[1] == "run":
         do_run(sys.argv[2:])
+    elif sys.argv[1] == "controls":
+        controls(sys.argv[2].split(","), int(sys.argv[3]), int(sys.argv[4]))
     elif sys.argv[1] == "decomp":
         decomp(sys.argv[2].split(","), int(sys.argv[3]), int(sys.argv[4]))
     elif sys.argv[1] == "one":
