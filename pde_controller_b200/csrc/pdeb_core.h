@@ -139,6 +139,22 @@ PDEB_HD bool pdeb_params_ok(int kind, int N, double L, double dt, double T, doub
  * current segment is fetched one segment ahead, so that crossing a knot never waits for memory: lanes of a warp
  * cross their knots at different steps, which makes the warp take this path in most steps.
  */
+/* 1/x to within an ulp: hardware seed + two Newton steps (5 instructions instead of the ~25 of an IEEE division with its
+ * slow-path call).  Used where a segment slope is formed at a knot crossing, which happens in most steps of a warp
+ * because its lanes cross their knots at different times. */
+PDEB_HD double pdeb_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+#else
+    return 1.0 / x;
+#endif
+}
+
 template <typename real>
 struct PdebPwl {
     double t1, tn;        /* end of the current segment (+inf on the last); time of the knot after it (+inf: none) */
@@ -157,7 +173,7 @@ struct PdebPwl {
         while (t >= t1) {
             t0 = (real)t1; y0 = y1;
             if (tn < INFINITY) {
-                slope = (real)(((double)yn - (double)y1) / (tn - t1));
+                slope = (real)(((double)yn - (double)y1) * pdeb_rcp(tn - t1));
                 t1 = tn; y1 = yn;
                 ++j;
                 if (j + 1 < nk) { tn = kt[(int64_t)(j + 1) * stride]; yn = (real)ky[(int64_t)(j + 1) * stride]; }
