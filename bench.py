@@ -31,8 +31,11 @@ WORKLOAD_TEXT = {
     "wave": "1D wave (Newmark beta=1/4 gamma=1/2), default mesh N=20 dt=0.0025, synthetic specs, fused STL robustness",
     "mixed": "mixed 50% heat (N=30) + 50% wave (N=20) synthetic eval set, sorted by kind",
     "heat_refined": "1D heat, refined mesh N=1024, 10,000 steps, synthetic specs/controls",
+    "controls_heat": "ONE 1D heat spec (default mesh) against many candidate PWL controls, arg-max on the device (search mode)",
+    "controls_wave": "ONE 1D wave spec (default mesh) against many candidate PWL controls, arg-max on the device (search mode)",
 }
-DEFAULT_BATCH = {"heat": 65536, "wave": 65536, "mixed": 65536, "heat_refined": 4096}
+DEFAULT_BATCH = {"heat": 65536, "wave": 65536, "mixed": 65536, "heat_refined": 4096, "controls_heat": 1048576,
+                 "controls_wave": 1048576}
 
 
 def peaks():
@@ -52,6 +55,22 @@ def measured_profile():
         with open(p) as f:
             return json.load(f)
     return {}
+
+
+def fp64_view(batch, copies, kernel_ms, prof):
+    """The compute view of the path (it is FP64-latency/issue bound, not HBM bound): executed FP64 flops (FMA = 2) and
+    FP64 instructions of `copies` evaluations of `batch` per launch against the measured DFMA rate of the GPU."""
+    flops, instr = batch.algorithmic_flops("executed")
+    survey, _ = batch.algorithmic_flops("survey")
+    peak = prof.get("fp64_peak_tflops")
+    ach = flops * copies / (kernel_ms * 1e-3) / 1e12
+    out = {"bound": "fp64 pipe", "achieved": ach, "unit": "TFLOP/s", "peak": peak, "frac": ach / peak if peak else None,
+           "pipe_slots_frac": (instr * copies / (kernel_ms * 1e-3)) / (peak * 1e12 / 2.0) if peak else None,
+           "peak_source": "measured DFMA rate, tools/probe/fp64_probe.cu (profiles/measured_b200.json)" if peak else None,
+           "executed_flops_per_launch": flops * copies, "survey_convention_flops_per_launch": survey * copies,
+           "note": "flops of the algorithm as implemented (DESIGN.md 4: 8 per row and step for heat, 20 for waves, 4 per "
+                   "clause node); pipe_slots_frac counts FP64 instructions, an add or multiply holds the pipe like an FMA"}
+    return out
 
 
 class ClockSampler(threading.Thread):
@@ -117,7 +136,20 @@ def run_reference(args, rank, world):
     from pde_controller_b200 import synth
     oracle.build()
     nthreads = os.cpu_count() or 1
-    batch = synth.make_batch(args.batch, args.workload, seed=args.seed, total=args.batch)
+    sample_note = f"{args.batch} samples per step"
+    if args.workload.startswith("controls_"):
+        # bounded sample of the same workload: the first 65,536 candidate controls of rank 0 for the same specification
+        wl = args.workload.split("_")[1]
+        spec = synth.make_batch(8, wl, seed=args.seed)
+        nk = int(spec.n_knots[3])
+        lo, hi = (0.0, 1e6) if wl == "heat" else (-5e3, 5e3)
+        m = min(args.batch, 65536)
+        y = np.random.Generator(np.random.PCG64([args.seed, 0])).uniform(lo, hi, size=(nk, args.batch))[:, :m]
+        batch = synth.replicate_spec(spec, 3, np.linspace(0.0, float(spec.T[3]), nk), y)
+        sample_note = f"{m} of the {args.batch} candidate controls per step"
+        args.batch = m
+    else:
+        batch = synth.make_batch(args.batch, args.workload, seed=args.seed, total=args.batch)
     times = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -134,7 +166,7 @@ def run_reference(args, rank, world):
         "config": {"workload": WORKLOAD_TEXT[args.workload], "batch": args.batch, "seed": args.seed,
                    "note": "reference femformal (Python 2 + Gurobi) is absent from the snapshot; this is the CPU oracle port"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port",
-                         "sample": f"{args.batch} samples per step, {len(times)} steps, OpenMP over samples"},
+                         "sample": f"{sample_note}, {len(times)} steps, OpenMP over samples"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -154,6 +186,95 @@ def cpu_baseline(args, batch):
         best = dt if best is None else min(best, dt)
     return {"value": batch.n / best, "unit": UNIT, "cores": nthreads, "kind": "port",
             "sample": f"the same {batch.n}-sample batch, best of 2 passes, C oracle -O3 + OpenMP over samples"}
+
+
+def run_controls(args, rank, local_rank, world):
+    """Search mode: every rank scores its own args.batch candidate controls for the same specification."""
+    import torch
+    import torch.distributed as dist
+    from pde_controller_b200 import native, synth
+    wl = args.workload.split("_")[1]
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    spec = synth.make_batch(8, wl, seed=args.seed)
+    s = 3
+    T, nk = float(spec.T[s]), int(spec.n_knots[s])
+    knot_t = np.linspace(0.0, T, nk)
+    lo, hi = (0.0, 1e6) if wl == "heat" else (-5e3, 5e3)
+    m = args.batch
+    pin = native.PinnedBuffer(8 * nk * m)
+    y = pin.array.view(np.float64).reshape(nk, m)
+    y[:] = np.random.Generator(np.random.PCG64([args.seed, rank])).uniform(lo, hi, size=(nk, m))
+    ev = native.ControlsEvaluator(spec, knot_t, capacity=m, sample=s, device=local_rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    first = ev.eval(y)
+    for _ in range(args.warmup):
+        ev.eval(None, m=m, want_robustness=False)
+    sampler = ClockSampler(nvml_index(local_rank))
+    barrier()
+    sampler.start()
+    wall0 = time.perf_counter()
+    kernel_ms, launches = 0.0, 0
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        r = ev.eval(None, m=m, want_robustness=False)       # candidates resident in HBM; CUDA events inside the library
+        kernel_ms += r["kernel_ms"]
+        launches += r["launches"]
+    barrier()
+    wall1 = time.perf_counter()
+    clocks = sampler.stop()
+    t_dev = torch.tensor([kernel_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    total_ms = float(t_dev.item())
+    total = m * world
+    value = total * args.steps / (total_ms * 1e-3)
+    # end to end: candidates from pinned host memory every step, robustness + status + arg-max back on the host
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = ev.eval(y)
+    torch.cuda.synchronize()
+    dt_ = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt_, op=dist.ReduceOp.MAX)
+    e2e = total * args.steps / float(dt_.item())
+    if not np.array_equal(r["robustness"], first["robustness"]):
+        raise SystemExit("bench: repeated evaluation of the same candidates differs")
+    if rank == 0:
+        peak, peak_src = peaks()
+        prof = measured_profile()
+        steps_sim = int(max(np.floor(spec.pred_thi[: int(spec.n_pred[s]), s] / spec.dt[s] + 1e-9)))
+        sub = synth.replicate_spec(spec, s, knot_t, np.zeros((nk, 1)))
+        alg_bytes = m * (8 * nk + 12)                      # per candidate: its knot values in, robustness + status out
+        kms = total_ms / args.steps
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": kms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD_TEXT[args.workload], "candidates_per_gpu": m, "knots": nk, "sim_steps": steps_sim,
+                       "n_pred": int(spec.n_pred[s]), "seed": args.seed, "l2": "flushed (256 MiB write) between timed steps",
+                       "wall_s_timed_region": wall1 - wall0},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(8 * nk * m), "d2h_bytes_per_step": int(12 * m)},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": alg_bytes / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg_bytes / (kms * 1e-3) / 1e9 / peak,
+                         "traffic": (prof.get("dram_bytes_per_launch", {}) or {}).get(f"{args.workload}:{m}:64"), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes},
+        }
+        line["roofline_fp64"] = fp64_view(sub, m, kms, prof)
+        print(json.dumps(line), flush=True)
+    ev.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
@@ -188,6 +309,9 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    if args.workload.startswith("controls_"):
+        run_controls(args, rank, local_rank, world)
+        return
     torch.cuda.set_device(local_rank)
     dev = local_rank
     if world > 1:
@@ -291,13 +415,7 @@ def main():
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
         prof = measured_profile()
         traffic = (prof.get("dram_bytes_per_launch", {}) or {}).get(f"{args.workload}:{args.batch}:{args.precision}")
-        alg_flops = host.algorithmic_flops()            # SURVEY.md §8d counting convention, executed steps only
-        fp64_peak = prof.get("fp64_peak_tflops")
-        fp64 = {"bound": "fp64 pipe", "achieved": alg_flops / (kernel_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
-                "peak": fp64_peak, "frac": (alg_flops / (kernel_ms * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None,
-                "peak_source": "measured DFMA rate, tools/probe/fp64_probe.cu (profiles/measured_b200.json)" if fp64_peak else None,
-                "algorithmic_flops_per_launch": alg_flops,
-                "note": "SURVEY.md 8(d) flop convention; the path is FP64-latency/issue bound, this is the view that explains it"}
+        fp64 = fp64_view(host, 1, kernel_ms, prof)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -275,17 +275,22 @@ class ProblemBatch:
         p = self.n_pred.astype(np.int64)
         return int(np.sum(105 + 16 * k + 50 * p + 3 * (2 * p - 1)))
 
-    def algorithmic_flops(self, executed_only: bool = True) -> int:
-        """SURVEY.md §8(d) counting convention (FMA = 2), summed over the batch:
-        heat S (15 n + 3 sum_p n_p), wave S (21 n + 3 sum_p n_p), plus 20 n one-off for assembly and factorisation;
-        n = free dofs, n_p = nodes inside predicate p's interval, counted on the steps of p's window only.
-        executed_only: S = steps up to the last observed one (what the kernels simulate) instead of the horizon."""
+    def algorithmic_flops(self, convention: str = "executed"):
+        """FP64 work of the batch, steps up to the last observed one (what the kernels simulate).
+
+        convention "survey":   SURVEY.md §8(d) (FMA = 2): heat S (15 n + 3 sum_p n_p), wave S (21 n + 3 sum_p n_p),
+                               + 20 n one-off for assembly and factorisation.
+        convention "executed": the operations of the algorithm AS IMPLEMENTED here: per step and row
+                               heat add + 3 FMA + mul = 8 flops in 5 instructions, wave 20 flops in 11 (incl. the
+                               Newmark predictor / corrector and the low part of the diagonal); per node of a clause
+                               interval and window step 2 FMA = 4 flops in 2 instructions.
+        Returns (flops, fp64_instructions); n = free dofs, n_p = nodes inside predicate p's interval."""
         n = self.n_elem.astype(np.float64)
         dt = self.dt
         S = self.steps().astype(np.float64)
         P = self.n_pred.astype(np.int64)
         h = self.L / n
-        clause = np.zeros(self.n)
+        node_steps = np.zeros(self.n)
         last = np.zeros(self.n)
         for j in range(self.pmax):
             live = j < P
@@ -295,9 +300,13 @@ class ProblemBatch:
             a0 = np.clip(np.ceil(self.pred_tlo[j] / dt - 1e-9), 0, S)
             a1 = np.clip(np.floor(self.pred_thi[j] / dt + 1e-9), 0, S)
             steps = np.maximum(a1 - a0 + 1, 1)
-            clause += np.where(live, 3.0 * nodes * steps, 0.0)
+            node_steps += np.where(live, nodes * steps, 0.0)
             last = np.maximum(last, np.where(live, a1, 0.0))
-        S_run = np.maximum(last, 1.0) if executed_only else S
-        per_step = np.where(self.kind == abi.KIND_HEAT, 15.0, 21.0) * n
-        return int(np.sum(S_run * per_step + clause + 20.0 * n))
-
+        S_run = np.maximum(last, 1.0)
+        heat = self.kind == abi.KIND_HEAT
+        if convention == "survey":
+            flops = np.sum(S_run * np.where(heat, 15.0, 21.0) * n + 3.0 * node_steps + 20.0 * n)
+            return int(flops), None
+        flops = np.sum(S_run * np.where(heat, 8.0, 20.0) * n + 4.0 * node_steps)
+        instr = np.sum(S_run * np.where(heat, 5.0, 11.0) * n + 2.0 * node_steps)
+        return int(flops), int(instr)

@@ -164,3 +164,24 @@ def make_batch(n: int, workload: str = "heat", seed: int = 0, start: int = 0, to
             dst += cnt
             i += cnt
     return batch
+
+
+def replicate_spec(spec: ProblemBatch, s: int, knot_t, knot_y) -> ProblemBatch:
+    """The m-sample batch a controls-family call stands for: sample `s` of `spec` once per column of knot_y [nk, m]
+    (used by the parity tests and by the CPU arm of the search-mode benchmark)."""
+    knot_y = np.asarray(knot_y, dtype=np.float64)
+    nk, m = knot_y.shape
+    b = ProblemBatch(m, max(nk, 1), spec.pmax, spec.tmax)
+    for name in b._names:
+        if name in ("knot_t", "knot_y", "n_knots"):
+            continue
+        src, dst = getattr(spec, name), getattr(b, name)
+        if src.ndim == 1:
+            dst[:] = src[s]
+        else:
+            dst[:, :] = src[:, s:s + 1]
+    b.n_knots[:] = nk
+    b.knot_t[:nk, :] = np.asarray(knot_t, dtype=np.float64)[:, None]
+    b.knot_y[:nk, :] = knot_y
+    return b
+

@@ -8,22 +8,7 @@ from pde_controller_b200 import ProblemBatch, default_conventions, native, synth
 pytestmark = pytest.mark.gpu
 
 
-def replicate(spec: ProblemBatch, s: int, knot_t, y):
-    """The m-sample batch the controls call stands for: sample s of `spec` with control column i of y."""
-    nk, m = y.shape
-    b = ProblemBatch(m, max(nk, 1), spec.pmax, spec.tmax)
-    for name in b._names:
-        src, dst = getattr(spec, name), getattr(b, name)
-        if name in ("knot_t", "knot_y", "n_knots"):
-            continue
-        if src.ndim == 1:
-            dst[:] = src[s]
-        else:
-            dst[:, :] = src[:, s:s + 1]
-    b.n_knots[:] = nk
-    b.knot_t[:nk, :] = np.asarray(knot_t)[:, None]
-    b.knot_y[:nk, :] = y
-    return b
+replicate = synth.replicate_spec
 
 
 def candidates(rng, wl, nk, m):
