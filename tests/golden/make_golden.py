@@ -49,6 +49,7 @@ def main():
                 records.append({
                     "source": f"{os.path.relpath(f, '/root/reference')}:{line_no}:{key}",
                     "problem": asdict(p),
+                    "sstl": rec.get("sstl"),            # the record's LaTeX twin (data), for the sstl cross-check tests
                     "controls": {n: (None if ctr[n] is None else [list(map(float, ctr[n][0])), list(map(float, ctr[n][1]))])
                                  for n in names},
                     "robustness": {n: float(rob[i]) for i, n in enumerate(names)},

@@ -1,0 +1,88 @@
+"""sSTL LaTeX <-> program cross-check on the reference's own 14 example records (tests/golden/records_v0.json holds
+each record's parsed program numbers and its `sstl` string) and on the formula shapes the reference's LaTeX grammar
+allows (eval_script.py:283-382; `(G ∧ G) ∨ (G ∧ G)` at utils/answer_extraction.py:379)."""
+import json
+import os
+
+import pytest
+
+from pde_controller_b200 import Predicate, Problem
+from pde_controller_b200.sstl import SstlError, cross_check, parse_sstl, to_latex
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def records():
+    with open(os.path.join(HERE, "golden", "records_v0.json")) as f:
+        return json.load(f)["records"]
+
+
+def problem_of(rec) -> Problem:
+    d = dict(rec["problem"])
+    d["predicates"] = [Predicate(**p) for p in d["predicates"]]
+    d["tree"] = [tuple(t) for t in d["tree"]]
+    return Problem(**d)
+
+
+@pytest.mark.parametrize("rec", records(), ids=lambda r: r["source"])
+def test_reference_records_are_self_consistent(rec):
+    assert cross_check(problem_of(rec), rec["sstl"]) == []
+
+
+@pytest.mark.parametrize("rec", records()[:6], ids=lambda r: r["source"])
+def test_round_trip(rec):
+    p = problem_of(rec)
+    preds, tree = parse_sstl(to_latex(p))
+    assert cross_check(p, to_latex(p)) == []
+    assert [(q.top, q.rel, q.t_lo, q.t_hi, q.x_lo, q.x_hi, q.m, q.b) for q in preds] == \
+           [(q.top, q.rel, q.t_lo, q.t_hi, float(q.x_lo), float(q.x_hi), q.m, q.b) for q in p.predicates]
+
+
+def test_detects_each_kind_of_mismatch():
+    rec = records()[0]
+    p = problem_of(rec)
+    s = rec["sstl"]
+    assert cross_check(p, s.replace("G_[[", "F_[[", 1)) != []
+    assert cross_check(p, s.replace("> 0", "< 0", 1)) != []
+    assert any("clause count" in m for m in cross_check(p, s.split("\\land")[0]))
+    assert cross_check(p, s.replace("\\land", "\\lor", 1)) == ["formula structure differs"]
+    q = problem_of(rec)
+    q.predicates[1].b += 1e-3
+    assert any("intercept" in m for m in cross_check(q, s))
+    assert cross_check(p, "not a formula") != []
+
+
+def test_disjunction_of_conjunctions_and_precedence():
+    c = ["G_[[0.5, 1.0]] (\\forall x \\in [1, 2]  (u(x) - (0.1 \\cdot x + 2.0) > 0))",
+         "F_[[1.5, 2]] (\\forall x \\in [3.0, 4.0]  (u(x) - (-2e-05 \\cdot x + -1.7281) < 0))",
+         "G_[[0, 3]] (\\forall x \\in [5, 6]  (u(x) - (0.0 \\cdot x + 1) = 0))",
+         "G_[[2, 3]] (\\forall x \\in [7, 8]  (u(x) - (1 \\cdot x - 4) \\geq 0.5))"]
+    preds, tree = parse_sstl(f"({c[0]} \\land {c[1]}) \\lor ({c[2]} \\land {c[3]})")
+    assert [q.label for q in preds] == ["A", "B", "C", "D"]
+    assert tree == [("leaf", 0, 0), ("leaf", 1, 0), ("and", 0, 1), ("leaf", 2, 0), ("leaf", 3, 0), ("and", 3, 4), ("or", 2, 5)]
+    assert preds[1].b == -1.7281 and preds[1].rel == "<" and preds[2].rel == "="
+    assert preds[3].b == pytest.approx(-3.5) and preds[3].rel == ">"          # "- 4" and the threshold folded in
+    # \land binds tighter than \lor without parentheses
+    _, t2 = parse_sstl(f"{c[0]} \\lor {c[1]} \\land {c[2]}")
+    assert t2[-1][0] == "or" and t2[-2][0] == "and"
+    with pytest.raises(SstlError):
+        parse_sstl(f"({c[0]} \\land {c[1]}")
+    with pytest.raises(SstlError):
+        parse_sstl("G_[[2, 1]] (\\forall x \\in [1, 2]  (u(x) - (0.1 \\cdot x + 2.0) > 0))")
+
+
+def test_check_records_flags_only_the_inconsistent_ones():
+    from pde_controller_b200.sstl import check_records
+    from pde_controller_b200.frontend import parse_program  # noqa: F401  (the gate parses the program text itself)
+    prog = ("from femformal.core.fem import heatlinfem as heatlinfem\nN = 30\nL = 100\n"
+            "rho = lambda x: 4e-06*450000000 if x < 30 or x > 60 else 5e-06*400000000\n"
+            "E = lambda x: 800000 if x < 30 or x > 60 else 1500000\nxpart = np.linspace(0, L, N + 1)\ng = [300, None]\n"
+            "f_nodal = np.zeros(N + 1)\ndt = .05\nT = 5\nfosys = heatlinfem.heatlinfem_mix(xpart, rho, E, g, f_nodal, dt)\n"
+            "apc0 = logic.APCont([10, 20], \">\", lambda x: 0.1 * x + 290.0, lambda x: 0.1)\n"
+            "cregions = {\"A\" : apc0}\ncspec = \"((G_[1.0, 2.0] (A)))\"")
+    good = "G_[[1.0, 2.0]] (\\forall x \\in [10, 20]  (u(x) - (0.1 \\cdot x + 290.0) > 0))"
+    items = [{"python": prog, "sstl": good}, {"python": prog, "sstl": good.replace("290.0", "291.0")},
+             {"python": "this is not a program", "sstl": good}]
+    bad = check_records(items)
+    assert [i for i, _ in bad] == [1, 2] and "intercept" in bad[0][1][0]
+
