@@ -290,6 +290,7 @@ def main():
     ap.add_argument("--gather", action="store_true", help="NCCL all_gather of the per-sample results after each step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-block", type=int, default=65536, help="samples per block of the end-to-end pipeline")
+    ap.add_argument("--explicit-knots", action="store_true", help="carry per-sample knot times instead of uniform knots")
     args = ap.parse_args()
     if args.batch is None:
         args.batch = DEFAULT_BATCH[args.workload]
@@ -320,8 +321,11 @@ def main():
 
     # this rank's shard of the global synthetic set (weak scaling: args.batch samples per GPU)
     total = args.batch * world
-    src = synth.make_batch(args.batch, args.workload, seed=args.seed, start=rank * args.batch, total=total)
-    host = native.pinned_batch(src.n, src.kmax, src.pmax, src.tmax)
+    # compact form: the synthetic controls sit on uniform knots (C11), so knot times are formed on the device
+    # (knot_t == NULL in the C ABI) instead of crossing PCIe; --explicit-knots sends them as per-sample arrays
+    uk = not args.explicit_knots
+    src = synth.make_batch(args.batch, args.workload, seed=args.seed, start=rank * args.batch, total=total, uniform_knots=uk)
+    host = native.pinned_batch(src.n, src.kmax, src.pmax, src.tmax, uniform_knots=uk)
     host.slab[:] = src.slab
     res = native.ResidentBatch(host, device=dev, stream=stream)
     rob_dev, _, st_dev = res.device_ptrs()
@@ -372,7 +376,8 @@ def main():
     # every step: the whole batch goes pinned host -> H2D -> plan -> kernels -> D2H (robustness + status) as
     # args.e2e_block-sample blocks double-buffered on two streams (native.BlockPipeline); run() returns after the
     # last byte of the results is back in host memory
-    pipe = native.BlockPipeline(src.n, src.kmax, src.pmax, src.tmax, block=args.e2e_block, device=dev, depth=2)
+    pipe = native.BlockPipeline(src.n, src.kmax, src.pmax, src.tmax, block=args.e2e_block, device=dev, depth=2,
+                                uniform_knots=uk)
     for g in range(2):
         pipe.fill(src, g)
 
@@ -422,7 +427,7 @@ def main():
             "dtype": "f64" if args.precision == 64 else "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_TEXT[args.workload], "batch_per_gpu": args.batch, "global_batch": total,
                        "precision": args.precision, "seed": args.seed, "l2": "flushed (256 MiB write) between timed steps",
-                       "gather": bool(rob_t is not None), "failed_samples": n_fail, "e2e_block": args.e2e_block, "e2e_pipeline_depth": 2, "e2e_value_depth1": e2e_sync,
+                       "gather": bool(rob_t is not None), "failed_samples": n_fail, "knots": "uniform (formed on device)" if uk else "explicit", "e2e_block": args.e2e_block, "e2e_pipeline_depth": 2, "e2e_value_depth1": e2e_sync,
                        "wall_s_timed_region": wall1 - wall0},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(12 * host.n)},

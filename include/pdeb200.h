@@ -130,7 +130,9 @@ typedef struct PdebBatch {
     const double*  E_out;
 
     const int32_t* n_knots;  /* [n] 0 = zero input */
-    const double*  knot_t;   /* [kmax][stride] ascending knot times of the PWL input at x = L */
+    const double*  knot_t;   /* [kmax][stride] ascending knot times of the PWL input at x = L;
+                                NULL = uniform knots linspace(0, T, n_knots) (convention C11), formed on the device:
+                                120 of the ~500 bytes per sample of the default heat layout need not cross PCIe */
     const double*  knot_y;   /* [kmax][stride] knot values (heat: flux, wave: force), added to F[N] */
 
     const int32_t* n_pred;   /* [n] clauses, 1..pmax */

@@ -92,7 +92,12 @@ static int unpack(const PdebBatch* in, int64_t s, Sample* p) {
     p->E_in = in->E_in[s]; p->E_out = in->E_out[s];
     p->nk = in->n_knots[s];
     if (p->nk < 0 || p->nk > in->kmax || p->nk > 64) return -1;
-    for (int j = 0; j < p->nk; ++j) { p->kt[j] = in->knot_t[j * st + s]; p->ky[j] = in->knot_y[j * st + s]; }
+    for (int j = 0; j < p->nk; ++j) {
+        /* knot_t == NULL: uniform knots, exactly numpy's linspace(0, T, nk) (C11) */
+        if (in->knot_t) p->kt[j] = in->knot_t[j * st + s];
+        else p->kt[j] = (j == p->nk - 1 && p->nk > 1) ? p->T : (double)j * (p->T / (double)(p->nk - 1 > 0 ? p->nk - 1 : 1));
+        p->ky[j] = in->knot_y[j * st + s];
+    }
     p->np = in->n_pred[s];
     if (p->np < 1 || p->np > in->pmax || p->np > PDEB_MAX_PRED) return -1;
     for (int j = 0; j < p->np; ++j) {

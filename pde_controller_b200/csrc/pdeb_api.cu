@@ -116,8 +116,9 @@ static int check_batch(const PdebBatch* in) {
     if (in->kmax < 1 || in->pmax < 1 || in->pmax > PDEB_MAX_PRED || in->tmax < 1 || in->tmax > PDEB_MAX_TREE)
         return fail(PDEB_E_ARG, "kmax / pmax / tmax out of range");
     if (in->n == 0) return 0;
+    /* knot_t may be NULL: uniform knots linspace(0, T, n_knots) (C11) */
     const void* req[] = {in->kind, in->n_elem, in->L, in->dt, in->T, in->g0, in->x_a, in->x_b, in->rho_in, in->rho_out,
-                         in->E_in, in->E_out, in->n_knots, in->knot_t, in->knot_y, in->n_pred, in->pred_xlo, in->pred_xhi,
+                         in->E_in, in->E_out, in->n_knots, in->knot_y, in->n_pred, in->pred_xlo, in->pred_xhi,
                          in->pred_m, in->pred_b, in->pred_tlo, in->pred_thi, in->pred_rel, in->pred_top, in->n_tree,
                          in->tree_op, in->tree_lhs, in->tree_rhs};
     for (const void* p : req) if (!p) return fail(PDEB_E_ARG, "a batch array is NULL");
@@ -145,7 +146,7 @@ static int upload(PdebResident* r, const PdebBatch* in, int64_t lo, int64_t hi, 
     PdebDevBatch& d = r->dev;
     const bool whole = lo == 0 && hi == r->n;
     const bool fast = whole && !knots_only && r->host_slab && in->slab_base && in->slab_bytes > 0 && in->stride == r->n &&
-                      (size_t)in->slab_bytes == r->slab_bytes &&
+                      (size_t)in->slab_bytes == r->slab_bytes && ((in->knot_t != nullptr) == (r->dev.knot_t != nullptr)) &&
                       (const unsigned char*)in->L - (const unsigned char*)in->slab_base ==
                           (const unsigned char*)r->dev.L - r->slab;
     if (fast) {
@@ -161,7 +162,8 @@ static int upload(PdebResident* r, const PdebBatch* in, int64_t lo, int64_t hi, 
         return cudaMemcpy2DAsync(dp, elem * r->stride, sp, elem * in->stride, elem * n, planes, cudaMemcpyHostToDevice, stream);
     };
     CK(copy(d.n_knots, in->n_knots, 4, 1));
-    CK(copy(d.knot_t, in->knot_t, 8, r->kmax));
+    if ((in->knot_t != nullptr) != (d.knot_t != nullptr)) return fail(PDEB_E_ARG, "knot_t must be given (or NULL) as at creation");
+    if (d.knot_t) CK(copy(d.knot_t, in->knot_t, 8, r->kmax));
     CK(copy(d.knot_y, in->knot_y, 8, r->kmax));
     if (knots_only) return 0;
     CK(copy(d.kind, in->kind, 1, 1));
@@ -206,7 +208,7 @@ static RangeView view_of(const PdebResident* r, int64_t lo, int64_t hi, int chun
     v.dev.n = hi - lo;
 #define OFF(f) v.dev.f = r->dev.f + lo
     OFF(kind); OFF(n_elem); OFF(L); OFF(dt); OFF(T); OFF(g0); OFF(x_a); OFF(x_b); OFF(rho_in); OFF(rho_out); OFF(E_in);
-    OFF(E_out); OFF(n_knots); OFF(knot_t); OFF(knot_y); OFF(n_pred); OFF(pred_xlo); OFF(pred_xhi); OFF(pred_m); OFF(pred_b);
+    OFF(E_out); OFF(n_knots); if (r->dev.knot_t) { OFF(knot_t); } OFF(knot_y); OFF(n_pred); OFF(pred_xlo); OFF(pred_xhi); OFF(pred_m); OFF(pred_b);
     OFF(pred_tlo); OFF(pred_thi); OFF(pred_rel); OFF(pred_top); OFF(n_tree); OFF(tree_op); OFF(tree_lhs); OFF(tree_rhs);
 #undef OFF
     v.out.robustness = r->out.robustness + lo;
@@ -273,7 +275,7 @@ static int resident_alloc(const PdebBatch* in, int device, PdebResident** outp) 
                            in->pred_m, in->pred_b, in->pred_tlo, in->pred_thi, in->pred_rel, in->pred_top, in->n_tree,
                            in->tree_op, in->tree_lhs, in->tree_rhs};
     const size_t elem[] = {1, 4, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 4, 8, 8, 4, 8, 8, 8, 8, 8, 8, 1, 1, 4, 1, 1, 1};
-    const int planes[] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, in->kmax, in->kmax, 1, in->pmax, in->pmax, in->pmax,
+    const int planes[] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, in->knot_t ? in->kmax : 0, in->kmax, 1, in->pmax, in->pmax, in->pmax,
                           in->pmax, in->pmax, in->pmax, in->pmax, in->pmax, 1, in->tmax, in->tmax, in->tmax};
     const int NF = 28;
     size_t off[NF];
@@ -282,6 +284,7 @@ static int resident_alloc(const PdebBatch* in, int device, PdebResident** outp) 
         for (int f = 0; f < NF; ++f) {
             const unsigned char* p = (const unsigned char*)hostp[f];
             const unsigned char* base = (const unsigned char*)in->slab_base;
+            if (!p) { off[f] = 0; continue; }               /* knot_t == NULL */
             if (n > 0 && (p < base || p + elem[f] * (size_t)n * planes[f] > base + in->slab_bytes)) {
                 delete r;
                 return fail(PDEB_E_ARG, "a batch array lies outside slab_base..slab_base+slab_bytes");
@@ -327,7 +330,7 @@ static int resident_alloc(const PdebBatch* in, int device, PdebResident** outp) 
     d.x_a = (const double*)(s + off[6]);          d.x_b = (const double*)(s + off[7]);
     d.rho_in = (const double*)(s + off[8]);       d.rho_out = (const double*)(s + off[9]);
     d.E_in = (const double*)(s + off[10]);        d.E_out = (const double*)(s + off[11]);
-    d.n_knots = (const int32_t*)(s + off[12]);    d.knot_t = (const double*)(s + off[13]);
+    d.n_knots = (const int32_t*)(s + off[12]);    d.knot_t = in->knot_t ? (const double*)(s + off[13]) : nullptr;
     d.knot_y = (const double*)(s + off[14]);      d.n_pred = (const int32_t*)(s + off[15]);
     d.pred_xlo = (const double*)(s + off[16]);    d.pred_xhi = (const double*)(s + off[17]);
     d.pred_m = (const double*)(s + off[18]);      d.pred_b = (const double*)(s + off[19]);
@@ -372,7 +375,7 @@ extern "C" int pdeb_resident_upload(PdebResident* r, const PdebBatch* in, void* 
 
 extern "C" int pdeb_resident_set_knots(PdebResident* r, const double* knot_t, const double* knot_y,
                                        const int32_t* n_knots, void* stream_) {
-    if (!r || !knot_t || !knot_y || !n_knots) return fail(PDEB_E_ARG, "NULL argument");
+    if (!r || !knot_y || !n_knots) return fail(PDEB_E_ARG, "NULL argument");
     DeviceGuard g(r->device);
     PdebBatch in{};
     in.n = r->n; in.stride = r->host_stride; in.kmax = r->kmax; in.pmax = r->pmax; in.tmax = r->tmax;
@@ -565,7 +568,7 @@ static PdebBatch shard_of(const PdebBatch* in, int64_t lo, int64_t hi) {
     s.slab_bytes = 0;
 #define OFF(f) s.f = in->f + lo
     OFF(kind); OFF(n_elem); OFF(L); OFF(dt); OFF(T); OFF(g0); OFF(x_a); OFF(x_b); OFF(rho_in); OFF(rho_out); OFF(E_in);
-    OFF(E_out); OFF(n_knots); OFF(knot_t); OFF(knot_y); OFF(n_pred); OFF(pred_xlo); OFF(pred_xhi); OFF(pred_m); OFF(pred_b);
+    OFF(E_out); OFF(n_knots); if (in->knot_t) { OFF(knot_t); } OFF(knot_y); OFF(n_pred); OFF(pred_xlo); OFF(pred_xhi); OFF(pred_m); OFF(pred_b);
     OFF(pred_tlo); OFF(pred_thi); OFF(pred_rel); OFF(pred_top); OFF(n_tree); OFF(tree_op); OFF(tree_lhs); OFF(tree_rhs);
 #undef OFF
     return s;

@@ -101,10 +101,10 @@ pdeb_chunk_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant_
     int64_t S = 0;
     if (!pdeb_params_ok(KIND, N, L, dt, T, g0, rho_in, rho_out, E_in, E_out) || N > G::CAP - 1) status = PDEB_ST_BADPARAM;
     if (np < 1 || np > b.pmax || nk < 0 || nk > b.kmax || nt < 1 || nt > b.tmax) status = PDEB_ST_BADPARAM;
-    const double* kt = b.knot_t + s;
+    const double* kt = b.knot_t ? b.knot_t + s : nullptr;      /* NULL: uniform knots */
     const double* ky = b.knot_y + s;
     if (status == PDEB_OK) {
-        for (int j = 1; j < nk; ++j)
+        for (int j = 1; j < nk && kt; ++j)
             if (!(kt[(int64_t)j * st] > kt[(int64_t)(j - 1) * st])) status = PDEB_ST_BADPARAM;
         for (int j = 0; j < np; ++j)
             if (b.pred_rel[(int64_t)j * st + s] > 2 || b.pred_top[(int64_t)j * st + s] > 1) status = PDEB_ST_BADPARAM;
@@ -171,7 +171,7 @@ pdeb_chunk_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant_
             const double wdev = -g0;
             const double m_o = rho_out * h, m_i = rho_in * h;
             double f0;
-            { PdebPwl<double> p0; p0.init(kt, ky, nk, st); f0 = p0.eval(0.0, kt, ky, st); }
+            { PdebPwl<double> p0; p0.init(kt, ky, nk, st, T); f0 = p0.eval(0.0, kt, ky, st); }
             double* scr_r = tab;                       /* rhs / solution by position */
             double* scr_c = tab + (G::CAP + 1);        /* Thomas multipliers by position */
             /* every lane: r_g = (R w0)_g (+ f0 at row N) for its R interior rows and its separator */
@@ -352,7 +352,7 @@ pdeb_chunk_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant_
     }
 
     PdebPwl<double> in;
-    in.init(kt, ky, (status == PDEB_OK) ? nk : 0, st);
+    in.init(kt, ky, (status == PDEB_OK) ? nk : 0, st, T);
     double f_prev = in.eval(0.0, kt, ky, st);
 
     /* clause data: lane j keeps clause j */

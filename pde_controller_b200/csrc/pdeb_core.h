@@ -161,14 +161,21 @@ struct PdebPwl {
     real t0, y0, slope;   /* current segment */
     real y1, yn;          /* values at t1 and tn */
     int nk, j;            /* j: index of the knot at t1 */
+    double ustep, uT;     /* uniform knots (knot_t == NULL in the batch): linspace(0, T, nk), exactly as numpy forms it */
 
-    PDEB_HD void init(const double* kt, const double* ky, int nk_, int64_t stride) {
-        nk = nk_; j = 0;
-        t0 = 0; slope = 0; y0 = 0; y1 = 0; yn = 0; t1 = INFINITY; tn = INFINITY;
-        if (nk >= 1) { y0 = y1 = (real)ky[0]; t1 = kt[0]; }
-        if (nk >= 2) { tn = kt[stride]; yn = (real)ky[stride]; }
+    /* time of knot q: from the batch, or q * (T / (nk-1)) with the last one set to T (one knot: t = 0) */
+    PDEB_HD double knot_time(const double* kt, int q, int64_t stride) const {
+        if (kt) return kt[(int64_t)q * stride];
+        return (q == nk - 1 && nk > 1) ? uT : (double)q * ustep;
     }
-    /* kt, ky already point at this sample's first knot; stride = plane stride */
+    PDEB_HD void init(const double* kt, const double* ky, int nk_, int64_t stride, double T = 0.0) {
+        nk = nk_; j = 0;
+        uT = T; ustep = (nk > 1) ? T / (double)(nk - 1) : 0.0;
+        t0 = 0; slope = 0; y0 = 0; y1 = 0; yn = 0; t1 = INFINITY; tn = INFINITY;
+        if (nk >= 1) { y0 = y1 = (real)ky[0]; t1 = knot_time(kt, 0, stride); }
+        if (nk >= 2) { tn = knot_time(kt, 1, stride); yn = (real)ky[stride]; }
+    }
+    /* kt, ky already point at this sample's first knot (kt may be NULL); stride = plane stride */
     PDEB_HD real eval(double t, const double* kt, const double* ky, int64_t stride) {
         while (t >= t1) {
             t0 = (real)t1; y0 = y1;
@@ -176,7 +183,7 @@ struct PdebPwl {
                 slope = (real)(((double)yn - (double)y1) * pdeb_rcp(tn - t1));
                 t1 = tn; y1 = yn;
                 ++j;
-                if (j + 1 < nk) { tn = kt[(int64_t)(j + 1) * stride]; yn = (real)ky[(int64_t)(j + 1) * stride]; }
+                if (j + 1 < nk) { tn = knot_time(kt, j + 1, stride); yn = (real)ky[(int64_t)(j + 1) * stride]; }
                 else tn = INFINITY;
             } else { slope = 0; t1 = INFINITY; }
         }
@@ -661,7 +668,7 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
 #endif
     PdebPwl<real> in;
     in.init(nullptr, nullptr, 0, 0);
-    const double* kt = b.knot_t + (live ? s : 0);
+    const double* kt = b.knot_t ? b.knot_t + (live ? s : 0) : nullptr;     /* NULL: uniform knots */
     const double* ky = b.knot_y + (live ? s : 0);
     PDEB_UNROLL
     for (int i = 0; i <= N + 1; ++i) tr.w[i] = 0;
@@ -682,7 +689,7 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
         if (!pdeb_params_ok(KIND, N, L, dt, T, g0, rho_in, rho_out, E_in, E_out)) status = PDEB_ST_BADPARAM;
         if (np < 1 || np > b.pmax || nk < 0 || nk > b.kmax || nt < 1 || nt > b.tmax) status = PDEB_ST_BADPARAM;
         if (status == PDEB_OK) {
-            for (int j = 1; j < nk; ++j)
+            for (int j = 1; j < nk && kt; ++j)
                 if (!(kt[(int64_t)j * st] > kt[(int64_t)(j - 1) * st])) status = PDEB_ST_BADPARAM;
             for (int j = 0; j < np; ++j)
                 if (b.pred_rel[(int64_t)j * st + s] > 2 || b.pred_top[(int64_t)j * st + s] > 1) status = PDEB_ST_BADPARAM;
@@ -698,7 +705,7 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
             const double cR = (1.0 - cv.theta) * dt;
             const bool ok = tr.setup(L, x_a, x_b, rho_in, rho_out, E_in, E_out, lumped, cv.material_sampling, cA, cR);
             if (!ok) status = PDEB_ST_NONFINITE;
-            in.init(kt, ky, nk, st);
+            in.init(kt, ky, nk, st, T);
             if (KIND == PDEB_KIND_WAVE && ok) {
                 const double f0 = (double)in.eval(0.0, kt, ky, st);
                 tr.wave_init(h, g0, f0, rho_in, rho_out, E_in, E_out, lumped);

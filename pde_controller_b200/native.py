@@ -119,10 +119,10 @@ class PinnedBuffer:
             pass
 
 
-def pinned_batch(n, kmax, pmax, tmax=None) -> ProblemBatch:
+def pinned_batch(n, kmax, pmax, tmax=None, uniform_knots=False) -> ProblemBatch:
     """An empty ProblemBatch whose slab is page-locked (fill it, then evaluate it every step)."""
-    buf = PinnedBuffer(ProblemBatch.nbytes_for(n, kmax, pmax, tmax))
-    b = ProblemBatch(n, kmax, pmax, tmax, buffer=buf.array)
+    buf = PinnedBuffer(ProblemBatch.nbytes_for(n, kmax, pmax, tmax, uniform_knots))
+    b = ProblemBatch(n, kmax, pmax, tmax, buffer=buf.array, uniform_knots=uniform_knots)
     b._pinned = buf
     return b
 
@@ -254,7 +254,8 @@ class BlockPipeline:
     route for the 2M-sample sweep: fill(batch, g), submit(g), ..., wait(g), read robustness[g] / status[g].
     """
 
-    def __init__(self, n: int, kmax: int, pmax: int, tmax=None, block: int = 65536, device: int = 0, depth: int = 2):
+    def __init__(self, n: int, kmax: int, pmax: int, tmax=None, block: int = 65536, device: int = 0, depth: int = 2,
+                 uniform_knots: bool = False):
         self._L = lib()
         self.n, self.device, self.depth = int(n), device, int(depth)
         self.bounds = [(lo, min(lo + block, n)) for lo in range(0, n, block)]
@@ -268,7 +269,7 @@ class BlockPipeline:
             self._pins += [rob, st]
             self.robustness.append(rob.array.view(np.float64)[:n])
             self.status.append(st.array.view(np.int32)[:n])
-            blks = [pinned_batch(hi - lo, kmax, pmax, tmax) for lo, hi in self.bounds]
+            blks = [pinned_batch(hi - lo, kmax, pmax, tmax, uniform_knots) for lo, hi in self.bounds]
             self.blocks.append(blks)
             self._outs.append([{"robustness": self.robustness[g][lo:hi], "status": self.status[g][lo:hi]}
                                for lo, hi in self.bounds])

@@ -86,9 +86,12 @@ def _align(x, a=64):
 class ProblemBatch:
     """SoA batch in one host slab.  Arrays are numpy views; 2-D arrays are [plane, sample]."""
 
-    def __init__(self, n: int, kmax: int, pmax: int, tmax: Optional[int] = None, buffer=None):
+    def __init__(self, n: int, kmax: int, pmax: int, tmax: Optional[int] = None, buffer=None, uniform_knots: bool = False):
+        """uniform_knots: the batch carries no knot times; every control is over linspace(0, T, n_knots) (convention
+        C11) and the times are formed on the device (`knot_t == NULL` in the C ABI): ~120 fewer bytes per sample."""
         if tmax is None:
             tmax = 2 * pmax - 1
+        self.uniform_knots = bool(uniform_knots)
         if not (1 <= pmax <= abi.MAX_PRED) or not (1 <= tmax <= abi.MAX_TREE) or kmax < 1:
             raise ValueError("kmax/pmax/tmax out of range")
         self.n, self.kmax, self.pmax, self.tmax = int(n), int(kmax), int(pmax), int(tmax)
@@ -104,7 +107,8 @@ class ProblemBatch:
 
         for f in _F64:
             add(f, np.float64, 1)
-        add("knot_t", np.float64, kmax)
+        if not self.uniform_knots:
+            add("knot_t", np.float64, kmax)
         add("knot_y", np.float64, kmax)
         for f in _PRED_F64:
             add(f, np.float64, pmax)
@@ -123,6 +127,7 @@ class ProblemBatch:
             buffer = np.frombuffer(buffer, dtype=np.uint8, count=off)
             buffer[:] = 0
         self.slab = buffer
+        self.knot_t = None
         self._names = []
         for name, dtype, planes, o in layout:
             cnt = self.n * planes
@@ -135,13 +140,13 @@ class ProblemBatch:
 
     # ---- construction -----------------------------------------------------
     @staticmethod
-    def nbytes_for(n, kmax, pmax, tmax=None):
+    def nbytes_for(n, kmax, pmax, tmax=None, uniform_knots=False):
         """Slab size of a batch, e.g. to allocate it in pinned memory first."""
         if tmax is None:
             tmax = 2 * pmax - 1
         off = 0
         n1 = max(n, 1)
-        for planes, isz in ([(1, 8)] * len(_F64) + [(kmax, 8)] * 2 + [(pmax, 8)] * len(_PRED_F64)
+        for planes, isz in ([(1, 8)] * len(_F64) + [(kmax, 8)] * (1 if uniform_knots else 2) + [(pmax, 8)] * len(_PRED_F64)
                             + [(1, 4)] * 4 + [(1, 1), (pmax, 1), (pmax, 1), (tmax, 1), (tmax, 1), (tmax, 1)]):
             off = _align(off + isz * n1 * planes)
         return off
@@ -207,7 +212,11 @@ class ProblemBatch:
             if len(t) > self.kmax:
                 raise ValueError("too many control knots for this batch")
             self.n_knots[s] = len(t)
-            self.knot_t[: len(t), s] = t
+            if self.uniform_knots:
+                if len(t) and not np.array_equal(np.asarray(t, dtype=np.float64), np.linspace(0.0, float(p.T), len(t))):
+                    raise ValueError("this batch carries uniform knots only: control times must be linspace(0, T, K)")
+            else:
+                self.knot_t[: len(t), s] = t
             self.knot_y[: len(t), s] = y
         else:
             self.n_knots[s] = 0
@@ -226,7 +235,8 @@ class ProblemBatch:
         p = Problem("heat" if self.kind[s] == abi.KIND_HEAT else "wave", int(self.n_elem[s]),
                     *[float(getattr(self, f)[s]) for f in _F64], predicates=preds, tree=tree)
         k = int(self.n_knots[s])
-        control = (self.knot_t[:k, s].copy(), self.knot_y[:k, s].copy()) if k else None
+        kt = np.linspace(0.0, float(self.T[s]), k) if self.uniform_knots else self.knot_t[:k, s].copy()
+        control = (kt, self.knot_y[:k, s].copy()) if k else None
         return p, control
 
     # ---- views ------------------------------------------------------------
@@ -236,6 +246,7 @@ class ProblemBatch:
         v.n, v.kmax, v.pmax, v.tmax = hi - lo, self.kmax, self.pmax, self.tmax
         v.stride = self.stride
         v.slab, v.slab_bytes = None, 0
+        v.uniform_knots, v.knot_t = self.uniform_knots, None
         v._names = list(self._names)
         for name in self._names:
             a = getattr(self, name)
@@ -252,6 +263,7 @@ class ProblemBatch:
             c.slab_bytes = self.slab_bytes
         else:
             c.slab_base, c.slab_bytes = None, 0
+        c.knot_t = None                                   # uniform knots unless the batch carries times
         for name in self._names:
             a = getattr(self, name)
             setattr(c, name, a.ctypes.data if a.size else None)
@@ -273,7 +285,8 @@ class ProblemBatch:
         """105 + 16 K + 50 P + 3 (2P-1) bytes per evaluation, summed over the batch."""
         k = self.n_knots.astype(np.int64)
         p = self.n_pred.astype(np.int64)
-        return int(np.sum(105 + 16 * k + 50 * p + 3 * (2 * p - 1)))
+        per_knot = 8 if self.uniform_knots else 16      # knot times are not carried when they are uniform
+        return int(np.sum(105 + per_knot * k + 50 * p + 3 * (2 * p - 1)))
 
     def algorithmic_flops(self, convention: str = "executed"):
         """FP64 work of the batch, steps up to the last observed one (what the kernels simulate).

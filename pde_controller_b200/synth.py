@@ -127,6 +127,8 @@ def _gen_block(workload: str, seed: int, block: int):
 
 def _copy_into(batch: ProblemBatch, dst_lo: int, f: dict, src_lo: int, cnt: int):
     for name, a in f.items():
+        if name == "knot_t" and batch.uniform_knots:
+            continue
         dst = getattr(batch, name)
         if a.ndim == 1:
             dst[dst_lo:dst_lo + cnt] = a[src_lo:src_lo + cnt]
@@ -135,7 +137,7 @@ def _copy_into(batch: ProblemBatch, dst_lo: int, f: dict, src_lo: int, cnt: int)
 
 
 def make_batch(n: int, workload: str = "heat", seed: int = 0, start: int = 0, total: int | None = None,
-               buffer=None) -> ProblemBatch:
+               buffer=None, uniform_knots: bool = False) -> ProblemBatch:
     """Samples [start, start+n) of `workload`.
 
     mixed: global indices below total//2 are heat, the rest wave (sorted by kind so that warps
@@ -143,7 +145,8 @@ def make_batch(n: int, workload: str = "heat", seed: int = 0, start: int = 0, to
     """
     if workload not in WORKLOADS:
         raise ValueError(f"unknown workload {workload!r}")
-    batch = ProblemBatch(n, KMAX[workload], PMAX, buffer=buffer)
+    # the synthetic controls sit on linspace(0, T, K) (C11), so the compact form without knot times describes the same set
+    batch = ProblemBatch(n, KMAX[workload], PMAX, buffer=buffer, uniform_knots=uniform_knots)
     if workload == "mixed":
         total = start + n if total is None else total
         half = total // 2

@@ -184,3 +184,22 @@ def test_pipelined_run_equals_resident_eval(oracle_lib):
         again = r.fetch()
         assert np.array_equal(again["robustness"], whole["robustness"])
         r.close()
+
+
+@pytest.mark.parametrize("wl", ["heat", "wave", "heat_refined"])
+def test_uniform_knots_form_matches_explicit(oracle_lib, wl):
+    """knot_t == NULL: times formed on the device; same results as the explicit arrays, through every entry point."""
+    n = 2048 if wl != "heat_refined" else 8
+    a = synth.make_batch(n, wl, seed=12)
+    b = synth.make_batch(n, wl, seed=12, uniform_knots=True)
+    ga = native.evaluate_batch(a)
+    gb = native.evaluate_batch(b)
+    assert np.array_equal(ga["robustness"], gb["robustness"]) and (ga["status"] == gb["status"]).all()
+    pb = native.pinned_batch(b.n, b.kmax, b.pmax, b.tmax, uniform_knots=True)
+    pb.slab[:] = b.slab
+    res = native.ResidentBatch(pb)
+    out = res.run(pb)
+    res.close()
+    assert np.array_equal(out["robustness"], ga["robustness"])
+    check(b, oracle_lib)
+

@@ -217,3 +217,18 @@ def test_bad_parameters_are_flagged_not_raised(oracle_lib):
     rob, st = oracle_lib.eval_batch(b)
     assert st[0] == 0 and st[1] == 3 and st[2] == 3 and st[3] == 2
     assert rob[1] == -100.0 and rob[2] == -100.0 and rob[3] == -100.0
+
+
+def test_uniform_knots_equal_explicit_linspace(oracle_lib):
+    """knot_t == NULL (uniform knots, C11) is the same input as explicit linspace(0, T, K) knots, bit for bit."""
+    from pde_controller_b200 import synth
+    for wl in ("heat", "wave"):
+        a = synth.make_batch(96, wl, seed=4)
+        b = synth.make_batch(96, wl, seed=4, uniform_knots=True)
+        assert b.knot_t is None and b.slab_bytes < a.slab_bytes
+        ra, sa = oracle_lib.eval_batch(a)
+        rb, sb = oracle_lib.eval_batch(b)
+        assert (sa == sb).all() and np.array_equal(ra, rb)
+        p, c = b.get_problem(5)
+        assert np.array_equal(c[0], a.knot_t[: len(c[0]), 5])
+
