@@ -7,6 +7,8 @@
  */
 #include <cuda_runtime.h>
 
+#include <mutex>
+
 #include "pdeb_core.h"
 #include "pdeb_launch.h"
 
@@ -145,29 +147,87 @@ static cudaError_t launch_reg(const PdebDevBatch& b, const PdebConventions& cv, 
 }
 
 
+/*
+ * Side streams for batches that hold several kernel variants (a mixed heat + wave set): the variants are independent,
+ * so the second one's blocks fill the SMs the first one's tail leaves idle (the longest trajectories of a launch
+ * finish alone).  One small pool per device, created on first use; fork / join with events on the caller's stream.
+ */
+#define PDEB_SIDE_STREAMS 3
+#define PDEB_MAX_DEVICES 64
+struct PdebSidePool {
+    cudaStream_t st[PDEB_SIDE_STREAMS] = {nullptr, nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join[PDEB_SIDE_STREAMS] = {nullptr, nullptr, nullptr};
+    bool ready = false;
+};
+static PdebSidePool g_side[PDEB_MAX_DEVICES];
+static std::mutex g_side_mutex;
+
+/* call with g_side_mutex held */
+static PdebSidePool* side_pool() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= PDEB_MAX_DEVICES) return nullptr;
+    PdebSidePool& p = g_side[dev];
+    if (!p.ready) {
+        cudaError_t e = cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming);
+        for (int i = 0; i < PDEB_SIDE_STREAMS && e == cudaSuccess; ++i) {
+            e = cudaStreamCreateWithFlags(&p.st[i], cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.join[i], cudaEventDisableTiming);
+        }
+        if (e != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        p.ready = true;
+    }
+    return &p;
+}
+
+static cudaError_t launch_variant(int v, const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out,
+                                  const PdebPlanBuffers& pb, int64_t first, int64_t count, int precision, cudaStream_t stream) {
+    switch (v) {
+    case 0:
+        return (precision == 32) ? launch_reg<PDEB_KIND_HEAT, 30, float>(b, cv, out, pb.order, first, count, stream)
+                                 : launch_reg<PDEB_KIND_HEAT, 30, double>(b, cv, out, pb.order, first, count, stream);
+    case 1:
+        return (precision == 32) ? launch_reg<PDEB_KIND_WAVE, 20, float>(b, cv, out, pb.order, first, count, stream)
+                                 : launch_reg<PDEB_KIND_WAVE, 20, double>(b, cv, out, pb.order, first, count, stream);
+    default:
+        if (v >= 2 && v <= 7) return pdeb_launch_chunk_heat(1 << (v - 2), b, cv, out, pb.order, first, count, stream);
+        if (v >= 8 && v <= 12) return pdeb_launch_chunk_wave(1 << (v - 8), b, cv, out, pb.order, first, count, stream);
+        return cudaSuccess;
+    }
+}
+
 int pdeb_launch_all(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out, const PdebPlanBuffers& pb,
                     const int32_t* vstart_count_host, int precision, cudaStream_t stream, int* launches) {
+    int live[PDEB_NUM_VARIANTS], nlive = 0;
+    for (int v = 0; v < PDEB_NUM_VARIANTS; ++v) if (vstart_count_host[2 * v + 1] > 0) live[nlive++] = v;
+    /* a stream that is being captured into a graph cannot be forked this way: keep those on one stream */
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (nlive > 1 && cudaStreamIsCapturing(stream, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusActive; }
+    /* the pool's events are shared by every caller on this device: the whole fork / launch / join sequence is enqueued
+     * under the lock (an event wait takes the record that is current when the wait is enqueued) */
+    std::unique_lock<std::mutex> lock(g_side_mutex, std::defer_lock);
+    const bool fork = nlive > 1 && cap == cudaStreamCaptureStatusNone;
+    if (fork) lock.lock();
+    PdebSidePool* pool = fork ? side_pool() : nullptr;
     cudaError_t e = cudaSuccess;
-    int nl = 0;
-    for (int v = 0; v < PDEB_NUM_VARIANTS && e == cudaSuccess; ++v) {
+    if (pool) e = cudaEventRecord(pool->fork, stream);
+    int used = 0;
+    /* the variant with the most work per sample last in the list goes first on the caller's stream: longest first */
+    for (int q = 0; q < nlive && e == cudaSuccess; ++q) {
+        const int v = live[q];
         const int64_t first = vstart_count_host[2 * v], count = vstart_count_host[2 * v + 1];
-        if (count <= 0) continue;
-        ++nl;
-        switch (v) {
-        case 0:
-            e = (precision == 32) ? launch_reg<PDEB_KIND_HEAT, 30, float>(b, cv, out, pb.order, first, count, stream)
-                                  : launch_reg<PDEB_KIND_HEAT, 30, double>(b, cv, out, pb.order, first, count, stream);
-            break;
-        case 1:
-            e = (precision == 32) ? launch_reg<PDEB_KIND_WAVE, 20, float>(b, cv, out, pb.order, first, count, stream)
-                                  : launch_reg<PDEB_KIND_WAVE, 20, double>(b, cv, out, pb.order, first, count, stream);
-            break;
-        default:
-            if (v >= 2 && v <= 7) e = pdeb_launch_chunk_heat(1 << (v - 2), b, cv, out, pb.order, first, count, stream);
-            else if (v >= 8 && v <= 12) e = pdeb_launch_chunk_wave(1 << (v - 8), b, cv, out, pb.order, first, count, stream);
-            break;
+        cudaStream_t st = stream;
+        if (pool && q > 0 && used < PDEB_SIDE_STREAMS) {
+            st = pool->st[used];
+            e = cudaStreamWaitEvent(st, pool->fork, 0);
+            if (e != cudaSuccess) break;
+        }
+        e = launch_variant(v, b, cv, out, pb, first, count, precision, st);
+        if (st != stream && e == cudaSuccess) {
+            e = cudaEventRecord(pool->join[used], st);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, pool->join[used], 0);
+            ++used;
         }
     }
-    if (launches) *launches = nl;
+    if (launches) *launches = nlive;
     return e == cudaSuccess ? 0 : (int)e;
 }
