@@ -34,6 +34,9 @@
 #define PDEB_CHUNK_NCLS 8      /* lane classes per trajectory: outer, inner, padding, <= 5 special */
 #define PDEB_CHUNK_NVEC 6      /* table values per row and class, as three 16-byte pairs: {e, dinv} {v, w} {rd, ror} */
 #define PDEB_CHUNK_WARPS 4     /* warps (trajectories) per block */
+#ifndef PDEB_CHUNK_MINBLOCKS
+#define PDEB_CHUNK_MINBLOCKS 1  /* resident blocks per SM the kernels are compiled for */
+#endif
 #define PDEB_FULL 0xffffffffu
 
 __device__ __forceinline__ double pdeb_shfl(double x, int src) { return __shfl_sync(PDEB_FULL, x, src); }
@@ -43,12 +46,18 @@ __device__ __forceinline__ double pdeb_shfl_dn1(double x, int lane) { double y =
 /* per-row coefficients of the step matrix A and of the right-hand-side operator R, as functions of the row */
 struct PdebRowCoef {
     double ad_o, ad_i, ao_o, ao_i, rd_o, rd_i, ro_o, ro_i;   /* per element, o = outer material, i = inner */
+    double kq_o, kq_i;       /* flux coefficient of an element: heat dt k, wave k (right-hand side in element-flux form) */
     double h, x_a, x_b;
     int N, sampling;
 
     __device__ __forceinline__ bool outer(int e) const {
         const double xs = (sampling == 1) ? e * h : (sampling == 2) ? (e + 1) * h : (e + 0.5) * h;
         return xs < x_a || xs > x_b;
+    }
+    /* element e joins nodes e and e+1, e = 0..N-1 (node 0 is the Dirichlet node, deviation 0); none outside */
+    __device__ __forceinline__ double kq(int e) const {
+        if (e < 0 || e > N - 1) return 0.0;
+        return outer(e) ? kq_o : kq_i;
     }
     /* row g in 1..N: diagonal and coupling to row g+1; rows outside are identity / empty */
     __device__ __forceinline__ void row(int g, double& Ad, double& Ao, double& Rd, double& Ro) const {
@@ -67,6 +76,21 @@ struct PdebRowCoef {
     }
 };
 
+/* masked max of the relation-transformed margins of a lane's R interior rows (PTX form of pdeb_core.h) */
+template <int L, int R>
+struct PdebChunkMargin {
+    static __device__ __forceinline__ void run(const double* x, double mh, double off, uint32_t and_mask, uint32_t xor_mask,
+                                               uint32_t rowmask, double* hi4) {
+        const double d = fma(-mh, (double)L, x[L] - off);
+        pdeb_masked_max<L>(hi4[L & 3], pdeb_signop(d, and_mask, xor_mask), rowmask);
+        PdebChunkMargin<L + 1, R>::run(x, mh, off, and_mask, xor_mask, rowmask, hi4);
+    }
+};
+template <int R>
+struct PdebChunkMargin<R, R> {
+    static __device__ __forceinline__ void run(const double*, double, double, uint32_t, uint32_t, uint32_t, double*) {}
+};
+
 template <int R>
 struct PdebChunkGeom {
     static constexpr int CAP = 32 * R + 31;                   /* positions */
@@ -78,7 +102,7 @@ struct PdebChunkGeom {
 };
 
 template <int KIND, int R>
-__global__ void __launch_bounds__(32 * PDEB_CHUNK_WARPS)
+__global__ void __launch_bounds__(32 * PDEB_CHUNK_WARPS, PDEB_CHUNK_MINBLOCKS)
 pdeb_chunk_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant__ PdebConventions cv,
                   const __grid_constant__ PdebDevOut out, const int32_t* __restrict__ order, int64_t first, int64_t count) {
     typedef PdebChunkGeom<R> G;
@@ -122,8 +146,8 @@ pdeb_chunk_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant_
     double vv[KIND == PDEB_KIND_WAVE ? R : 1], aa[KIND == PDEB_KIND_WAVE ? R : 1];
     double xs = 0.0, vs = 0.0, as = 0.0;          /* separator state */
     double a_last = 0.0, a_first_next = 0.0;      /* A couplings of the own separator to both sides */
-    double rs_d = 0.0, rs_l = 0.0, rs_r = 0.0;    /* R at the separator: diagonal, left, right */
-    double rol0 = 0.0;                            /* R coupling of the first interior row to the previous separator */
+    double rs_d = 0.0, rs_l = 0.0, rs_r = 0.0;    /* rs_r: flux coefficient of the element right of the separator (rs_d, rs_l: set-up scratch) */
+    double rol0 = 0.0;                            /* flux coefficient of the element between the previous separator and row 0 */
     double pcr_a[5], pcr_g[5], dinvS = 1.0;
     int cls = 2;
     const int lumped = (KIND == PDEB_KIND_HEAT) ? cv.mass_heat : cv.mass_wave;
@@ -140,6 +164,8 @@ pdeb_chunk_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant_
         rc.rd_i = (KIND == PDEB_KIND_HEAT) ? md_i - cR * k_i : -k_i;
         rc.ro_o = (KIND == PDEB_KIND_HEAT) ? mo_o + cR * k_o : k_o;
         rc.ro_i = (KIND == PDEB_KIND_HEAT) ? mo_i + cR * k_i : k_i;
+        rc.kq_o = (KIND == PDEB_KIND_HEAT) ? dt * k_o : k_o;
+        rc.kq_i = (KIND == PDEB_KIND_HEAT) ? dt * k_i : k_i;
         rc.h = h; rc.x_a = x_a; rc.x_b = x_b; rc.N = (status == PDEB_OK) ? N : 0; rc.sampling = cv.material_sampling;
     }
     if (status != PDEB_OK) { S = 0; np = 0; }
@@ -147,7 +173,7 @@ pdeb_chunk_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant_
         /* class of this lane: rows g0r .. g0r+R-1 with g0r = base + 1 - shift */
         const int g_first = base + 1 - shift, g_last = g_first + R - 1;
         bool special = false;
-        if (g_last < 1) cls = 2;                                           /* all padding */
+        if (g_last < 0) cls = 2;                                           /* all padding (a lane that holds the Dirichlet row needs the flux coefficient of element 0: special) */
         else if (g_first >= 2 && g_last <= rc.N - 1) {
             /* elements g_first-1 .. g_last all exist: uniform if they share one material */
             const bool o0 = rc.outer(g_first - 1);
@@ -256,9 +282,9 @@ pdeb_chunk_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant_
         for (int l = 0; l < R; ++l) {
             double Ad, Ao, Rd, Ro;
             rc.row(g_first + l, Ad, Ao, Rd, Ro);
-            PdebD2 rr; rr.x = Rd; rr.y = Ro;
+            PdebD2 rr; rr.x = 0.0; rr.y = rc.kq(g_first + l);            /* flux coefficient of the element right of row l */
             t_rr[l] = rr;
-            if (l == R - 1) { a_last = Ao; rs_l = Ro; }
+            if (l == R - 1) a_last = Ao;
         }
         for (int l = 0; l < M; ++l) {                                 /* top sweep */
             double Ad, Ao, Rd, Ro;
@@ -303,8 +329,9 @@ pdeb_chunk_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant_
         {
             double Adp, Rdp, rfirst;
             rc.row(g_first - 1, Adp, a_first, Rdp, rfirst);
-            if (lane == 0) { a_first = 0.0; rfirst = 0.0; }
-            rol0 = rfirst;
+            if (lane == 0) a_first = 0.0;
+            (void)rfirst;
+            rol0 = rc.kq(g_first - 1);                                   /* element between the previous separator and row 0 */
         }
         __syncwarp();
         /* pass 2: spikes v = A_loc^-1 (a_first e_0), w = A_loc^-1 (a_last e_{R-1}) */
@@ -320,8 +347,9 @@ pdeb_chunk_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant_
         __syncwarp();
         /* separator row and Schur complement */
         double As, Ao_s;
-        rc.row(base + R + 1 - shift, As, Ao_s, rs_d, rs_r);
-        if (lane == 31) { As = 1.0; Ao_s = 0.0; rs_d = 0.0; rs_r = 0.0; rs_l = 0.0; a_last = 0.0; }
+        rc.row(base + R + 1 - shift, As, Ao_s, rs_d, rs_l);
+        rs_r = rc.kq(base + R + 1 - shift);                             /* element between the separator and the next lane's row 0 */
+        if (lane == 31) { As = 1.0; Ao_s = 0.0; rs_r = 0.0; a_last = 0.0; }
         a_first_next = Ao_s;
         const double v_last = t_vw[R - 1].x, w_last = t_vw[R - 1].y;
         const double v0 = t_vw[0].x, w0 = t_vw[0].y;
@@ -349,6 +377,15 @@ pdeb_chunk_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant_
         dinvS = 1.0 / Sdi;
         if (!isfinite(dinvS)) ok = false;
         if (__any_sync(PDEB_FULL, !ok) && status == PDEB_OK) { status = PDEB_ST_NONFINITE; S = 0; np = 0; }
+        /*
+         * The Dirichlet node (row 0, an identity row that is decoupled from row 1) receives the flux of element 0 on
+         * its right-hand side in the element-flux form; its increment must stay 0, so its pivot inverse is zeroed
+         * (its lane is a special class: the table is its own).
+         */
+        __syncwarp();
+        if (g_first <= 0 && g_first + R - 1 >= 0) t_ed[-g_first].y = 0.0;
+        if (base + R + 1 - shift == 0) dinvS = 0.0;
+        __syncwarp();
     }
 
     PdebPwl<double> in;
@@ -412,13 +449,10 @@ pdeb_chunk_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant_
             const int l_lo = ilo + shift - base - 1, l_hi = ihi + shift - base - 1;
             const double off = fma(mh, (double)(base + 1 - shift), c0);
             double hi4[4] = { -INFINITY, -INFINITY, -INFINITY, -INFINITY };
-#pragma unroll
-            for (int l = 0; l < R; ++l) {
-                const double d = fma(-mh, (double)l, x[l] - off);
-                const double g = pdeb_signop(d, and_mask, xor_mask);
-                const bool tk = (l >= l_lo) & (l <= l_hi) & (g > hi4[l & 3]);
-                hi4[l & 3] = tk ? g : hi4[l & 3];
-            }
+            /* bit l: local row l lies inside the clause interval (R <= 32) */
+            const int b_lo = l_lo < 0 ? 0 : l_lo, b_hi = l_hi > R - 1 ? R - 1 : l_hi;
+            const uint32_t rowmask = (b_lo <= b_hi) ? ((b_hi >= 31 ? 0xffffffffu : ((1u << (b_hi + 1)) - 1u)) & ~((1u << b_lo) - 1u)) : 0u;
+            PdebChunkMargin<0, R>::run(x, mh, off, and_mask, xor_mask, rowmask, hi4);
             {
                 const double d = fma(-mh, (double)R, xs - off);
                 const double g = pdeb_signop(d, and_mask, xor_mask);
@@ -489,38 +523,51 @@ pdeb_chunk_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant_
         f_prev = f_next;
         {
             const double xs_prev = pdeb_shfl_up1(xs, lane), x_nf = pdeb_shfl_dn1(x[0], lane);
-            /* right-hand side R x of the interior block (all rows independent) */
-            double ror_prev = rol0;
-#pragma unroll
-            for (int l = 0; l < R; ++l) {
-                const PdebD2 rr = t_rr[l];
-                const double xl = (l == 0) ? xs_prev : x[l - 1], xr = (l == R - 1) ? xs : x[l + 1];
-                double r = fma(rr.x, x[l], fma(ror_prev, xl, rr.y * xr));
-                if (l == R - 1) r += (lane == 31) ? fN : 0.0;
-                y[l] = r;
-                ror_prev = rr.y;
-            }
-            /* twisted solve: two independent elimination chains meet at row M, two independent back-substitutions leave it */
+            /*
+             * Right-hand side in ELEMENT-FLUX form: Q_e = kq_e (x_{e+1} - x_e), row i gets Q_i - Q_{i-1} (+ load at the
+             * free end).  Heat solves for the INCREMENT  A (x' - x) = dt (f - K x), waves for  A a' = f' - K d~.
+             * The assembled form R x = R_ii x_i + R_i,i-1 x_{i-1} + R_i,i+1 x_{i+1} costs the same three operations
+             * but cancels: on refined meshes |R_ii x| is ~ (k dt / m) times the result, and 10,000 steps carried that
+             * rounding to 1.6e-9 of the parity scale; differences of neighbouring values do not cancel.
+             */
+            const double q_sep = t_rr[R - 1].y * (xs - x[R - 1]);              /* element between row R-1 and the separator */
+            const double rsep = rs_r * (x_nf - xs) - q_sep;
+            /*
+             * Twisted solve with the right-hand side formed row by row inside the two elimination chains (top rows
+             * ascending, bottom rows descending, meeting at row M).
+             */
             {
                 double zt = 0.0, zb = 0.0, e_top = 0.0;
+                double q_top = rol0 * (x[0] - xs_prev);       /* flux of the element left of the top chain's row */
+                double q_bot = q_sep;                         /* flux of the element right of the bottom chain's row */
 #pragma unroll
-                for (int l = 0; l < M; ++l) {
-                    const PdebD2 ed = t_ed[l];
-                    const double z = (l > 0) ? fma(-e_top, zt, y[l]) : y[l];
-                    zt = z;
-                    y[l] = z * ed.y;
-                    e_top = ed.x;
-                }
-#pragma unroll
-                for (int l = R - 1; l > M; --l) {
-                    const PdebD2 ed = t_ed[l];
-                    const double z = (l < R - 1) ? fma(-ed.x, zb, y[l]) : y[l];
-                    zb = z;
-                    y[l] = z * ed.y;
+                for (int j = 0; j < R; ++j) {
+                    const int it = j, ib = R - 1 - j;
+                    if (it < M) {
+                        const PdebD2 ed = t_ed[it];
+                        const double q = t_rr[it].y * (x[it + 1] - x[it]);
+                        const double r = q - q_top;
+                        const double z = (it > 0) ? fma(-e_top, zt, r) : r;
+                        zt = z;
+                        y[it] = z * ed.y;
+                        e_top = ed.x;
+                        q_top = q;
+                    }
+                    if (ib > M) {
+                        const PdebD2 ed = t_ed[ib];
+                        const double q = t_rr[ib - 1].y * (x[ib] - x[ib - 1]);
+                        double r = q_bot - q;
+                        if (ib == R - 1) r += (lane == 31) ? fN : 0.0;
+                        const double z = (ib < R - 1) ? fma(-ed.x, zb, r) : r;
+                        zb = z;
+                        y[ib] = z * ed.y;
+                        q_bot = q;
+                    }
                 }
                 {
                     const PdebD2 ed = t_ed[M];
-                    double z = y[M];
+                    double z = q_bot - q_top;
+                    if (M == R - 1) z += (lane == 31) ? fN : 0.0;
                     if (M > 0) z = fma(-e_top, zt, z);
                     if (M < R - 1) z = fma(-ed.x, zb, z);
                     y[M] = z * ed.y;
@@ -531,7 +578,6 @@ pdeb_chunk_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant_
                 for (int l = M + 1; l < R; ++l) y[l] = fma(-t_ed[l - 1].x, y[l - 1], y[l]);
             }
             /* Schur right-hand side and PCR across the lanes */
-            const double rsep = fma(rs_d, xs, fma(rs_l, x[R - 1], rs_r * x_nf));
             const double y_nf = pdeb_shfl_dn1(y[0], lane);
             double sh = (lane == 31) ? 0.0 : fma(-a_last, y[R - 1], fma(-a_first_next, y_nf, rsep));
 #pragma unroll
@@ -544,8 +590,11 @@ pdeb_chunk_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant_
             const double xs_new_prev = pdeb_shfl_up1(xs_new, lane);
             if (KIND == PDEB_KIND_HEAT) {
 #pragma unroll
-                for (int l = 0; l < R; ++l) { const PdebD2 vw = t_vw[l]; x[l] = fma(-vw.x, xs_new_prev, fma(-vw.y, xs_new, y[l])); }
-                xs = xs_new;
+                for (int l = 0; l < R; ++l) {
+                    const PdebD2 vw = t_vw[l];
+                    x[l] += fma(-vw.x, xs_new_prev, fma(-vw.y, xs_new, y[l]));       /* the solve returned the increment */
+                }
+                xs += xs_new;
             } else {
                 const double cw4 = cv.newmark_beta * dt * dt, cw5 = cv.newmark_gamma * dt;
 #pragma unroll
