@@ -83,8 +83,9 @@ struct PdebDevOut {
  *   reals: 0 mh = m*h (profile slope per node index), 1 c0 = b - g0, 2 acc (running temporal min / max),
  *          3, 4 xi of the two interval end points inside their elements (only read when info bit 3 is set)
  *   words: 0 klo, 1 khi (window steps), 2 nmask (bit i: node i inside [x_lo,x_hi]),
- *          3 info (bits 0-1 rel, bit 2 top, bit 3 needs the interpolated end points,
- *                  bits 4-8 / 9-13 element of end point 0 / 1)
+ *          3 info (bits 0-1 rel, bit 2 top, bit 3 needs the interpolated end points (general form),
+ *                  bits 4-8 / 9-13 element of end point 0 / 1, bit 14 interval inside ONE element:
+ *                  nmask then holds that element's two nodes)
  */
 #define PDEB_SLOT_REALS 5
 #define PDEB_SLOT_WORDS 4
@@ -141,7 +142,8 @@ PDEB_HD bool pdeb_params_ok(int kind, int N, double L, double dt, double T, doub
  */
 /* 1/x to within an ulp: hardware seed + two Newton steps (5 instructions instead of the ~25 of an IEEE division with its
  * slow-path call).  Used where a segment slope is formed at a knot crossing, which happens in most steps of a warp
- * because its lanes cross their knots at different times. */
+ * because its lanes cross their knots at different times, and for the ~60 (heat) / ~120 (waves) reciprocals of the
+ * per-sample set-up (scales, pivots, the double-double quotients of the wave diagonal). */
 PDEB_HD double pdeb_rcp(double x) {
 #if defined(__CUDA_ARCH__)
     double r;
@@ -152,6 +154,15 @@ PDEB_HD double pdeb_rcp(double x) {
     return fma(r, e, r);
 #else
     return 1.0 / x;
+#endif
+}
+
+/* A/B switch of tools/variant_bench.py: -DPDEB_SETUP_IEEE keeps IEEE divisions in the set-up */
+PDEB_HD double pdeb_rcp_setup(double x) {
+#ifdef PDEB_SETUP_IEEE
+    return 1.0 / x;
+#else
+    return pdeb_rcp(x);
 #endif
 }
 
@@ -341,7 +352,7 @@ struct PdebTrajReg {
             stab[0] = (real)sp;
             PDEB_UNROLL
             for (int i = 2; i <= N; ++i) {
-                sp = 1.0 / (PDEB_EL(i - 1, q.ro_o, q.ro_i) * sp);
+                sp = pdeb_rcp_setup(PDEB_EL(i - 1, q.ro_o, q.ro_i) * sp);
                 stab[(i - 1) * tstride] = (real)sp;
                 if (i == N) sN = (real)sp;
             }
@@ -357,7 +368,7 @@ struct PdebTrajReg {
             double piv = s2 * (PDEB_EL(i - 1, q.ad_o, q.ad_i) + PDEB_EL(i, q.ad_o, q.ad_i));
             if (i > 1) { const double aol = PDEB_EL(i - 1, as_o, as_i), ci = aol * dtop; setc(i - 1, (real)ci); piv -= ci * aol; }
             if (!(piv > 0.0)) ok = false;
-            dtop = 1.0 / piv;
+            dtop = pdeb_rcp_setup(piv);
             real2 t;
             t.x = (real)(s2 * (PDEB_EL(i - 1, q.rd_o, q.rd_i) + PDEB_EL(i, q.rd_o, q.rd_i)));
             t.y = (real)dtop;
@@ -369,7 +380,7 @@ struct PdebTrajReg {
             double piv = s2 * (PDEB_EL(i - 1, q.ad_o, q.ad_i) + ((i < N) ? PDEB_EL(i, q.ad_o, q.ad_i) : 0.0));
             if (i < N) { const double aor = PDEB_EL(i, as_o, as_i), ci = aor * dbot; setc(i, (real)ci); piv -= ci * aor; }
             if (!(piv > 0.0)) ok = false;
-            dbot = 1.0 / piv;
+            dbot = pdeb_rcp_setup(piv);
             real2 t;
             t.x = (real)(s2 * (PDEB_EL(i - 1, q.rd_o, q.rd_i) + ((i < N) ? PDEB_EL(i, q.rd_o, q.rd_i) : 0.0)));
             t.y = (real)dbot;
@@ -383,7 +394,7 @@ struct PdebTrajReg {
             setc(M, (real)cb);
             const double piv = s2 * (PDEB_EL(M - 1, q.ad_o, q.ad_i) + PDEB_EL(M, q.ad_o, q.ad_i)) - ct * aol - cb * aor;
             if (!(piv > 0.0)) ok = false;
-            const double dm = 1.0 / piv;
+            const double dm = pdeb_rcp_setup(piv);
             if (!isfinite(dm) || !isfinite(dtop) || !isfinite(dbot)) ok = false;
             real2 t;
             t.x = (real)(s2 * (PDEB_EL(M - 1, q.rd_o, q.rd_i) + PDEB_EL(M, q.rd_o, q.rd_i)));
@@ -403,9 +414,9 @@ struct PdebTrajReg {
                 const double si = (double)stab[(i - 1) * tstride];
                 double ah, al, bh = 0.0, bl = 0.0;
                 if (i > 1) {
-                    const double sm = (double)stab[(i - 2) * tstride];
-                    ah = si / sm;
-                    al = fma(-ah, sm, si) / sm;
+                    const double sm = (double)stab[(i - 2) * tstride], rm = pdeb_rcp_setup(sm);
+                    ah = si * rm;
+                    al = fma(-ah, sm, si) * rm;
                 } else {
                     const double k0 = -PDEB_EL(0, q.rd_o, q.rd_i);
                     const double ph = si * si, pl = fma(si, si, -ph);
@@ -413,9 +424,9 @@ struct PdebTrajReg {
                     al = fma(ph, k0, -ah) + pl * k0;
                 }
                 if (i < N) {
-                    const double sp = (double)stab[i * tstride];
-                    bh = si / sp;
-                    bl = fma(-bh, sp, si) / sp;
+                    const double sp = (double)stab[i * tstride], rp = pdeb_rcp_setup(sp);
+                    bh = si * rp;
+                    bl = fma(-bh, sp, si) * rp;
                 }
                 const double sh = ah + bh, bb = sh - ah;
                 const double err = (ah - (sh - bb)) + (bh - bb);
@@ -539,18 +550,53 @@ struct PdebMarginLoop<END, END, real, STRIDE> {
     static PDEB_HD void run(const real*, const real*, real, real, uint32_t, uint32_t, uint32_t, real*) {}
 };
 
+/* masked max over the nodes, left in PDEB_MARGIN_ACC partial accumulators (node I goes to hi[I % PDEB_MARGIN_ACC]; -inf where
+ * no node of that residue class is in the mask) */
+template <int N, typename real, int STRIDE>
+PDEB_HD void pdeb_clause_partials(const real* w, const real* stab, real mh, real c0, uint32_t nmask, uint32_t and_mask,
+                                  uint32_t xor_mask, real* hi) {
+    for (int q = 0; q < PDEB_MARGIN_ACC; ++q) hi[q] = (real)(-INFINITY);
+    PdebMarginLoop<0, N + 1, real, STRIDE>::run(w, stab, mh, c0, nmask, and_mask, xor_mask, hi);
+}
+template <typename real>
+PDEB_HD real pdeb_partials_max(const real* hi) {
+    static_assert(PDEB_MARGIN_ACC == 4, "four partial accumulators");
+    const real a = hi[0] > hi[2] ? hi[0] : hi[2], b = hi[1] > hi[3] ? hi[1] : hi[3];
+    return a > b ? a : b;
+}
+
 /* max over the nodes of the interval of the relation-transformed node margin (-inf if the interval holds no node) */
 template <int N, typename real, int STRIDE>
 PDEB_HD real pdeb_clause_gmax(const real* w, const real* stab, real mh, real c0, uint32_t nmask, uint32_t and_mask, uint32_t xor_mask) {
     real hi[PDEB_MARGIN_ACC];
-    for (int q = 0; q < PDEB_MARGIN_ACC; ++q) hi[q] = (real)(-INFINITY);
-    PdebMarginLoop<0, N + 1, real, STRIDE>::run(w, stab, mh, c0, nmask, and_mask, xor_mask, hi);
-    PDEB_UNROLL
-    for (int span = PDEB_MARGIN_ACC / 2; span >= 1; span >>= 1) {
-        PDEB_UNROLL
-        for (int q = 0; q < span; ++q) hi[q] = hi[q] > hi[q + span] ? hi[q] : hi[q + span];
-    }
-    return hi[0];
+    pdeb_clause_partials<N, real, STRIDE>(w, stab, mh, c0, nmask, and_mask, xor_mask, hi);
+    return pdeb_partials_max<real>(hi);
+}
+
+/*
+ * Interval strictly inside ONE element e (it holds no node, C8): the margin lives on the two interpolated end points
+ *     d(xi) = d_e + xi (d_{e+1} - d_e).
+ * The masked loop itself delivers the two RAW node margins: with the mask {e, e+1} and the identity sign treatment,
+ * consecutive nodes fall into different partial accumulators, hi[e % ACC] = d_e and hi[(e+1) % ACC] = d_{e+1}.
+ * So the common case of the end-point rule costs a handful of selects after the loop every lane runs anyway,
+ * instead of a copy of the state to local memory (pdeb_endpoint_gmax below, kept for region_rule 1).
+ */
+template <typename real>
+PDEB_HD real pdeb_pick4(const real* hi, uint32_t q) {
+    static_assert(PDEB_MARGIN_ACC == 4, "pdeb_pick4 selects among four partial accumulators");
+    const real lo2 = (q & 1u) ? hi[1] : hi[0], hi2 = (q & 1u) ? hi[3] : hi[2];
+    return (q & 2u) ? hi2 : lo2;
+}
+template <typename real>
+PDEB_HD real pdeb_inelement_gmax(const real* hi, uint32_t e, real xi0, real xi1, uint32_t and_mask, uint32_t xor_mask) {
+    const real de = pdeb_pick4<real>(hi, e), df = pdeb_pick4<real>(hi, e + 1u);
+    const real dd = df - de;
+    const real g0 = pdeb_signop(fma(xi0, dd, de), and_mask, xor_mask);
+    const real g1 = pdeb_signop(fma(xi1, dd, de), and_mask, xor_mask);
+    real g = (real)(-INFINITY);
+    if (g0 > g) g = g0;
+    if (g1 > g) g = g1;
+    return g;
 }
 
 /*
@@ -727,8 +773,20 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
             slots.R(j, 4) = (real)cd.xi[1];
             slots.W(j, 0) = (uint32_t)cd.klo;
             slots.W(j, 1) = (uint32_t)cd.khi;
-            slots.W(j, 2) = cd.nmask;
-            slots.W(j, 3) = cd.info;
+            uint32_t nm = cd.nmask, info = cd.info;
+#ifndef PDEB_NO_INEL   /* A/B switch of tools/variant_bench.py */
+            if ((info & 8u) && nm == 0u && ((info >> 4) & 31u) == ((info >> 9) & 31u))
+#else
+            if (false)
+#endif
+            {
+                /* interval inside one element: the masked loop extracts the two node margins (pdeb_inelement_gmax) */
+                const uint32_t e = (info >> 4) & 31u;
+                nm = (1u << e) | (1u << (e + 1u));
+                info = (info & ~8u) | (1u << 14);
+            }
+            slots.W(j, 2) = nm;
+            slots.W(j, 3) = info;
             const int32_t a1 = cd.khi;
             if (a1 > k_end) k_end = a1;
         }
@@ -768,7 +826,13 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
             const uint32_t rel = info & 3u;
             const uint32_t and_mask = (rel == PDEB_REL_EQ) ? 0x7fffffffu : 0xffffffffu;
             const uint32_t xor_mask = (rel == PDEB_REL_GT) ? 0x80000000u : 0u;
-            real gmax = pdeb_clause_gmax<N, real, STRIDE>(tr.w, tr.stab, mh, c0, nm, and_mask, xor_mask);
+            const bool inel = (info >> 14) & 1u;     /* raw node margins of one element wanted: identity sign treatment */
+            real hi[PDEB_MARGIN_ACC];
+            pdeb_clause_partials<N, real, STRIDE>(tr.w, tr.stab, mh, c0, nm, inel ? 0xffffffffu : and_mask, inel ? 0u : xor_mask, hi);
+            real gmax = pdeb_partials_max<real>(hi);
+            if (PDEB_ANY(inel)) {
+                if (inel) gmax = pdeb_inelement_gmax<real>(hi, (info >> 4) & 31u, slots.R(j, 3), slots.R(j, 4), and_mask, xor_mask);
+            }
             if (PDEB_ANY(has && (info & 8u))) {
                 if (has && (info & 8u)) {
                     const real ge = pdeb_endpoint_gmax<N, real, STRIDE>(tr.w, tr.stab, mh, c0, info, slots.R(j, 3), slots.R(j, 4),

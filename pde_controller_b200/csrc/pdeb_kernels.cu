@@ -39,8 +39,8 @@ pdeb_reg_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant__ 
 }
 
 /*
- * Plan: order the samples so that every warp gets trajectories of the same kernel variant and
- * (nearly) the same number of time steps, longest first.  Three tiny kernels: keys + histogram,
+ * Plan: order the samples so that every warp gets trajectories of the same kernel variant, (nearly) the same
+ * number of time steps, longest first, and windows that open at about the same point of the run.  Three tiny kernels: keys + histogram,
  * exclusive scan of the PDEB_PLAN_BINS bins, scatter.  Samples no variant of this build covers
  * are flagged here (status BADPARAM, robustness -100), never dropped silently.
  */
@@ -50,21 +50,39 @@ __device__ __forceinline__ int pdeb_plan_key(const PdebDevBatch& b, const PdebCo
     if (v < 0) return -1;
     const double T = b.T[s], dt = b.dt[s];
     int64_t S = 1;
+    int sub = 0;
     if (T > 0 && dt > 0 && isfinite(T) && isfinite(dt)) {
         S = pdeb_step_count(T, dt, cv.steps_rule);
         /* the kernels stop at the last observed step: order by that */
         const int np = b.n_pred[s];
-        double last = 0.0;
+        double last = 0.0, first = 4.0e9;
         for (int j = 0; j < np && j < b.pmax; ++j) {
             const double q = b.pred_thi[(int64_t)j * b.stride + s] / dt;
             const double a1 = (cv.window_rule == 1) ? trunc(q) : floor(q + PDEB_EPS);
             if (a1 > last) last = a1;
+            const double p = b.pred_tlo[(int64_t)j * b.stride + s] / dt;
+            const double a0 = (cv.window_rule == 1) ? trunc(p) : ceil(p - PDEB_EPS);
+            if (a0 < first) first = a0;
         }
         if (last < (double)S) S = (int64_t)last;
         if (S < 1) S = 1;
+        /* second key: where in the run the first window opens.  A warp runs a clause pass in every step in which ANY
+         * of its lanes has an open window, so lanes whose windows open together share their idle prefix. */
+        if (first > 0.0) {
+            const double f = first * PDEB_PLAN_FBINS / ((double)S + 1.0);
+            sub = (f >= (double)(PDEB_PLAN_FBINS - 1)) ? PDEB_PLAN_FBINS - 1 : (int)f;
+        }
     }
-    if (S > PDEB_PLAN_SBINS - 1) S = PDEB_PLAN_SBINS - 1;
-    return v * PDEB_PLAN_SBINS + (PDEB_PLAN_SBINS - 1 - (int)S);     /* descending in S inside a variant */
+    /* first key: steps in buckets, descending inside a variant (longest first).  Half of the buckets are
+     * PDEB_PLAN_SWIDTH steps wide, the next quarters 8x and 512x that (then one bucket for everything longer) */
+    constexpr int64_t H = PDEB_PLAN_SBUCKETS / 2, Q = PDEB_PLAN_SBUCKETS / 4, W = PDEB_PLAN_SWIDTH;
+    int64_t sb = S / W;
+    if (sb >= H) {
+        sb = H + (S - H * W) / (8 * W);
+        if (sb >= H + Q) sb = H + Q + (S - H * W - Q * 8 * W) / (512 * W);
+    }
+    if (sb > PDEB_PLAN_SBUCKETS - 1) sb = PDEB_PLAN_SBUCKETS - 1;
+    return v * PDEB_PLAN_SBINS + (PDEB_PLAN_SBUCKETS - 1 - (int)sb) * PDEB_PLAN_FBINS + sub;
 }
 
 __global__ void pdeb_plan_keys_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant__ PdebConventions cv,

@@ -8,18 +8,13 @@
 
 #ifndef PDEB_REG_THREADS
 #define PDEB_REG_THREADS 128
-
-/* sets the thread-local message pdeb_last_error() returns (pdeb_api.cu) */
-void pdeb_set_last_error(const char* msg);
-
 #endif
 #ifndef PDEB_REG_MINBLOCKS
 #define PDEB_REG_MINBLOCKS 2   /* resident blocks per SM the register family is compiled for */
+#endif
 
 /* sets the thread-local message pdeb_last_error() returns (pdeb_api.cu) */
 void pdeb_set_last_error(const char* msg);
-
-#endif
 
 /*
  * Kernel variants.  0: heat N=30 and 1: wave N=20 are the register family (thread per trajectory);
@@ -43,7 +38,18 @@ PDEB_HD int pdeb_variant_of(int kind, int n_elem) {
     return -1;
 }
 
-#define PDEB_PLAN_SBINS 4096                                    /* step-count bins per variant */
+/*
+ * Plan bins of one variant: PDEB_PLAN_SBUCKETS buckets of PDEB_PLAN_SWIDTH steps (longest first), each split into
+ * PDEB_PLAN_FBINS classes of "where in the run the first window opens" (pdeb_plan_key).
+ */
+#define PDEB_PLAN_SBINS 4096
+#ifndef PDEB_PLAN_FBINS
+#define PDEB_PLAN_FBINS 16
+#endif
+#ifndef PDEB_PLAN_SWIDTH
+#define PDEB_PLAN_SWIDTH 8
+#endif
+#define PDEB_PLAN_SBUCKETS (PDEB_PLAN_SBINS / PDEB_PLAN_FBINS)
 #define PDEB_PLAN_BINS (PDEB_VARIANT_SLOTS * PDEB_PLAN_SBINS)   /* multiple of 1024 */
 
 cudaError_t pdeb_launch_chunk_heat(int R, const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out,
@@ -66,9 +72,5 @@ int pdeb_plan(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut
 /* enqueue the compute kernels of every non-empty variant; returns 0 or a cudaError_t value */
 int pdeb_launch_all(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out, const PdebPlanBuffers& pb,
                     const int32_t* vstart_count_host, int precision, cudaStream_t stream, int* launches);
-
-
-/* sets the thread-local message pdeb_last_error() returns (pdeb_api.cu) */
-void pdeb_set_last_error(const char* msg);
 
 #endif
