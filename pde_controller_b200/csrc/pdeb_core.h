@@ -202,6 +202,90 @@ struct PdebPwl {
     }
 };
 
+/*
+ * The same input for the register family, with the NEXT knot staged in shared memory.
+ * In that family the lanes of a warp cross their knots at different steps, so a warp runs the crossing code in about
+ * half of its steps, and a knot fetched into a register there stalls the whole warp for a global-memory latency: the
+ * value has to be merged into the register the loop carries, which the compiler does with a move that waits for the
+ * load right where it was issued (measured: 7.6 % of the heat kernel in that one stall).  Here the crossing reads the
+ * knot from a per-thread shared-memory slot (two doubles: value, time) and refills the slot with an ASYNCHRONOUS copy
+ * (cp.async, global -> shared, no register destination) that has the ~20 steps until the next crossing to land.
+ * Arithmetic and knot semantics are those of PdebPwl.
+ */
+template <typename real, int STRIDE>
+struct PdebPwlStaged {
+    double t1;            /* end of the current segment (+inf on the last) */
+    real t0, y0, slope;   /* current segment */
+    real y1;              /* value at t1 */
+    int nk, j;            /* j: index of the knot at t1 */
+    double ustep, uT;     /* uniform knots, as in PdebPwl */
+    /* shared, + tid: slot[0] value of knot j+1, slot[STRIDE] its time (explicit knot times only) */
+#if defined(__CUDA_ARCH__)
+    uint32_t slot;        /* shared-window address */
+#else
+    double* slot;
+#endif
+
+    PDEB_HD double knot_time(const double* kt, int q, int64_t stride) const {
+        if (kt) return kt[(int64_t)q * stride];
+        return (q == nk - 1 && nk > 1) ? uT : (double)q * ustep;
+    }
+    /* start the copy of knot q into the slot */
+    PDEB_HD void stage(const double* kt, const double* ky, int q, int64_t stride) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(slot), "l"(ky + (int64_t)q * stride) : "memory");
+        if (kt)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(slot + (uint32_t)(STRIDE * sizeof(double))),
+                         "l"(kt + (int64_t)q * stride) : "memory");
+#else
+        slot[0] = ky[(int64_t)q * stride];
+        if (kt) slot[STRIDE] = kt[(int64_t)q * stride];
+#endif
+    }
+    /* staged value (which = 0) or time (which = 1), once the copy has landed */
+    PDEB_HD double staged(int which) const {
+#if defined(__CUDA_ARCH__)
+        double v;
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(slot + (uint32_t)(which * STRIDE * sizeof(double))) : "memory");
+        return v;
+#else
+        return slot[which * STRIDE];
+#endif
+    }
+    PDEB_HD void init(const double* kt, const double* ky, int nk_, int64_t stride, double T, double* slot_) {
+        nk = nk_; j = 0;
+#if defined(__CUDA_ARCH__)
+        slot = (uint32_t)__cvta_generic_to_shared(slot_);
+#else
+        slot = slot_;
+#endif
+        uT = T; ustep = (nk > 1) ? T / (double)(nk - 1) : 0.0;
+        t0 = 0; slope = 0; y0 = 0; y1 = 0; t1 = INFINITY;
+        if (nk >= 1) { y0 = y1 = (real)ky[0]; t1 = knot_time(kt, 0, stride); }
+        if (nk >= 2) stage(kt, ky, 1, stride);
+    }
+    PDEB_HD real eval(double t, const double* kt, const double* ky, int64_t stride) {
+        while (t >= t1) {
+            t0 = (real)t1; y0 = y1;
+            double tn = INFINITY;
+            real yn = 0;
+            if (j + 1 < nk) {
+                yn = (real)staged(0);
+                tn = kt ? staged(1) : knot_time(nullptr, j + 1, 0);
+            }
+            if (tn < INFINITY) {
+                slope = (real)(((double)yn - (double)y1) * pdeb_rcp(tn - t1));
+                t1 = tn; y1 = yn;
+                ++j;
+                if (j + 1 < nk) stage(kt, ky, j + 1, stride);
+            } else { slope = 0; t1 = INFINITY; }
+        }
+        return fma(slope, (real)(t - (double)t0), y0);
+    }
+};
+#define PDEB_PWL_SLOT_BYTES (2 * sizeof(double))   /* per thread */
+
 struct alignas(16) PdebD2 { double x, y; };
 struct alignas(8) PdebF2 { float x, y; };
 template <typename real> struct PdebVec2;
@@ -697,7 +781,7 @@ PDEB_HD PdebClauseData pdeb_clause_data(double m, double bb, double xlo, double 
 template <int KIND, int N, typename real, int STRIDE>
 PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out, int64_t s,
                           typename PdebVec2<real>::type* table, real* stab, PdebClauseSlots<real, STRIDE> slots, bool live,
-                          real* ctab = nullptr) {
+                          double* pwl_slot, real* ctab = nullptr) {
     /* `live` is false for padding lanes of a partially filled warp: they run the loop with S = 0 */
     const int64_t st = b.stride;
     int status = PDEB_OK;
@@ -712,8 +796,8 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
 #if PDEB_C_SMEM
     tr.ctab = ctab;
 #endif
-    PdebPwl<real> in;
-    in.init(nullptr, nullptr, 0, 0);
+    PdebPwlStaged<real, STRIDE> in;
+    in.init(nullptr, nullptr, 0, 0, 0.0, pwl_slot);
     const double* kt = b.knot_t ? b.knot_t + (live ? s : 0) : nullptr;     /* NULL: uniform knots */
     const double* ky = b.knot_y + (live ? s : 0);
     PDEB_UNROLL
@@ -751,7 +835,7 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
             const double cR = (1.0 - cv.theta) * dt;
             const bool ok = tr.setup(L, x_a, x_b, rho_in, rho_out, E_in, E_out, lumped, cv.material_sampling, cA, cR);
             if (!ok) status = PDEB_ST_NONFINITE;
-            in.init(kt, ky, nk, st, T);
+            in.init(kt, ky, nk, st, T, pwl_slot);
             if (KIND == PDEB_KIND_WAVE && ok) {
                 const double f0 = (double)in.eval(0.0, kt, ky, st);
                 tr.wave_init(h, g0, f0, rho_in, rho_out, E_in, E_out, lumped);

@@ -35,7 +35,11 @@ pdeb_reg_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant__ 
 #if PDEB_C_SMEM
     ctab = stab + (size_t)PDEB_REG_THREADS * N * (KIND == PDEB_KIND_WAVE ? 2 : 1);
 #endif
-    pdeb_run_reg<KIND, N, real, PDEB_REG_THREADS>(b, cv, out, s, table, stab, slots, live, ctab);
+    /* staged knot of the piecewise-linear input: two doubles per thread behind the clause slots (8-byte aligned:
+     * every area before it is a multiple of 8 bytes per thread) */
+    double* pwl_slot = reinterpret_cast<double*>(pdeb_smem + pdeb_table_smem_bytes<real>(PDEB_REG_THREADS, N, KIND) +
+                                                 pdeb_clause_smem_bytes<real>(PDEB_REG_THREADS, b.pmax)) + threadIdx.x;
+    pdeb_run_reg<KIND, N, real, PDEB_REG_THREADS>(b, cv, out, s, table, stab, slots, live, pwl_slot, ctab);
 }
 
 /*
@@ -153,7 +157,8 @@ template <int KIND, int N, typename real>
 static cudaError_t launch_reg(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out,
                               const int32_t* order, int64_t first, int64_t count, cudaStream_t stream) {
     if (count <= 0) return cudaSuccess;
-    const size_t smem = pdeb_table_smem_bytes<real>(PDEB_REG_THREADS, N, KIND) + pdeb_clause_smem_bytes<real>(PDEB_REG_THREADS, b.pmax);
+    const size_t smem = pdeb_table_smem_bytes<real>(PDEB_REG_THREADS, N, KIND) + pdeb_clause_smem_bytes<real>(PDEB_REG_THREADS, b.pmax) +
+                        PDEB_PWL_SLOT_BYTES * PDEB_REG_THREADS;
     auto kern = pdeb_reg_kernel<KIND, N, real>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

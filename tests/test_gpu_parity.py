@@ -84,6 +84,44 @@ def test_edge_cases(oracle_lib):
         assert got["robustness"][s] == pytest.approx(tree[-1], rel=1e-12, abs=1e-10)
 
 
+def _stress_batch(wl, n, seed):
+    """Overlapping windows (several clauses open in the same step), intervals strictly inside one element for most
+    lanes (the in-element end-point rule), nested and identical windows, controls with many short segments."""
+    b = synth.make_batch(n, wl, seed=seed)
+    rng = np.random.default_rng(seed)
+    T = b.T
+    for j in range(b.pmax):
+        u = np.sort(rng.uniform(0, 1, (2, n)), axis=0)
+        b.pred_tlo[j] = np.round(u[0] * T, 4)
+        b.pred_thi[j] = np.round(u[1] * T, 4)
+    b.pred_tlo[1, : n // 8] = b.pred_tlo[0, : n // 8]          # identical windows
+    b.pred_thi[1, : n // 8] = b.pred_thi[0, : n // 8]
+    h = b.L / b.n_elem
+    e = rng.integers(0, b.n_elem.max(), (b.pmax, n))
+    inside = rng.uniform(0, 1, (b.pmax, n)) < 0.6
+    lo = (e + rng.uniform(0.05, 0.45, e.shape)) * h
+    hi = (e + rng.uniform(0.55, 0.95, e.shape)) * h
+    b.pred_xlo[...] = np.where(inside, lo, b.pred_xlo)
+    b.pred_xhi[...] = np.where(inside, hi, b.pred_xhi)
+    live = np.arange(b.pmax)[:, None] < b.n_pred
+    for name in ("pred_xlo", "pred_xhi", "pred_tlo", "pred_thi"):
+        getattr(b, name)[...] = np.where(live, getattr(b, name), 0.0)
+    # every knot slot in use, non-uniform times
+    K = b.kmax
+    b.n_knots[:] = K
+    t = np.sort(rng.uniform(0.02, 0.98, (K, n)), axis=0) * T
+    t[0] = 0.0
+    b.knot_t[...] = t
+    b.knot_y[...] = rng.uniform(-1, 1, (K, n)) * (1e6 if wl == "heat" else 5e3)
+    return b
+
+
+@pytest.mark.parametrize("wl", ["heat", "wave"])
+@pytest.mark.parametrize("kw", [{}, dict(region_rule=1)])
+def test_overlapping_windows_in_element_intervals_dense_knots(oracle_lib, wl, kw):
+    check(_stress_batch(wl, 4096, 31), oracle_lib, conv=default_conventions(**kw))
+
+
 def test_empty_and_ragged_batches(oracle_lib):
     e = ProblemBatch(0, 4, 2)
     out = native.evaluate_batch(e)

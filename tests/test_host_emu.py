@@ -62,3 +62,17 @@ def test_device_code_fp32_mode(emu, oracle_lib):
         rob, st, _ = run_emu(emu, b, conv, 32)
         assert (st == ref_st).all()
         assert rel_err(rob, ref, b).max() <= tol
+
+
+@pytest.mark.parametrize("wl", ["heat", "wave"])
+@pytest.mark.parametrize("kw", [{}, dict(region_rule=1)])
+def test_device_code_overlapping_windows_in_element_intervals(emu, oracle_lib, wl, kw):
+    """Same stress set as the GPU test: several clauses open at once, intervals inside one element, dense knots."""
+    from parity import rel_err
+    from test_gpu_parity import _stress_batch
+    conv = default_conventions(**kw)
+    b = _stress_batch(wl, 256, 31)
+    ref, ref_st, ref_cl = oracle_lib.eval_batch(b, conv, want_clauses=True)
+    rob, st, cl = run_emu(emu, b, conv)
+    assert (st == ref_st).all()
+    assert rel_err(rob, ref, b).max() <= TOL64
