@@ -374,16 +374,18 @@ def main():
 
     # ---- end to end through the public API with HOST buffers ("e2e") ----
     # every step: the whole batch goes pinned host -> H2D -> plan -> kernels -> D2H (robustness + status) as
-    # args.e2e_block-sample blocks double-buffered on two streams (native.BlockPipeline); run() returns after the
+    # args.e2e_block-sample blocks, E2E_DEPTH generations of buffers on as many streams (native.BlockPipeline); run() returns after the
     # last byte of the results is back in host memory
-    pipe = native.BlockPipeline(src.n, src.kmax, src.pmax, src.tmax, block=args.e2e_block, device=dev, depth=2,
+    E2E_DEPTH = 3
+    pipe = native.BlockPipeline(src.n, src.kmax, src.pmax, src.tmax, block=args.e2e_block, device=dev, depth=E2E_DEPTH,
                                 uniform_knots=uk)
-    for g in range(2):
+    for g in range(E2E_DEPTH):
         pipe.fill(src, g)
 
     def e2e_loop(depth):
-        """K steps; depth 1 = wait for every step before the next, depth 2 = step i+1 is enqueued while step i runs
-        (its buffers are the other generation), which is how a sweep over many batches uses the API."""
+        """K steps; depth 1 = wait for every step before the next, depth d = steps i+1 .. i+d-1 are enqueued while step i
+        runs (their buffers are the other generations), which is how a sweep over many batches uses the API: the
+        host->device copy engine never waits for the host."""
         barrier()
         t0 = time.perf_counter()
         for i in range(args.steps):
@@ -402,10 +404,10 @@ def main():
     for _ in range(3):
         pipe.run(args.precision)
     e2e_sync = e2e_loop(1)
-    e2e_value = e2e_loop(2)
+    e2e_value = e2e_loop(E2E_DEPTH)
     res.eval(args.precision, stream=stream)
     res.fetch(stream=stream, out=out_host)
-    if not (np.array_equal(pipe.robustness[0], out_host["robustness"]) and np.array_equal(pipe.robustness[1], out_host["robustness"])):
+    if not all(np.array_equal(pipe.robustness[g], out_host["robustness"]) for g in range(E2E_DEPTH)):
         raise SystemExit("bench: pipelined end-to-end results differ from the resident evaluation")
     h2d_bytes = pipe.h2d_bytes
     pipe.close()
@@ -427,7 +429,7 @@ def main():
             "dtype": "f64" if args.precision == 64 else "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_TEXT[args.workload], "batch_per_gpu": args.batch, "global_batch": total,
                        "precision": args.precision, "seed": args.seed, "l2": "flushed (256 MiB write) between timed steps",
-                       "gather": bool(rob_t is not None), "failed_samples": n_fail, "knots": "uniform (formed on device)" if uk else "explicit", "e2e_block": args.e2e_block, "e2e_pipeline_depth": 2, "e2e_value_depth1": e2e_sync,
+                       "gather": bool(rob_t is not None), "failed_samples": n_fail, "knots": "uniform (formed on device)" if uk else "explicit", "e2e_block": args.e2e_block, "e2e_pipeline_depth": E2E_DEPTH, "e2e_value_depth1": e2e_sync,
                        "wall_s_timed_region": wall1 - wall0},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(12 * host.n)},

@@ -245,7 +245,7 @@ class ResidentBatch:
 
 
 class BlockPipeline:
-    """Streams batches through the GPU as fixed-size blocks, double-buffered on two streams.
+    """Streams batches through the GPU as fixed-size blocks, multi-buffered on `max(2, depth)` streams.
 
     Every block has its own page-locked host slab (one H2D copy), its own resident image and its own slice of
     page-locked result arrays; the upload of one block overlaps the kernels of the previous one and the download
@@ -259,7 +259,9 @@ class BlockPipeline:
         self._L = lib()
         self.n, self.device, self.depth = int(n), device, int(depth)
         self.bounds = [(lo, min(lo + block, n)) for lo in range(0, n, block)]
-        self.streams = [self._L.pdeb_stream_create(device), self._L.pdeb_stream_create(device)]
+        # one stream per generation (at least two: the blocks of one generation alternate between streams), so that
+        # waiting for generation g never waits for work submitted after it
+        self.streams = [self._L.pdeb_stream_create(device) for _ in range(max(2, self.depth))]
         if not all(self.streams):
             raise NativeError("stream creation failed")
         self.blocks, self.residents, self.robustness, self.status, self._outs, self._pins = [], [], [], [], [], []
@@ -275,7 +277,8 @@ class BlockPipeline:
                                for lo, hi in self.bounds])
             res = []
             for b in blks:
-                res.append((ResidentBatch(b, device=device, stream=self.streams[slot & 1]), slot & 1))
+                si = slot % len(self.streams)
+                res.append((ResidentBatch(b, device=device, stream=self.streams[si]), si))
                 slot += 1
             self.residents.append(res)
         self._sync_all()
