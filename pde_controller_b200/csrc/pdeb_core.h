@@ -39,8 +39,10 @@
 
 #if defined(__CUDA_ARCH__)
 #define PDEB_ANY(x) __any_sync(0xffffffffu, (x))
+#define PDEB_WARP_OR(x) __reduce_or_sync(0xffffffffu, (x))
 #else
 #define PDEB_ANY(x) (x)
+#define PDEB_WARP_OR(x) (x)
 #endif
 
 #define PDEB_EPS 1e-9
@@ -78,37 +80,40 @@ struct PdebDevOut {
 };
 
 /*
- * Per-thread clause slots in shared memory, laid out [clause][field][thread] in two areas
- * (reals, then 32-bit words) so that a thread needs only two base pointers:
- *   reals: 0 mh = m*h (profile slope per node index), 1 c0 = b - g0, 2 acc (running temporal min / max),
- *          3, 4 xi of the two interval end points inside their elements (only read when info bit 3 is set)
- *   words: 0 klo, 1 khi (window steps), 2 nmask (bit i: node i inside [x_lo,x_hi]),
- *          3 info (bits 0-1 rel, bit 2 top, bit 3 needs the interpolated end points (general form),
- *                  bits 4-8 / 9-13 element of end point 0 / 1, bit 14 interval inside ONE element:
- *                  nmask then holds that element's two nodes)
+ * Per-thread clause slots in shared memory: 7 cells of 8 bytes per clause, laid out [clause][cell][thread], so that
+ * ONE per-thread base serves every field and the cells of the clause a lane is working on are base + immediate:
+ *   0 mh = m*h (profile slope per node index)     1 c0 = b - g0
+ *   2 A  running maximum over the window steps of (G: gmax, F: -gmax), gmax = max over the nodes of the
+ *        relation-transformed margin; turned into the clause value (G: -A, F: A, + eq_eps for the band rule) once,
+ *        after the time loop
+ *   3, 4 xi of the two interval end points inside their elements (interpolated end points only)
+ *   5 { nmask (bit i: node i inside [x_lo,x_hi]), info }      6 { klo, khi } window steps
+ *   info: bits 0-1 rel, bit 2 top, bit 3 needs the interpolated end points (general form),
+ *         bits 4-8 / 9-13 element of end point 0 / 1, bit 14 interval inside ONE element (nmask then holds that
+ *         element's two nodes)
+ * Reals are stored as `real` at the start of their cell (the FP32 build leaves the upper halves unused).
  */
-#define PDEB_SLOT_REALS 5
-#define PDEB_SLOT_WORDS 4
+#define PDEB_SLOT_CELLS 7
+struct alignas(8) PdebU2 { uint32_t x, y; };
 template <typename real, int STRIDE>
 struct PdebClauseSlots {
-    real* rbase;       /* + tid */
-    uint32_t* wbase;   /* + tid */
-    /* STRIDE = threads per block, a compile-time constant so that every field is base + immediate offset */
-    PDEB_HD real& R(int p, int f) const { return rbase[(p * PDEB_SLOT_REALS + f) * STRIDE]; }
-    PDEB_HD uint32_t& W(int p, int f) const { return wbase[(p * PDEB_SLOT_WORDS + f) * STRIDE]; }
+    unsigned char* base;   /* + tid * 8 */
+    PDEB_HD unsigned char* cell(int p, int f) const { return base + (size_t)((p * PDEB_SLOT_CELLS + f) * STRIDE) * 8; }
+    PDEB_HD real& R(int p, int f) const { return *reinterpret_cast<real*>(cell(p, f)); }
+    PDEB_HD PdebU2& NI(int p) const { return *reinterpret_cast<PdebU2*>(cell(p, 5)); }     /* { nmask, info } */
+    PDEB_HD PdebU2& WIN(int p) const { return *reinterpret_cast<PdebU2*>(cell(p, 6)); }    /* { klo, khi } */
 };
 
 template <typename real>
 PDEB_HD size_t pdeb_clause_smem_bytes(int threads, int pmax) {
-    return (size_t)threads * pmax * (PDEB_SLOT_REALS * sizeof(real) + PDEB_SLOT_WORDS * sizeof(uint32_t));
+    return (size_t)threads * pmax * PDEB_SLOT_CELLS * 8;
 }
 
 template <typename real, int STRIDE>
 PDEB_HD PdebClauseSlots<real, STRIDE> pdeb_clause_slots(void* base, int pmax, int tid) {
     PdebClauseSlots<real, STRIDE> s;
-    real* r = (real*)base;
-    s.rbase = r + tid;
-    s.wbase = (uint32_t*)(r + (size_t)PDEB_SLOT_REALS * STRIDE * pmax) + tid;
+    (void)pmax;
+    s.base = (unsigned char*)base + (size_t)tid * 8;
     return s;
 }
 
@@ -852,11 +857,12 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
                                                           b.pred_top[(int64_t)j * st + s], L, h, dt, g0, S, cv);
             slots.R(j, 0) = (real)cd.mh;
             slots.R(j, 1) = (real)cd.c0;
-            slots.R(j, 2) = (((cd.info >> 2) & 1u) == PDEB_TOP_G) ? (real)INFINITY : (real)(-INFINITY);
+            slots.R(j, 2) = (real)(-INFINITY);
             slots.R(j, 3) = (real)cd.xi[0];
             slots.R(j, 4) = (real)cd.xi[1];
-            slots.W(j, 0) = (uint32_t)cd.klo;
-            slots.W(j, 1) = (uint32_t)cd.khi;
+            PdebU2 win;
+            win.x = (uint32_t)cd.klo; win.y = (uint32_t)cd.khi;
+            slots.WIN(j) = win;
             uint32_t nm = cd.nmask, info = cd.info;
 #ifndef PDEB_NO_INEL   /* A/B switch of tools/variant_bench.py */
             if ((info & 8u) && nm == 0u && ((info >> 4) & 31u) == ((info >> 9) & 31u))
@@ -869,8 +875,9 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
                 nm = (1u << e) | (1u << (e + 1u));
                 info = (info & ~8u) | (1u << 14);
             }
-            slots.W(j, 2) = nm;
-            slots.W(j, 3) = info;
+            PdebU2 ni;
+            ni.x = nm; ni.y = info;
+            slots.NI(j) = ni;
             const int32_t a1 = cd.khi;
             if (a1 > k_end) k_end = a1;
         }
@@ -878,57 +885,90 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
     }
 
     real f_prev = in.eval(0.0, kt, ky, st);
-    int32_t next_ev = 0;      /* next step at which the set of open windows may change */
+    int32_t next_ev = 0;      /* next step at which the set of open windows may change (every window closes by S32 + 1) */
     uint32_t open = 0;        /* bit j: step k is inside clause j's window */
+    int cur = 0;              /* lowest open clause (0 when none is open) */
+    /* what this lane needs from the pass of the current step: bit 0 a clause is open, bit 1 more than one is,
+     * bit 2 / 3 the clause `cur` takes its end points from one element / in the general interpolated form.
+     * It changes at window events only; each step ONE warp-wide OR of it decides every branch of the pass. */
+    uint32_t flags = 0;
+    const real eq_shift = (cv.eq_rule == 1) ? (real)cv.eq_eps : (real)0;
 
     for (int32_t k = 0;; ++k) {
-        const bool on = (k <= S32);
-        if (on && k == next_ev) {
+        if (k == next_ev) {
             open = 0;
             next_ev = 0x7fffffff;
             for (int j = 0; j < np; ++j) {
-                const int32_t a0 = (int32_t)slots.W(j, 0), a1 = (int32_t)slots.W(j, 1);
+                const PdebU2 win = slots.WIN(j);
+                const int32_t a0 = (int32_t)win.x, a1 = (int32_t)win.y;
                 if (k >= a0 && k <= a1) { open |= (1u << j); if (a1 + 1 < next_ev) next_ev = a1 + 1; }
                 else if (k < a0 && a0 < next_ev) next_ev = a0;
             }
+            cur = open ? __builtin_ffs((int)open) - 1 : 0;
+            flags = 0;
+            if (open) {
+                const uint32_t info = slots.NI(cur).y;
+                flags = 1u | ((open & (open - 1u)) ? 2u : 0u) | (((info >> 14) & 1u) << 2) | (info & 8u);
+            }
         }
         /* ---- (1) reduce the open clauses on the state of step k ---- */
-        uint32_t todo = on ? open : 0u;
-        while (PDEB_ANY(todo != 0u)) {
-            const bool has = todo != 0u;
-            int j = 0;
-            if (has) { j = __builtin_ffs((int)todo) - 1; todo &= todo - 1u; }
-            real mh = 0, c0 = 0, acc = 0;
-            uint32_t nm = 0, info = 0;
-            if (has) {
-                mh = slots.R(j, 0);
-                c0 = slots.R(j, 1);
-                acc = slots.R(j, 2);
-                nm = slots.W(j, 2);
-                info = slots.W(j, 3);
-            }
+        const uint32_t wf = PDEB_WARP_OR(flags);
+        if (wf & 1u) {
+            /* every lane runs the pass on its clause `cur`; a lane without an open clause does so with an empty mask */
+            const bool has = flags & 1u;
+            const real mh = slots.R(cur, 0), c0 = slots.R(cur, 1);
+            const PdebU2 ni = slots.NI(cur);
+            const uint32_t nm = has ? ni.x : 0u, info = ni.y;
             const uint32_t rel = info & 3u;
             const uint32_t and_mask = (rel == PDEB_REL_EQ) ? 0x7fffffffu : 0xffffffffu;
             const uint32_t xor_mask = (rel == PDEB_REL_GT) ? 0x80000000u : 0u;
-            const bool inel = (info >> 14) & 1u;     /* raw node margins of one element wanted: identity sign treatment */
+            const bool inel = flags & 4u;            /* raw node margins of one element wanted: identity sign treatment */
             real hi[PDEB_MARGIN_ACC];
             pdeb_clause_partials<N, real, STRIDE>(tr.w, tr.stab, mh, c0, nm, inel ? 0xffffffffu : and_mask, inel ? 0u : xor_mask, hi);
             real gmax = pdeb_partials_max<real>(hi);
-            if (PDEB_ANY(inel)) {
-                if (inel) gmax = pdeb_inelement_gmax<real>(hi, (info >> 4) & 31u, slots.R(j, 3), slots.R(j, 4), and_mask, xor_mask);
+            if (wf & 4u) {
+                if (inel) gmax = pdeb_inelement_gmax<real>(hi, (info >> 4) & 31u, slots.R(cur, 3), slots.R(cur, 4), and_mask, xor_mask);
             }
-            if (PDEB_ANY(has && (info & 8u))) {
-                if (has && (info & 8u)) {
-                    const real ge = pdeb_endpoint_gmax<N, real, STRIDE>(tr.w, tr.stab, mh, c0, info, slots.R(j, 3), slots.R(j, 4),
+            if (wf & 8u) {
+                if (flags & 8u) {
+                    const real ge = pdeb_endpoint_gmax<N, real, STRIDE>(tr.w, tr.stab, mh, c0, info, slots.R(cur, 3), slots.R(cur, 4),
                                                                         and_mask, xor_mask);
                     if (ge > gmax) gmax = ge;
                 }
             }
-            /* ">" min d = -max(-d); "<" min(-d) = -max(d); "=" -max|d| (+ eq_eps for the band rule, 0 otherwise) */
-            const real r = (rel == PDEB_REL_EQ) ? ((cv.eq_rule == 1) ? (real)cv.eq_eps : (real)0) - gmax : -gmax;
-            if (has) {
-                const bool take = (((info >> 2) & 1u) == PDEB_TOP_G) ? (r < acc) : (r > acc);
-                if (take || r != r) slots.R(j, 2) = r;
+            /* G: min over steps of -gmax = -(max gmax); F: max over steps of -gmax: one running max either way */
+            const real v = (((info >> 2) & 1u) == PDEB_TOP_G) ? gmax : -gmax;
+            if (has && v > slots.R(cur, 2)) slots.R(cur, 2) = v;
+            if (wf & 2u) {
+                /* lanes with several open windows: their remaining clauses, one pass per clause */
+                uint32_t todo = (flags & 2u) ? (open & (open - 1u)) : 0u;
+                while (PDEB_ANY(todo != 0u)) {
+                    const bool has2 = todo != 0u;
+                    int j = 0;
+                    if (has2) { j = __builtin_ffs((int)todo) - 1; todo &= todo - 1u; }
+                    const real mh2 = slots.R(j, 0), c02 = slots.R(j, 1);
+                    const PdebU2 ni2 = slots.NI(j);
+                    const uint32_t nm2 = has2 ? ni2.x : 0u, info2 = ni2.y;
+                    const uint32_t rel2 = info2 & 3u;
+                    const uint32_t am2 = (rel2 == PDEB_REL_EQ) ? 0x7fffffffu : 0xffffffffu;
+                    const uint32_t xm2 = (rel2 == PDEB_REL_GT) ? 0x80000000u : 0u;
+                    const bool inel2 = has2 && ((info2 >> 14) & 1u);
+                    real hj[PDEB_MARGIN_ACC];
+                    pdeb_clause_partials<N, real, STRIDE>(tr.w, tr.stab, mh2, c02, nm2, inel2 ? 0xffffffffu : am2, inel2 ? 0u : xm2, hj);
+                    real g2 = pdeb_partials_max<real>(hj);
+                    if (PDEB_ANY(inel2)) {
+                        if (inel2) g2 = pdeb_inelement_gmax<real>(hj, (info2 >> 4) & 31u, slots.R(j, 3), slots.R(j, 4), am2, xm2);
+                    }
+                    if (PDEB_ANY(has2 && (info2 & 8u))) {
+                        if (has2 && (info2 & 8u)) {
+                            const real ge = pdeb_endpoint_gmax<N, real, STRIDE>(tr.w, tr.stab, mh2, c02, info2, slots.R(j, 3),
+                                                                                slots.R(j, 4), am2, xm2);
+                            if (ge > g2) g2 = ge;
+                        }
+                    }
+                    const real v2 = (((info2 >> 2) & 1u) == PDEB_TOP_G) ? g2 : -g2;
+                    if (has2 && v2 > slots.R(j, 2)) slots.R(j, 2) = v2;
+                }
             }
         }
         if (!PDEB_ANY(k < S32)) break;
@@ -966,6 +1006,13 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
     }
 
     if (!live) return;
+    /* ---- clause values from the running maxima: G -A, F A; "=" under the band rule adds eq_eps ---- */
+    for (int j = 0; j < np; ++j) {
+        const uint32_t info = slots.NI(j).y;
+        const real A = slots.R(j, 2);
+        const real r = (((info >> 2) & 1u) == PDEB_TOP_G) ? -A : A;
+        slots.R(j, 2) = ((info & 3u) == PDEB_REL_EQ) ? r + eq_shift : r;
+    }
     /* ---- formula tree and outputs ---- */
     double val[PDEB_MAX_TREE];
     double rob = PDEB_FAILED_ROBUSTNESS;
