@@ -40,9 +40,11 @@
 #if defined(__CUDA_ARCH__)
 #define PDEB_ANY(x) __any_sync(0xffffffffu, (x))
 #define PDEB_WARP_OR(x) __reduce_or_sync(0xffffffffu, (x))
+#define PDEB_WARP_MAX(x) __reduce_max_sync(0xffffffffu, (x))
 #else
 #define PDEB_ANY(x) (x)
 #define PDEB_WARP_OR(x) (x)
+#define PDEB_WARP_MAX(x) (x)
 #endif
 
 #define PDEB_EPS 1e-9
@@ -894,7 +896,8 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
     uint32_t flags = 0;
     const real eq_shift = (cv.eq_rule == 1) ? (real)cv.eq_eps : (real)0;
 
-    for (int32_t k = 0;; ++k) {
+    /* window events of step k: which clauses are open from here on, and what the pass needs to know about them */
+    auto window_events = [&](int32_t k) {
         if (k == next_ev) {
             open = 0;
             next_ev = 0x7fffffff;
@@ -911,12 +914,17 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
                 flags = 1u | ((open & (open - 1u)) ? 2u : 0u) | (((info >> 14) & 1u) << 2) | (info & 8u);
             }
         }
+    };
+    const int32_t Smax = PDEB_WARP_MAX(S32);     /* the warp steps until its longest lane is done */
+    window_events(0);
+    uint32_t wf = PDEB_WARP_OR(flags);
+
+    for (int32_t k = 0;; ++k) {
         /* ---- (1) reduce the open clauses on the state of step k ---- */
-        const uint32_t wf = PDEB_WARP_OR(flags);
         if (wf & 1u) {
             /* every lane runs the pass on its clause `cur`; a lane without an open clause does so with an empty mask */
             const bool has = flags & 1u;
-            const real mh = slots.R(cur, 0), c0 = slots.R(cur, 1);
+            const real mh = slots.R(cur, 0), c0 = slots.R(cur, 1), A = slots.R(cur, 2);
             const PdebU2 ni = slots.NI(cur);
             const uint32_t nm = has ? ni.x : 0u, info = ni.y;
             const uint32_t rel = info & 3u;
@@ -938,7 +946,7 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
             }
             /* G: min over steps of -gmax = -(max gmax); F: max over steps of -gmax: one running max either way */
             const real v = (((info >> 2) & 1u) == PDEB_TOP_G) ? gmax : -gmax;
-            if (has && v > slots.R(cur, 2)) slots.R(cur, 2) = v;
+            if (has && v > A) slots.R(cur, 2) = v;
             if (wf & 2u) {
                 /* lanes with several open windows: their remaining clauses, one pass per clause */
                 uint32_t todo = (flags & 2u) ? (open & (open - 1u)) : 0u;
@@ -971,7 +979,10 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
                 }
             }
         }
-        if (!PDEB_ANY(k < S32)) break;
+        if (k >= Smax) break;
+        /* the windows of step k+1 are settled before the solve, which hides the latency of the warp-wide OR */
+        window_events(k + 1);
+        wf = PDEB_WARP_OR(flags);
         /* ---- (2) advance to step k+1 (lanes that are done keep stepping; nobody looks at them) ---- */
         {
             const real f_next = in.eval((double)(k + 1) * dt, kt, ky, st);
