@@ -401,8 +401,8 @@ def main():
             dist.all_reduce(dt_, op=dist.ReduceOp.MAX)
         return total * args.steps / float(dt_.item())
 
-    for _ in range(3):
-        pipe.run(args.precision)
+    for g in range(E2E_DEPTH):                    # every generation of buffers once (also: results valid for the check below)
+        pipe.run(args.precision, gen=g)
     e2e_sync = e2e_loop(1)
     e2e_value = e2e_loop(E2E_DEPTH)
     res.eval(args.precision, stream=stream)
