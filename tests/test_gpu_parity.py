@@ -122,6 +122,56 @@ def test_overlapping_windows_in_element_intervals_dense_knots(oracle_lib, wl, kw
     check(_stress_batch(wl, 4096, 31), oracle_lib, conv=default_conventions(**kw))
 
 
+def _wide_batch(wl, n, seed, pmax=8, n_elem=None):
+    """Up to PDEB_MAX_PRED = 8 clauses per sample with random overlapping windows and a random and/or tree."""
+    from pde_controller_b200 import abi
+    src = synth.make_batch(n, wl, seed=seed)
+    rng = np.random.default_rng(seed)
+    b = ProblemBatch(n, src.kmax, pmax)
+    for name in src._names:
+        a, d = getattr(src, name), getattr(b, name)
+        if a.ndim == 1:
+            d[:] = a
+        elif name.startswith("knot"):
+            d[...] = a
+    if n_elem is not None:
+        b.n_elem[:] = n_elem
+    P = rng.integers(1, pmax + 1, n)
+    b.n_pred[:] = P
+    L, T, g0 = b.L, b.T, b.g0
+    x = np.sort(np.floor(rng.uniform(0, 1, (2, pmax, n)) * L), axis=0)
+    b.pred_xlo[...], b.pred_xhi[...] = x[0], np.minimum(np.where(x[1] <= x[0], x[0] + 1.0, x[1]), L)
+    t = np.sort(rng.uniform(0, 1, (2, pmax, n)), axis=0) * T
+    b.pred_tlo[...], b.pred_thi[...] = np.round(t[0], 4), np.round(t[1], 4)
+    if wl == "wave":
+        b.pred_m[...] = rng.uniform(-5e-5, 5e-5, (pmax, n))
+        b.pred_b[...] = rng.uniform(-3, 3, (pmax, n))
+    else:
+        b.pred_m[...] = rng.uniform(-0.5, 0.5, (pmax, n))
+        b.pred_b[...] = g0 + rng.uniform(-30, 40, (pmax, n)) - b.pred_m * 0.5 * (b.pred_xlo + b.pred_xhi)
+    b.pred_rel[...] = rng.integers(0, 3, (pmax, n))
+    b.pred_top[...] = rng.integers(0, 2, (pmax, n))
+    live = np.arange(pmax)[:, None] < P
+    for name in ("pred_xlo", "pred_xhi", "pred_m", "pred_b", "pred_tlo", "pred_thi"):
+        getattr(b, name)[...] = np.where(live, getattr(b, name), 0.0)
+    # left-associated tree: leaf0, leaf1, join1, leaf2, join2, ... with random and / or joins
+    b.tree_op[0], b.tree_lhs[0] = abi.TREE_LEAF, 0
+    for q in range(1, pmax):
+        leaf, join = 2 * q - 1, 2 * q
+        b.tree_op[leaf], b.tree_lhs[leaf] = abi.TREE_LEAF, q
+        b.tree_op[join] = np.where(rng.uniform(0, 1, n) < 0.5, abi.TREE_AND, abi.TREE_OR)
+        b.tree_lhs[join], b.tree_rhs[join] = (0 if q == 1 else 2 * q - 2), leaf
+    b.n_tree[:] = 2 * P - 1
+    return b
+
+
+@pytest.mark.parametrize("wl,n_elem", [("heat", None), ("wave", None), ("heat", 47), ("wave", 33)])
+def test_eight_clauses_per_sample(oracle_lib, wl, n_elem):
+    """PDEB_MAX_PRED clauses: the clause slots take most of the shared memory (one block per SM), several windows are
+    open in most steps (the generic second loop of the clause pass), deep formula trees; register and chunk families."""
+    check(_wide_batch(wl, 1024, 41, n_elem=n_elem), oracle_lib)
+
+
 def test_empty_and_ragged_batches(oracle_lib):
     e = ProblemBatch(0, 4, 2)
     out = native.evaluate_batch(e)

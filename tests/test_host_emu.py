@@ -76,3 +76,17 @@ def test_device_code_overlapping_windows_in_element_intervals(emu, oracle_lib, w
     rob, st, cl = run_emu(emu, b, conv)
     assert (st == ref_st).all()
     assert rel_err(rob, ref, b).max() <= TOL64
+
+
+@pytest.mark.parametrize("wl", ["heat", "wave"])
+def test_device_code_eight_clauses(emu, oracle_lib, wl):
+    from parity import rel_err
+    from test_gpu_parity import _wide_batch
+    conv = default_conventions()
+    b = _wide_batch(wl, 192, 41)
+    ref, ref_st, ref_cl = oracle_lib.eval_batch(b, conv, want_clauses=True)
+    rob, st, cl = run_emu(emu, b, conv)
+    assert (st == ref_st).all()
+    assert rel_err(rob, ref, b).max() <= TOL64
+    live = (np.arange(b.pmax)[:, None] < b.n_pred) & (ref_st == 0)
+    assert np.allclose(cl[:, :b.n][live], ref_cl[:, :b.n][live], rtol=1e-9, atol=1e-9)
