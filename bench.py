@@ -57,10 +57,10 @@ def measured_profile():
     return {}
 
 
-def fp64_view(batch, copies, kernel_ms, prof):
+def fp64_view(batch, copies, kernel_ms, prof, wave_form="a"):
     """The compute view of the path (it is FP64-latency/issue bound, not HBM bound): executed FP64 flops (FMA = 2) and
     FP64 instructions of `copies` evaluations of `batch` per launch against the measured DFMA rate of the GPU."""
-    flops, instr = batch.algorithmic_flops("executed")
+    flops, instr = batch.algorithmic_flops("executed", wave_form=wave_form)
     survey, _ = batch.algorithmic_flops("survey")
     peak = prof.get("fp64_peak_tflops")
     ach = flops * copies / (kernel_ms * 1e-3) / 1e12
@@ -68,8 +68,8 @@ def fp64_view(batch, copies, kernel_ms, prof):
            "pipe_slots_frac": (instr * copies / (kernel_ms * 1e-3)) / (peak * 1e12 / 2.0) if peak else None,
            "peak_source": "measured DFMA rate, tools/probe/fp64_probe.cu (profiles/measured_b200.json)" if peak else None,
            "executed_flops_per_launch": flops * copies, "survey_convention_flops_per_launch": survey * copies,
-           "note": "flops of the algorithm as implemented (DESIGN.md 4: 8 per row and step for heat, 20 for waves, 4 per "
-                   "clause node); pipe_slots_frac counts FP64 instructions, an add or multiply holds the pipe like an FMA"}
+           "note": "flops of the algorithm as implemented (DESIGN.md 4: 8 per row and step for heat, 20 for waves (15 in the "
+                   "momentum form of the controls family), 4 per clause node); pipe_slots_frac counts FP64 instructions, an add or multiply holds the pipe like an FMA"}
     return out
 
 
@@ -270,7 +270,8 @@ def run_controls(args, rank, local_rank, world):
                          "traffic": (prof.get("dram_bytes_per_launch", {}) or {}).get(f"{args.workload}:{m}:64"), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes},
         }
-        line["roofline_fp64"] = fp64_view(sub, m, kms, prof)
+        # the controls family steps waves in momentum form under the default conventions (pdeb_controls.cu)
+        line["roofline_fp64"] = fp64_view(sub, m, kms, prof, wave_form="momentum")
         print(json.dumps(line), flush=True)
     ev.close()
     if world > 1:

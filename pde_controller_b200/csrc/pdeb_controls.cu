@@ -35,17 +35,22 @@
 #ifndef PDEB_CTL_MINBLOCKS_WAVE
 #define PDEB_CTL_MINBLOCKS_WAVE 3
 #endif
+#ifndef PDEB_CTL_MINBLOCKS_WAVE_MOM
+#define PDEB_CTL_MINBLOCKS_WAVE_MOM 3      /* momentum form of the wave step: two state vectors */
+#endif
 #define PDEB_CTL_KMAX 32
 
 template <int N>
 struct PdebSpecConst {
     double rd[N + 1], rl[N + 1], dinv[N + 1], c[N + 1], s[N + 1];   /* index = node 1..N; rl: low part of R~_ii (waves) */
     double w0[N + 1], a0_base[N + 1], a0_unit[N + 1];             /* waves: scaled initial state, a0 = base + f0 unit */
+    double mu[N + 1];                                             /* waves, momentum form: 2 m_i s_i^2 (lumped nodal mass m_i) */
     double knot_t[PDEB_CTL_KMAX];
     PdebClauseData cl[PDEB_MAX_PRED];
     double sN, dt, th_dt, eq_eps;
     double cw1, cw2, cw3, cw4, cw5;
     int32_t nk, np, nt, k_end;
+    int32_t momentum, pad_;                                        /* waves: 1 = the step runs in momentum form (below) */
     uint8_t tree_op[PDEB_MAX_TREE];
     int8_t tree_lhs[PDEB_MAX_TREE], tree_rhs[PDEB_MAX_TREE];
 };
@@ -94,8 +99,9 @@ struct PdebCtlGroups<N, 32> {
 };
 
 /* z[1..N] <- A~^-1 (R~ x + fNs e_N): the twisted solve of pdeb_core.h with every factor a constant-bank operand */
-template <int KIND, int N>
-__device__ __forceinline__ void pdeb_ctl_solve(const PdebSpecConst<N>& sp, const double* x, double fNs, double* z) {
+template <int KIND, int N, bool ADD = false>
+__device__ __forceinline__ void pdeb_ctl_solve(const PdebSpecConst<N>& sp, const double* x, double fNs, double* z,
+                                               const double* add = nullptr) {
     constexpr int M = (N + 1) / 2;
     double zt = 0, zb = 0;
 #pragma unroll
@@ -103,6 +109,7 @@ __device__ __forceinline__ void pdeb_ctl_solve(const PdebSpecConst<N>& sp, const
         const int it = 1 + j, ib = N - j;
         if (it < M) {
             double r = x[it - 1] + x[it + 1];
+            if (ADD) r += add[it];
             if (KIND == PDEB_KIND_WAVE) r = fma(sp.rl[it], x[it], r);
             r = fma(sp.rd[it], x[it], r);
             if (it > 1) r = fma(-sp.c[it - 1], zt, r);
@@ -111,6 +118,7 @@ __device__ __forceinline__ void pdeb_ctl_solve(const PdebSpecConst<N>& sp, const
         }
         if (ib > M) {
             double r = x[ib - 1] + ((ib == N) ? fNs : x[ib + 1]);
+            if (ADD) r += add[ib];
             if (KIND == PDEB_KIND_WAVE) r = fma(sp.rl[ib], x[ib], r);
             r = fma(sp.rd[ib], x[ib], r);
             if (ib < N) r = fma(-sp.c[ib], zb, r);
@@ -120,6 +128,7 @@ __device__ __forceinline__ void pdeb_ctl_solve(const PdebSpecConst<N>& sp, const
     }
     {
         double r = x[M - 1] + x[M + 1];
+        if (ADD) r += add[M];
         if (KIND == PDEB_KIND_WAVE) r = fma(sp.rl[M], x[M], r);
         r = fma(sp.rd[M], x[M], r);
         r = fma(-sp.c[M - 1], zt, r);
@@ -134,8 +143,19 @@ __device__ __forceinline__ void pdeb_ctl_solve(const PdebSpecConst<N>& sp, const
     }
 }
 
-template <int KIND, int N, int PMAX>
-__global__ void __launch_bounds__(PDEB_CTL_THREADS, (KIND == PDEB_KIND_HEAT) ? PDEB_CTL_MINBLOCKS_HEAT : PDEB_CTL_MINBLOCKS_WAVE)
+/*
+ * MOMENTUM FORM of the wave step (MOM; Newmark beta = 1/4, gamma = 1/2 with lumped mass, the defaults C2 / C5).
+ * With c = beta dt^2, M a_k = f_k - K d_k at every step (true at k = 0 by the definition of a0) turns the a-form into
+ *     (M + c K) delta = -2c K d + p + c (f + f') e_N,    d' = d + delta,    p' = 2 M delta - p,      p = dt M v, p_0 = 0,
+ * i.e. two state vectors instead of three and, in the scaled unknowns of pdeb_core.h (same S, same factors of
+ * A~ = S (M + c K) S, same R~ = S (-K) S), with eta = delta~ / 2c and pi = S p / 2c:
+ *     eta = A~^-1 (R~ x~ + pi + s_N (f + f')/2 e_N),    x~' = x~ + 2c eta,    pi' = mu eta - pi,    mu_i = 2 m_i s_i^2
+ * 9 FP64 operations per row and step instead of 11; the right-hand side is still made of increments (K d through the
+ * consistent double-double diagonal, the momentum), so the rounding behaviour is that of the a-form.
+ */
+template <int KIND, int N, int PMAX, bool MOM = false>
+__global__ void __launch_bounds__(PDEB_CTL_THREADS, (KIND == PDEB_KIND_HEAT) ? PDEB_CTL_MINBLOCKS_HEAT
+                                                    : (MOM ? PDEB_CTL_MINBLOCKS_WAVE_MOM : PDEB_CTL_MINBLOCKS_WAVE))
 pdeb_controls_kernel(const __grid_constant__ PdebSpecConst<N> sp, const double* __restrict__ ky, int64_t stride, int64_t m,
                      const __grid_constant__ PdebCtlOut out) {
     const int64_t t = (int64_t)blockIdx.x * PDEB_CTL_THREADS + threadIdx.x;
@@ -143,7 +163,8 @@ pdeb_controls_kernel(const __grid_constant__ PdebSpecConst<N> sp, const double* 
     const double* y = ky + (live ? t : 0);
 
     double w[N + 2];
-    double v[KIND == PDEB_KIND_WAVE ? N + 2 : 1], a[KIND == PDEB_KIND_WAVE ? N + 2 : 1];
+    double v[KIND == PDEB_KIND_WAVE ? N + 2 : 1];            /* velocity; momentum form: pi */
+    double a[(KIND == PDEB_KIND_WAVE && !MOM) ? N + 2 : 1];
     double acc[PMAX];
 #pragma unroll
     for (int i = 0; i <= N + 1; ++i) w[i] = 0;
@@ -171,9 +192,9 @@ pdeb_controls_kernel(const __grid_constant__ PdebSpecConst<N> sp, const double* 
     double f_prev = input(0.0);
     if (KIND == PDEB_KIND_WAVE) {
 #pragma unroll
-        for (int i = 0; i <= N + 1; ++i) { v[i] = 0; a[i] = 0; }
+        for (int i = 0; i <= N + 1; ++i) { v[i] = 0; if (!MOM) a[i] = 0; }
 #pragma unroll
-        for (int i = 1; i <= N; ++i) { w[i] = sp.w0[i]; a[i] = fma(f_prev, sp.a0_unit[i], sp.a0_base[i]); }
+        for (int i = 1; i <= N; ++i) { w[i] = sp.w0[i]; if (!MOM) a[i] = fma(f_prev, sp.a0_unit[i], sp.a0_base[i]); }
     }
 
     const int32_t k_end = sp.k_end;
@@ -222,6 +243,16 @@ pdeb_controls_kernel(const __grid_constant__ PdebSpecConst<N> sp, const double* 
             pdeb_ctl_solve<KIND, N>(sp, w, sp.sN * fb, z);
 #pragma unroll
             for (int i = 1; i <= N; ++i) w[i] = z[i];
+        } else if (MOM) {
+            double z[N + 2];
+            z[0] = 0; z[N + 1] = 0;
+            pdeb_ctl_solve<KIND, N, true>(sp, w, sp.sN * (0.5 * (f_prev + f_next)), z, v);
+            const double c2 = 2.0 * sp.cw4;
+#pragma unroll
+            for (int i = 1; i <= N; ++i) {
+                w[i] = fma(c2, z[i], w[i]);
+                v[i] = fma(sp.mu[i], z[i], -v[i]);
+            }
         } else {
 #pragma unroll
             for (int i = 1; i <= N; ++i) {
@@ -372,6 +403,14 @@ static int build_spec(const PdebBatch* in, int64_t s, const PdebConventions& cv,
         tr.wave_init(h, g0, 1.0, rho_in, rho_out, E_in, E_out, lumped);
         for (int i = 1; i <= N; ++i) sp.a0_unit[i] = tr.a[i] - sp.a0_base[i];
     }
+    sp.momentum = 0;
+    if constexpr (KIND == PDEB_KIND_WAVE) {
+        sp.momentum = (lumped && cv.newmark_beta == 0.25 && cv.newmark_gamma == 0.5) ? 1 : 0;
+        for (int i = 1; i <= N; ++i) {
+            const double ml = (tr.outer(i - 1) ? rho_out : rho_in) * h, mr = (i < N) ? (tr.outer(i) ? rho_out : rho_in) * h : 0.0;
+            sp.mu[i] = (ml + mr) * stab[i - 1] * stab[i - 1];       /* 2 * (ml + mr)/2 * s_i^2 */
+        }
+    }
     sp.sN = tr.sN; sp.dt = dt; sp.th_dt = cv.theta * dt; sp.eq_eps = (cv.eq_rule == 1) ? cv.eq_eps : 0.0;
     sp.cw1 = dt; sp.cw2 = 0.5 * (1.0 - 2.0 * cv.newmark_beta) * dt * dt; sp.cw3 = (1.0 - cv.newmark_gamma) * dt;
     sp.cw4 = cv.newmark_beta * dt * dt; sp.cw5 = cv.newmark_gamma * dt;
@@ -443,6 +482,13 @@ template <int KIND, int N>
 static cudaError_t launch_controls(const PdebSpecConst<N>& sp, int pmax, const double* ky, int64_t stride, int64_t m,
                                    const PdebCtlOut& out, cudaStream_t stream) {
     const unsigned blocks = (unsigned)((m + PDEB_CTL_THREADS - 1) / PDEB_CTL_THREADS);
+    if constexpr (KIND == PDEB_KIND_WAVE) {
+        if (sp.momentum) {
+            if (pmax <= 3) pdeb_controls_kernel<KIND, N, 3, true><<<blocks, PDEB_CTL_THREADS, 0, stream>>>(sp, ky, stride, m, out);
+            else pdeb_controls_kernel<KIND, N, PDEB_MAX_PRED, true><<<blocks, PDEB_CTL_THREADS, 0, stream>>>(sp, ky, stride, m, out);
+            return cudaGetLastError();
+        }
+    }
     if (pmax <= 3) pdeb_controls_kernel<KIND, N, 3><<<blocks, PDEB_CTL_THREADS, 0, stream>>>(sp, ky, stride, m, out);
     else pdeb_controls_kernel<KIND, N, PDEB_MAX_PRED><<<blocks, PDEB_CTL_THREADS, 0, stream>>>(sp, ky, stride, m, out);
     return cudaGetLastError();

@@ -288,14 +288,15 @@ class ProblemBatch:
         per_knot = 8 if self.uniform_knots else 16      # knot times are not carried when they are uniform
         return int(np.sum(105 + per_knot * k + 50 * p + 3 * (2 * p - 1)))
 
-    def algorithmic_flops(self, convention: str = "executed"):
+    def algorithmic_flops(self, convention: str = "executed", wave_form: str = "a"):
         """FP64 work of the batch, steps up to the last observed one (what the kernels simulate).
 
         convention "survey":   SURVEY.md §8(d) (FMA = 2): heat S (15 n + 3 sum_p n_p), wave S (21 n + 3 sum_p n_p),
                                + 20 n one-off for assembly and factorisation.
         convention "executed": the operations of the algorithm AS IMPLEMENTED here: per step and row
                                heat add + 3 FMA + mul = 8 flops in 5 instructions, wave 20 flops in 11 (incl. the
-                               Newmark predictor / corrector and the low part of the diagonal); per node of a clause
+                               Newmark predictor / corrector and the low part of the diagonal; wave_form "momentum",
+                               the controls family under the default conventions: 15 flops in 9); per node of a clause
                                interval and window step 2 FMA = 4 flops in 2 instructions.
         Returns (flops, fp64_instructions); n = free dofs, n_p = nodes inside predicate p's interval."""
         n = self.n_elem.astype(np.float64)
@@ -320,6 +321,7 @@ class ProblemBatch:
         if convention == "survey":
             flops = np.sum(S_run * np.where(heat, 15.0, 21.0) * n + 3.0 * node_steps + 20.0 * n)
             return int(flops), None
-        flops = np.sum(S_run * np.where(heat, 8.0, 20.0) * n + 4.0 * node_steps)
-        instr = np.sum(S_run * np.where(heat, 5.0, 11.0) * n + 2.0 * node_steps)
+        wf, wi = (15.0, 9.0) if wave_form == "momentum" else (20.0, 11.0)
+        flops = np.sum(S_run * np.where(heat, 8.0, wf) * n + 4.0 * node_steps)
+        instr = np.sum(S_run * np.where(heat, 5.0, wi) * n + 2.0 * node_steps)
         return int(flops), int(instr)

@@ -73,6 +73,28 @@ def test_controls_equal_batch_path():
     assert got["best_index"] == int(np.argmax(got["robustness"]))
 
 
+@pytest.mark.parametrize("kw", [{}, dict(newmark_beta=0.3025, newmark_gamma=0.6)])
+def test_wave_controls_equal_batch_path(oracle_lib, kw):
+    """Waves: the controls family steps in momentum form under the default conventions (two state vectors) and in the
+    a-form otherwise; both must agree with the batch kernels (a-form) and with the oracle."""
+    conv = default_conventions(**kw)
+    spec = synth.make_batch(6, "wave", seed=4)
+    rng = np.random.Generator(np.random.PCG64(11))
+    for s in (0, 3, 5):
+        knot_t = np.linspace(0.0, float(spec.T[s]), 5)
+        y = candidates(rng, "wave", 5, 2048)
+        ev = native.ControlsEvaluator(spec, knot_t, capacity=2048, sample=s, conv=conv)
+        got = ev.eval(y)
+        ev.close()
+        rep = replicate(spec, s, knot_t, y)
+        ref = native.evaluate_batch(rep, conv=conv)
+        assert (got["status"] == ref["status"]).all()
+        assert rel_err(got["robustness"], ref["robustness"], rep).max() <= TOL_FP64
+        orc, orc_st = oracle_lib.eval_batch(rep, conv)
+        assert (got["status"] == orc_st).all()
+        assert rel_err(got["robustness"], orc, rep).max() <= TOL_FP64
+
+
 def test_bad_spec_fails_every_candidate():
     spec = synth.make_batch(2, "heat", seed=3)
     spec.E_in[0] = -1.0
