@@ -184,8 +184,41 @@ def cpu_baseline(args, batch):
         oracle.eval_batch(batch, nthreads=nthreads)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return {"value": batch.n / best, "unit": UNIT, "cores": nthreads, "kind": "port",
-            "sample": f"the same {batch.n}-sample batch, best of 2 passes, C oracle -O3 + OpenMP over samples"}
+    out = {"value": batch.n / best, "unit": UNIT, "cores": nthreads, "kind": "port",
+           "sample": f"the same {batch.n}-sample batch, best of 2 passes, C oracle -O3 + OpenMP over samples"}
+    out["context"] = cpu_context(batch, nthreads)
+    return out
+
+
+def cpu_context(batch, nthreads):
+    """The two context figures of BASELINE.md section 3 (neither is the baseline): the numpy restatement on one core
+    (closest in spirit to femformal's numpy time loops) and the ceiling of the reference's process-per-sample design
+    (eval_script.py:48-59 spawns `conda run ... python` per sample from cpu_count // 2 workers, simulate_gt.py:64-65):
+    the spawn rate of an EMPTY interpreter times that worker count."""
+    import subprocess
+    from oracle import pde_oracle_np
+    ctx = {}
+    try:
+        k = min(batch.n, 12)
+        t0 = time.perf_counter()
+        for s in range(k):
+            p, ctl = batch.get_problem(s)
+            pde_oracle_np.evaluate(p, ctl)
+        ctx["numpy_port_1core"] = {"value": k / (time.perf_counter() - t0), "unit": UNIT, "sample": f"first {k} samples"}
+    except Exception as e:  # context only: never fails the bench
+        ctx["numpy_port_1core"] = {"error": repr(e)}
+    try:
+        k = 10
+        t0 = time.perf_counter()
+        for _ in range(k):
+            subprocess.run([sys.executable, "-c", "pass"], check=True)
+        per = (time.perf_counter() - t0) / k
+        workers = max(nthreads // 2, 1)
+        ctx["process_per_sample_floor"] = {"value": workers / per, "unit": UNIT, "workers": workers,
+                                           "sample": f"{k} spawns of an empty interpreter, {per * 1e3:.1f} ms each"}
+    except Exception as e:
+        ctx["process_per_sample_floor"] = {"error": repr(e)}
+    return ctx
 
 
 def run_controls(args, rank, local_rank, world):
