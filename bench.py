@@ -325,6 +325,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-block", type=int, default=65536, help="samples per block of the end-to-end pipeline")
     ap.add_argument("--explicit-knots", action="store_true", help="carry per-sample knot times instead of uniform knots")
+    ap.add_argument("--e2e-planar", action="store_true",
+                    help="end-to-end path moves the plane-major slab instead of the packed transfer form (PdebPackedBatch)")
     args = ap.parse_args()
     if args.batch is None:
         args.batch = DEFAULT_BATCH[args.workload]
@@ -407,12 +409,13 @@ def main():
     value = total * args.steps / (total_ms * 1e-3)
 
     # ---- end to end through the public API with HOST buffers ("e2e") ----
-    # every step: the whole batch goes pinned host -> H2D -> plan -> kernels -> D2H (robustness + status) as
+    # every step: the whole batch goes pinned host -> H2D (packed transfer form) -> unpack + plan -> kernels -> D2H
+    # (robustness + status) as
     # args.e2e_block-sample blocks, E2E_DEPTH generations of buffers on as many streams (native.BlockPipeline); run() returns after the
     # last byte of the results is back in host memory
     E2E_DEPTH = 3
     pipe = native.BlockPipeline(src.n, src.kmax, src.pmax, src.tmax, block=args.e2e_block, device=dev, depth=E2E_DEPTH,
-                                uniform_knots=uk)
+                                uniform_knots=uk, packed=not args.e2e_planar)
     for g in range(E2E_DEPTH):
         pipe.fill(src, g)
 
@@ -463,7 +466,8 @@ def main():
             "dtype": "f64" if args.precision == 64 else "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_TEXT[args.workload], "batch_per_gpu": args.batch, "global_batch": total,
                        "precision": args.precision, "seed": args.seed, "l2": "flushed (256 MiB write) between timed steps",
-                       "gather": bool(rob_t is not None), "failed_samples": n_fail, "knots": "uniform (formed on device)" if uk else "explicit", "e2e_block": args.e2e_block, "e2e_pipeline_depth": E2E_DEPTH, "e2e_value_depth1": e2e_sync,
+                       "gather": bool(rob_t is not None), "failed_samples": n_fail, "knots": "uniform (formed on device)" if uk else "explicit", "e2e_block": args.e2e_block, "e2e_pipeline_depth": E2E_DEPTH,
+                       "e2e_format": "planar slab" if args.e2e_planar else "packed transfer form (ragged lists, unpacked on the device)", "e2e_value_depth1": e2e_sync,
                        "wall_s_timed_region": wall1 - wall0},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(12 * host.n)},

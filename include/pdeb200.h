@@ -196,6 +196,39 @@ typedef struct PdebResident PdebResident;
 
 int  pdeb_resident_create(const PdebBatch* in, int device, void* stream, PdebResident** out);
 int  pdeb_resident_upload(PdebResident* r, const PdebBatch* in, void* stream);  /* same shape: refill the image */
+
+/*
+ * Packed TRANSFER form of a batch.  The end-to-end rate of this path is host->device bandwidth divided by the bytes per
+ * sample (the kernels wait for PCIe, not the other way round), and a third of the plane-major layout is slots a sample
+ * does not use (knot planes beyond n_knots, clause planes beyond n_pred, tree planes beyond n_tree).  Here every
+ * per-sample LIST is ragged: sample after sample, only the entries in use; the small integers are narrow.  The default
+ * heat set is 280 instead of 382 bytes per sample.  The library copies the block with ONE transfer, forms the list
+ * offsets on the device (prefix sums of the counts) and scatters the lists into the plane-major resident image, so the
+ * kernels, the plan and every other entry point are untouched.  What it carries is what eval_robustness_helper's two
+ * strings carry in the reference (eval/eval_script.py:43-79), as numbers.
+ */
+typedef struct PdebPackedBatch {
+    int64_t n;
+    int32_t kmax, pmax, tmax, reserved0;             /* list bounds: the shape of the resident image this refills */
+    int64_t total_knots, total_pred, total_tree;      /* lengths of the flat arrays: sums of the counts */
+    const void* slab_base;                            /* REQUIRED: every array below inside one contiguous host block */
+    int64_t     slab_bytes;                           /* (page-locked for an asynchronous copy: pdeb_host_alloc) */
+    const uint8_t*  kind;                             /* [n] */
+    const uint16_t* n_elem;                           /* [n] */
+    const double *L, *dt, *T, *g0, *x_a, *x_b, *rho_in, *rho_out, *E_in, *E_out;    /* [n] each */
+    const uint16_t* n_knots;                          /* [n] */
+    const uint8_t*  n_pred;                           /* [n] */
+    const uint8_t*  n_tree;                           /* [n] */
+    const double* knot_t;                             /* [total_knots], or NULL = uniform knots (as at creation) */
+    const double* knot_y;                             /* [total_knots] */
+    const double *pred_xlo, *pred_xhi, *pred_m, *pred_b, *pred_tlo, *pred_thi;      /* [total_pred] each */
+    const uint8_t *pred_rel, *pred_top;               /* [total_pred] */
+    const uint8_t* tree_op;                           /* [total_tree] */
+    const int8_t *tree_lhs, *tree_rhs;                /* [total_tree] */
+} PdebPackedBatch;
+
+/* refill the image of `r` (same n / kmax / pmax / tmax) from the packed form; one H2D copy + 3 small launches + the plan */
+int  pdeb_resident_upload_packed(PdebResident* r, const PdebPackedBatch* in, void* stream);
 /* upload + evaluate + fetch of a batch of the resident shape in one pipelined pass (H2D / kernels / D2H of
    successive chunks overlap on two internal streams); synchronises before returning */
 int  pdeb_resident_run(PdebResident* r, const PdebBatch* in, int precision, const PdebConventions* conv,

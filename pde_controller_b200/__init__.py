@@ -6,6 +6,6 @@ plus the batched forms the GPU path is built for:
     eval_robustness_batch, ProblemBatch, evaluate_batch
 """
 from .abi import default_conventions  # noqa: F401
-from .problem import Predicate, Problem, ProblemBatch, default_knot_times  # noqa: F401
+from .problem import PackedBatch, Predicate, Problem, ProblemBatch, default_knot_times  # noqa: F401
 
-__all__ = ["Predicate", "Problem", "ProblemBatch", "default_knot_times", "default_conventions"]
+__all__ = ["PackedBatch", "Predicate", "Problem", "ProblemBatch", "default_knot_times", "default_conventions"]

@@ -102,6 +102,30 @@ class PdebBatch(C.Structure):
     ]
 
 
+class PdebPackedBatch(C.Structure):
+    """Packed transfer form (include/pdeb200.h): ragged lists, narrow counts, one contiguous block."""
+    _fields_ = [
+        ("n", C.c_int64),
+        ("kmax", C.c_int32),
+        ("pmax", C.c_int32),
+        ("tmax", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("total_knots", C.c_int64),
+        ("total_pred", C.c_int64),
+        ("total_tree", C.c_int64),
+        ("slab_base", _P),
+        ("slab_bytes", C.c_int64),
+        ("kind", _P), ("n_elem", _P),
+        ("L", _P), ("dt", _P), ("T", _P), ("g0", _P), ("x_a", _P), ("x_b", _P),
+        ("rho_in", _P), ("rho_out", _P), ("E_in", _P), ("E_out", _P),
+        ("n_knots", _P), ("n_pred", _P), ("n_tree", _P),
+        ("knot_t", _P), ("knot_y", _P),
+        ("pred_xlo", _P), ("pred_xhi", _P), ("pred_m", _P), ("pred_b", _P), ("pred_tlo", _P), ("pred_thi", _P),
+        ("pred_rel", _P), ("pred_top", _P),
+        ("tree_op", _P), ("tree_lhs", _P), ("tree_rhs", _P),
+    ]
+
+
 class PdebTiming(C.Structure):
     _fields_ = [
         ("h2d_ms", C.c_float),
@@ -123,6 +147,7 @@ EXPORTS = [
     "pdeb_eval_batch_multi",
     "pdeb_resident_create",
     "pdeb_resident_upload",
+    "pdeb_resident_upload_packed",
     "pdeb_resident_run",
     "pdeb_resident_eval",
     "pdeb_resident_set_knots",

@@ -102,6 +102,8 @@ struct PdebResident {
     int32_t vsc_host[2 * PDEB_NUM_VARIANTS] = {0};   /* first index / count of each variant inside `order` (whole batch) */
     int plan_launches = 0;
     bool plan_stale = false;         /* the last run planned chunk by chunk: whole-batch order must be rebuilt */
+    unsigned char* pstage = nullptr; /* packed uploads: the transferred block | list offsets | block sums (lazy) */
+    size_t pstage_cap = 0, pstage_off = 0;
     cudaStream_t pipe[2] = {nullptr, nullptr};        /* internal streams of the pipelined run */
     cudaEvent_t pev[3] = {nullptr, nullptr, nullptr};
 };
@@ -134,6 +136,7 @@ extern "C" void pdeb_resident_destroy(PdebResident* r) {
     if (r->slab) cudaFree(r->slab);
     if (r->outs) cudaFree(r->outs);
     if (r->plan) cudaFree(r->plan);
+    if (r->pstage) cudaFree(r->pstage);
     for (auto& st : r->pipe) if (st) cudaStreamDestroy(st);
     for (auto& e : r->pev) if (e) cudaEventDestroy(e);
     delete r;
@@ -371,6 +374,188 @@ extern "C" int pdeb_resident_upload(PdebResident* r, const PdebBatch* in, void* 
     rc = upload(r, in, 0, r->n, (cudaStream_t)stream_, false);
     if (rc == 0) { host_variant_counts(in, 0, r->n, r->vsc_host); rc = plan_view(r, view_of(r, 0, r->n, 0), (cudaStream_t)stream_); }
     return rc;
+}
+
+/* ---- packed transfer form (PdebPackedBatch): one copy, offsets by prefix sums on the device, scatter into the image ---- */
+#define PDEB_SCAN_BLOCK 1024
+
+struct PdebPackedDev {
+    const uint8_t* kind; const uint16_t* n_elem;
+    const double *L, *dt, *T, *g0, *x_a, *x_b, *rho_in, *rho_out, *E_in, *E_out;
+    const uint16_t* n_knots; const uint8_t *n_pred, *n_tree;
+    const double *knot_t, *knot_y, *pred_xlo, *pred_xhi, *pred_m, *pred_b, *pred_tlo, *pred_thi;
+    const uint8_t *pred_rel, *pred_top, *tree_op;
+    const int8_t *tree_lhs, *tree_rhs;
+};
+
+/* exclusive prefix sums of the three count arrays inside each block of PDEB_SCAN_BLOCK samples + the block totals */
+__global__ void __launch_bounds__(PDEB_SCAN_BLOCK)
+pdeb_pack_scan_kernel(int64_t n, const uint16_t* __restrict__ nk, const uint8_t* __restrict__ np, const uint8_t* __restrict__ nt,
+                      int kmax, int pmax, int tmax, int32_t* __restrict__ off /* [3][n] */, int32_t* __restrict__ bsum /* [3][blocks] */) {
+    __shared__ int32_t wsum[3][32];
+    const int64_t i = (int64_t)blockIdx.x * PDEB_SCAN_BLOCK + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int32_t v[3] = {0, 0, 0};
+    /* a list holds at most as many entries as the image has planes (larger counts are flagged by the kernels) */
+    if (i < n) { v[0] = min((int)nk[i], kmax); v[1] = min((int)np[i], pmax); v[2] = min((int)nt[i], tmax); }
+    int32_t inc[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        int32_t x = v[q];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        inc[q] = x;
+        if (lane == 31) wsum[q][warp] = x;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            int32_t x = wsum[q][lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            wsum[q][lane] = x;                                  /* inclusive over the warps */
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const int32_t before = (warp > 0 ? wsum[q][warp - 1] : 0) + inc[q] - v[q];
+        if (i < n) off[(int64_t)q * n + i] = before;
+        if (threadIdx.x == PDEB_SCAN_BLOCK - 1) bsum[(int64_t)q * gridDim.x + blockIdx.x] = wsum[q][31];
+    }
+}
+
+/* one block: block totals -> exclusive offsets of the blocks (in place), any number of blocks */
+__global__ void __launch_bounds__(PDEB_SCAN_BLOCK) pdeb_pack_blocksum_kernel(int32_t* __restrict__ bsum, int blocks) {
+    __shared__ int32_t part[PDEB_SCAN_BLOCK];
+    __shared__ int32_t carry;
+    for (int q = 0; q < 3; ++q) {
+        if (threadIdx.x == 0) carry = 0;
+        __syncthreads();
+        for (int base = 0; base < blocks; base += PDEB_SCAN_BLOCK) {
+            const int i = base + threadIdx.x;
+            const int32_t v = (i < blocks) ? bsum[(int64_t)q * blocks + i] : 0;
+            part[threadIdx.x] = v;
+            __syncthreads();
+            for (int o = 1; o < PDEB_SCAN_BLOCK; o <<= 1) {
+                const int32_t y = (threadIdx.x >= o) ? part[threadIdx.x - o] : 0;
+                __syncthreads();
+                part[threadIdx.x] += y;
+                __syncthreads();
+            }
+            if (i < blocks) bsum[(int64_t)q * blocks + i] = carry + part[threadIdx.x] - v;
+            __syncthreads();
+            if (threadIdx.x == PDEB_SCAN_BLOCK - 1) carry += part[threadIdx.x];
+            __syncthreads();
+        }
+    }
+}
+
+/* scatter one sample per thread into the plane-major image (unused list slots keep whatever they held: nobody reads them) */
+__global__ void pdeb_unpack_kernel(const __grid_constant__ PdebPackedDev p, const __grid_constant__ PdebDevBatch d,
+                                   const int32_t* __restrict__ off, const int32_t* __restrict__ bsum, int blocks) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = d.n, st = d.stride;
+    if (s >= n) return;
+    const int blk = (int)(s / PDEB_SCAN_BLOCK);
+    ((uint8_t*)d.kind)[s] = p.kind[s];
+    ((int32_t*)d.n_elem)[s] = p.n_elem[s];
+    ((double*)d.L)[s] = p.L[s];             ((double*)d.dt)[s] = p.dt[s];
+    ((double*)d.T)[s] = p.T[s];             ((double*)d.g0)[s] = p.g0[s];
+    ((double*)d.x_a)[s] = p.x_a[s];         ((double*)d.x_b)[s] = p.x_b[s];
+    ((double*)d.rho_in)[s] = p.rho_in[s];   ((double*)d.rho_out)[s] = p.rho_out[s];
+    ((double*)d.E_in)[s] = p.E_in[s];       ((double*)d.E_out)[s] = p.E_out[s];
+    int nk = p.n_knots[s], np = p.n_pred[s], nt = p.n_tree[s];
+    ((int32_t*)d.n_knots)[s] = nk; ((int32_t*)d.n_pred)[s] = np; ((int32_t*)d.n_tree)[s] = nt;
+    /* counts beyond the image's planes are flagged by the kernels (BADPARAM); never write outside the image */
+    if (nk > d.kmax) nk = d.kmax;
+    if (np > d.pmax) np = d.pmax;
+    if (nt > d.tmax) nt = d.tmax;
+    const int64_t ok = (int64_t)off[s] + bsum[blk];
+    const int64_t op = (int64_t)off[n + s] + bsum[blocks + blk];
+    const int64_t ot = (int64_t)off[2 * n + s] + bsum[2 * blocks + blk];
+    for (int j = 0; j < nk; ++j) {
+        ((double*)d.knot_y)[(int64_t)j * st + s] = p.knot_y[ok + j];
+        if (d.knot_t) ((double*)d.knot_t)[(int64_t)j * st + s] = p.knot_t[ok + j];
+    }
+    for (int j = 0; j < np; ++j) {
+        const int64_t q = (int64_t)j * st + s;
+        ((double*)d.pred_xlo)[q] = p.pred_xlo[op + j];  ((double*)d.pred_xhi)[q] = p.pred_xhi[op + j];
+        ((double*)d.pred_m)[q] = p.pred_m[op + j];      ((double*)d.pred_b)[q] = p.pred_b[op + j];
+        ((double*)d.pred_tlo)[q] = p.pred_tlo[op + j];  ((double*)d.pred_thi)[q] = p.pred_thi[op + j];
+        ((uint8_t*)d.pred_rel)[q] = p.pred_rel[op + j]; ((uint8_t*)d.pred_top)[q] = p.pred_top[op + j];
+    }
+    for (int j = 0; j < nt; ++j) {
+        const int64_t q = (int64_t)j * st + s;
+        ((uint8_t*)d.tree_op)[q] = p.tree_op[ot + j];
+        ((int8_t*)d.tree_lhs)[q] = p.tree_lhs[ot + j];
+        ((int8_t*)d.tree_rhs)[q] = p.tree_rhs[ot + j];
+    }
+}
+
+extern "C" int pdeb_resident_upload_packed(PdebResident* r, const PdebPackedBatch* in, void* stream_) {
+    if (!r || !in) return fail(PDEB_E_ARG, "NULL argument");
+    if (in->n != r->n || in->kmax != r->kmax || in->pmax != r->pmax || in->tmax != r->tmax)
+        return fail(PDEB_E_ARG, "packed batch shape differs from the resident image");
+    if ((in->knot_t != nullptr) != (r->dev.knot_t != nullptr)) return fail(PDEB_E_ARG, "knot_t must be given (or NULL) as at creation");
+    if (r->n == 0) return 0;
+    if (!in->slab_base || in->slab_bytes <= 0) return fail(PDEB_E_ARG, "the packed form needs slab_base / slab_bytes");
+    if (in->total_knots < 0 || in->total_pred < 0 || in->total_tree < 0 || in->total_knots > (int64_t)r->n * r->kmax ||
+        in->total_pred > (int64_t)r->n * r->pmax || in->total_tree > (int64_t)r->n * r->tmax || in->total_knots > 0x7fffffff)
+        return fail(PDEB_E_ARG, "packed list totals out of range");
+    const unsigned char* base = (const unsigned char*)in->slab_base;
+    const int64_t n = r->n;
+    struct Arr { const void* p; size_t bytes; };
+    const size_t tk = (size_t)in->total_knots, tp = (size_t)in->total_pred, tt = (size_t)in->total_tree, nn = (size_t)n;
+    const Arr arrs[] = {{in->kind, nn}, {in->n_elem, 2 * nn}, {in->L, 8 * nn}, {in->dt, 8 * nn}, {in->T, 8 * nn}, {in->g0, 8 * nn},
+                        {in->x_a, 8 * nn}, {in->x_b, 8 * nn}, {in->rho_in, 8 * nn}, {in->rho_out, 8 * nn}, {in->E_in, 8 * nn},
+                        {in->E_out, 8 * nn}, {in->n_knots, 2 * nn}, {in->n_pred, nn}, {in->n_tree, nn}, {in->knot_y, 8 * tk},
+                        {in->pred_xlo, 8 * tp}, {in->pred_xhi, 8 * tp}, {in->pred_m, 8 * tp}, {in->pred_b, 8 * tp},
+                        {in->pred_tlo, 8 * tp}, {in->pred_thi, 8 * tp}, {in->pred_rel, tp}, {in->pred_top, tp},
+                        {in->tree_op, tt}, {in->tree_lhs, tt}, {in->tree_rhs, tt}, {in->knot_t, in->knot_t ? 8 * tk : 0}};
+    for (const Arr& a : arrs) {
+        if (!a.p) { if (a.bytes) return fail(PDEB_E_ARG, "a packed array is NULL"); continue; }
+        const unsigned char* q = (const unsigned char*)a.p;
+        if (q < base || q + a.bytes > base + in->slab_bytes) return fail(PDEB_E_ARG, "a packed array lies outside the slab");
+    }
+    DeviceGuard g(r->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    /* staging: worst-case block (every list full, 64 bytes of alignment slack per array) | offsets [3][n] | block sums */
+    const int blocks = (int)((n + PDEB_SCAN_BLOCK - 1) / PDEB_SCAN_BLOCK);
+    if (!r->pstage) {
+        const size_t worst = nn * (1 + 2 + 80 + 2 + 1 + 1) + 8 * nn * r->kmax * (r->dev.knot_t ? 2 : 1) + 50 * nn * r->pmax +
+                             3 * nn * r->tmax + 64 * 32;
+        r->pstage_off = align_up(worst, 256);
+        r->pstage_cap = r->pstage_off + align_up(12 * nn, 256) + align_up(12 * (size_t)blocks, 256);
+        cudaError_t ce = cudaMalloc((void**)&r->pstage, r->pstage_cap);
+        if (ce != cudaSuccess) { r->pstage = nullptr; return fail(PDEB_E_NOMEM, "packed staging buffer", ce); }
+    }
+    if ((size_t)in->slab_bytes > r->pstage_off) return fail(PDEB_E_ARG, "packed slab larger than the worst case of this shape");
+    CK(cudaMemcpyAsync(r->pstage, base, (size_t)in->slab_bytes, cudaMemcpyHostToDevice, stream));
+    PdebPackedDev p;
+#define DEVP(f) p.f = in->f ? (decltype(p.f))(r->pstage + ((const unsigned char*)in->f - base)) : nullptr
+    DEVP(kind); DEVP(n_elem); DEVP(L); DEVP(dt); DEVP(T); DEVP(g0); DEVP(x_a); DEVP(x_b); DEVP(rho_in); DEVP(rho_out);
+    DEVP(E_in); DEVP(E_out); DEVP(n_knots); DEVP(n_pred); DEVP(n_tree); DEVP(knot_t); DEVP(knot_y); DEVP(pred_xlo);
+    DEVP(pred_xhi); DEVP(pred_m); DEVP(pred_b); DEVP(pred_tlo); DEVP(pred_thi); DEVP(pred_rel); DEVP(pred_top);
+    DEVP(tree_op); DEVP(tree_lhs); DEVP(tree_rhs);
+#undef DEVP
+    int32_t* off = (int32_t*)(r->pstage + r->pstage_off);
+    int32_t* bsum = (int32_t*)(r->pstage + r->pstage_off + align_up(12 * nn, 256));
+    pdeb_pack_scan_kernel<<<blocks, PDEB_SCAN_BLOCK, 0, stream>>>(n, p.n_knots, p.n_pred, p.n_tree, r->kmax, r->pmax, r->tmax, off, bsum);
+    pdeb_pack_blocksum_kernel<<<1, PDEB_SCAN_BLOCK, 0, stream>>>(bsum, blocks);
+    pdeb_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p, r->dev, off, bsum, blocks);
+    CK(cudaGetLastError());
+    /* variants of the samples: a pass over two small host arrays, as for the plain form */
+    int32_t cnt[PDEB_NUM_VARIANTS] = {0};
+    for (int64_t s = 0; s < n; ++s) {
+        const int v = pdeb_variant_of(in->kind[s], in->n_elem[s]);
+        if (v >= 0) ++cnt[v];
+    }
+    int32_t run = 0;
+    for (int v = 0; v < PDEB_NUM_VARIANTS; ++v) { r->vsc_host[2 * v] = run; r->vsc_host[2 * v + 1] = cnt[v]; run += cnt[v]; }
+    r->plan_stale = false;
+    return plan_view(r, view_of(r, 0, r->n, 0), stream);
 }
 
 extern "C" int pdeb_resident_set_knots(PdebResident* r, const double* knot_t, const double* knot_y,

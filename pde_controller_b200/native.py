@@ -35,6 +35,7 @@ def lib():
         L.pdeb_version.restype = C.c_int
         L.pdeb_device_count.restype = C.c_int
         L.pdeb_last_error.restype = C.c_char_p
+        L.pdeb_default_conventions.argtypes = [C.c_void_p]
         L.pdeb_host_alloc.restype = C.c_void_p
         L.pdeb_host_alloc.argtypes = [C.c_int64]
         L.pdeb_host_free.argtypes = [C.c_void_p]
@@ -48,6 +49,8 @@ def lib():
         L.pdeb_resident_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.pdeb_resident_upload.restype = C.c_int
         L.pdeb_resident_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pdeb_resident_upload_packed.restype = C.c_int
+        L.pdeb_resident_upload_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.pdeb_resident_run.restype = C.c_int
         L.pdeb_resident_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p]
@@ -127,6 +130,15 @@ def pinned_batch(n, kmax, pmax, tmax=None, uniform_knots=False) -> ProblemBatch:
     return b
 
 
+def pinned_packed(n, kmax, pmax, tmax=None, uniform_knots=False):
+    """An empty PackedBatch in page-locked memory (pack() into it, then upload_packed it)."""
+    from .problem import PackedBatch
+    buf = PinnedBuffer(PackedBatch.capacity_for(n, kmax, pmax, tmax, uniform_knots) + 64)
+    p = PackedBatch(n, kmax, pmax, tmax, buffer=buf.array, uniform_knots=uniform_knots)
+    p._pinned = buf
+    return p
+
+
 def evaluate_batch(batch: ProblemBatch, device: int = 0, precision: int = 64, conv=None, want_clauses: bool = False,
                    stream: int = 0, timing: bool = False):
     """One-shot: H2D, kernels, D2H.  -> dict(robustness, status[, clause][, timing])."""
@@ -181,6 +193,11 @@ class ResidentBatch:
     def upload(self, batch: Optional[ProblemBatch] = None, stream: int = 0):
         cb = (batch or self.batch).as_c()
         _check(self._L.pdeb_resident_upload(self._h, C.addressof(cb), stream or None), "pdeb_resident_upload")
+
+    def upload_packed(self, packed, stream: int = 0):
+        """Refill the image from the packed transfer form (problem.PackedBatch): one smaller copy, unpacked on the device."""
+        cp = packed.as_c()
+        _check(self._L.pdeb_resident_upload_packed(self._h, C.addressof(cp), stream or None), "pdeb_resident_upload_packed")
 
     def run(self, batch: Optional[ProblemBatch] = None, precision: int = 64, conv=None, want_clauses: bool = False,
             stream: int = 0, out=None, timing: bool = False):
@@ -255,7 +272,7 @@ class BlockPipeline:
     """
 
     def __init__(self, n: int, kmax: int, pmax: int, tmax=None, block: int = 65536, device: int = 0, depth: int = 2,
-                 uniform_knots: bool = False):
+                 uniform_knots: bool = False, packed: bool = False):
         self._L = lib()
         self.n, self.device, self.depth = int(n), device, int(depth)
         self.bounds = [(lo, min(lo + block, n)) for lo in range(0, n, block)]
@@ -264,6 +281,8 @@ class BlockPipeline:
         self.streams = [self._L.pdeb_stream_create(device) for _ in range(max(2, self.depth))]
         if not all(self.streams):
             raise NativeError("stream creation failed")
+        self.packed = bool(packed)       # blocks cross PCIe in the packed transfer form (ragged lists, narrow counts)
+        self.packs = []
         self.blocks, self.residents, self.robustness, self.status, self._outs, self._pins = [], [], [], [], [], []
         slot = 0
         for g in range(self.depth):
@@ -273,6 +292,8 @@ class BlockPipeline:
             self.status.append(st.array.view(np.int32)[:n])
             blks = [pinned_batch(hi - lo, kmax, pmax, tmax, uniform_knots) for lo, hi in self.bounds]
             self.blocks.append(blks)
+            self.packs.append([pinned_packed(hi - lo, kmax, pmax, tmax, uniform_knots) for lo, hi in self.bounds]
+                              if self.packed else [None] * len(self.bounds))
             self._outs.append([{"robustness": self.robustness[g][lo:hi], "status": self.status[g][lo:hi]}
                                for lo, hi in self.bounds])
             res = []
@@ -285,15 +306,20 @@ class BlockPipeline:
 
     def fill(self, batch: ProblemBatch, gen: int = 0):
         """Copy a whole batch into the blocks of one generation (host side)."""
-        for (lo, hi), blk in zip(self.bounds, self.blocks[gen]):
+        for (lo, hi), blk, pk in zip(self.bounds, self.blocks[gen], self.packs[gen]):
             for name in blk._names:
                 getattr(blk, name)[...] = getattr(batch, name)[..., lo:hi]
+            if pk is not None:
+                pk.pack(blk)
 
     def submit(self, gen: int = 0, precision: int = 64, conv=None):
         """Enqueue upload + plan + kernels + download of every block of generation `gen`; does not wait."""
-        for blk, (res, si), out in zip(self.blocks[gen], self.residents[gen], self._outs[gen]):
+        for blk, pk, (res, si), out in zip(self.blocks[gen], self.packs[gen], self.residents[gen], self._outs[gen]):
             st = self.streams[si]
-            res.upload(blk, stream=st)
+            if pk is not None:
+                res.upload_packed(pk, stream=st)
+            else:
+                res.upload(blk, stream=st)
             res.eval(precision, conv, stream=st)
             res.fetch_async(out, stream=st)
 
@@ -313,6 +339,8 @@ class BlockPipeline:
 
     @property
     def h2d_bytes(self):
+        if self.packed:
+            return sum(p.nbytes for p in self.packs[0])
         return sum(b.slab_bytes for b in self.blocks[0])
 
     def close(self):

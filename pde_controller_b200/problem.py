@@ -325,3 +325,124 @@ class ProblemBatch:
         flops = np.sum(S_run * np.where(heat, 8.0, wf) * n + 4.0 * node_steps)
         instr = np.sum(S_run * np.where(heat, 5.0, wi) * n + 2.0 * node_steps)
         return int(flops), int(instr)
+
+
+class PackedBatch:
+    """Packed TRANSFER form of a ProblemBatch (PdebPackedBatch of include/pdeb200.h): every per-sample list ragged
+    (sample after sample, only the entries in use), the counts narrow, all arrays in one 64-byte-aligned block.
+
+    The end-to-end rate of the path is host->device bandwidth over bytes per sample; this form is what a producer that
+    cares about it (the synthetic sweep, a dataset loader) writes.  `capacity_for` gives the worst-case block size of a
+    shape, so one page-locked buffer serves every batch of that shape; `pack(batch)` refills it."""
+
+    _SCALARS = [("kind", np.uint8), ("n_elem", np.uint16)] + [(f, np.float64) for f in _F64] + \
+               [("n_knots", np.uint16), ("n_pred", np.uint8), ("n_tree", np.uint8)]
+    _KNOT = [("knot_t", np.float64), ("knot_y", np.float64)]
+    _PRED = [(f, np.float64) for f in _PRED_F64] + [("pred_rel", np.uint8), ("pred_top", np.uint8)]
+    _TREE = [("tree_op", np.uint8), ("tree_lhs", np.int8), ("tree_rhs", np.int8)]
+
+    @classmethod
+    def capacity_for(cls, n, kmax, pmax, tmax=None, uniform_knots=False):
+        tmax = 2 * pmax - 1 if tmax is None else tmax
+        total = 0
+        for _, dt in cls._SCALARS:
+            total = _align(total + np.dtype(dt).itemsize * max(n, 1))
+        for name, dt in cls._KNOT:
+            if name == "knot_t" and uniform_knots:
+                continue
+            total = _align(total + np.dtype(dt).itemsize * max(n, 1) * kmax)
+        for _, dt in cls._PRED:
+            total = _align(total + np.dtype(dt).itemsize * max(n, 1) * pmax)
+        for _, dt in cls._TREE:
+            total = _align(total + np.dtype(dt).itemsize * max(n, 1) * tmax)
+        return total
+
+    def __init__(self, n, kmax, pmax, tmax=None, buffer=None, uniform_knots=False):
+        self.n, self.kmax, self.pmax = int(n), int(kmax), int(pmax)
+        self.tmax = int(2 * pmax - 1 if tmax is None else tmax)
+        self.uniform_knots = bool(uniform_knots)
+        cap = self.capacity_for(n, kmax, pmax, self.tmax, uniform_knots)
+        if buffer is None:
+            buffer = np.zeros(cap + 64, dtype=np.uint8)
+        a = buffer.ctypes.data
+        self._buffer = buffer
+        self._slab = buffer[(-a) % 64:][:cap]
+        self.nbytes = 0                      # bytes in use after pack(): what crosses PCIe
+        self.totals = (0, 0, 0)
+        self._views = {}
+
+    def pack(self, b: "ProblemBatch"):
+        """Refill from a plane-major batch of the same shape (vectorised; lists come out sample-major)."""
+        if (b.n, b.kmax, b.pmax, b.tmax) != (self.n, self.kmax, self.pmax, self.tmax) or b.uniform_knots != self.uniform_knots:
+            raise ValueError("batch shape differs from this packed buffer")
+        n = self.n
+        if b.n_elem.max(initial=0) > 65535 or b.n_knots.max(initial=0) > 65535 or b.n_elem.min(initial=0) < 0 or \
+                b.n_knots.min(initial=0) < 0 or b.n_pred.min(initial=0) < 0 or b.n_tree.min(initial=0) < 0 or \
+                b.n_pred.max(initial=0) > 255 or b.n_tree.max(initial=0) > 255:
+            raise ValueError("a count does not fit the packed form's narrow integers")
+        nk = np.minimum(b.n_knots[:n], self.kmax)
+        npd = np.minimum(b.n_pred[:n], self.pmax)
+        nt = np.minimum(b.n_tree[:n], self.tmax)
+        masks = {"k": (np.arange(self.kmax)[None, :] < nk[:, None]), "p": (np.arange(self.pmax)[None, :] < npd[:, None]),
+                 "t": (np.arange(self.tmax)[None, :] < nt[:, None])}
+        off = 0
+        self._views = {}
+
+        def put(name, arr):
+            nonlocal off
+            nb = arr.nbytes
+            self._slab[off:off + nb] = arr.view(np.uint8).reshape(-1)
+            self._views[name] = (off, arr.dtype, arr.size)
+            off = _align(off + max(nb, 1))
+
+        for name, dt in self._SCALARS:
+            put(name, np.ascontiguousarray(getattr(b, name)[:n].astype(dt, copy=False)))
+        # counts as the image will hold them: the kernels flag counts beyond the planes, so keep the caller's values
+        for name, dt in self._KNOT:
+            if name == "knot_t" and self.uniform_knots:
+                continue
+            put(name, np.ascontiguousarray(getattr(b, name)[:, :n].T[masks["k"]]))
+        for name, dt in self._PRED:
+            put(name, np.ascontiguousarray(getattr(b, name)[:, :n].T[masks["p"]]))
+        for name, dt in self._TREE:
+            put(name, np.ascontiguousarray(getattr(b, name)[:, :n].T[masks["t"]]))
+        self.nbytes = off
+        self.totals = (int(nk.sum()), int(npd.sum()), int(nt.sum()))
+        return self
+
+    def unpack(self) -> "ProblemBatch":
+        """The plane-major batch this block stands for (numpy restatement of the device-side unpack; used by the tests).
+        Unused list slots are zero."""
+        b = ProblemBatch(self.n, self.kmax, self.pmax, self.tmax, uniform_knots=self.uniform_knots)
+        base = self._slab
+
+        def get(name):
+            off, dt, size = self._views[name]
+            return base[off:off + size * np.dtype(dt).itemsize].view(dt)
+
+        for name, _ in self._SCALARS:
+            getattr(b, name)[:] = get(name)
+        nk = np.minimum(b.n_knots, self.kmax)
+        npd = np.minimum(b.n_pred, self.pmax)
+        nt = np.minimum(b.n_tree, self.tmax)
+        for group, cnt, planes in ((self._KNOT, nk, self.kmax), (self._PRED, npd, self.pmax), (self._TREE, nt, self.tmax)):
+            mask = np.arange(planes)[None, :] < cnt[:, None]
+            for name, _ in group:
+                if name == "knot_t" and self.uniform_knots:
+                    continue
+                dst = np.zeros((self.n, planes), dtype=getattr(b, name).dtype)
+                dst[mask] = get(name)
+                getattr(b, name)[:, : self.n] = dst.T
+        return b
+
+    def as_c(self) -> abi.PdebPackedBatch:
+        c = abi.PdebPackedBatch()
+        c.n, c.kmax, c.pmax, c.tmax = self.n, self.kmax, self.pmax, self.tmax
+        c.total_knots, c.total_pred, c.total_tree = self.totals
+        base = self._slab.ctypes.data
+        c.slab_base, c.slab_bytes = base, self.nbytes
+        for name, (off, _, _) in self._views.items():
+            setattr(c, name, base + off)
+        if self.uniform_knots:
+            c.knot_t = None
+        return c

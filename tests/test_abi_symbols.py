@@ -30,6 +30,16 @@ def test_every_declared_symbol_is_exported(so):
         assert hasattr(so, name), name
 
 
+def test_every_pointer_taking_export_has_argtypes():
+    """ctypes passes an undeclared argument as a C int: a 64-bit pointer would be truncated (a crash on the GPU box)."""
+    L = native.lib()
+    no_args = {"pdeb_version", "pdeb_device_count", "pdeb_last_error"}
+    for name in abi.EXPORTS:
+        if name in no_args:
+            continue
+        assert getattr(L, name).argtypes, name
+
+
 def test_version_and_defaults(so):
     assert so.pdeb_version() == abi.ABI_VERSION
     c = abi.PdebConventions()
@@ -44,6 +54,30 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(abi.PdebConventions) == 8 * 4 + 4 * 8
     assert ctypes.sizeof(abi.PdebBatch) == 2 * 8 + 4 * 4 + 8 + 8 + 28 * 8
     assert ctypes.sizeof(abi.PdebTiming) == 4 * 4 + 2 * 4
+    # int64 + 4 int32 + 3 int64 + ptr + int64 + 28 ptr
+    assert ctypes.sizeof(abi.PdebPackedBatch) == 8 + 4 * 4 + 3 * 8 + 8 + 8 + 28 * 8
+
+
+def test_packed_transfer_form_round_trip():
+    """PackedBatch (ragged lists, narrow counts) carries exactly the entries a batch uses: pack -> numpy unpack."""
+    import numpy as np
+    from pde_controller_b200 import PackedBatch, synth
+    for wl, uk, n in (("heat", True, 1000), ("wave", False, 257), ("mixed", False, 2049), ("heat", False, 1)):
+        b = synth.make_batch(n, wl, seed=3, uniform_knots=uk)
+        b.n_knots[: min(5, n)] = 0                       # empty lists
+        pk = PackedBatch(b.n, b.kmax, b.pmax, b.tmax, uniform_knots=uk).pack(b)
+        assert pk.nbytes < b.slab_bytes and pk.nbytes <= PackedBatch.capacity_for(b.n, b.kmax, b.pmax, b.tmax, uk)
+        u = pk.unpack()
+        cnts = {"knot": b.n_knots, "pred": b.n_pred, "tree": b.n_tree}
+        for name in b._names:
+            a, c = getattr(b, name), getattr(u, name)
+            if a.ndim == 1:
+                assert np.array_equal(a, c), name
+            else:
+                live = np.arange(a.shape[0])[:, None] < cnts[name[:4]][None, :]
+                assert np.array_equal(a[:, : b.n][live], c[:, : b.n][live]), name
+        c = pk.as_c()
+        assert (c.total_knots, c.total_pred, c.total_tree) == (int(b.n_knots.sum()), int(b.n_pred.sum()), int(b.n_tree.sum()))
 
 
 def test_no_cpu_fallback_without_device():
