@@ -360,7 +360,10 @@ def main():
     # compact form: the synthetic controls sit on uniform knots (C11), so knot times are formed on the device
     # (knot_t == NULL in the C ABI) instead of crossing PCIe; --explicit-knots sends them as per-sample arrays
     uk = not args.explicit_knots
-    src = synth.make_batch(args.batch, args.workload, seed=args.seed, start=rank * args.batch, total=total, uniform_knots=uk)
+    # mixed: every rank takes its 1/N slice of each kind (contiguous ranges of the kind-sorted set would leave the
+    # last ranks with waves only, three times the work of the first ones)
+    src = synth.make_batch(args.batch, args.workload, seed=args.seed, start=rank * args.batch, total=total, uniform_knots=uk,
+                           kind_slice=(rank, world) if args.workload == "mixed" and world > 1 else None)
     host = native.pinned_batch(src.n, src.kmax, src.pmax, src.tmax, uniform_knots=uk)
     host.slab[:] = src.slab
     res = native.ResidentBatch(host, device=dev, stream=stream)

@@ -137,17 +137,27 @@ def _copy_into(batch: ProblemBatch, dst_lo: int, f: dict, src_lo: int, cnt: int)
 
 
 def make_batch(n: int, workload: str = "heat", seed: int = 0, start: int = 0, total: int | None = None,
-               buffer=None, uniform_knots: bool = False) -> ProblemBatch:
+               buffer=None, uniform_knots: bool = False, kind_slice: tuple | None = None) -> ProblemBatch:
     """Samples [start, start+n) of `workload`.
 
     mixed: global indices below total//2 are heat, the rest wave (sorted by kind so that warps
     are homogeneous); `total` defaults to start+n.
+    kind_slice = (rank, world), mixed only: the n-sample shard of rank `rank` when every rank takes its 1/world slice of
+    EACH kind of the global set of world * n samples (heat samples [rank n/2, (rank+1) n/2) and the same wave samples):
+    contiguous index ranges of a kind-sorted set would give the first ranks only heat and the last ones only waves,
+    and waves cost three times as much (balance mixed batches by cost, not by count).
     """
     if workload not in WORKLOADS:
         raise ValueError(f"unknown workload {workload!r}")
     # the synthetic controls sit on linspace(0, T, K) (C11), so the compact form without knot times describes the same set
     batch = ProblemBatch(n, KMAX[workload], PMAX, buffer=buffer, uniform_knots=uniform_knots)
-    if workload == "mixed":
+    if workload == "mixed" and kind_slice is not None:
+        rank, world = kind_slice
+        if not (0 <= rank < world):
+            raise ValueError("kind_slice rank out of range")
+        nh = n // 2
+        pieces = [("heat", rank * nh, (rank + 1) * nh), ("wave", rank * (n - nh), (rank + 1) * (n - nh))]
+    elif workload == "mixed":
         total = start + n if total is None else total
         half = total // 2
         pieces = []

@@ -77,3 +77,22 @@ def test_cost_balanced_bounds():
     assert loads.max() / loads.mean() < 1.05
     by_count = np.array([cost[l:h].sum() for l, h in (sharding.shard_bounds(b.n, r, 8) for r in range(8))])
     assert loads.max() <= by_count.max()
+
+
+def test_kind_slices_partition_the_mixed_set_and_balance_cost():
+    """make_batch(kind_slice=(r, R)): the R shards are a partition of the global mixed set, each with both kinds."""
+    R, n = 4, 2048
+    whole = synth.make_batch(R * n, "mixed", seed=5)
+    key = lambda x: set(map(tuple, np.stack([x.kind, x.L, x.T, x.g0, x.E_in, x.pred_b[0]]).T.tolist()))
+    parts = [synth.make_batch(n, "mixed", seed=5, kind_slice=(r, R)) for r in range(R)]
+    union = set()
+    for p in parts:
+        assert (p.kind == 0).sum() == n // 2 and (p.kind == 1).sum() == n - n // 2
+        k = key(p)
+        assert len(k) == n and not (k & union)
+        union |= k
+    assert union == key(whole)
+    loads = np.array([sharding.batch_cost(p).sum() for p in parts])
+    assert loads.max() / loads.mean() < 1.05
+    contiguous = np.array([sharding.batch_cost(synth.make_batch(n, "mixed", seed=5, start=r * n, total=R * n)).sum() for r in range(R)])
+    assert contiguous.max() / contiguous.mean() > 1.3
