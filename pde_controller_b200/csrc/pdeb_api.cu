@@ -232,21 +232,32 @@ static RangeView view_of(const PdebResident* r, int64_t lo, int64_t hi, int chun
  */
 static void host_variant_counts(const PdebBatch* in, int64_t lo, int64_t hi, int32_t* vsc) {
     int32_t cnt[PDEB_NUM_VARIANTS] = {0};
+    int last_kind = -1, last_ne = -1, last_v = -1;      /* the variant is looked up only where (kind, mesh) changes */
+    int64_t len = 0;
     for (int64_t s = lo; s < hi; ++s) {
-        const int v = pdeb_variant_of(in->kind[s], in->n_elem[s]);
-        if (v >= 0) ++cnt[v];
+        const int k = in->kind[s], ne = in->n_elem[s];
+        if (k != last_kind || ne != last_ne) {
+            if (last_v >= 0) cnt[last_v] += (int32_t)len;
+            len = 0;
+            last_kind = k; last_ne = ne;
+            last_v = pdeb_variant_of(k, ne);
+        }
+        ++len;
     }
+    if (last_v >= 0) cnt[last_v] += (int32_t)len;
     int32_t run = 0;
     for (int v = 0; v < PDEB_NUM_VARIANTS; ++v) { vsc[2 * v] = run; vsc[2 * v + 1] = cnt[v]; run += cnt[v]; }
 }
 
 /* order a range by kernel variant and step count (device side, 3 launches, asynchronous) */
-static int plan_view(PdebResident* r, const RangeView& v, cudaStream_t stream) {
+static int plan_view(PdebResident* r, const RangeView& v, const int32_t* vsc, cudaStream_t stream) {
     if (v.dev.n == 0) return 0;
     PdebConventions cv;
     pdeb_default_conventions(&cv);
     int nl = 0;
-    int rc = pdeb_plan(v.dev, cv, v.out, v.pb, stream, &nl);
+    uint32_t live = 0;                       /* variants this range holds (host counts) */
+    for (int q = 0; q < PDEB_NUM_VARIANTS; ++q) if (vsc[2 * q + 1] > 0) live |= 1u << q;
+    int rc = pdeb_plan(v.dev, cv, v.out, v.pb, live, stream, &nl);
     if (rc) return fail(PDEB_E_CUDA, "plan launch", (cudaError_t)rc);
     r->plan_launches = nl;
     return 0;
@@ -355,7 +366,7 @@ extern "C" int pdeb_resident_create(const PdebBatch* in, int device, void* strea
     if (rc) return rc;
     DeviceGuard g(device);
     rc = upload(r, in, 0, r->n, (cudaStream_t)stream_, false);
-    if (rc == 0) { host_variant_counts(in, 0, r->n, r->vsc_host); rc = plan_view(r, view_of(r, 0, r->n, 0), (cudaStream_t)stream_); }
+    if (rc == 0) { host_variant_counts(in, 0, r->n, r->vsc_host); rc = plan_view(r, view_of(r, 0, r->n, 0), r->vsc_host, (cudaStream_t)stream_); }
     if (rc) { pdeb_resident_destroy(r); return rc; }
     *outp = r;
     return 0;
@@ -372,7 +383,7 @@ extern "C" int pdeb_resident_upload(PdebResident* r, const PdebBatch* in, void* 
         return fail(PDEB_E_ARG, "batch slab layout differs from the resident image");
     DeviceGuard g(r->device);
     rc = upload(r, in, 0, r->n, (cudaStream_t)stream_, false);
-    if (rc == 0) { host_variant_counts(in, 0, r->n, r->vsc_host); rc = plan_view(r, view_of(r, 0, r->n, 0), (cudaStream_t)stream_); }
+    if (rc == 0) { host_variant_counts(in, 0, r->n, r->vsc_host); rc = plan_view(r, view_of(r, 0, r->n, 0), r->vsc_host, (cudaStream_t)stream_); }
     return rc;
 }
 
@@ -519,6 +530,35 @@ extern "C" int pdeb_resident_upload_packed(PdebResident* r, const PdebPackedBatc
         const unsigned char* q = (const unsigned char*)a.p;
         if (q < base || q + a.bytes > base + in->slab_bytes) return fail(PDEB_E_ARG, "a packed array lies outside the slab");
     }
+    /* one pass over the small host arrays: the variants of the samples (as for the plain form) and the list totals, which
+     * must be the sums of the counts (the device forms the offsets from the counts: a wrong total would read past a list) */
+    int32_t cnt[PDEB_NUM_VARIANTS] = {0};
+    int64_t sk = 0, sp = 0, stt = 0;
+    {
+        /* this runs on the submitting host thread once per upload, i.e. inside the end-to-end rate: plain loops the
+         * compiler vectorises, and the variant of a sample is looked up only where (kind, mesh) changes */
+        const int kmax = r->kmax, pmax = r->pmax, tmax = r->tmax;
+        const uint16_t* nk = in->n_knots;
+        const uint8_t *npd = in->n_pred, *ntr = in->n_tree;
+        for (int64_t s = 0; s < n; ++s) sk += nk[s] < kmax ? nk[s] : kmax;
+        for (int64_t s = 0; s < n; ++s) sp += npd[s] < pmax ? npd[s] : pmax;
+        for (int64_t s = 0; s < n; ++s) stt += ntr[s] < tmax ? ntr[s] : tmax;
+        int last_kind = -1, last_ne = -1, last_v = -1;
+        int64_t run = 0;
+        for (int64_t s = 0; s < n; ++s) {
+            const int k = in->kind[s], ne = in->n_elem[s];
+            if (k != last_kind || ne != last_ne) {
+                if (last_v >= 0) cnt[last_v] += (int32_t)run;
+                run = 0;
+                last_kind = k; last_ne = ne;
+                last_v = pdeb_variant_of(k, ne);
+            }
+            ++run;
+        }
+        if (last_v >= 0) cnt[last_v] += (int32_t)run;
+    }
+    if (sk != in->total_knots || sp != in->total_pred || stt != in->total_tree)
+        return fail(PDEB_E_ARG, "packed list totals are not the sums of the (clamped) counts");
     DeviceGuard g(r->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     /* staging: worst-case block (every list full, 64 bytes of alignment slack per array) | offsets [3][n] | block sums */
@@ -546,16 +586,10 @@ extern "C" int pdeb_resident_upload_packed(PdebResident* r, const PdebPackedBatc
     pdeb_pack_blocksum_kernel<<<1, PDEB_SCAN_BLOCK, 0, stream>>>(bsum, blocks);
     pdeb_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p, r->dev, off, bsum, blocks);
     CK(cudaGetLastError());
-    /* variants of the samples: a pass over two small host arrays, as for the plain form */
-    int32_t cnt[PDEB_NUM_VARIANTS] = {0};
-    for (int64_t s = 0; s < n; ++s) {
-        const int v = pdeb_variant_of(in->kind[s], in->n_elem[s]);
-        if (v >= 0) ++cnt[v];
-    }
     int32_t run = 0;
     for (int v = 0; v < PDEB_NUM_VARIANTS; ++v) { r->vsc_host[2 * v] = run; r->vsc_host[2 * v + 1] = cnt[v]; run += cnt[v]; }
     r->plan_stale = false;
-    return plan_view(r, view_of(r, 0, r->n, 0), stream);
+    return plan_view(r, view_of(r, 0, r->n, 0), r->vsc_host, stream);
 }
 
 extern "C" int pdeb_resident_set_knots(PdebResident* r, const double* knot_t, const double* knot_y,
@@ -579,7 +613,7 @@ extern "C" int pdeb_resident_eval(PdebResident* r, int precision, const PdebConv
     if (conv) cv = *conv; else pdeb_default_conventions(&cv);
     int launches = 0;
     if (r->plan_stale) {
-        int prc = plan_view(r, view_of(r, 0, r->n, 0), stream);
+        int prc = plan_view(r, view_of(r, 0, r->n, 0), r->vsc_host, stream);
         if (prc) return prc;
         r->plan_stale = false;
     }
@@ -702,7 +736,7 @@ extern "C" int pdeb_resident_run(PdebResident* r, const PdebBatch* in, int preci
         if (rc) return rc;
         RangeView v = view_of(r, lo, hi, c);
         host_variant_counts(in, lo, hi, v.vsc);
-        rc = plan_view(r, v, st);
+        rc = plan_view(r, v, v.vsc, st);
         if (rc) return rc;
         int nl = 0;
         const int lrc = pdeb_launch_all(v.dev, cv, v.out, v.pb, v.vsc, precision, st, &nl);

@@ -65,9 +65,10 @@ struct PdebPlanBuffers {
     int32_t* vstart_count;  /* [2 * PDEB_NUM_VARIANTS] first index / count of each variant inside order */
 };
 
-/* order the batch (3 launches); flags samples no variant covers */
+/* order the batch (3 launches); flags samples no variant covers.  live_variants: bit v set if the batch may hold samples
+ * of variant v (known on the host from kind / n_elem); only those variants' bins are scanned */
 int pdeb_plan(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out, const PdebPlanBuffers& pb,
-              cudaStream_t stream, int* launches);
+              uint32_t live_variants, cudaStream_t stream, int* launches);
 
 /* enqueue the compute kernels of every non-empty variant; returns 0 or a cudaError_t value */
 int pdeb_launch_all(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out, const PdebPlanBuffers& pb,

@@ -408,6 +408,7 @@ class PackedBatch:
             put(name, np.ascontiguousarray(getattr(b, name)[:, :n].T[masks["t"]]))
         self.nbytes = off
         self.totals = (int(nk.sum()), int(npd.sum()), int(nt.sum()))
+        self._c = None
         return self
 
     def unpack(self) -> "ProblemBatch":
@@ -436,6 +437,10 @@ class PackedBatch:
         return b
 
     def as_c(self) -> abi.PdebPackedBatch:
+        """The C view of the block (cached until the next pack(): it is built once per upload otherwise, on the thread
+        that feeds the GPU)."""
+        if getattr(self, "_c", None) is not None:
+            return self._c
         c = abi.PdebPackedBatch()
         c.n, c.kmax, c.pmax, c.tmax = self.n, self.kmax, self.pmax, self.tmax
         c.total_knots, c.total_pred, c.total_tree = self.totals
@@ -445,4 +450,5 @@ class PackedBatch:
             setattr(c, name, base + off)
         if self.uniform_knots:
             c.knot_t = None
+        self._c = c
         return c

@@ -101,6 +101,19 @@ def test_packed_upload_equals_planar_upload(oracle_lib):
         assert np.array_equal(got["clause"][live], ref["clause"][live])
 
 
+def test_packed_upload_rejects_inconsistent_totals():
+    import ctypes as C
+    from pde_controller_b200 import native, synth
+    b = synth.make_batch(300, "heat", seed=6)
+    res = native.ResidentBatch(b)
+    pk = native.pinned_packed(b.n, b.kmax, b.pmax, b.tmax).pack(b)
+    cp = pk.as_c()
+    cp.total_knots -= 1
+    rc = native.lib().pdeb_resident_upload_packed(res._h, C.addressof(cp), None)
+    assert rc == -1 and b"totals" in native.lib().pdeb_last_error()
+    res.close()
+
+
 def test_block_pipeline_packed_matches_planar():
     import numpy as np
     from pde_controller_b200 import native, synth
