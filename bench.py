@@ -199,12 +199,16 @@ def cpu_context(batch, nthreads):
     from oracle import pde_oracle_np
     ctx = {}
     try:
-        k = min(batch.n, 12)
-        t0 = time.perf_counter()
-        for s in range(k):
-            p, ctl = batch.get_problem(s)
-            pde_oracle_np.evaluate(p, ctl)
-        ctx["numpy_port_1core"] = {"value": k / (time.perf_counter() - t0), "unit": UNIT, "sample": f"first {k} samples"}
+        # the restatement solves a DENSE system every step: bounded to the default meshes and to ~2 s
+        if int(batch.n_elem[: min(batch.n, 12)].max(initial=0)) > 64:
+            ctx["numpy_port_1core"] = {"skipped": "dense per-step solves: default meshes only"}
+        else:
+            k, t0 = 0, time.perf_counter()
+            while k < min(batch.n, 12) and time.perf_counter() - t0 < 2.0:
+                p, ctl = batch.get_problem(k)
+                pde_oracle_np.evaluate(p, ctl)
+                k += 1
+            ctx["numpy_port_1core"] = {"value": k / (time.perf_counter() - t0), "unit": UNIT, "sample": f"first {k} samples"}
     except Exception as e:  # context only: never fails the bench
         ctx["numpy_port_1core"] = {"error": repr(e)}
     try:
