@@ -194,6 +194,22 @@ def test_c_oracle_matches_numpy_restatement(oracle_lib):
             np.testing.assert_allclose(cl[: len(clause), s], clause, rtol=0, atol=1e-10 * max(scale, np.abs(clause).max()))
 
 
+@pytest.mark.parametrize("wl", ["heat", "wave"])
+def test_c_oracle_matches_numpy_restatement_on_stress_shapes(oracle_lib, wl):
+    """The shapes the GPU stress tests use (overlapping windows, intervals inside one element, dense non-uniform knots,
+    eight clauses with and/or trees): the checker itself is checked there by its independent numpy twin."""
+    from test_gpu_parity import _stress_batch, _wide_batch
+    for b in (_stress_batch(wl, 20, 31), _wide_batch(wl, 20, 41)):
+        rob, st, cl = oracle_lib.eval_batch(b, want_clauses=True)
+        assert (st == 0).all()
+        for s in range(b.n):
+            p, c = b.get_problem(s)
+            r, clause = onp.evaluate(p, c)
+            scale = max(abs(r), 1e-3 * (abs(p.g0) + 1.0 + np.abs(c[1]).max() * p.L / min(p.E_in, p.E_out)))
+            assert abs(rob[s] - r) <= 1e-9 * scale
+            np.testing.assert_allclose(cl[: len(clause), s], clause, rtol=0, atol=1e-9 * max(scale, np.abs(clause).max()))
+
+
 def test_conventions_change_results(oracle_lib):
     """Each declared convention flag is live (moves the result) and is honoured by both restatements."""
     from pde_controller_b200 import synth
