@@ -274,18 +274,52 @@ def run_controls(args, rank, local_rank, world):
     total_ms = float(t_dev.item())
     total = m * world
     value = total * args.steps / (total_ms * 1e-3)
-    # end to end: candidates from pinned host memory every step, robustness + status + arg-max back on the host
+    # end to end: candidates from pinned host memory every step, robustness + status + arg-max back on the host.
+    # The candidates go through TWO evaluators (halves) on two streams, each driven by its own host thread (the C call
+    # releases the GIL), so the upload of one half overlaps the kernel of the other: a stream of candidate sets is
+    # bound by max(copy, kernel) instead of their sum.
+    L = native.lib()
+    mh = (m + 1) // 2
+    bounds = [(0, mh), (mh, m)] if m > 1 else [(0, m)]
+    evs, pins, ys, streams, outs = [], [], [], [], []
+    for lo_, hi_ in bounds:
+        pb_ = native.PinnedBuffer(8 * nk * (hi_ - lo_))
+        yy = pb_.array.view(np.float64).reshape(nk, hi_ - lo_)
+        yy[:] = y[:, lo_:hi_]
+        pr_, ps_ = native.PinnedBuffer(8 * (hi_ - lo_)), native.PinnedBuffer(4 * (hi_ - lo_))   # page-locked results
+        pins += [pb_, pr_, ps_]; ys.append(yy)
+        outs.append({"robustness": pr_.array.view(np.float64), "status": ps_.array.view(np.int32)})
+        evs.append(native.ControlsEvaluator(spec, knot_t, capacity=hi_ - lo_, sample=s, device=local_rank))
+        streams.append(L.pdeb_stream_create(local_rank))
+    last = [None] * len(bounds)
+
+    def half(i, reps):
+        for _ in range(reps):
+            last[i] = evs[i].eval(ys[i], stream=streams[i], out=outs[i])
+
+    for i in range(len(bounds)):
+        half(i, 1)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        r = ev.eval(y)
+    ths = [threading.Thread(target=half, args=(i, args.steps)) for i in range(len(bounds))]
+    for t_ in ths:
+        t_.start()
+    for t_ in ths:
+        t_.join()
     torch.cuda.synchronize()
     dt_ = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(dt_, op=dist.ReduceOp.MAX)
     e2e = total * args.steps / float(dt_.item())
-    if not np.array_equal(r["robustness"], first["robustness"]):
+    e2e_rob = np.concatenate([x["robustness"] for x in last])
+    if not np.array_equal(e2e_rob, first["robustness"]):
         raise SystemExit("bench: repeated evaluation of the same candidates differs")
+    best = max(last, key=lambda x: x["best_value"])
+    if best["best_value"] != first["best_value"]:
+        raise SystemExit("bench: arg-max over the halves differs from the arg-max over all candidates")
+    for e_, st_ in zip(evs, streams):
+        e_.close()
+        L.pdeb_stream_destroy(st_)
     if rank == 0:
         peak, peak_src = peaks()
         prof = measured_profile()
@@ -299,6 +333,7 @@ def run_controls(args, rank, local_rank, world):
             "data": "synthetic",
             "config": {"workload": WORKLOAD_TEXT[args.workload], "candidates_per_gpu": m, "knots": nk, "sim_steps": steps_sim,
                        "n_pred": int(spec.n_pred[s]), "seed": args.seed, "l2": "flushed (256 MiB write) between timed steps",
+                       "e2e_overlap": "two halves of the candidates on two streams, one host thread each",
                        "wall_s_timed_region": wall1 - wall0},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(8 * nk * m), "d2h_bytes_per_step": int(12 * m)},
             "gpu_launches": int(launches), "clocks": clocks,

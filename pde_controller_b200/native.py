@@ -378,8 +378,10 @@ class ControlsEvaluator:
                                             _conv_ptr(conv), C.addressof(self._h)), "pdeb_controls_create")
 
     def eval(self, knot_y: Optional[np.ndarray], m: Optional[int] = None, want_robustness: bool = True,
-             want_clauses: bool = False, stream: int = 0):
+             want_clauses: bool = False, stream: int = 0, out=None):
         """knot_y: [n_knots, m] (plane-major, C-contiguous) or None to re-evaluate the values already on the device.
+        out: optional dict of preallocated result arrays ("robustness" f64[m], "status" i32[m]); page-locked ones
+        (PinnedBuffer) keep the download at PCIe speed and asynchronous to other streams.
         Returns dict(robustness, status, [clause], best_index, best_value, kernel_ms, launches)."""
         if knot_y is not None:
             knot_y = np.ascontiguousarray(knot_y, dtype=np.float64)
@@ -388,8 +390,13 @@ class ControlsEvaluator:
             m = knot_y.shape[1]
         if m is None or not (1 <= m <= self.capacity):
             raise ValueError("number of candidates out of range")
-        rob = np.empty(m, dtype=np.float64) if want_robustness else None
-        st = np.empty(m, dtype=np.int32) if want_robustness else None
+        if out is not None and want_robustness:
+            rob, st = out["robustness"][:m], out["status"][:m]
+            if rob.dtype != np.float64 or st.dtype != np.int32 or not rob.flags.c_contiguous or not st.flags.c_contiguous:
+                raise ValueError("out arrays must be contiguous f64 / i32")
+        else:
+            rob = np.empty(m, dtype=np.float64) if want_robustness else None
+            st = np.empty(m, dtype=np.int32) if want_robustness else None
         cl = np.empty((self.n_pred, m), dtype=np.float64) if want_clauses else None
         bi, bv, tm = C.c_int64(-1), C.c_double(0.0), abi.PdebTiming()
         _check(self._L.pdeb_controls_eval(self._h, m, _ptr(knot_y), _ptr(rob), _ptr(cl), _ptr(st), C.addressof(bi),
