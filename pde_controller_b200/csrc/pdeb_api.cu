@@ -250,14 +250,14 @@ static void host_variant_counts(const PdebBatch* in, int64_t lo, int64_t hi, int
 }
 
 /* order a range by kernel variant and step count (device side, 3 launches, asynchronous) */
-static int plan_view(PdebResident* r, const RangeView& v, const int32_t* vsc, cudaStream_t stream) {
+static int plan_view(PdebResident* r, const RangeView& v, const int32_t* vsc, cudaStream_t stream, bool keys_done = false) {
     if (v.dev.n == 0) return 0;
     PdebConventions cv;
     pdeb_default_conventions(&cv);
     int nl = 0;
     uint32_t live = 0;                       /* variants this range holds (host counts) */
     for (int q = 0; q < PDEB_NUM_VARIANTS; ++q) if (vsc[2 * q + 1] > 0) live |= 1u << q;
-    int rc = pdeb_plan(v.dev, cv, v.out, v.pb, live, stream, &nl);
+    int rc = pdeb_plan(v.dev, cv, v.out, v.pb, live, stream, &nl, keys_done);
     if (rc) return fail(PDEB_E_CUDA, "plan launch", (cudaError_t)rc);
     r->plan_launches = nl;
     return 0;
@@ -439,33 +439,43 @@ pdeb_pack_scan_kernel(int64_t n, const uint16_t* __restrict__ nk, const uint8_t*
 
 /* one block: block totals -> exclusive offsets of the blocks (in place), any number of blocks */
 __global__ void __launch_bounds__(PDEB_SCAN_BLOCK) pdeb_pack_blocksum_kernel(int32_t* __restrict__ bsum, int blocks) {
-    __shared__ int32_t part[PDEB_SCAN_BLOCK];
-    __shared__ int32_t carry;
-    for (int q = 0; q < 3; ++q) {
-        if (threadIdx.x == 0) carry = 0;
-        __syncthreads();
-        for (int base = 0; base < blocks; base += PDEB_SCAN_BLOCK) {
-            const int i = base + threadIdx.x;
-            const int32_t v = (i < blocks) ? bsum[(int64_t)q * blocks + i] : 0;
-            part[threadIdx.x] = v;
-            __syncthreads();
-            for (int o = 1; o < PDEB_SCAN_BLOCK; o <<= 1) {
-                const int32_t y = (threadIdx.x >= o) ? part[threadIdx.x - o] : 0;
-                __syncthreads();
-                part[threadIdx.x] += y;
-                __syncthreads();
-            }
-            if (i < blocks) bsum[(int64_t)q * blocks + i] = carry + part[threadIdx.x] - v;
-            __syncthreads();
-            if (threadIdx.x == PDEB_SCAN_BLOCK - 1) carry += part[threadIdx.x];
-            __syncthreads();
+    __shared__ int32_t wsum[3][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int32_t carry[3] = {0, 0, 0};
+    for (int base = 0; base < blocks; base += PDEB_SCAN_BLOCK) {
+        const int i = base + threadIdx.x;
+        int32_t v[3], inc[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            v[q] = (i < blocks) ? bsum[(int64_t)q * blocks + i] : 0;
+            int32_t x = v[q];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            inc[q] = x;
+            if (lane == 31) wsum[q][warp] = x;
         }
+        __syncthreads();
+        if (warp < 3) {
+            int32_t x = wsum[warp][lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            wsum[warp][lane] = x;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            if (i < blocks) bsum[(int64_t)q * blocks + i] = carry[q] + (warp > 0 ? wsum[q][warp - 1] : 0) + inc[q] - v[q];
+            carry[q] += wsum[q][31];
+        }
+        __syncthreads();
     }
 }
 
 /* scatter one sample per thread into the plane-major image (unused list slots keep whatever they held: nobody reads them) */
 __global__ void pdeb_unpack_kernel(const __grid_constant__ PdebPackedDev p, const __grid_constant__ PdebDevBatch d,
-                                   const int32_t* __restrict__ off, const int32_t* __restrict__ bsum, int blocks) {
+                                   const int32_t* __restrict__ off, const int32_t* __restrict__ bsum, int blocks,
+                                   const __grid_constant__ PdebConventions cv, const __grid_constant__ PdebDevOut out,
+                                   int32_t* __restrict__ keys, int32_t* __restrict__ hist) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n = d.n, st = d.stride;
     if (s >= n) return;
@@ -503,6 +513,8 @@ __global__ void pdeb_unpack_kernel(const __grid_constant__ PdebPackedDev p, cons
         ((int8_t*)d.tree_lhs)[q] = p.tree_lhs[ot + j];
         ((int8_t*)d.tree_rhs)[q] = p.tree_rhs[ot + j];
     }
+    /* the plan's sort key and histogram of this sample, while its data are at hand (saves the plan's keys pass) */
+    pdeb_plan_count(d, cv, out, s, keys, hist);
 }
 
 extern "C" int pdeb_resident_upload_packed(PdebResident* r, const PdebPackedBatch* in, void* stream_) {
@@ -582,14 +594,17 @@ extern "C" int pdeb_resident_upload_packed(PdebResident* r, const PdebPackedBatc
 #undef DEVP
     int32_t* off = (int32_t*)(r->pstage + r->pstage_off);
     int32_t* bsum = (int32_t*)(r->pstage + r->pstage_off + align_up(12 * nn, 256));
+    PdebConventions pcv;
+    pdeb_default_conventions(&pcv);                      /* the plan orders by the default step / window rules */
+    CK(cudaMemsetAsync(r->pb.hist, 0, sizeof(int32_t) * PDEB_PLAN_BINS, stream));
     pdeb_pack_scan_kernel<<<blocks, PDEB_SCAN_BLOCK, 0, stream>>>(n, p.n_knots, p.n_pred, p.n_tree, r->kmax, r->pmax, r->tmax, off, bsum);
     pdeb_pack_blocksum_kernel<<<1, PDEB_SCAN_BLOCK, 0, stream>>>(bsum, blocks);
-    pdeb_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p, r->dev, off, bsum, blocks);
+    pdeb_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p, r->dev, off, bsum, blocks, pcv, r->out, r->pb.keys, r->pb.hist);
     CK(cudaGetLastError());
     int32_t run = 0;
     for (int v = 0; v < PDEB_NUM_VARIANTS; ++v) { r->vsc_host[2 * v] = run; r->vsc_host[2 * v + 1] = cnt[v]; run += cnt[v]; }
     r->plan_stale = false;
-    return plan_view(r, view_of(r, 0, r->n, 0), r->vsc_host, stream);
+    return plan_view(r, view_of(r, 0, r->n, 0), r->vsc_host, stream, true);
 }
 
 extern "C" int pdeb_resident_set_knots(PdebResident* r, const double* knot_t, const double* knot_y,

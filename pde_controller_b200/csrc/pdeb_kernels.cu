@@ -48,59 +48,12 @@ pdeb_reg_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant__ 
  * exclusive scan of the PDEB_PLAN_BINS bins, scatter.  Samples no variant of this build covers
  * are flagged here (status BADPARAM, robustness -100), never dropped silently.
  */
-__device__ __forceinline__ int pdeb_plan_key(const PdebDevBatch& b, const PdebConventions& cv, int64_t s) {
-    const int kind = b.kind[s], N = b.n_elem[s];
-    const int v = pdeb_variant_of(kind, N);
-    if (v < 0) return -1;
-    const double T = b.T[s], dt = b.dt[s];
-    int64_t S = 1;
-    int sub = 0;
-    if (T > 0 && dt > 0 && isfinite(T) && isfinite(dt)) {
-        S = pdeb_step_count(T, dt, cv.steps_rule);
-        /* the kernels stop at the last observed step: order by that */
-        const int np = b.n_pred[s];
-        double last = 0.0, first = 4.0e9;
-        for (int j = 0; j < np && j < b.pmax; ++j) {
-            const double q = b.pred_thi[(int64_t)j * b.stride + s] / dt;
-            const double a1 = (cv.window_rule == 1) ? trunc(q) : floor(q + PDEB_EPS);
-            if (a1 > last) last = a1;
-            const double p = b.pred_tlo[(int64_t)j * b.stride + s] / dt;
-            const double a0 = (cv.window_rule == 1) ? trunc(p) : ceil(p - PDEB_EPS);
-            if (a0 < first) first = a0;
-        }
-        if (last < (double)S) S = (int64_t)last;
-        if (S < 1) S = 1;
-        /* second key: where in the run the first window opens.  A warp runs a clause pass in every step in which ANY
-         * of its lanes has an open window, so lanes whose windows open together share their idle prefix. */
-        if (first > 0.0) {
-            const double f = first * PDEB_PLAN_FBINS / ((double)S + 1.0);
-            sub = (f >= (double)(PDEB_PLAN_FBINS - 1)) ? PDEB_PLAN_FBINS - 1 : (int)f;
-        }
-    }
-    /* first key: steps in buckets, descending inside a variant (longest first).  Half of the buckets are
-     * PDEB_PLAN_SWIDTH steps wide, the next quarters 8x and 512x that (then one bucket for everything longer) */
-    constexpr int64_t H = PDEB_PLAN_SBUCKETS / 2, Q = PDEB_PLAN_SBUCKETS / 4, W = PDEB_PLAN_SWIDTH;
-    int64_t sb = S / W;
-    if (sb >= H) {
-        sb = H + (S - H * W) / (8 * W);
-        if (sb >= H + Q) sb = H + Q + (S - H * W - Q * 8 * W) / (512 * W);
-    }
-    if (sb > PDEB_PLAN_SBUCKETS - 1) sb = PDEB_PLAN_SBUCKETS - 1;
-    return v * PDEB_PLAN_SBINS + (PDEB_PLAN_SBUCKETS - 1 - (int)sb) * PDEB_PLAN_FBINS + sub;
-}
-
 __global__ void pdeb_plan_keys_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant__ PdebConventions cv,
                                       const __grid_constant__ PdebDevOut out, int32_t* __restrict__ keys,
                                       int32_t* __restrict__ hist) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= b.n) return;
-    const int key = pdeb_plan_key(b, cv, s);
-    keys[s] = key;
-    if (key >= 0) { atomicAdd(&hist[key], 1); return; }
-    out.robustness[s] = PDEB_FAILED_ROBUSTNESS;
-    if (out.status) out.status[s] = PDEB_ST_BADPARAM;
-    if (out.clause)
-        for (int j = 0; j < b.pmax; ++j) out.clause[(int64_t)j * b.stride + s] = PDEB_FAILED_ROBUSTNESS;
+    pdeb_plan_count(b, cv, out, s, keys, hist);
 }
 
 /*
@@ -155,16 +108,19 @@ __global__ void pdeb_plan_scatter_kernel(int64_t n, const int32_t* __restrict__ 
 }
 
 int pdeb_plan(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out, const PdebPlanBuffers& pb,
-              uint32_t live_variants, cudaStream_t stream, int* launches) {
+              uint32_t live_variants, cudaStream_t stream, int* launches, bool keys_done) {
     if (b.n <= 0) { if (launches) *launches = 0; return 0; }
-    cudaError_t e = cudaMemsetAsync(pb.hist, 0, sizeof(int32_t) * PDEB_PLAN_BINS, stream);
-    if (e != cudaSuccess) return (int)e;
+    cudaError_t e = cudaSuccess;
     const int threads = 256;
     const unsigned blocks = (unsigned)((b.n + threads - 1) / threads);
-    pdeb_plan_keys_kernel<<<blocks, threads, 0, stream>>>(b, cv, out, pb.keys, pb.hist);
+    if (!keys_done) {
+        e = cudaMemsetAsync(pb.hist, 0, sizeof(int32_t) * PDEB_PLAN_BINS, stream);
+        if (e != cudaSuccess) return (int)e;
+        pdeb_plan_keys_kernel<<<blocks, threads, 0, stream>>>(b, cv, out, pb.keys, pb.hist);
+    }
     pdeb_plan_scan_kernel<<<1, 1024, 0, stream>>>(pb.hist, pb.vstart_count, live_variants);
     pdeb_plan_scatter_kernel<<<blocks, threads, 0, stream>>>(b.n, pb.keys, pb.hist, pb.order);
-    if (launches) *launches = 3;
+    if (launches) *launches = keys_done ? 2 : 3;
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }

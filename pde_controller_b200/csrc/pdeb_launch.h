@@ -52,6 +52,64 @@ PDEB_HD int pdeb_variant_of(int kind, int n_elem) {
 #define PDEB_PLAN_SBUCKETS (PDEB_PLAN_SBINS / PDEB_PLAN_FBINS)
 #define PDEB_PLAN_BINS (PDEB_VARIANT_SLOTS * PDEB_PLAN_SBINS)   /* multiple of 1024 */
 
+#if defined(__CUDACC__)
+/* sort key of sample s (pdeb_plan): variant, step bucket (longest first), where the first window opens; -1: no variant */
+__device__ __forceinline__ int pdeb_plan_key(const PdebDevBatch& b, const PdebConventions& cv, int64_t s) {
+    const int kind = b.kind[s], N = b.n_elem[s];
+    const int v = pdeb_variant_of(kind, N);
+    if (v < 0) return -1;
+    const double T = b.T[s], dt = b.dt[s];
+    int64_t S = 1;
+    int sub = 0;
+    if (T > 0 && dt > 0 && isfinite(T) && isfinite(dt)) {
+        S = pdeb_step_count(T, dt, cv.steps_rule);
+        /* the kernels stop at the last observed step: order by that */
+        const int np = b.n_pred[s];
+        double last = 0.0, first = 4.0e9;
+        for (int j = 0; j < np && j < b.pmax; ++j) {
+            const double q = b.pred_thi[(int64_t)j * b.stride + s] / dt;
+            const double a1 = (cv.window_rule == 1) ? trunc(q) : floor(q + PDEB_EPS);
+            if (a1 > last) last = a1;
+            const double p = b.pred_tlo[(int64_t)j * b.stride + s] / dt;
+            const double a0 = (cv.window_rule == 1) ? trunc(p) : ceil(p - PDEB_EPS);
+            if (a0 < first) first = a0;
+        }
+        if (last < (double)S) S = (int64_t)last;
+        if (S < 1) S = 1;
+        /* second key: where in the run the first window opens.  A warp runs a clause pass in every step in which ANY
+         * of its lanes has an open window, so lanes whose windows open together share their idle prefix. */
+        if (first > 0.0) {
+            const double f = first * PDEB_PLAN_FBINS / ((double)S + 1.0);
+            sub = (f >= (double)(PDEB_PLAN_FBINS - 1)) ? PDEB_PLAN_FBINS - 1 : (int)f;
+        }
+    }
+    /* first key: steps in buckets, descending inside a variant (longest first).  Half of the buckets are
+     * PDEB_PLAN_SWIDTH steps wide, the next quarters 8x and 512x that (then one bucket for everything longer) */
+    constexpr int64_t H = PDEB_PLAN_SBUCKETS / 2, Q = PDEB_PLAN_SBUCKETS / 4, W = PDEB_PLAN_SWIDTH;
+    int64_t sb = S / W;
+    if (sb >= H) {
+        sb = H + (S - H * W) / (8 * W);
+        if (sb >= H + Q) sb = H + Q + (S - H * W - Q * 8 * W) / (512 * W);
+    }
+    if (sb > PDEB_PLAN_SBUCKETS - 1) sb = PDEB_PLAN_SBUCKETS - 1;
+    return v * PDEB_PLAN_SBINS + (PDEB_PLAN_SBUCKETS - 1 - (int)sb) * PDEB_PLAN_FBINS + sub;
+}
+
+/* key + histogram of sample s; a sample no variant covers is flagged here (status BADPARAM, robustness -100).
+ * Shared by the plan's keys kernel and by the unpack kernel of the packed transfer form, which has just written the
+ * sample it counts (a thread reads its own writes). */
+__device__ __forceinline__ void pdeb_plan_count(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out, int64_t s,
+                                                int32_t* __restrict__ keys, int32_t* __restrict__ hist) {
+    const int key = pdeb_plan_key(b, cv, s);
+    keys[s] = key;
+    if (key >= 0) { atomicAdd(&hist[key], 1); return; }
+    out.robustness[s] = PDEB_FAILED_ROBUSTNESS;
+    if (out.status) out.status[s] = PDEB_ST_BADPARAM;
+    if (out.clause)
+        for (int j = 0; j < b.pmax; ++j) out.clause[(int64_t)j * b.stride + s] = PDEB_FAILED_ROBUSTNESS;
+}
+#endif
+
 cudaError_t pdeb_launch_chunk_heat(int R, const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out,
                                    const int32_t* order, int64_t first, int64_t count, cudaStream_t stream);
 cudaError_t pdeb_launch_chunk_wave(int R, const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out,
@@ -66,9 +124,10 @@ struct PdebPlanBuffers {
 };
 
 /* order the batch (3 launches); flags samples no variant covers.  live_variants: bit v set if the batch may hold samples
- * of variant v (known on the host from kind / n_elem); only those variants' bins are scanned */
+ * of variant v (known on the host from kind / n_elem); only those variants' bins are scanned.  keys_done: the keys and
+ * the histogram have already been formed on `stream` (pdeb_plan_count from the unpack kernel): scan + scatter only */
 int pdeb_plan(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out, const PdebPlanBuffers& pb,
-              uint32_t live_variants, cudaStream_t stream, int* launches);
+              uint32_t live_variants, cudaStream_t stream, int* launches, bool keys_done = false);
 
 /* enqueue the compute kernels of every non-empty variant; returns 0 or a cudaError_t value */
 int pdeb_launch_all(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out, const PdebPlanBuffers& pb,
