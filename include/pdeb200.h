@@ -215,17 +215,28 @@ typedef struct PdebPackedBatch {
     int64_t     slab_bytes;                           /* (page-locked for an asynchronous copy: pdeb_host_alloc) */
     const uint8_t*  kind;                             /* [n] */
     const uint16_t* n_elem;                           /* [n] */
-    const double *L, *dt, *T, *g0, *x_a, *x_b, *rho_in, *rho_out, *E_in, *E_out;    /* [n] each */
+    /* real-valued arrays: stored as enc[] says (below); the value every consumer sees is the f64 it encodes, bit for bit */
+    const void *L, *dt, *T, *g0, *x_a, *x_b, *rho_in, *rho_out, *E_in, *E_out;      /* [n] each */
     const uint16_t* n_knots;                          /* [n] */
     const uint8_t*  n_pred;                           /* [n] */
     const uint8_t*  n_tree;                           /* [n] */
-    const double* knot_t;                             /* [total_knots], or NULL = uniform knots (as at creation) */
-    const double* knot_y;                             /* [total_knots] */
-    const double *pred_xlo, *pred_xhi, *pred_m, *pred_b, *pred_tlo, *pred_thi;      /* [total_pred] each */
+    const void* knot_t;                               /* [total_knots], or NULL = uniform knots (as at creation) */
+    const void* knot_y;                               /* [total_knots] */
+    const void *pred_xlo, *pred_xhi, *pred_m, *pred_b, *pred_tlo, *pred_thi;        /* [total_pred] each */
     const uint8_t *pred_rel, *pred_top;               /* [total_pred] */
     const uint8_t* tree_op;                           /* [total_tree] */
     const int8_t *tree_lhs, *tree_rhs;                /* [total_tree] */
+    /* LOSSLESS storage of each real-valued array, index PDEB_PK_*: PDEB_ENC_F64 as is; PDEB_ENC_F32 as float, allowed
+       only if every value is exactly representable (lengths, interval ends, Dirichlet values are integers in the
+       reference's data); PDEB_ENC_ONE a single f64 standing for every entry (a set sharing one time step) */
+    uint8_t enc[24];
 } PdebPackedBatch;
+#define PDEB_ENC_F64 0
+#define PDEB_ENC_F32 1
+#define PDEB_ENC_ONE 2
+enum { PDEB_PK_L = 0, PDEB_PK_DT, PDEB_PK_T, PDEB_PK_G0, PDEB_PK_XA, PDEB_PK_XB, PDEB_PK_RHO_IN, PDEB_PK_RHO_OUT, PDEB_PK_E_IN,
+       PDEB_PK_E_OUT, PDEB_PK_KNOT_T, PDEB_PK_KNOT_Y, PDEB_PK_XLO, PDEB_PK_XHI, PDEB_PK_M, PDEB_PK_B, PDEB_PK_TLO, PDEB_PK_THI,
+       PDEB_PK_COUNT };
 
 /* refill the image of `r` (same n / kmax / pmax / tmax) from the packed form; one H2D copy + 3 small launches + the plan */
 int  pdeb_resident_upload_packed(PdebResident* r, const PdebPackedBatch* in, void* stream);

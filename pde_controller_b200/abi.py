@@ -123,7 +123,15 @@ class PdebPackedBatch(C.Structure):
         ("pred_xlo", _P), ("pred_xhi", _P), ("pred_m", _P), ("pred_b", _P), ("pred_tlo", _P), ("pred_thi", _P),
         ("pred_rel", _P), ("pred_top", _P),
         ("tree_op", _P), ("tree_lhs", _P), ("tree_rhs", _P),
+        ("enc", C.c_uint8 * 24),
     ]
+
+
+# lossless encodings of the real-valued arrays of the packed form, and their slots in PdebPackedBatch.enc
+ENC_F64, ENC_F32, ENC_ONE = 0, 1, 2
+PK_INDEX = {name: i for i, name in enumerate(
+    ["L", "dt", "T", "g0", "x_a", "x_b", "rho_in", "rho_out", "E_in", "E_out", "knot_t", "knot_y",
+     "pred_xlo", "pred_xhi", "pred_m", "pred_b", "pred_tlo", "pred_thi"])}
 
 
 class PdebTiming(C.Structure):

@@ -392,12 +392,19 @@ extern "C" int pdeb_resident_upload(PdebResident* r, const PdebBatch* in, void* 
 
 struct PdebPackedDev {
     const uint8_t* kind; const uint16_t* n_elem;
-    const double *L, *dt, *T, *g0, *x_a, *x_b, *rho_in, *rho_out, *E_in, *E_out;
+    const void* real[PDEB_PK_COUNT];     /* the real-valued arrays, index PDEB_PK_*, stored as enc[] says */
     const uint16_t* n_knots; const uint8_t *n_pred, *n_tree;
-    const double *knot_t, *knot_y, *pred_xlo, *pred_xhi, *pred_m, *pred_b, *pred_tlo, *pred_thi;
     const uint8_t *pred_rel, *pred_top, *tree_op;
     const int8_t *tree_lhs, *tree_rhs;
+    uint8_t enc[24];
 };
+/* entry i of real-valued array a (the encoding is a kernel parameter: uniform, no divergence) */
+__device__ __forceinline__ double pk_ld(const PdebPackedDev& p, int a, int64_t i) {
+    const int e = p.enc[a];
+    if (e == PDEB_ENC_F64) return ((const double*)p.real[a])[i];
+    if (e == PDEB_ENC_F32) return (double)((const float*)p.real[a])[i];
+    return ((const double*)p.real[a])[0];
+}
 
 /* exclusive prefix sums of the three count arrays inside each block of PDEB_SCAN_BLOCK samples + the block totals */
 __global__ void __launch_bounds__(PDEB_SCAN_BLOCK)
@@ -482,11 +489,11 @@ __global__ void pdeb_unpack_kernel(const __grid_constant__ PdebPackedDev p, cons
     const int blk = (int)(s / PDEB_SCAN_BLOCK);
     ((uint8_t*)d.kind)[s] = p.kind[s];
     ((int32_t*)d.n_elem)[s] = p.n_elem[s];
-    ((double*)d.L)[s] = p.L[s];             ((double*)d.dt)[s] = p.dt[s];
-    ((double*)d.T)[s] = p.T[s];             ((double*)d.g0)[s] = p.g0[s];
-    ((double*)d.x_a)[s] = p.x_a[s];         ((double*)d.x_b)[s] = p.x_b[s];
-    ((double*)d.rho_in)[s] = p.rho_in[s];   ((double*)d.rho_out)[s] = p.rho_out[s];
-    ((double*)d.E_in)[s] = p.E_in[s];       ((double*)d.E_out)[s] = p.E_out[s];
+    ((double*)d.L)[s] = pk_ld(p, PDEB_PK_L, s);             ((double*)d.dt)[s] = pk_ld(p, PDEB_PK_DT, s);
+    ((double*)d.T)[s] = pk_ld(p, PDEB_PK_T, s);             ((double*)d.g0)[s] = pk_ld(p, PDEB_PK_G0, s);
+    ((double*)d.x_a)[s] = pk_ld(p, PDEB_PK_XA, s);          ((double*)d.x_b)[s] = pk_ld(p, PDEB_PK_XB, s);
+    ((double*)d.rho_in)[s] = pk_ld(p, PDEB_PK_RHO_IN, s);   ((double*)d.rho_out)[s] = pk_ld(p, PDEB_PK_RHO_OUT, s);
+    ((double*)d.E_in)[s] = pk_ld(p, PDEB_PK_E_IN, s);       ((double*)d.E_out)[s] = pk_ld(p, PDEB_PK_E_OUT, s);
     int nk = p.n_knots[s], np = p.n_pred[s], nt = p.n_tree[s];
     ((int32_t*)d.n_knots)[s] = nk; ((int32_t*)d.n_pred)[s] = np; ((int32_t*)d.n_tree)[s] = nt;
     /* counts beyond the image's planes are flagged by the kernels (BADPARAM); never write outside the image */
@@ -497,14 +504,14 @@ __global__ void pdeb_unpack_kernel(const __grid_constant__ PdebPackedDev p, cons
     const int64_t op = (int64_t)off[n + s] + bsum[blocks + blk];
     const int64_t ot = (int64_t)off[2 * n + s] + bsum[2 * blocks + blk];
     for (int j = 0; j < nk; ++j) {
-        ((double*)d.knot_y)[(int64_t)j * st + s] = p.knot_y[ok + j];
-        if (d.knot_t) ((double*)d.knot_t)[(int64_t)j * st + s] = p.knot_t[ok + j];
+        ((double*)d.knot_y)[(int64_t)j * st + s] = pk_ld(p, PDEB_PK_KNOT_Y, ok + j);
+        if (d.knot_t) ((double*)d.knot_t)[(int64_t)j * st + s] = pk_ld(p, PDEB_PK_KNOT_T, ok + j);
     }
     for (int j = 0; j < np; ++j) {
         const int64_t q = (int64_t)j * st + s;
-        ((double*)d.pred_xlo)[q] = p.pred_xlo[op + j];  ((double*)d.pred_xhi)[q] = p.pred_xhi[op + j];
-        ((double*)d.pred_m)[q] = p.pred_m[op + j];      ((double*)d.pred_b)[q] = p.pred_b[op + j];
-        ((double*)d.pred_tlo)[q] = p.pred_tlo[op + j];  ((double*)d.pred_thi)[q] = p.pred_thi[op + j];
+        ((double*)d.pred_xlo)[q] = pk_ld(p, PDEB_PK_XLO, op + j);  ((double*)d.pred_xhi)[q] = pk_ld(p, PDEB_PK_XHI, op + j);
+        ((double*)d.pred_m)[q] = pk_ld(p, PDEB_PK_M, op + j);      ((double*)d.pred_b)[q] = pk_ld(p, PDEB_PK_B, op + j);
+        ((double*)d.pred_tlo)[q] = pk_ld(p, PDEB_PK_TLO, op + j);  ((double*)d.pred_thi)[q] = pk_ld(p, PDEB_PK_THI, op + j);
         ((uint8_t*)d.pred_rel)[q] = p.pred_rel[op + j]; ((uint8_t*)d.pred_top)[q] = p.pred_top[op + j];
     }
     for (int j = 0; j < nt; ++j) {
@@ -531,12 +538,19 @@ extern "C" int pdeb_resident_upload_packed(PdebResident* r, const PdebPackedBatc
     const int64_t n = r->n;
     struct Arr { const void* p; size_t bytes; };
     const size_t tk = (size_t)in->total_knots, tp = (size_t)in->total_pred, tt = (size_t)in->total_tree, nn = (size_t)n;
-    const Arr arrs[] = {{in->kind, nn}, {in->n_elem, 2 * nn}, {in->L, 8 * nn}, {in->dt, 8 * nn}, {in->T, 8 * nn}, {in->g0, 8 * nn},
-                        {in->x_a, 8 * nn}, {in->x_b, 8 * nn}, {in->rho_in, 8 * nn}, {in->rho_out, 8 * nn}, {in->E_in, 8 * nn},
-                        {in->E_out, 8 * nn}, {in->n_knots, 2 * nn}, {in->n_pred, nn}, {in->n_tree, nn}, {in->knot_y, 8 * tk},
-                        {in->pred_xlo, 8 * tp}, {in->pred_xhi, 8 * tp}, {in->pred_m, 8 * tp}, {in->pred_b, 8 * tp},
-                        {in->pred_tlo, 8 * tp}, {in->pred_thi, 8 * tp}, {in->pred_rel, tp}, {in->pred_top, tp},
-                        {in->tree_op, tt}, {in->tree_lhs, tt}, {in->tree_rhs, tt}, {in->knot_t, in->knot_t ? 8 * tk : 0}};
+    const void* realp[PDEB_PK_COUNT] = {in->L, in->dt, in->T, in->g0, in->x_a, in->x_b, in->rho_in, in->rho_out, in->E_in,
+                                        in->E_out, in->knot_t, in->knot_y, in->pred_xlo, in->pred_xhi, in->pred_m, in->pred_b,
+                                        in->pred_tlo, in->pred_thi};
+    const size_t realn[PDEB_PK_COUNT] = {nn, nn, nn, nn, nn, nn, nn, nn, nn, nn, tk, tk, tp, tp, tp, tp, tp, tp};
+    std::vector<Arr> arrs = {{in->kind, nn}, {in->n_elem, 2 * nn}, {in->n_knots, 2 * nn}, {in->n_pred, nn}, {in->n_tree, nn},
+                             {in->pred_rel, tp}, {in->pred_top, tp}, {in->tree_op, tt}, {in->tree_lhs, tt}, {in->tree_rhs, tt}};
+    for (int a = 0; a < PDEB_PK_COUNT; ++a) {
+        if (in->enc[a] > PDEB_ENC_ONE) return fail(PDEB_E_ARG, "unknown encoding of a packed array");
+        if (a == PDEB_PK_KNOT_T && !in->knot_t) continue;
+        const size_t bytes = in->enc[a] == PDEB_ENC_F64 ? 8 * realn[a] : in->enc[a] == PDEB_ENC_F32 ? 4 * realn[a] : (realn[a] ? 8 : 0);
+        arrs.push_back({realp[a], bytes});
+        if (realp[a] && ((uintptr_t)realp[a] & 7u)) return fail(PDEB_E_ARG, "a packed array is not 8-byte aligned");
+    }
     for (const Arr& a : arrs) {
         if (!a.p) { if (a.bytes) return fail(PDEB_E_ARG, "a packed array is NULL"); continue; }
         const unsigned char* q = (const unsigned char*)a.p;
@@ -587,11 +601,12 @@ extern "C" int pdeb_resident_upload_packed(PdebResident* r, const PdebPackedBatc
     CK(cudaMemcpyAsync(r->pstage, base, (size_t)in->slab_bytes, cudaMemcpyHostToDevice, stream));
     PdebPackedDev p;
 #define DEVP(f) p.f = in->f ? (decltype(p.f))(r->pstage + ((const unsigned char*)in->f - base)) : nullptr
-    DEVP(kind); DEVP(n_elem); DEVP(L); DEVP(dt); DEVP(T); DEVP(g0); DEVP(x_a); DEVP(x_b); DEVP(rho_in); DEVP(rho_out);
-    DEVP(E_in); DEVP(E_out); DEVP(n_knots); DEVP(n_pred); DEVP(n_tree); DEVP(knot_t); DEVP(knot_y); DEVP(pred_xlo);
-    DEVP(pred_xhi); DEVP(pred_m); DEVP(pred_b); DEVP(pred_tlo); DEVP(pred_thi); DEVP(pred_rel); DEVP(pred_top);
+    DEVP(kind); DEVP(n_elem); DEVP(n_knots); DEVP(n_pred); DEVP(n_tree); DEVP(pred_rel); DEVP(pred_top);
     DEVP(tree_op); DEVP(tree_lhs); DEVP(tree_rhs);
 #undef DEVP
+    for (int a = 0; a < PDEB_PK_COUNT; ++a)
+        p.real[a] = realp[a] ? (const void*)(r->pstage + ((const unsigned char*)realp[a] - base)) : nullptr;
+    memcpy(p.enc, in->enc, sizeof p.enc);
     int32_t* off = (int32_t*)(r->pstage + r->pstage_off);
     int32_t* bsum = (int32_t*)(r->pstage + r->pstage_off + align_up(12 * nn, 256));
     PdebConventions pcv;

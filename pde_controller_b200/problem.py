@@ -388,8 +388,20 @@ class PackedBatch:
         off = 0
         self._views = {}
 
+        self.enc = {}
+
         def put(name, arr):
             nonlocal off
+            if name in abi.PK_INDEX:
+                # lossless storage: one value for all / float where every value is exactly a float / as is.
+                # Compared as BIT PATTERNS, so -0.0, infinities and NaN payloads survive (or force the f64 form).
+                bits = arr.view(np.uint64)
+                if arr.size > 1 and np.all(bits == bits[0]):
+                    self.enc[name], arr = abi.ENC_ONE, arr[:1].copy()
+                elif arr.size > 0 and np.array_equal(arr.astype(np.float32).astype(np.float64).view(np.uint64), bits):
+                    self.enc[name], arr = abi.ENC_F32, arr.astype(np.float32)
+                else:
+                    self.enc[name] = abi.ENC_F64
             nb = arr.nbytes
             self._slab[off:off + nb] = arr.view(np.uint8).reshape(-1)
             self._views[name] = (off, arr.dtype, arr.size)
@@ -419,7 +431,13 @@ class PackedBatch:
 
         def get(name):
             off, dt, size = self._views[name]
-            return base[off:off + size * np.dtype(dt).itemsize].view(dt)
+            a = base[off:off + size * np.dtype(dt).itemsize].view(dt)
+            e = self.enc.get(name, abi.ENC_F64)
+            if e == abi.ENC_F32:
+                return a.astype(np.float64)
+            if e == abi.ENC_ONE:
+                return a[0]                      # broadcast by the assignment
+            return a
 
         for name, _ in self._SCALARS:
             getattr(b, name)[:] = get(name)
@@ -450,5 +468,7 @@ class PackedBatch:
             setattr(c, name, base + off)
         if self.uniform_knots:
             c.knot_t = None
+        for name, e in self.enc.items():
+            c.enc[abi.PK_INDEX[name]] = e
         self._c = c
         return c

@@ -55,7 +55,7 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(abi.PdebBatch) == 2 * 8 + 4 * 4 + 8 + 8 + 28 * 8
     assert ctypes.sizeof(abi.PdebTiming) == 4 * 4 + 2 * 4
     # int64 + 4 int32 + 3 int64 + ptr + int64 + 28 ptr
-    assert ctypes.sizeof(abi.PdebPackedBatch) == 8 + 4 * 4 + 3 * 8 + 8 + 8 + 28 * 8
+    assert ctypes.sizeof(abi.PdebPackedBatch) == 8 + 4 * 4 + 3 * 8 + 8 + 8 + 28 * 8 + 24
 
 
 def test_packed_transfer_form_round_trip():
@@ -78,6 +78,34 @@ def test_packed_transfer_form_round_trip():
                 assert np.array_equal(a[:, : b.n][live], c[:, : b.n][live]), name
         c = pk.as_c()
         assert (c.total_knots, c.total_pred, c.total_tree) == (int(b.n_knots.sum()), int(b.n_pred.sum()), int(b.n_tree.sum()))
+        if n > 1:
+            # the synthetic sets have integer lengths / interval ends (stored as float) and, per kind, one time step
+            assert pk.enc["dt"] == (abi.ENC_F64 if wl == "mixed" else abi.ENC_ONE)
+            assert pk.enc["L"] == abi.ENC_F32 and pk.enc["pred_xlo"] == abi.ENC_F32
+            assert pk.enc["pred_m"] == abi.ENC_F64 and pk.enc["knot_y"] == abi.ENC_F64
+
+
+def test_packed_encodings_are_lossless_bit_for_bit():
+    """-0.0, infinities, NaNs and values one ulp away from a float must come back with the same BITS."""
+    import numpy as np
+    from pde_controller_b200 import PackedBatch, synth
+    b = synth.make_batch(64, "heat", seed=4)
+    b.g0[:] = 300.0
+    b.g0[3] = -0.0                                       # not equal in bits to 0.0: no "one value" / stays exact as float
+    b.L[5] = np.nextafter(100.0, 200.0)                  # not a float: the whole array stays f64
+    b.x_a[:] = 0.0
+    b.x_a[7] = -0.0                                      # all "equal" numerically, different bits
+    b.pred_b[0, 9] = np.inf
+    b.knot_y[0, 11] = np.nan
+    pk = PackedBatch(b.n, b.kmax, b.pmax, b.tmax).pack(b)
+    assert pk.enc["L"] == abi.ENC_F64 and pk.enc["g0"] == abi.ENC_F32 and pk.enc["x_a"] == abi.ENC_F32
+    u = pk.unpack()
+    for name in ("g0", "L", "x_a"):
+        assert np.array_equal(getattr(u, name).view(np.uint64), getattr(b, name).view(np.uint64)), name
+    live = np.arange(b.pmax)[:, None] < b.n_pred[None, :]
+    assert np.array_equal(u.pred_b[live].view(np.uint64), b.pred_b[live].view(np.uint64))
+    livek = np.arange(b.kmax)[:, None] < b.n_knots[None, :]
+    assert np.array_equal(u.knot_y[livek].view(np.uint64), b.knot_y[livek].view(np.uint64))
 
 
 def test_no_cpu_fallback_without_device():

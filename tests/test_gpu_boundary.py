@@ -101,6 +101,29 @@ def test_packed_upload_equals_planar_upload(oracle_lib):
         assert np.array_equal(got["clause"][live], ref["clause"][live])
 
 
+def test_packed_encodings_on_device_are_bit_exact():
+    """Arrays stored as float / as one value / as f64 (with -0.0, an off-float value) decode to the same image bits:
+    results equal the planar upload bitwise, per clause."""
+    import numpy as np
+    from pde_controller_b200 import abi, native, synth
+    b = synth.make_batch(4096, "heat", seed=12)
+    b.g0[::7] = np.nextafter(b.g0[::7], 1e9)           # g0 is no longer float-exact: stays f64
+    b.x_a[5] = -0.0
+    b.E_in[:] = 1.0e6                                   # one value for all
+    pk = native.pinned_packed(b.n, b.kmax, b.pmax, b.tmax).pack(b)
+    assert pk.enc["g0"] == abi.ENC_F64 and pk.enc["E_in"] == abi.ENC_ONE and pk.enc["L"] == abi.ENC_F32
+    ref = native.evaluate_batch(b, want_clauses=True)
+    res = native.ResidentBatch(b)
+    res.upload(synth.make_batch(b.n, "heat", seed=77))  # something else in the image first
+    res.upload_packed(pk)
+    res.eval()
+    got = res.fetch(want_clauses=True)
+    res.close()
+    assert np.array_equal(got["robustness"], ref["robustness"]) and np.array_equal(got["status"], ref["status"])
+    live = np.arange(b.pmax)[:, None] < b.n_pred[None, :]
+    assert np.array_equal(got["clause"][live], ref["clause"][live])
+
+
 def test_packed_upload_rejects_inconsistent_totals():
     import ctypes as C
     from pde_controller_b200 import native, synth
