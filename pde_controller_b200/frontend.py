@@ -15,6 +15,7 @@ import ast
 import math
 import re
 import textwrap
+import warnings
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -469,7 +470,9 @@ def parse_program(text: str) -> Problem:
         raise ParseError("program is not text")
     src = textwrap.dedent(text.replace("\x00", "")).strip()
     try:
-        mod = ast.parse(src)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", SyntaxWarning)     # generated text: "invalid decimal literal" and the like
+            mod = ast.parse(src)
     except (SyntaxError, ValueError, RecursionError, MemoryError) as e:
         raise ParseError(f"not parseable: {e}")
     env: Dict[str, object] = {}

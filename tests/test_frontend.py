@@ -123,3 +123,49 @@ def test_batch_packing_round_trip():
     assert q == p and np.array_equal(c[0], ctrl[0]) and np.array_equal(c[1], ctrl[1])
     assert b.get_problem(1)[1] is None
     assert b.algorithmic_bytes() == (105 + 16 * 10 + 50 * 2 + 9) + (105 + 0 + 50 * 2 + 9)
+
+
+def test_fuzzed_programs_parse_or_raise_parse_error_only():
+    """LLM output is untrusted text: any mutation of a valid program either parses to a Problem or raises ParseError —
+    no other exception type, no execution, no hang (hypothesis; character- and line-level edits, splices of two programs)."""
+    from hypothesis import HealthCheck, given, settings, strategies as st
+
+    wave = render_program(synth.make_batch(1, "wave", seed=3).get_problem(0)[0])
+    alphabet = "0123456789.eE+-*/()[]{}<>=:,\"' \nxlambdaNLTgdtorifelsenp_GF&|AB#\\\x00"
+
+    @st.composite
+    def mutated(draw):
+        text = draw(st.sampled_from([HEAT, wave]))
+        for _ in range(draw(st.integers(1, 6))):
+            kind = draw(st.integers(0, 4))
+            i = draw(st.integers(0, max(len(text) - 1, 0)))
+            if kind == 0:
+                text = text[:i] + text[i + draw(st.integers(1, 12)):]
+            elif kind == 1:
+                text = text[:i] + draw(st.text(alphabet, max_size=12)) + text[i:]
+            elif kind == 2:
+                lines = text.split("\n")
+                j = draw(st.integers(0, len(lines) - 1))
+                del lines[j]
+                text = "\n".join(lines)
+            elif kind == 3:
+                other = wave if text.startswith("\nfrom femformal.core.fem import heat") else HEAT
+                j = draw(st.integers(0, len(other) - 1))
+                text = text[:i] + other[j:]
+            else:
+                lines = text.split("\n")
+                j, k = draw(st.integers(0, len(lines) - 1)), draw(st.integers(0, len(lines) - 1))
+                lines[j], lines[k] = lines[k], lines[j]
+                text = "\n".join(lines)
+        return text
+
+    @settings(max_examples=400, deadline=2000, suppress_health_check=[HealthCheck.too_slow])
+    @given(mutated())
+    def run(text):
+        try:
+            p = parse_program(text)
+        except ParseError:
+            return
+        assert isinstance(p, Problem) and p.n_elem >= 1 and p.dt > 0 and p.T > 0 and len(p.predicates) >= 1
+
+    run()
