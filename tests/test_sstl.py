@@ -86,3 +86,45 @@ def test_check_records_flags_only_the_inconsistent_ones():
     bad = check_records(items)
     assert [i for i, _ in bad] == [1, 2] and "intercept" in bad[0][1][0]
 
+
+
+def test_fuzzed_latex_and_cspec_parse_or_raise_their_own_error_only():
+    """Generated sSTL LaTeX / cspec text: mutations either parse or raise SstlError / ParseError, nothing else."""
+    from hypothesis import HealthCheck, given, settings, strategies as st
+    from pde_controller_b200.frontend import ParseError, parse_cspec
+
+    latex_seeds = [r["sstl"] for r in records()][:6]
+    cspec_seeds = ["((F_[0.5, 2.25] (A)) & (G_[4.125, 7.5] (B)))", "(((G_[0, 1] (A)) & (G_[1, 2] (B))) | (F_[2, 3] (C)))"]
+    alphabet = "0123456789.eE+-*/()[]{}<>=:,_\\ \nGFUABCxu&|^landorfitcd\x00"
+
+    def mutations(seeds):
+        @st.composite
+        def mut(draw):
+            text = draw(st.sampled_from(seeds))
+            for _ in range(draw(st.integers(1, 5))):
+                i = draw(st.integers(0, max(len(text) - 1, 0)))
+                if draw(st.booleans()):
+                    text = text[:i] + text[i + draw(st.integers(1, 10)):]
+                else:
+                    text = text[:i] + draw(st.text(alphabet, max_size=10)) + text[i:]
+            return text
+        return mut()
+
+    @settings(max_examples=300, deadline=2000, suppress_health_check=[HealthCheck.too_slow])
+    @given(mutations(latex_seeds))
+    def run_latex(text):
+        try:
+            parse_sstl(text)
+        except SstlError:
+            pass
+
+    @settings(max_examples=300, deadline=2000, suppress_health_check=[HealthCheck.too_slow])
+    @given(mutations(cspec_seeds))
+    def run_cspec(text):
+        try:
+            parse_cspec(text)
+        except ParseError:
+            pass
+
+    run_latex()
+    run_cspec()
