@@ -375,6 +375,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    if args.gpus != world and rank == 0:
+        sys.stderr.write(f"bench: --gpus {args.gpus} but WORLD_SIZE={world}: N>1 runs are launched with torch.distributed.run "
+                         f"(one rank per GPU); this process reports n_gpus={world}\n")
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
