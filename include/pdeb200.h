@@ -238,6 +238,16 @@ enum { PDEB_PK_L = 0, PDEB_PK_DT, PDEB_PK_T, PDEB_PK_G0, PDEB_PK_XA, PDEB_PK_XB,
        PDEB_PK_E_OUT, PDEB_PK_KNOT_T, PDEB_PK_KNOT_Y, PDEB_PK_XLO, PDEB_PK_XHI, PDEB_PK_M, PDEB_PK_B, PDEB_PK_TLO, PDEB_PK_THI,
        PDEB_PK_COUNT };
 
+/*
+ * Host-side producer of the packed form (no device involved): packs the plane-major batch `in` into `slab`
+ * (`capacity` bytes, 8-byte aligned; page-locked if it is to be uploaded asynchronously) and fills `*out` with pointers
+ * into it, choosing each real-valued array's storage tag by bit comparison.  pdeb_packed_capacity is the worst case of a
+ * shape, so one buffer serves every batch of that shape.  Returns PDEB_E_ARG if a count does not fit the narrow
+ * integers or the slab is too small.
+ */
+int64_t pdeb_packed_capacity(int64_t n, int32_t kmax, int32_t pmax, int32_t tmax, int32_t with_knot_t);
+int  pdeb_pack_batch(const PdebBatch* in, void* slab, int64_t capacity, PdebPackedBatch* out);
+
 /* refill the image of `r` (same n / kmax / pmax / tmax) from the packed form; one H2D copy + 3 small launches + the plan */
 int  pdeb_resident_upload_packed(PdebResident* r, const PdebPackedBatch* in, void* stream);
 /* upload + evaluate + fetch of a batch of the resident shape in one pipelined pass (H2D / kernels / D2H of

@@ -156,6 +156,8 @@ EXPORTS = [
     "pdeb_resident_create",
     "pdeb_resident_upload",
     "pdeb_resident_upload_packed",
+    "pdeb_packed_capacity",
+    "pdeb_pack_batch",
     "pdeb_resident_run",
     "pdeb_resident_eval",
     "pdeb_resident_set_knots",

@@ -387,6 +387,118 @@ extern "C" int pdeb_resident_upload(PdebResident* r, const PdebBatch* in, void* 
     return rc;
 }
 
+/* ---- host-side producer of the packed transfer form ------------------------------------------------------------- */
+static size_t pk_align(size_t x) { return (x + 63) / 64 * 64; }
+
+extern "C" int64_t pdeb_packed_capacity(int64_t n, int32_t kmax, int32_t pmax, int32_t tmax, int32_t with_knot_t) {
+    const size_t n1 = (size_t)(n > 0 ? n : 1);
+    size_t t = 0;
+    t = pk_align(t + n1);                                   /* kind */
+    t = pk_align(t + 2 * n1);                               /* n_elem */
+    for (int q = 0; q < 10; ++q) t = pk_align(t + 8 * n1);  /* real scalars */
+    t = pk_align(t + 2 * n1);                               /* n_knots */
+    t = pk_align(t + n1);                                   /* n_pred */
+    t = pk_align(t + n1);                                   /* n_tree */
+    for (int q = 0; q < (with_knot_t ? 2 : 1); ++q) t = pk_align(t + 8 * n1 * (size_t)kmax);
+    for (int q = 0; q < 6; ++q) t = pk_align(t + 8 * n1 * (size_t)pmax);
+    for (int q = 0; q < 2; ++q) t = pk_align(t + n1 * (size_t)pmax);
+    for (int q = 0; q < 3; ++q) t = pk_align(t + n1 * (size_t)tmax);
+    return (int64_t)t;
+}
+
+/* storage tag of `cnt` doubles produced by get(i): one value / float-exact / as is (bit comparison) */
+template <typename Get>
+static int pk_choose(size_t cnt, Get get) {
+    if (cnt == 0) return PDEB_ENC_F64;
+    bool same = cnt > 1, f32 = true;
+    uint64_t first;
+    { const double v0 = get(0); memcpy(&first, &v0, 8); }
+    for (size_t i = 0; i < cnt && (same || f32); ++i) {
+        const double v = get(i);
+        uint64_t b, rb;
+        memcpy(&b, &v, 8);
+        if (b != first) same = false;
+        const double r = (double)(float)v;
+        memcpy(&rb, &r, 8);
+        if (rb != b) f32 = false;
+    }
+    return same ? PDEB_ENC_ONE : (f32 ? PDEB_ENC_F32 : PDEB_ENC_F64);
+}
+
+extern "C" int pdeb_pack_batch(const PdebBatch* in, void* slab_, int64_t capacity, PdebPackedBatch* out) {
+    if (!out || !slab_) return fail(PDEB_E_ARG, "NULL argument");
+    int rc = check_batch(in);
+    if (rc) return rc;
+    if ((uintptr_t)slab_ & 7u) return fail(PDEB_E_ARG, "the slab must be 8-byte aligned");
+    const int64_t n = in->n, st = in->stride;
+    const int kmax = in->kmax, pmax = in->pmax, tmax = in->tmax;
+    if (capacity < pdeb_packed_capacity(n, kmax, pmax, tmax, in->knot_t ? 1 : 0)) return fail(PDEB_E_ARG, "slab smaller than pdeb_packed_capacity");
+    unsigned char* slab = (unsigned char*)slab_;
+    memset(out, 0, sizeof *out);
+    out->n = n; out->kmax = kmax; out->pmax = pmax; out->tmax = tmax;
+    out->slab_base = slab;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { unsigned char* p = slab + off; off = pk_align(off + (bytes ? bytes : 1)); return p; };
+    /* counts: range check, clamp to the planes for the list lengths, offsets */
+    std::vector<int32_t> ok((size_t)n + 1), op((size_t)n + 1), ot((size_t)n + 1);
+    for (int64_t s = 0; s < n; ++s) {
+        const int32_t a = in->n_knots[s], b = in->n_pred[s], c = in->n_tree[s], e = in->n_elem[s];
+        if (a < 0 || a > 65535 || b < 0 || b > 255 || c < 0 || c > 255 || e < 0 || e > 65535)
+            return fail(PDEB_E_ARG, "a count does not fit the packed form's narrow integers");
+        ok[s + 1] = ok[s] + (a < kmax ? a : kmax);
+        op[s + 1] = op[s] + (b < pmax ? b : pmax);
+        ot[s + 1] = ot[s] + (c < tmax ? c : tmax);
+    }
+    out->total_knots = ok[n]; out->total_pred = op[n]; out->total_tree = ot[n];
+    { uint8_t* d = take((size_t)n); memcpy(d, in->kind, (size_t)n); out->kind = d; }
+    { uint16_t* d = (uint16_t*)take(2 * (size_t)n); for (int64_t s = 0; s < n; ++s) d[s] = (uint16_t)in->n_elem[s]; out->n_elem = d; }
+    /* a real-valued array of `cnt` entries produced by get(i), stored under its tag */
+    auto put_real = [&](int slot, size_t cnt, auto get) -> const void* {
+        const int e = pk_choose(cnt, get);
+        out->enc[slot] = (uint8_t)e;
+        if (e == PDEB_ENC_ONE) { double* d = (double*)take(8); d[0] = get(0); return d; }
+        if (e == PDEB_ENC_F32) { float* d = (float*)take(4 * cnt); for (size_t i = 0; i < cnt; ++i) d[i] = (float)get(i); return d; }
+        double* d = (double*)take(8 * cnt);
+        for (size_t i = 0; i < cnt; ++i) d[i] = get(i);
+        return d;
+    };
+    const double* scal[10] = {in->L, in->dt, in->T, in->g0, in->x_a, in->x_b, in->rho_in, in->rho_out, in->E_in, in->E_out};
+    const void** scal_out[10] = {&out->L, &out->dt, &out->T, &out->g0, &out->x_a, &out->x_b, &out->rho_in, &out->rho_out, &out->E_in, &out->E_out};
+    for (int q = 0; q < 10; ++q) { const double* a = scal[q]; *scal_out[q] = put_real(q, (size_t)n, [a](size_t i) { return a[i]; }); }
+    { uint16_t* d = (uint16_t*)take(2 * (size_t)n); for (int64_t s = 0; s < n; ++s) d[s] = (uint16_t)in->n_knots[s]; out->n_knots = d; }
+    { uint8_t* d = take((size_t)n); for (int64_t s = 0; s < n; ++s) d[s] = (uint8_t)in->n_pred[s]; out->n_pred = d; }
+    { uint8_t* d = take((size_t)n); for (int64_t s = 0; s < n; ++s) d[s] = (uint8_t)in->n_tree[s]; out->n_tree = d; }
+    /* lists: entry i of the flat array is (sample, plane) in sample-major order; an index table turns i into its source */
+    auto list_index = [&](const std::vector<int32_t>& offs) {
+        std::vector<int64_t> src((size_t)offs[n]);
+        for (int64_t s = 0; s < n; ++s)
+            for (int32_t j = 0, c = offs[s + 1] - offs[s]; j < c; ++j) src[(size_t)offs[s] + j] = (int64_t)j * st + s;
+        return src;
+    };
+    {
+        const std::vector<int64_t> src = list_index(ok);
+        if (in->knot_t) { const double* a = in->knot_t; out->knot_t = put_real(PDEB_PK_KNOT_T, src.size(), [a, &src](size_t i) { return a[src[i]]; }); }
+        const double* a = in->knot_y;
+        out->knot_y = put_real(PDEB_PK_KNOT_Y, src.size(), [a, &src](size_t i) { return a[src[i]]; });
+    }
+    {
+        const std::vector<int64_t> src = list_index(op);
+        const double* pr[6] = {in->pred_xlo, in->pred_xhi, in->pred_m, in->pred_b, in->pred_tlo, in->pred_thi};
+        const void** po[6] = {&out->pred_xlo, &out->pred_xhi, &out->pred_m, &out->pred_b, &out->pred_tlo, &out->pred_thi};
+        for (int q = 0; q < 6; ++q) { const double* a = pr[q]; *po[q] = put_real(PDEB_PK_XLO + q, src.size(), [a, &src](size_t i) { return a[src[i]]; }); }
+        uint8_t* d = take(src.size()); for (size_t i = 0; i < src.size(); ++i) d[i] = in->pred_rel[src[i]]; out->pred_rel = d;
+        d = take(src.size()); for (size_t i = 0; i < src.size(); ++i) d[i] = in->pred_top[src[i]]; out->pred_top = d;
+    }
+    {
+        const std::vector<int64_t> src = list_index(ot);
+        uint8_t* d = take(src.size()); for (size_t i = 0; i < src.size(); ++i) d[i] = in->tree_op[src[i]]; out->tree_op = d;
+        int8_t* e = (int8_t*)take(src.size()); for (size_t i = 0; i < src.size(); ++i) e[i] = in->tree_lhs[src[i]]; out->tree_lhs = e;
+        e = (int8_t*)take(src.size()); for (size_t i = 0; i < src.size(); ++i) e[i] = in->tree_rhs[src[i]]; out->tree_rhs = e;
+    }
+    out->slab_bytes = (int64_t)off;
+    return 0;
+}
+
 /* ---- packed transfer form (PdebPackedBatch): one copy, offsets by prefix sums on the device, scatter into the image ---- */
 #define PDEB_SCAN_BLOCK 1024
 

@@ -49,6 +49,10 @@ def lib():
         L.pdeb_resident_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.pdeb_resident_upload.restype = C.c_int
         L.pdeb_resident_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pdeb_packed_capacity.restype = C.c_int64
+        L.pdeb_packed_capacity.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+        L.pdeb_pack_batch.restype = C.c_int
+        L.pdeb_pack_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.pdeb_resident_upload_packed.restype = C.c_int
         L.pdeb_resident_upload_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.pdeb_resident_run.restype = C.c_int

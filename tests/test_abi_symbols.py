@@ -119,3 +119,38 @@ def test_no_cpu_fallback_without_device():
     with pytest.raises(native.NativeError):
         native.ControlsEvaluator(b, [0.0, 1.0], capacity=8)
 
+
+
+def test_native_packer_equals_numpy_packer():
+    """pdeb_pack_batch (host-side C, no device involved) and the numpy packer produce the same block: sizes, storage
+    tags, totals and decoded content, including the bit-level corner cases."""
+    import numpy as np
+    from pde_controller_b200 import PackedBatch, synth
+    L = native.lib()
+    cases = [synth.make_batch(n, wl, seed=3, uniform_knots=uk)
+             for wl, uk, n in (("heat", True, 4096), ("wave", False, 3001), ("mixed", False, 2049), ("heat", False, 1))]
+    odd = synth.make_batch(64, "heat", seed=4)
+    odd.g0[3] = -0.0
+    odd.L[5] = np.nextafter(100.0, 200.0)
+    odd.x_a[:] = 0.0
+    odd.x_a[7] = -0.0
+    odd.pred_b[0, 9] = np.inf
+    odd.knot_y[0, 11] = np.nan
+    odd.E_in[:] = 1.0e6
+    cases.append(odd)
+    for b in cases:
+        b.n_knots[: min(5, b.n)] = 0
+        a = PackedBatch(b.n, b.kmax, b.pmax, b.tmax, uniform_knots=b.uniform_knots).pack(b, use_native=False)
+        c = PackedBatch(b.n, b.kmax, b.pmax, b.tmax, uniform_knots=b.uniform_knots).pack(b, use_native=True)
+        assert (a.nbytes, a.totals, a.enc) == (c.nbytes, c.totals, c.enc)
+        ua, uc = a.unpack(), c.unpack()
+        for name in b._names:
+            if name == "knot_t" and b.uniform_knots:
+                continue
+            assert np.array_equal(getattr(ua, name).view(np.uint8), getattr(uc, name).view(np.uint8)), name
+        assert L.pdeb_packed_capacity(b.n, b.kmax, b.pmax, b.tmax, 0 if b.uniform_knots else 1) <= \
+            PackedBatch.capacity_for(b.n, b.kmax, b.pmax, b.tmax, b.uniform_knots)
+    big = synth.make_batch(8, "heat", seed=1)
+    big.n_elem[2] = 70000                                  # does not fit u16
+    with pytest.raises(ValueError):
+        PackedBatch(big.n, big.kmax, big.pmax, big.tmax).pack(big, use_native=True)
