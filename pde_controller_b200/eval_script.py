@@ -22,7 +22,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import abi, native
-from .frontend import ParseError, parse_program
+from .frontend import ParseError, parse_many, parse_program  # noqa: F401
 from .problem import Problem, ProblemBatch
 
 _DEVICE = 0
@@ -48,8 +48,9 @@ def is_correct(pred, ans, prec=1e-3):
 
 def eval_robustness_batch(programs: Sequence[str], natural_language: Optional[Sequence[str]] = None,
                           controls: Optional[Sequence] = None, device: Optional[int] = None,
-                          precision: Optional[int] = None, conventions=None, return_status: bool = False):
-    """Evaluate many programs in one GPU call.
+                          precision: Optional[int] = None, conventions=None, return_status: bool = False,
+                          parse_workers: Optional[int] = None):
+    """Evaluate many programs in one GPU call (long lists are parsed by worker processes: frontend.parse_many).
 
     -> (robustness list, runtime list[, status array]).  A program that does not parse, or a
     simulation that fails, yields robustness -100 (the failure label of simulate_gt.py:59);
@@ -62,11 +63,9 @@ def eval_robustness_batch(programs: Sequence[str], natural_language: Optional[Se
         raise ValueError("controls must have one entry per program")
     problems: List[Optional[Problem]] = []
     status = np.zeros(n, dtype=np.int32)
-    for i, text in enumerate(programs):
-        try:
-            problems.append(parse_program(text))
-        except ParseError:
-            problems.append(None)
+    for i, (prob, _msg) in enumerate(parse_many(programs, workers=parse_workers)):
+        problems.append(prob)
+        if prob is None:
             status[i] = abi.ST_PARSE
     live = [i for i in range(n) if problems[i] is not None]
     rob = np.full(n, abi.FAILED_ROBUSTNESS, dtype=np.float64)

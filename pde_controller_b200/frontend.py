@@ -589,3 +589,44 @@ def render_program(p: Problem) -> str:
             txt.append(f"({txt[l]} {'&' if op == 'and' else '|'} {txt[r]})")
     lines.append(f'cspec = "{txt[-1]}"')
     return "\n".join(lines) + "\n"
+
+
+def _parse_chunk(texts):
+    """Worker of parse_many: never raises; (problem, None) or (None, message) per text."""
+    out = []
+    for t in texts:
+        try:
+            out.append((parse_program(t), None))
+        except ParseError as e:
+            out.append((None, str(e)))
+    return out
+
+
+def parse_many(texts, workers: Optional[int] = None, min_parallel: int = 2000):
+    """parse_program over a list, in worker processes for long lists.
+
+    One program takes ~1 ms of interpreter time (half of it Python's own `ast.parse`), five orders of magnitude more than
+    its evaluation on the GPU, so for the sweep sizes of the reference (a 2 M-sample corpus) the front-end, not the
+    kernels, sets the wall time: the list is cut into chunks and parsed by `workers` processes (default: the CPUs of
+    the box, at most 32).  The workers are forked (no re-import of the caller's main module, which "spawn" would run
+    again) and only ever run this pure-Python parser: they never touch CUDA, the same contract as a forked data-loader
+    worker.  Returns a list of (Problem, None) / (None, message)."""
+    texts = list(texts)
+    n = len(texts)
+    if workers is None:
+        import os
+        workers = min(os.cpu_count() or 1, 32)
+    if n < min_parallel or workers <= 1:
+        return _parse_chunk(texts)
+    import concurrent.futures as cf
+    import multiprocessing as mp
+    chunk = max(256, -(-n // (workers * 8)))
+    parts = [texts[i:i + chunk] for i in range(0, n, chunk)]
+    try:
+        ctx = mp.get_context("fork")
+        with cf.ProcessPoolExecutor(max_workers=workers, mp_context=ctx) as ex:
+            res = list(ex.map(_parse_chunk, parts))
+    except (OSError, RuntimeError, cf.process.BrokenProcessPool):
+        return _parse_chunk(texts)                # a box that cannot start workers: same result, one process
+    return [x for part in res for x in part]
+

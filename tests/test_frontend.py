@@ -169,3 +169,18 @@ def test_fuzzed_programs_parse_or_raise_parse_error_only():
         assert isinstance(p, Problem) and p.n_elem >= 1 and p.dt > 0 and p.T > 0 and len(p.predicates) >= 1
 
     run()
+
+
+def test_parse_many_in_worker_processes_equals_serial():
+    """frontend.parse_many: long lists are parsed by forked workers; same problems, same failures, same order."""
+    from pde_controller_b200.frontend import parse_many
+    b = synth.make_batch(600, "mixed", seed=2)
+    texts = [render_program(b.get_problem(s)[0]) for s in range(b.n)]
+    texts[17] = "garbage"
+    texts[301] = texts[301].replace("dt = ", "dt = 0 * ")
+    serial = parse_many(texts, workers=1)
+    par = parse_many(texts, workers=4, min_parallel=100)
+    assert len(par) == len(texts)
+    assert [x[0] for x in par] == [x[0] for x in serial]
+    assert par[17][0] is None and par[301][0] is None and par[17][1]
+    assert sum(p is None for p, _ in par) == 2
