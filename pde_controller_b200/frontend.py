@@ -464,11 +464,111 @@ def _affine(p: _Lambda, what: str) -> Tuple[float, float]:
     return v.c1, v.c0
 
 
-def parse_program(text: str) -> Problem:
-    """Interpret one femformal-dialect program.  Raises ParseError on anything outside the dialect."""
+# ---------------------------------------------------------------------------
+# fast path: the canonical template
+# ---------------------------------------------------------------------------
+# Every program of the reference's records (and of render_program) is the SAME dozen lines with different numbers
+# (SURVEY.md Appendix A).  Interpreting one through `ast` costs ~1 ms; matching the template with one regular expression
+# and converting its numbers costs ~40 us.  The match is deliberately strict (anchored, fixed spelling of every line,
+# thresholds of rho and E textually identical, labels A, B, C... in order, a conjunction spelt flat or left-nested): anything else is NOT an error here, it simply falls through to the general interpreter below, so the two
+# routes cannot disagree on what they both accept (tests compare them on every record, on synthetic sets and under fuzz).
+# a number: written so that every string has ONE way to match (digits are never shared between two quantifiers), or a
+# near-miss of the template would make the matcher backtrack exponentially; generated text is untrusted input
+_RE_NUM = r"[-+]?(?:\d+(?:\.\d*)?|\.\d+)(?:[eE][-+]?\d+)?"
+_VAL = rf"({_RE_NUM})(?:\s*\*\s*({_RE_NUM}))?"
+
+def _fast_regex():
+    num = _RE_NUM
+    val = lambda a, b: rf"(?P<{a}>{num})(?:\*(?P<{b}>{num}))?"
+    pat = (
+        rf"(?:from femformal\.core\.fem import (?P<imod>heatlinfem|mechlinfem) as (?P=imod)\n+)?"
+        rf"N = (?P<N>\d+)\n+"
+        rf"L = (?P<L>{num})\n+"
+        rf"rho = lambda x: {val('ro1', 'ro2')} if x < (?P<xa>{num}) or x > (?P<xb>{num}) else {val('ri1', 'ri2')}\n+"
+        rf"E = lambda x: {val('eo1', 'eo2')} if x < (?P=xa) or x > (?P=xb) else {val('ei1', 'ei2')}\n+"
+        rf"xpart = np\.linspace\(0, L, N \+ 1\)\n+"
+        rf"g = \[(?P<g0>{num}), None\]\n+"
+        rf"f_nodal = np\.zeros\(N \+ 1\)\n+"
+        rf"dt = (?P<dt>{num})\n+"
+        rf"T = (?P<T>{num})\n+"
+        rf"(?P<sys>fosys = heatlinfem\.heatlinfem_mix|sosys = mechlinfem\.mechlinfem)\(xpart, rho, E, g, f_nodal, dt\)\n+"
+        rf"(?P<apcs>(?:apc\d = logic\.APCont\(\[{num}, {num}\], \"[<>=]\", lambda x: {num} \* x \+ {num}, lambda x: {num}\)\n+){{1,8}})"
+        rf"cregions = \{{(?P<regs>[^}}\n]*)\}}\n+"
+        rf"cspec = \"(?P<spec>[^\"\n]*)\"\s*"
+    )
+    return re.compile(pat)
+
+
+_FAST = _fast_regex()
+_FAST_APC = re.compile(rf"apc(\d) = logic\.APCont\(\[({_RE_NUM}), ({_RE_NUM})\], \"([<>=])\", lambda x: ({_RE_NUM}) \* x \+ ({_RE_NUM}), lambda x: {_RE_NUM}\)")
+_FAST_CLAUSE = re.compile(rf"\(([GF])_\[({_RE_NUM}), ({_RE_NUM})\] \(([A-H])\)\)")
+
+
+def _parse_fast(src: str) -> Optional[Problem]:
+    """The canonical template, or None (then the general interpreter decides)."""
+    if len(src) > 8192:
+        return None
+    m = _FAST.fullmatch(src)
+    if m is None:
+        return None
+    heat = m["sys"].startswith("fosys")
+    if m["imod"] is not None and (m["imod"] == "heatlinfem") != heat:
+        return None
+    f = float
+    N = int(m["N"])
+    L, dt, T, g0, x_a, x_b = f(m["L"]), f(m["dt"]), f(m["T"]), f(m["g0"]), f(m["xa"]), f(m["xb"])
+    prod = lambda a, b: f(m[a]) * f(m[b]) if m[b] is not None else f(m[a])
+    rho_out, rho_in, E_out, E_in = prod("ro1", "ro2"), prod("ri1", "ri2"), prod("eo1", "eo2"), prod("ei1", "ei2")
+    # the checks the general route makes on these values; when one fails, let IT word the error
+    if not (2 <= N <= abi.MAX_ELEM) or not (L > 0 and math.isfinite(L)) or not (dt > 0 and T > 0 and math.isfinite(dt) and math.isfinite(T)):
+        return None
+    if not all(v > 0 and math.isfinite(v) for v in (rho_in, rho_out, E_in, E_out)) or not math.isfinite(g0):
+        return None
+    apcs = _FAST_APC.findall(m["apcs"])
+    P = len(apcs)
+    labels = "ABCDEFGH"[:P]
+    if [int(a[0]) for a in apcs] != list(range(P)):
+        return None
+    if m["regs"].strip() != ", ".join(f'"{labels[j]}" : apc{j}' for j in range(P)):
+        return None
+    # cspec: (C0) | ((C0) & (C1)) | (((C0) & (C1)) & (C2)) ... with the labels in order
+    spec = m["spec"]
+    cl = _FAST_CLAUSE.findall(spec)
+    if len(cl) != P or "".join(c[3] for c in cl) != labels:
+        return None
+    parts = [f"({c[0]}_[{c[1]}, {c[2]}] ({c[3]}))" for c in cl]
+    nested = parts[0]
+    for q in parts[1:]:
+        nested = f"({nested} & {q})"
+    flat = "(" + " & ".join(parts) + ")"          # the spelling of the reference's records: ((A) & (B) & (C)), ((A))
+    if spec != nested and spec != flat:
+        return None
+    preds, tree = [], []
+    for j, (a, c) in enumerate(zip(apcs, cl)):
+        x_lo, x_hi, t_lo, t_hi = f(a[1]), f(a[2]), f(c[1]), f(c[2])
+        if x_hi < x_lo or not (t_hi >= t_lo) or t_lo < 0 or not all(map(math.isfinite, (x_lo, x_hi, f(a[4]), f(a[5])))):
+            return None
+        preds.append(Predicate(x_lo, x_hi, a[3], f(a[4]), f(a[5]), c[0], t_lo, t_hi, labels[j]))
+        tree.append(("leaf", j, 0))
+        if j >= 1:
+            tree.append(("and", 0 if j == 1 else len(tree) - 2, len(tree) - 1))
+    return Problem("heat" if heat else "wave", N, L, dt, T, g0, x_a, x_b, rho_in, rho_out, E_in, E_out, preds, tree)
+
+
+def parse_program(text: str, fast: Optional[bool] = None) -> Problem:
+    """Interpret one femformal-dialect program.  Raises ParseError on anything outside the dialect.
+
+    fast: None = try the canonical-template matcher first, then the general interpreter; False = general interpreter
+    only; True = template matcher only (ParseError if the text is not the template; used by the tests)."""
     if not isinstance(text, str):
         raise ParseError("program is not text")
     src = textwrap.dedent(text.replace("\x00", "")).strip()
+    if fast is None or fast:
+        p = _parse_fast(src)
+        if p is not None:
+            return p
+        if fast:
+            raise ParseError("not the canonical template")
     try:
         with warnings.catch_warnings():
             warnings.simplefilter("ignore", SyntaxWarning)     # generated text: "invalid decimal literal" and the like
