@@ -46,6 +46,28 @@ def test_heat_steady_state_constant_flux(oracle_lib):
     np.testing.assert_allclose(traj[-1], expect, rtol=1e-12)
 
 
+# (i') the same closed form pins the material-sampling convention (C1) on interfaces that do NOT sit on nodes:
+#      element e takes the material found at its midpoint / left node / right node, with the strict outer test
+#      "x < x_a or x > x_b" of the reference's lambdas (one_d_heat/examples.jsonl:1)
+@pytest.mark.parametrize("sampling", [0, 1, 2])
+def test_heat_steady_state_pins_material_sampling(oracle_lib, sampling):
+    p = heat_problem(T=3000.0, dt=5.0, x_a=31.0, x_b=58.5)
+    q = 2.5e5
+    conv = default_conventions(theta=1.0, material_sampling=sampling)
+    traj, rob, cl, st = traj_of(oracle_lib, p, const_control(p, q), conv)
+    assert st == 0
+    h = p.L / p.n_elem
+    xs = {0: lambda e: (e + 0.5) * h, 1: lambda e: e * h, 2: lambda e: (e + 1) * h}[sampling]
+    E = np.array([p.E_out if (xs(e) < p.x_a or xs(e) > p.x_b) else p.E_in for e in range(p.n_elem)])
+    expect = p.g0 + q * np.concatenate([[0.0], np.cumsum(h / E)])
+    np.testing.assert_allclose(traj[-1], expect, rtol=1e-12)
+    # the three conventions really differ on this rod (each moves one of the two interface elements)
+    layouts = []
+    for pick in (lambda e: (e + 0.5) * h, lambda e: e * h, lambda e: (e + 1) * h):
+        layouts.append(tuple(p.E_out if (pick(e) < p.x_a or pick(e) > p.x_b) else p.E_in for e in range(p.n_elem)))
+    assert len(set(layouts)) == 3
+
+
 def _modes(N):
     th = (2 * np.arange(1, N + 1) - 1) * math.pi / (2 * N)
     i = np.arange(1, N + 1)
