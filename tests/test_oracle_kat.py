@@ -122,6 +122,54 @@ def test_wave_modal_period_elongation(oracle_lib):
         np.testing.assert_allclose(traj[k, 1:], expect, rtol=0, atol=1e-9 * np.abs(traj).max())
 
 
+def _modal_mass_and_lambda(N, h, rho, E, lumped):
+    """Discrete eigenvalues and modal masses of the Dirichlet-free rod for both mass conventions (C2)."""
+    th, phi = _modes(N)
+    if lumped:
+        lam = 2 * E / (rho * h * h) * (1 - np.cos(th))
+        m = np.full(N, rho * h)
+        m[-1] *= 0.5
+        mj = (phi * phi * m[:, None]).sum(0)
+    else:
+        lam = 6 * E / (rho * h * h) * (1 - np.cos(th)) / (2 + np.cos(th))
+        M = np.zeros((N, N))
+        for i in range(N):
+            M[i, i] = rho * h * (2 / 3 if i < N - 1 else 1 / 3)
+            if i + 1 < N:
+                M[i, i + 1] = M[i + 1, i] = rho * h / 6
+        mj = np.einsum("ij,ik,kj->j", phi, M, phi)
+    return phi, lam, mj
+
+
+# (ii') / (iii') the NON-default mass conventions, same closed forms: heat with lumped mass, waves with consistent mass
+def test_heat_modal_amplification_lumped_mass(oracle_lib):
+    N, L, rho, E, q = 30, 120.0, 2000.0, 1.0e6, 3.0e5
+    p = heat_problem(N=N, L=L, T=6.0, rho_in=rho, rho_out=rho, E_in=E, E_out=E)
+    traj, _, _, st = traj_of(oracle_lib, p, const_control(p, q), default_conventions(mass_heat=1))
+    assert st == 0
+    phi, lam, mj = _modal_mass_and_lambda(N, L / N, rho, E, lumped=True)
+    css = q * phi[-1] / (mj * lam)
+    amp = (1 - 0.5 * p.dt * lam) / (1 + 0.5 * p.dt * lam)
+    S = traj.shape[0] - 1
+    for k in (0, 1, 7, S // 2, S):
+        expect = p.g0 + phi @ (css * (1 - amp ** k))
+        np.testing.assert_allclose(traj[k, 1:], expect, rtol=0, atol=1e-9 * np.abs(expect).max())
+
+
+def test_wave_modal_period_elongation_consistent_mass(oracle_lib):
+    N, L, rho, E, F = 20, 1.0e5, 8e-6, 2e8, 3000.0
+    p = wave_problem(N=N, L=L, T=1.0, rho_in=rho, rho_out=rho, E_in=E, E_out=E)
+    traj, _, _, st = traj_of(oracle_lib, p, const_control(p, F), default_conventions(mass_wave=0))
+    assert st == 0
+    phi, lam, mj = _modal_mass_and_lambda(N, L / N, rho, E, lumped=False)
+    css = F * phi[-1] / (mj * lam)
+    ang = 2 * np.arctan(np.sqrt(lam) * p.dt / 2)
+    S = traj.shape[0] - 1
+    for k in (0, 1, 13, S // 2, S):
+        expect = phi @ (css * (1 - np.cos(k * ang)))
+        np.testing.assert_allclose(traj[k, 1:], expect, rtol=0, atol=1e-9 * np.abs(traj).max())
+
+
 # (iii) energy is conserved exactly once the force is back to zero
 def test_wave_energy_conservation(oracle_lib):
     p = wave_problem(T=1.5)
