@@ -235,6 +235,35 @@ def test_stl_window_edge_cases(oracle_lib):
     assert cl[3] == (traj[39:41] - 299.0).min(axis=1).max()
 
 
+# (iv') the NON-default STL conventions (C7 truncation of the window bounds, C8 end points always included, C9 band
+#       rule for "="), recomputed by hand on the oracle's own trajectory
+def test_stl_non_default_conventions_hand_computed(oracle_lib):
+    L, T, dt = 100.0, 3.0, 0.05
+    h = L / 30
+    preds = [
+        Predicate(11.0, 52.0, ">", 0.0, 299.0, "G", 1.04, 2.03),     # trunc: steps 20..40; nodes 4..15 + end points 11, 52
+        Predicate(20.0, 40.0, "=", 0.0, 300.5, "F", 0.52, 1.99),      # trunc: steps 10..39; band eps: eps - |u - p|
+    ]
+    p = heat_problem(L=L, T=T, dt=dt, preds=preds)
+    p.tree = [("leaf", 0, 0), ("leaf", 1, 0), ("and", 0, 1)]
+    conv = default_conventions(window_rule=1, region_rule=1, eq_rule=1, eq_eps=0.75)
+    traj, rob, cl, st = traj_of(oracle_lib, p, (np.array([0.0, 3.0]), np.array([0.0, 6e5])), conv)
+    assert st == 0
+
+    def at(xx):
+        e = int(xx // h)
+        xi = (xx - e * h) / h
+        return traj[:, e] + xi * (traj[:, e + 1] - traj[:, e])
+
+    nodes = traj[:, 4:16] - 299.0
+    ends = np.stack([at(11.0) - 299.0, at(52.0) - 299.0], axis=1)
+    m0 = np.minimum(nodes.min(axis=1), ends.min(axis=1))[20:41].min()
+    inner = np.concatenate([traj[:, 6:13], np.stack([at(20.0), at(40.0)], axis=1)], axis=1)
+    m1 = (0.75 - np.abs(inner - 300.5)).min(axis=1)[10:40].max()
+    assert cl[0] == pytest.approx(m0, rel=1e-13) and cl[1] == pytest.approx(m1, rel=1e-13)
+    assert rob == pytest.approx(min(m0, m1), rel=1e-13)
+
+
 # (v) second-order convergence in h of the end-point value
 def test_mesh_refinement_order_two(oracle_lib):
     errs = []
