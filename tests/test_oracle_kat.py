@@ -170,6 +170,33 @@ def test_wave_modal_period_elongation_consistent_mass(oracle_lib):
         np.testing.assert_allclose(traj[k, 1:], expect, rtol=0, atol=1e-9 * np.abs(traj).max())
 
 
+# (iii'') general Newmark (beta, gamma), e.g. with numerical damping: the discrete modes decouple the scheme exactly, so the
+#        rod must equal the superposition of N scalar oscillators, each stepped by the three-line Newmark recurrence
+@pytest.mark.parametrize("beta,gamma", [(0.3025, 0.6), (0.25, 0.5), (0.5, 0.9)])
+def test_wave_general_newmark_equals_modal_superposition(oracle_lib, beta, gamma):
+    N, L, rho, E = 20, 1.0e5, 8e-6, 2e8
+    p = wave_problem(N=N, L=L, T=0.6, rho_in=rho, rho_out=rho, E_in=E, E_out=E)
+    knots = (np.array([0.0, 0.1, 0.35, 0.6]), np.array([0.0, 2500.0, -1500.0, 500.0]))
+    traj, _, _, st = traj_of(oracle_lib, p, knots, default_conventions(newmark_beta=beta, newmark_gamma=gamma))
+    assert st == 0
+    phi, lam, mj = _modal_mass_and_lambda(N, L / N, rho, E, lumped=True)
+    dt = p.dt
+    S = traj.shape[0] - 1
+    f = np.interp(np.arange(S + 1) * dt, knots[0], knots[1])
+    q = np.zeros(N); v = np.zeros(N)
+    a = f[0] * phi[-1] / mj - lam * q
+    out = [phi @ q]
+    for k in range(S):
+        qp = q + dt * v + (0.5 - beta) * dt * dt * a
+        vp = v + (1 - gamma) * dt * a
+        an = (f[k + 1] * phi[-1] / mj - lam * qp) / (1 + beta * dt * dt * lam)
+        q = qp + beta * dt * dt * an
+        v = vp + gamma * dt * an
+        a = an
+        out.append(phi @ q)
+    np.testing.assert_allclose(traj[:, 1:], np.array(out), rtol=0, atol=1e-9 * np.abs(traj).max())
+
+
 # (iii) energy is conserved exactly once the force is back to zero
 def test_wave_energy_conservation(oracle_lib):
     p = wave_problem(T=1.5)
