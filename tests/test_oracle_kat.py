@@ -197,6 +197,64 @@ def test_wave_general_newmark_equals_modal_superposition(oracle_lib, beta, gamma
     np.testing.assert_allclose(traj[:, 1:], np.array(out), rtol=0, atol=1e-9 * np.abs(traj).max())
 
 
+def _dense_two_material(p, lumped):
+    """Dense M, K of the free dofs of a two-material rod (midpoint sampling), assembled here element by element."""
+    N, h = p.n_elem, p.L / p.n_elem
+    M = np.zeros((N + 1, N + 1)); K = np.zeros((N + 1, N + 1))
+    for e in range(N):
+        xm = (e + 0.5) * h
+        out = xm < p.x_a or xm > p.x_b
+        rho, E = (p.rho_out, p.E_out) if out else (p.rho_in, p.E_in)
+        K[e:e + 2, e:e + 2] += E / h * np.array([[1.0, -1.0], [-1.0, 1.0]])
+        M[e:e + 2, e:e + 2] += (rho * h / 2 * np.eye(2)) if lumped else (rho * h / 6 * np.array([[2.0, 1.0], [1.0, 2.0]]))
+    return M[1:, 1:], K[1:, 1:]
+
+
+# (vi) HETEROGENEOUS rods, time-dependent input: the generalised eigenvectors of (K, M) (scipy, dense) decouple both
+#      schemes exactly; every mode is then a scalar recurrence.  Independent of the banded assembly and of the
+#      tridiagonal solves of the code under test.
+def test_two_material_heat_equals_modal_theta_method(oracle_lib):
+    from scipy.linalg import eigh
+    p = heat_problem(T=5.0, x_a=31.0, x_b=58.5)
+    knots = (np.array([0.0, 1.0, 2.5, 5.0]), np.array([0.0, 6e5, 1e5, 4e5]))
+    traj, _, _, st = traj_of(oracle_lib, p, knots)
+    assert st == 0
+    M, K = _dense_two_material(p, lumped=False)
+    lam, V = eigh(K, M)                                   # V^T M V = I
+    S = traj.shape[0] - 1
+    f = np.interp(np.arange(S + 1) * p.dt, knots[0], knots[1])
+    q = np.zeros(p.n_elem)
+    out = [V @ q]
+    for k in range(S):
+        load = V[-1] * 0.5 * (f[k] + f[k + 1])            # theta = 1/2
+        q = ((1 - 0.5 * p.dt * lam) * q + p.dt * load) / (1 + 0.5 * p.dt * lam)
+        out.append(V @ q)
+    np.testing.assert_allclose(traj[:, 1:] - p.g0, np.array(out), rtol=0, atol=1e-9 * np.abs(traj - p.g0).max())
+
+
+def test_two_material_wave_equals_modal_newmark(oracle_lib):
+    from scipy.linalg import eigh
+    p = wave_problem(T=0.8)
+    knots = (np.array([0.0, 0.2, 0.5, 0.8]), np.array([0.0, 3000.0, -2000.0, 1000.0]))
+    traj, _, _, st = traj_of(oracle_lib, p, knots)
+    assert st == 0
+    M, K = _dense_two_material(p, lumped=True)
+    lam, V = eigh(K, M)
+    dt, beta, gamma = p.dt, 0.25, 0.5
+    S = traj.shape[0] - 1
+    f = np.interp(np.arange(S + 1) * dt, knots[0], knots[1])
+    q = np.zeros(p.n_elem); v = np.zeros(p.n_elem)
+    a = f[0] * V[-1] - lam * q
+    out = [V @ q]
+    for k in range(S):
+        qp = q + dt * v + (0.5 - beta) * dt * dt * a
+        vp = v + (1 - gamma) * dt * a
+        an = (f[k + 1] * V[-1] - lam * qp) / (1 + beta * dt * dt * lam)
+        q, v, a = qp + beta * dt * dt * an, vp + gamma * dt * an, an
+        out.append(V @ q)
+    np.testing.assert_allclose(traj[:, 1:], np.array(out), rtol=0, atol=1e-8 * np.abs(traj).max())
+
+
 # (iii) energy is conserved exactly once the force is back to zero
 def test_wave_energy_conservation(oracle_lib):
     p = wave_problem(T=1.5)
