@@ -267,6 +267,9 @@ int  pdeb_resident_fetch_async(PdebResident* r, double* robustness_out, double* 
 void* pdeb_stream_create(int device);
 void  pdeb_stream_destroy(void* stream);
 int   pdeb_stream_sync(void* stream);
+/* the order the kernels walk the batch in (sample ids grouped by kernel variant, longest trajectories first), as formed
+   under the conventions of the last evaluation: diagnostics and tests of the plan.  order_out [n]; synchronises. */
+int  pdeb_resident_plan_order(PdebResident* r, int32_t* order_out, void* stream);
 /* device pointers of the results (f64[n], f64[pmax][stride], i32[n]) for zero-copy consumers */
 int  pdeb_resident_device_ptrs(PdebResident* r, void** robustness_dev, void** clause_dev, void** status_dev);
 void pdeb_resident_destroy(PdebResident* r);

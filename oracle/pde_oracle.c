@@ -215,8 +215,19 @@ static void apply_K(int N, const double* ke, const double* d, double* out) {
  * Simulate one sample.  traj (optional) receives d at every step, (S+1) x (N+1);
  * vel (optional) the wave velocity.  clause[j] receives per-clause robustness.
  */
+/* per-thread workspace: grown on demand, reused across samples (the per-sample path allocates nothing) */
+typedef struct { double* buf; size_t cap; } Workspace;
+static double* ws_get(Workspace* w, size_t doubles) {
+    if (w->cap < doubles) {
+        free(w->buf);
+        w->buf = (double*)malloc(doubles * sizeof(double));
+        w->cap = w->buf ? doubles : 0;
+    }
+    return w->buf;
+}
+
 static int eval_one(const Sample* p, const PdebConventions* c, double* rob_out, double* clause,
-                    double* traj, double* vel, int64_t traj_cap_rows, int64_t* S_out) {
+                    double* traj, double* vel, int64_t traj_cap_rows, int64_t* S_out, Workspace* ws) {
     int N = p->N, n = N; /* n free dofs: nodes 1..N */
     double h = p->L / N;
     int64_t S = step_count(p->T, p->dt, c->steps_rule);
@@ -225,8 +236,9 @@ static int eval_one(const Sample* p, const PdebConventions* c, double* rob_out, 
     double dt = p->dt;
     int lumped = (p->kind == PDEB_KIND_HEAT) ? c->mass_heat : c->mass_wave;
 
-    double* buf = (double*)calloc((size_t)(N + 1) * 16, sizeof(double));
+    double* buf = ws_get(ws, (size_t)(N + 1) * 18);
     if (!buf) return PDEB_ST_BADPARAM;
+    memset(buf, 0, sizeof(double) * (size_t)(N + 1) * 18);
     double *x = buf, *ke = x + (N + 1), *me = ke + (N + 1);
     double *Mlo = me + (N + 1), *Mdi = Mlo + (N + 1), *Mup = Mdi + (N + 1);
     double *Alo = Mup + (N + 1), *Adi = Alo + (N + 1), *Aup = Adi + (N + 1);
@@ -253,8 +265,7 @@ static int eval_one(const Sample* p, const PdebConventions* c, double* rob_out, 
         Aup[i] = Mup[i] - coefK * kr;
     }
     /* factor the free-dof blocks (rows/cols 1..N): pointers offset by one */
-    double *cpM = (double*)calloc((size_t)(N + 1) * 2, sizeof(double)), *invM = cpM + (N + 1);
-    if (!cpM) { free(buf); return PDEB_ST_BADPARAM; }
+    double *cpM = Kd + (N + 1), *invM = cpM + (N + 1);
     tri_factor(n, Mlo + 1, Mdi + 1, Mup + 1, cpM + 1, invM + 1);
     tri_factor(n, Alo + 1, Adi + 1, Aup + 1, cpA + 1, invA + 1);
 
@@ -277,6 +288,11 @@ static int eval_one(const Sample* p, const PdebConventions* c, double* rob_out, 
         klo[j] = a0; khi[j] = a1;
         acc[j] = (p->top[j] == PDEB_TOP_G) ? INFINITY : -INFINITY;
     }
+    /* nothing after the last observed step can change the result: the evaluation stops there (the same work the
+     * CUDA kernels do); a trajectory dump marches on to the horizon S */
+    int64_t k_stop = 0;
+    for (int j = 0; j < p->np; ++j) if (khi[j] > k_stop) k_stop = khi[j];
+    if (traj || vel) k_stop = S;
 
     /* initial state */
     double d0 = (p->kind == PDEB_KIND_HEAT) ? p->g0 : 0.0;
@@ -298,11 +314,14 @@ static int eval_one(const Sample* p, const PdebConventions* c, double* rob_out, 
         if (vel && k < traj_cap_rows) memcpy(vel + k * (N + 1), v, sizeof(double) * (N + 1));
         for (int j = 0; j < p->np; ++j) {
             if (k < klo[j] || k > khi[j]) continue;
+            /* a state that is not finite at an observed step is an error of the sample (status NONFINITE), whatever
+             * the min / max below make of NaN margins */
+            for (int i = 1; i <= N; ++i) if (!isfinite(d[i])) status = PDEB_ST_NONFINITE;
             double r = spatial_margin(p, j, d, x, h, c);
             if (p->top[j] == PDEB_TOP_G) { if (r < acc[j] || isnan(r)) acc[j] = r; }
             else                         { if (r > acc[j] || isnan(r)) acc[j] = r; }
         }
-        if (k == S) break;
+        if (k >= k_stop) break;
         double t1 = (double)(k + 1) * dt;
         double f1 = pwl(p, t1);
         if (p->kind == PDEB_KIND_HEAT) {
@@ -347,8 +366,6 @@ static int eval_one(const Sample* p, const PdebConventions* c, double* rob_out, 
     for (int j = 0; j < p->np; ++j) if (!isfinite(acc[j])) status = PDEB_ST_NONFINITE;
     if (clause) for (int j = 0; j < p->np; ++j) clause[j] = acc[j];
     *rob_out = (status == PDEB_OK) ? rob : PDEB_FAILED_ROBUSTNESS;
-    free(cpM);
-    free(buf);
     return status;
 }
 
@@ -365,7 +382,10 @@ int pdeo_eval_batch(const PdebBatch* in, const PdebConventions* conv, double* ro
     (void)nthreads;
 #endif
     int64_t n = in->n;
-#pragma omp parallel for schedule(dynamic, 64)
+#pragma omp parallel
+    {
+    Workspace ws = { NULL, 0 };
+#pragma omp for schedule(dynamic, 64)
     for (int64_t s = 0; s < n; ++s) {
         Sample p;
         double cl[PDEB_MAX_PRED];
@@ -373,10 +393,12 @@ int pdeo_eval_batch(const PdebBatch* in, const PdebConventions* conv, double* ro
         int st;
         for (int j = 0; j < PDEB_MAX_PRED; ++j) cl[j] = PDEB_FAILED_ROBUSTNESS;
         if (unpack(in, s, &p) != 0) st = PDEB_ST_BADPARAM;
-        else st = eval_one(&p, &c, &r, cl, NULL, NULL, 0, NULL);
+        else st = eval_one(&p, &c, &r, cl, NULL, NULL, 0, NULL, &ws);
         robustness_out[s] = r;
         if (status_out) status_out[s] = st;
         if (clause_out) for (int j = 0; j < in->pmax; ++j) clause_out[j * in->stride + s] = (j < PDEB_MAX_PRED) ? cl[j] : PDEB_FAILED_ROBUSTNESS;
+    }
+    free(ws.buf);
     }
     return PDEB_E_OK;
 }
@@ -398,7 +420,9 @@ int pdeo_trajectory(const PdebBatch* in, int64_t s, const PdebConventions* conv,
     Sample p;
     if (unpack(in, s, &p) != 0) return PDEB_ST_BADPARAM;
     double r, cl[PDEB_MAX_PRED];
-    int st = eval_one(&p, &c, &r, cl, traj, vel, cap_rows, NULL);
+    Workspace ws = { NULL, 0 };
+    int st = eval_one(&p, &c, &r, cl, traj, vel, cap_rows, NULL, &ws);
+    free(ws.buf);
     if (robustness_out) *robustness_out = r;
     if (clause_out) for (int j = 0; j < p.np; ++j) clause_out[j] = cl[j];
     return st;

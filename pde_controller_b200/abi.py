@@ -161,6 +161,7 @@ EXPORTS = [
     "pdeb_resident_run",
     "pdeb_resident_eval",
     "pdeb_resident_set_knots",
+    "pdeb_resident_plan_order",
     "pdeb_controls_create",
     "pdeb_controls_eval",
     "pdeb_controls_destroy",

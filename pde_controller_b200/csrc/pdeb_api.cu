@@ -102,6 +102,8 @@ struct PdebResident {
     int32_t vsc_host[2 * PDEB_NUM_VARIANTS] = {0};   /* first index / count of each variant inside `order` (whole batch) */
     int plan_launches = 0;
     bool plan_stale = false;         /* the last run planned chunk by chunk: whole-batch order must be rebuilt */
+    int plan_steps_rule = 0, plan_window_rule = 0;   /* conventions the current order was formed under (they decide the
+                                                        last observed step and where windows open: the plan's keys) */
     unsigned char* pstage = nullptr; /* packed uploads: the transferred block | list offsets | block sums (lazy) */
     size_t pstage_cap = 0, pstage_off = 0;
     cudaStream_t pipe[2] = {nullptr, nullptr};        /* internal streams of the pipelined run */
@@ -249,11 +251,24 @@ static void host_variant_counts(const PdebBatch* in, int64_t lo, int64_t hi, int
     for (int v = 0; v < PDEB_NUM_VARIANTS; ++v) { vsc[2 * v] = run; vsc[2 * v + 1] = cnt[v]; run += cnt[v]; }
 }
 
+/* The FP32 time loop exists for the register family only (default meshes: heat N = 30, wave N = 20).  A batch that holds
+ * other meshes is refused rather than silently evaluated in FP64 under an FP32 label. */
+static int check_precision(int precision, const int32_t* vsc) {
+    if (precision != 32) return 0;
+    for (int v = 2; v < PDEB_NUM_VARIANTS; ++v)
+        if (vsc[2 * v + 1] > 0)
+            return fail(PDEB_E_ARG, "precision 32 is implemented for the default meshes only (heat N=30, wave N=20): this batch holds other meshes");
+    return 0;
+}
+
 /* order a range by kernel variant and step count (device side, 3 launches, asynchronous) */
-static int plan_view(PdebResident* r, const RangeView& v, const int32_t* vsc, cudaStream_t stream, bool keys_done = false) {
+static int plan_view(PdebResident* r, const RangeView& v, const int32_t* vsc, cudaStream_t stream, bool keys_done = false,
+                     const PdebConventions* conv = nullptr) {
     if (v.dev.n == 0) return 0;
     PdebConventions cv;
-    pdeb_default_conventions(&cv);
+    if (conv) cv = *conv; else pdeb_default_conventions(&cv);
+    r->plan_steps_rule = cv.steps_rule;
+    r->plan_window_rule = cv.window_rule;
     int nl = 0;
     uint32_t live = 0;                       /* variants this range holds (host counts) */
     for (int q = 0; q < PDEB_NUM_VARIANTS; ++q) if (vsc[2 * q + 1] > 0) live |= 1u << q;
@@ -754,8 +769,11 @@ extern "C" int pdeb_resident_eval(PdebResident* r, int precision, const PdebConv
     PdebConventions cv;
     if (conv) cv = *conv; else pdeb_default_conventions(&cv);
     int launches = 0;
-    if (r->plan_stale) {
-        int prc = plan_view(r, view_of(r, 0, r->n, 0), r->vsc_host, stream);
+    { int prc = check_precision(precision, r->vsc_host); if (prc) return prc; }
+    /* the order was formed at upload under the default step / window rules: a caller that evaluates under others gets
+     * the batch re-ordered under ITS rules (results do not depend on the order, warp homogeneity does) */
+    if (r->plan_stale || cv.steps_rule != r->plan_steps_rule || cv.window_rule != r->plan_window_rule) {
+        int prc = plan_view(r, view_of(r, 0, r->n, 0), r->vsc_host, stream, false, &cv);
         if (prc) return prc;
         r->plan_stale = false;
     }
@@ -809,6 +827,15 @@ extern "C" void pdeb_stream_destroy(void* stream) { if (stream) cudaStreamDestro
 extern "C" int pdeb_stream_sync(void* stream) {
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int pdeb_resident_plan_order(PdebResident* r, int32_t* order_out, void* stream_) {
+    if (!r || !order_out) return fail(PDEB_E_ARG, "NULL argument");
+    DeviceGuard g(r->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (r->n > 0) CK(cudaMemcpyAsync(order_out, r->pb.order, 4 * (size_t)r->n, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
     return 0;
 }
 
@@ -868,6 +895,12 @@ extern "C" int pdeb_resident_run(PdebResident* r, const PdebBatch* in, int preci
     if (nch < 1) nch = 1;
     if (nch > PDEB_MAX_CHUNKS) nch = PDEB_MAX_CHUNKS;
     int launches = 0;
+    {
+        int32_t vall[2 * PDEB_NUM_VARIANTS];
+        host_variant_counts(in, 0, n, vall);
+        rc = check_precision(precision, vall);
+        if (rc) return rc;
+    }
     if (timing) CK(cudaEventRecord(r->ev[0], user));
     CK(cudaEventRecord(r->pev[0], user));
     for (int i = 0; i < 2; ++i) CK(cudaStreamWaitEvent(r->pipe[i], r->pev[0], 0));
@@ -878,7 +911,7 @@ extern "C" int pdeb_resident_run(PdebResident* r, const PdebBatch* in, int preci
         if (rc) return rc;
         RangeView v = view_of(r, lo, hi, c);
         host_variant_counts(in, lo, hi, v.vsc);
-        rc = plan_view(r, v, v.vsc, st);
+        rc = plan_view(r, v, v.vsc, st, false, &cv);
         if (rc) return rc;
         int nl = 0;
         const int lrc = pdeb_launch_all(v.dev, cv, v.out, v.pb, v.vsc, precision, st, &nl);

@@ -433,9 +433,11 @@ pdeb_chunk_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant_
     for (int o = 16; o >= 1; o >>= 1) { const int32_t other = __shfl_xor_sync(PDEB_FULL, S32, o); S32 = other > S32 ? other : S32; }
     const double eq_eps = (cv.eq_rule == 1) ? cv.eq_eps : 0.0;
 
+    bool bad_state = false;     /* sticky: state not finite at an observed step (the maxima below drop NaN margins) */
     for (int32_t k = 0;; ++k) {
         /* ---- (1) clauses whose window contains step k ---- */
         unsigned open = __ballot_sync(PDEB_FULL, lane < np && k >= c_klo && k <= c_khi);
+        if (open) bad_state = bad_state || !(xs - xs == 0.0) || !(x[0] - x[0] == 0.0) || !(x[R - 1] - x[R - 1] == 0.0);
         while (open) {
             const int j = __ffs(open) - 1;
             open &= open - 1u;
@@ -633,7 +635,7 @@ pdeb_chunk_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant_
         if (status == PDEB_OK) {
             rob = val[nt - 1];
             if (!isfinite(rob)) status = PDEB_ST_NONFINITE;
-            if (__any_sync(PDEB_FULL, lane < np && !isfinite(c_acc))) status = PDEB_ST_NONFINITE;
+            if (__any_sync(PDEB_FULL, (lane < np && !isfinite(c_acc)) || bad_state)) status = PDEB_ST_NONFINITE;
         }
     }
     if (lane == 0) {

@@ -200,6 +200,7 @@ pdeb_controls_kernel(const __grid_constant__ PdebSpecConst<N> sp, const double* 
     }
 
     const int32_t k_end = sp.k_end;
+    bool bad_state = false;      /* sticky: state not finite at an observed step (see pdeb_run_reg) */
     for (int32_t k = 0;; ++k) {
         /* ---- clauses whose window contains step k (uniform) ---- */
 #pragma unroll
@@ -233,6 +234,7 @@ pdeb_controls_kernel(const __grid_constant__ PdebSpecConst<N> sp, const double* 
                 const double r = (rel == PDEB_REL_EQ) ? sp.eq_eps - gmax : -gmax;
                 const bool take = (((cd.info >> 2) & 1u) == PDEB_TOP_G) ? (r < acc[j]) : (r > acc[j]);
                 if (take || r != r) acc[j] = r;
+                if (!(w[(N + 1) / 2] - w[(N + 1) / 2] == 0.0)) bad_state = true;
             }
         }
         if (k >= k_end) break;
@@ -297,7 +299,7 @@ pdeb_controls_kernel(const __grid_constant__ PdebSpecConst<N> sp, const double* 
     double rob = NAN;
 #pragma unroll
     for (int q = 0; q < 2 * PMAX - 1; ++q) if (q == sp.nt - 1) rob = val[q];
-    if (!isfinite(rob)) status = PDEB_ST_NONFINITE;
+    if (!isfinite(rob) || bad_state) status = PDEB_ST_NONFINITE;
 #pragma unroll
     for (int j = 0; j < PMAX; ++j) if (j < sp.np && !isfinite(acc[j])) status = PDEB_ST_NONFINITE;
     out.robustness[t] = (status == PDEB_OK) ? rob : PDEB_FAILED_ROBUSTNESS;

@@ -885,6 +885,12 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
      * bit 2 / 3 the clause `cur` takes its end points from one element / in the general interpolated form.
      * It changes at window events only; each step ONE warp-wide OR of it decides every branch of the pass. */
     uint32_t flags = 0;
+    /* sticky: the state was not finite at an OBSERVED step (status NONFINITE).  The running maxima below drop NaN
+     * margins, so this is tested on the state itself: the step matrix couples every row (both elimination chains and
+     * the back substitution run through non-zero multipliers), so one non-finite value (an inf / NaN control knot
+     * reaching the load) makes EVERY row non-finite within that step, and it never heals: the twist row stands for
+     * all of them */
+    bool bad_state = false;
     const real eq_shift = (cv.eq_rule == 1) ? (real)cv.eq_eps : (real)0;
 
     /* window events of step k: which clauses are open from here on, and what the pass needs to know about them */
@@ -938,6 +944,10 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
             /* G: min over steps of -gmax = -(max gmax); F: max over steps of -gmax: one running max either way */
             const real v = (((info >> 2) & 1u) == PDEB_TOP_G) ? gmax : -gmax;
             if (has && v > A) slots.R(cur, 2) = v;
+            {
+                const real wm = tr.w[PdebTrajReg<KIND, N, real, STRIDE>::M];
+                if (has && !(wm - wm == (real)0)) bad_state = true;
+            }
             if (wf & 2u) {
                 /* lanes with several open windows: their remaining clauses, one pass per clause */
                 uint32_t todo = (flags & 2u) ? (open & (open - 1u)) : 0u;
@@ -1034,7 +1044,7 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
         }
         if (status == PDEB_OK) {
             rob = val[nt - 1];
-            if (!isfinite(rob)) status = PDEB_ST_NONFINITE;
+            if (!isfinite(rob) || bad_state) status = PDEB_ST_NONFINITE;
             for (int j = 0; j < np; ++j) if (!isfinite((double)slots.R(j, 2))) status = PDEB_ST_NONFINITE;
         }
     }

@@ -9,8 +9,14 @@ the GPU; `eval_robustness_batch` does a whole list in ONE call, which is what re
 process pool of simulate_gt.py:62-89.
 
 Differences that are deliberate and documented in INTEGRATION.md:
-  * the control input is an explicit argument (`control=`); the reference synthesises it with
-    Gurobi inside femformal, which is out of scope.  None means zero input.
+  * the reference returns the robustness under the input femformal SYNTHESISES with Gurobi
+    (eval_robustness_wrapper.py:16); the MILP is out of scope, so the control is an argument here:
+      - an explicit piecewise-linear input `(knot_times, knot_values)` -> robustness under it;
+      - `"search"` (the default of the reference-named helpers): the sampling surrogate of the synthesis
+        (search.search_controls, controls family on the GPU) finds an input and the robustness UNDER THAT
+        input is returned -- the closest stand-in for the reference's number this tier allows;
+      - `"zero"`: zero input, on request only (never silently under the reference's function names).
+    The mode is a parameter (`configure(control_mode=...)`, `controls=`) and callers record it.
   * `runtime` is the batch wall time divided by the batch size.
 """
 from __future__ import annotations
@@ -28,12 +34,28 @@ from .problem import Problem, ProblemBatch
 _DEVICE = 0
 _PRECISION = 64
 _CONV = None
+_CONTROL_MODE = "search"
+_SEARCH = {"population": 4096, "generations": 6, "seed": 0}
+CONTROL_MODES = ("search", "zero")
 
 
-def configure(device: int = 0, precision: int = 64, conventions=None):
-    """Process-wide defaults of the helpers below (device ordinal, 64/32-bit time loop, convention flags)."""
-    global _DEVICE, _PRECISION, _CONV
+def configure(device: int = 0, precision: int = 64, conventions=None, control_mode: Optional[str] = None,
+              search: Optional[dict] = None):
+    """Process-wide defaults of the helpers below: device ordinal, 64/32-bit time loop, convention flags, what a
+    sample WITHOUT an explicit control is evaluated under (`control_mode`: "search" | "zero") and the search budget
+    (`search`: population, generations, seed, elite_frac, bounds)."""
+    global _DEVICE, _PRECISION, _CONV, _CONTROL_MODE, _SEARCH
     _DEVICE, _PRECISION, _CONV = device, precision, conventions
+    if control_mode is not None:
+        if control_mode not in CONTROL_MODES:
+            raise ValueError(f"control_mode must be one of {CONTROL_MODES}")
+        _CONTROL_MODE = control_mode
+    if search is not None:
+        _SEARCH = {**_SEARCH, **search}
+
+
+def control_mode() -> str:
+    return _CONTROL_MODE
 
 
 def is_correct(pred, ans, prec=1e-3):
@@ -47,20 +69,33 @@ def is_correct(pred, ans, prec=1e-3):
 
 
 def eval_robustness_batch(programs: Sequence[str], natural_language: Optional[Sequence[str]] = None,
-                          controls: Optional[Sequence] = None, device: Optional[int] = None,
+                          controls=None, device: Optional[int] = None,
                           precision: Optional[int] = None, conventions=None, return_status: bool = False,
-                          parse_workers: Optional[int] = None):
+                          parse_workers: Optional[int] = None, return_controls: bool = False, search: Optional[dict] = None):
     """Evaluate many programs in one GPU call (long lists are parsed by worker processes: frontend.parse_many).
 
-    -> (robustness list, runtime list[, status array]).  A program that does not parse, or a
+    controls: a list with one entry per program -- `(knot_times, knot_values)` or None -- or one of the mode strings
+    "search" / "zero" for every program, or None (= the process-wide mode, `configure(control_mode=)`, "search" unless
+    changed).  An entry that is None is evaluated under the mode: "search" runs the sampling surrogate of the
+    reference's control synthesis per program (search.search_controls) and evaluates under the input it found,
+    "zero" evaluates under zero input.  `search` overrides the search budget for this call.
+
+    -> (robustness list, runtime list[, status array][, controls used]).  A program that does not parse, or a
     simulation that fails, yields robustness -100 (the failure label of simulate_gt.py:59);
     nothing raises per sample.
     """
     t0 = time.perf_counter()
     n = len(programs)
+    mode = _CONTROL_MODE
+    if isinstance(controls, str):
+        if controls not in CONTROL_MODES:
+            raise ValueError(f"controls must be a list or one of {CONTROL_MODES}")
+        mode, controls = controls, None
     controls = list(controls) if controls is not None else [None] * n
     if len(controls) != n:
         raise ValueError("controls must have one entry per program")
+    dev = _DEVICE if device is None else device
+    conv = conventions if conventions is not None else _CONV
     problems: List[Optional[Problem]] = []
     status = np.zeros(n, dtype=np.int32)
     for i, (prob, _msg) in enumerate(parse_many(programs, workers=parse_workers)):
@@ -70,24 +105,37 @@ def eval_robustness_batch(programs: Sequence[str], natural_language: Optional[Se
     live = [i for i in range(n) if problems[i] is not None]
     rob = np.full(n, abi.FAILED_ROBUSTNESS, dtype=np.float64)
     if live:
+        need = [i for i in live if controls[i] is None]
+        if need and mode == "search":
+            from . import search as _search
+            found = _search.search_controls([problems[i] for i in need], device=dev, conv=conv, **{**_SEARCH, **(search or {})})
+            for i, f in zip(need, found):
+                controls[i] = (f["knot_t"], f["knot_y"]) if f["knot_y"] is not None else None
+        # the number returned is ALWAYS the batch kernels' robustness under the control in `controls` (found or given)
         batch = ProblemBatch.from_problems([problems[i] for i in live], [controls[i] for i in live])
-        out = native.evaluate_batch(batch, device=_DEVICE if device is None else device,
-                                    precision=_PRECISION if precision is None else precision,
-                                    conv=conventions if conventions is not None else _CONV)
+        out = native.evaluate_batch(batch, device=dev, precision=_PRECISION if precision is None else precision, conv=conv)
         rob[live] = out["robustness"]
         status[live] = out["status"]
     runtime = (time.perf_counter() - t0) / max(n, 1)
     res = ([float(r) for r in rob], [runtime] * n)
-    return res + (status,) if return_status else res
+    if return_status:
+        res = res + (status,)
+    if return_controls:
+        res = res + (controls,)
+    return res
 
 
 def eval_robustness_helper(robustness, natural_language, verbose=False, control=None):
     """Same call as the reference's helper (its first argument is the PROGRAM text, eval_script.py:43).
 
+    control: `(knot_times, knot_values)`, "search", "zero", or None = the process-wide mode ("search" unless
+    `configure(control_mode=...)` says otherwise: the reference's number is the robustness under a SYNTHESISED input,
+    eval_robustness_wrapper.py:16, never under zero input).
     Raises RuntimeError when the program cannot be evaluated, as the reference does on a non-zero
     exit of the wrapper process (eval_script.py:63-65); callers turn that into the -100 label.
     """
-    rob, rt, st = eval_robustness_batch([robustness], [natural_language], [control], return_status=True)
+    rob, rt, st = eval_robustness_batch([robustness], [natural_language], control if isinstance(control, str) else [control],
+                                        return_status=True)
     if verbose:
         print(json.dumps({"robustness": rob[0], "runtime": rt[0]}))
     if st[0] != abi.OK:
@@ -111,9 +159,24 @@ def eval_robustness_DPO(item, pred_key='predicted_intermediate_python', nl_key='
     return eval_robustness_helper(pred, nl, control=control)
 
 
-def wrapper_main(argv=None):
-    """The wire format of eval_robustness_wrapper.py:13-21: argv = [nl, program] -> one JSON line."""
+def wrapper_main(argv=None, out=None):
+    """The wire format of eval_robustness_wrapper.py:13-21: argv = [nl_in_prompt, llm_output] -> EXACTLY one JSON line
+    {"robustness": r, "runtime": t} on stdout and nothing else (the reference's caller json.loads the whole of stdout,
+    eval_script.py:67-72); a failure exits non-zero with the message on stderr (what :63-65 turns into RuntimeError).
+    The executable twin is pde_controller_b200/eval_robustness_wrapper.py.  The mode of a call without a control is the
+    process-wide one; PDEC_CONTROL_MODE=zero|search in the environment overrides it for a subprocess."""
+    import os
     import sys
     argv = sys.argv[1:] if argv is None else argv
-    robustness, runtime = eval_robustness_helper(argv[1], argv[0])
-    print(json.dumps({"robustness": robustness, "runtime": runtime}))
+    out = sys.stdout if out is None else out
+    if len(argv) < 2:
+        sys.stderr.write("usage: eval_robustness_wrapper.py <natural language> <program>\n")
+        return 2
+    env_mode = os.environ.get("PDEC_CONTROL_MODE")
+    try:
+        robustness, runtime = eval_robustness_helper(argv[1], argv[0], control=env_mode if env_mode in CONTROL_MODES else None)
+    except Exception as e:                     # non-zero exit, nothing on stdout
+        sys.stderr.write(f"{type(e).__name__}: {e}\n")
+        return 1
+    out.write(json.dumps({"robustness": robustness, "runtime": runtime}) + "\n")
+    return 0

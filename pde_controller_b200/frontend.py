@@ -500,6 +500,9 @@ def _fast_regex():
 
 
 _FAST = _fast_regex()
+# an integer literal with a leading zero ("02298576") is a SyntaxError for Python (2 and 3 alike; "0123.5", "1e-06" and
+# "00" are fine): the template matcher must not accept what the interpreter of the dialect rejects
+_LEADING_ZERO_INT = re.compile(r"(?<![\w.])(?<![eE][-+])0\d*[1-9]\d*(?![\d.eE])")
 _FAST_APC = re.compile(rf"apc(\d) = logic\.APCont\(\[({_RE_NUM}), ({_RE_NUM})\], \"([<>=])\", lambda x: ({_RE_NUM}) \* x \+ ({_RE_NUM}), lambda x: {_RE_NUM}\)")
 _FAST_CLAUSE = re.compile(rf"\(([GF])_\[({_RE_NUM}), ({_RE_NUM})\] \(([A-H])\)\)")
 
@@ -509,7 +512,7 @@ def _parse_fast(src: str) -> Optional[Problem]:
     if len(src) > 8192:
         return None
     m = _FAST.fullmatch(src)
-    if m is None:
+    if m is None or _LEADING_ZERO_INT.search(src):
         return None
     heat = m["sys"].startswith("fosys")
     if m["imod"] is not None and (m["imod"] == "heatlinfem") != heat:
@@ -556,6 +559,21 @@ def _parse_fast(src: str) -> Optional[Problem]:
 
 
 def parse_program(text: str, fast: Optional[bool] = None) -> Problem:
+    """Program text -> Problem.  The ONLY exception this raises is ParseError: whatever a malformed program makes the
+    interpreter below throw (TypeError from arithmetic on odd operands inside a material lambda, an unhashable
+    relation, RecursionError, OverflowError ...) is converted, so that batch callers can label the sample -100
+    (simulate_gt.py:59 of the reference) and go on.  See _parse_program for the dialect."""
+    try:
+        return _parse_program(text, fast)
+    except ParseError:
+        raise
+    except (RecursionError, MemoryError) as e:
+        raise ParseError(f"program too deep or too large: {type(e).__name__}")
+    except Exception as e:
+        raise ParseError(f"cannot interpret program: {e!r}")
+
+
+def _parse_program(text: str, fast: Optional[bool] = None) -> Problem:
     """Interpret one femformal-dialect program.  Raises ParseError on anything outside the dialect.
 
     fast: None = try the canonical-template matcher first, then the general interpreter; False = general interpreter
@@ -697,7 +715,7 @@ def _parse_chunk(texts):
     for t in texts:
         try:
             out.append((parse_program(t), None))
-        except ParseError as e:
+        except Exception as e:          # parse_program raises ParseError only; belt and braces for the worker pool
             out.append((None, str(e)))
     return out
 

@@ -71,6 +71,8 @@ def lib():
         L.pdeb_stream_destroy.argtypes = [C.c_void_p]
         L.pdeb_stream_sync.restype = C.c_int
         L.pdeb_stream_sync.argtypes = [C.c_void_p]
+        L.pdeb_resident_plan_order.restype = C.c_int
+        L.pdeb_resident_plan_order.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.pdeb_resident_device_ptrs.restype = C.c_int
         L.pdeb_resident_device_ptrs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pdeb_resident_destroy.argtypes = [C.c_void_p]
@@ -246,6 +248,12 @@ class ResidentBatch:
         """Enqueue the D2H copies of robustness + status into `out` (page-locked arrays); no synchronisation."""
         _check(self._L.pdeb_resident_fetch_async(self._h, _ptr(out["robustness"]), None, _ptr(out["status"]), stream or None),
                "pdeb_resident_fetch_async")
+
+    def plan_order(self, stream: int = 0) -> np.ndarray:
+        """Sample ids in the order the kernels walk them (as formed under the conventions of the last eval)."""
+        order = np.empty(self.batch.n, dtype=np.int32)
+        _check(self._L.pdeb_resident_plan_order(self._h, _ptr(order), stream or None), "pdeb_resident_plan_order")
+        return order
 
     def device_ptrs(self):
         r, c, s = C.c_void_p(), C.c_void_p(), C.c_void_p()

@@ -7,9 +7,11 @@ three rates).  `evaluate_future` (simulate_gt.py:62-89: one future per sample, 3
 `eval_robustness_batch`.  A sample whose program cannot be evaluated is labelled -100, exactly what
 simulate_gt.py:55-59 / :144-147 count as "failed"; there are no timeouts any more.
 
-Controls: the reference's labels are the robustness under the MILP-synthesised input (out of scope here).  This driver
-evaluates under the control given per record in the optional `control_key` field ({"t": [...], "y": [...]}), else zero
-input.
+Controls: the reference's labels are the robustness under the MILP-synthesised input (out of scope here).  A record
+that carries an input in the optional `control_key` field ({"t": [...], "y": [...]}) is evaluated under it; every other
+record under `--control`: "search" (default: the sampling surrogate of the synthesis, search.search_controls; the
+label is the robustness under the input found, and the input is written back into the record) or "zero" (zero
+input, on request).  The mode is recorded in metrics.json ("control_mode").
 """
 from __future__ import annotations
 
@@ -21,16 +23,33 @@ import random
 from .eval_script import eval_robustness_batch
 
 
-def evaluate_future(eval_fn, tasks, _timeout=300, python_key="python", nl_key="nl", control_key="control"):
+def evaluate_future(eval_fn, tasks, _timeout=300, python_key="python", nl_key="nl", control_key="control",
+                    control_mode=None, write_back=False, search=None):
     """Drop-in for simulate_gt.evaluate_future: -> (robustness tuple, time tuple, timeout_cnt).
 
     `eval_fn` is accepted for signature compatibility and ignored: the whole task list goes to the GPU at once.
+    control_mode: "search" | "zero" | None (= eval_script's process-wide mode) for the records without an input of
+    their own; write_back stores the input a record was evaluated under in task[control_key].
     """
+    from . import eval_script
     controls = []
     for t in tasks:
         c = t.get(control_key)
         controls.append((c["t"], c["y"]) if isinstance(c, dict) and "t" in c and "y" in c else None)
-    rob, rt = eval_robustness_batch([t[python_key] for t in tasks], [t.get(nl_key, "") for t in tasks], controls)
+    mode = control_mode or eval_script.control_mode()
+    if mode not in eval_script.CONTROL_MODES:
+        raise ValueError(f"control mode must be one of {eval_script.CONTROL_MODES}")
+    prev = eval_script.control_mode()
+    eval_script.configure(eval_script._DEVICE, eval_script._PRECISION, eval_script._CONV, control_mode=mode)
+    try:
+        rob, rt, used = eval_robustness_batch([t[python_key] for t in tasks], [t.get(nl_key, "") for t in tasks], controls,
+                                              return_controls=True, search=search)
+    finally:
+        eval_script.configure(eval_script._DEVICE, eval_script._PRECISION, eval_script._CONV, control_mode=prev)
+    if write_back:
+        for t, c in zip(tasks, used):
+            if c is not None and control_key not in t:
+                t[control_key] = {"t": [float(x) for x in c[0]], "y": [float(x) for x in c[1]]}
     return tuple(rob), tuple(rt), 0
 
 
@@ -58,7 +77,10 @@ def main(args):
 
     metrics = {"n_samples": len(test_data)}
     if args.eval_robustness:
-        rob, times, timeouts = evaluate_future(None, test_data, control_key=args.control_key)
+        rob, times, timeouts = evaluate_future(None, test_data, control_key=args.control_key, control_mode=args.control,
+                                               write_back=True,
+                                               search={"population": args.search_population, "generations": args.search_generations})
+        metrics["control_mode"] = args.control
         for item, r, t in zip(test_data, rob, times):
             if "robustness" not in item:
                 item["robustness"] = r
@@ -94,6 +116,10 @@ def build_parser():
     p.add_argument("--nl_key", type=str, default="nl")
     p.add_argument("--robustness_key", type=str, default="robustness")
     p.add_argument("--control_key", type=str, default="control")
+    p.add_argument("--control", type=str, default="search", choices=["search", "zero"],
+                   help="what a record without an input of its own is evaluated under (module docstring)")
+    p.add_argument("--search_population", type=int, default=4096)
+    p.add_argument("--search_generations", type=int, default=6)
     p.add_argument("--max_num_examples", type=int, default=None)
     p.add_argument("--infer_on_train_set", action="store_true")
     p.add_argument("--eval_robustness", action="store_true")

@@ -88,10 +88,26 @@ def test_general_material_callables_are_fitted():
                         "E = lambda x: 1e6 if x < 20 else (2e6 if x < 60 else 3e6)"),
     lambda t: t.replace("N = 30", "N = 30\nwhile True: pass"),
     lambda t: t.replace("N = 30", "N = 10**9"),
+    # exceptions other than ParseError raised BEHIND the guarded interpreter loop (advisor, round 1):
+    # TypeError inside the material lambda when it is sampled, unhashable relation in APCont
+    lambda t: t.replace("rho = lambda x: 4.2e-06*455000000 if", "rho = lambda x: -'a' if"),
+    lambda t: t.replace('logic.APCont([11, 40], "="', "logic.APCont([11, 40], [1]"),
+    lambda t: t.replace("L = 140", "L = 1e308 * 1e308"),
+    lambda t: t.replace("g = [305, None]", "g = [{}, None]"),
 ])
 def test_malformed_or_hostile_programs_raise_parse_error(mutate):
     with pytest.raises(ParseError):
         parse_program(mutate(HEAT))
+
+
+def test_parse_many_turns_every_failure_into_a_message():
+    """One malformed program must not abort the batch (contract of eval_robustness_batch / simulate_gt)."""
+    from pde_controller_b200.frontend import parse_many
+    bad = HEAT.replace("rho = lambda x: 4.2e-06*455000000 if", "rho = lambda x: -'a' if")
+    out = parse_many([HEAT, bad, HEAT.replace('logic.APCont([11, 40], "="', "logic.APCont([11, 40], [1]"), "", None])
+    assert out[0][0] is not None and out[0][1] is None
+    for prob, msg in out[1:]:
+        assert prob is None and isinstance(msg, str) and msg
 
 
 def test_stray_statements_are_never_executed(tmp_path):

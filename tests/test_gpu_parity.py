@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from parity import TOL_FP32, TOL_FP64, field_scale, rel_err
+from parity import TOL_FP32, TOL_FP64, field_scale, pure_rel_err, rel_err
 from pde_controller_b200 import Predicate, Problem, ProblemBatch, default_conventions, native, synth
 
 pytestmark = pytest.mark.gpu
@@ -20,6 +20,16 @@ def check(batch, oracle_lib, conv=None, precision=64, tol=TOL_FP64):
     err = rel_err(got["robustness"], ref, batch)
     assert err.max() <= tol, f"max rel err {err.max():.3e} at sample {err.argmax()}"
     ok = ref_st == 0
+    # the literal "1e-9 relative" of the north star, no floor, next to the floored metric (FP64 only: both must hold)
+    pure, cnt = pure_rel_err(got["robustness"][ok], ref[ok])
+    print(f"parity n={batch.n}: floored max {err.max():.2e}, pure relative max {pure:.2e} over {cnt} samples with |r| >= 1e-6")
+    # (reported, not asserted: the quotient by |r| is dominated by the one or two samples of a set whose robustness
+    # happens to be ~1e-6..1e-3 of the field, which is what the floor of the asserted metric is for)
+    import json, os
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/parity_report.jsonl", "a") as f:
+        f.write(json.dumps({"n": int(batch.n), "kinds": sorted(set(int(k) for k in batch.kind)), "precision": precision,
+                            "floored_max": float(err.max()), "pure_relative_max": pure, "pure_relative_samples": cnt}) + "\n")
     assert (got["robustness"][~ok] == -100.0).all()
     for j in range(batch.pmax):
         live = ok & (batch.n_pred > j)
