@@ -23,11 +23,28 @@ from typing import List, Tuple
 from .problem import Predicate, Problem
 
 _NUM = r"[-+]?(?:\d+\.?\d*|\.\d+)(?:[eE][-+]?\d+)?"
-_CLAUSE = re.compile(
+_UNUM = r"(?:\d+\.?\d*|\.\d+)(?:[eE][-+]?\d+)?"          # unsigned
+_MUL = r"(?:\\cdot|\\times|\*)"
+# header of a clause up to (and including) "u(x)":  TOP_[[t0, t1]] (\forall x \in [a, b] ( u(x)
+_HEAD = re.compile(
     r"\s*(?P<top>[GF])_\[\[\s*(?P<t0>" + _NUM + r")\s*,\s*(?P<t1>" + _NUM + r")\s*\]\]\s*"
     r"\(\s*\\forall\s+x\s*\\in\s*\[\s*(?P<a>" + _NUM + r")\s*,\s*(?P<b>" + _NUM + r")\s*\]\s*"
-    r"\(\s*u\(x\)\s*(?:-\s*\(\s*(?P<m>" + _NUM + r")\s*(?:\\cdot|\*)\s*x\s*(?P<sgn>[-+])\s*(?P<c>" + _NUM + r")\s*\)\s*)?"
-    r"(?P<rel>\\leq|\\geq|<=|>=|<|>|=)\s*(?P<thr>" + _NUM + r")\s*\)\s*\)")
+    r"\(\s*u\(x\)\s*")
+# the profile inside "- ( ... )", in the five spellings the reference's parse_clause accepts
+# (test/PDEcontrol/evaluation/eval/eval_script.py:347-355: pattern1 .. pattern5), each as (slope, intercept) pieces:
+#   1  m \cdot x + c            (c may carry its own sign: "+ -1.7281")
+#   2  x / (d) + c               slope 1/d; the sign in front of x negates it
+#   3  x \cdot m + c
+#   4  x \cdot (m) + c
+#   5  mx + c                    juxtaposition
+_TAIL = r"(?:\s*(?P<sgn>[-+])\s*(?P<c>" + _NUM + r"))?\s*"
+_PROFILES = [
+    re.compile(r"(?P<m>" + _NUM + r")\s*" + _MUL + r"\s*x" + _TAIL),
+    re.compile(r"(?P<xs>[-+]?)\s*x\s*/\s*\(?\s*(?P<d>" + _UNUM + r")\s*\)?" + _TAIL),
+    re.compile(r"(?P<xs>[-+]?)\s*x\s*" + _MUL + r"\s*\(?\s*(?P<m>" + _NUM + r")\s*\)?" + _TAIL),
+    re.compile(r"(?P<m>" + _NUM + r")\s*x" + _TAIL),
+]
+_REL = re.compile(r"\s*(?P<rel>\\leq|\\geq|\\neq|<=|>=|!=|<|>|=)\s*(?P<thr>" + _NUM + r")\s*\)\s*\)")
 _JUNCTION = re.compile(r"\s*(\\land|\\lor|\\wedge|\\vee|&|\|)")
 
 
@@ -36,14 +53,64 @@ class SstlError(ValueError):
 
 
 def _rel(tok: str) -> str:
-    return {"\\leq": "<", "<=": "<", "\\geq": ">", ">=": ">"}.get(tok, tok)
+    """The relation of the IR: the reference's clause grammar also knows <=, >=, \\leq, \\geq (the same robustness as
+    the strict forms) and != / \\neq, which no APCont can state: it is kept as "!=" so that the cross-check reports it."""
+    return {"\\leq": "<", "<=": "<", "\\geq": ">", ">=": ">", "\\neq": "!="}.get(tok, tok)
+
+
+def _match_clause(s: str, i: int):
+    """One clause at position i -> (end, dict) or None.  dict: top, t0, t1, a, b (floats), slope, icpt, rel, thr."""
+    h = _HEAD.match(s, i)
+    if not h:
+        return None
+    j = h.end()
+    slope, icpt = 0.0, 0.0
+    if j < len(s) and s[j] == "-":
+        # u(x) - ( PROFILE )
+        k = j + 1
+        while k < len(s) and s[k].isspace():
+            k += 1
+        if k >= len(s) or s[k] != "(":
+            return None
+        k += 1
+        while k < len(s) and s[k].isspace():
+            k += 1
+        hit = None
+        for rx in _PROFILES:
+            m = rx.match(s, k)
+            if m and m.end() < len(s) and s[m.end()] == ")":
+                hit = m
+                break
+        if hit is None:
+            return None
+        g = hit.groupdict()
+        if g.get("d") is not None:
+            d = float(g["d"])
+            if d == 0.0:
+                raise SstlError("sstl: division by zero in a profile")
+            slope = 1.0 / d
+        else:
+            slope = float(g["m"])
+        if g.get("xs") == "-":
+            slope = -slope
+        if g.get("c") is not None:
+            icpt = float(g["c"]) * (-1.0 if g["sgn"] == "-" else 1.0)
+        j = hit.end() + 1
+    r = _REL.match(s, j)
+    if not r:
+        return None
+    out = {"top": h.group("top"), "t0": float(h.group("t0")), "t1": float(h.group("t1")), "a": float(h.group("a")),
+           "b": float(h.group("b")), "slope": slope, "icpt": icpt, "rel": _rel(r.group("rel")), "thr": float(r.group("thr")),
+           "text": s[i:r.end()].strip()}
+    return r.end(), out
 
 
 class _Parser:
     """or := and (lor and)* ; and := unary (land unary)* ; unary := clause | '(' or ')'"""
 
-    def __init__(self, text: str):
+    def __init__(self, text: str, truncate_positions: bool = False):
         self.s, self.i = text, 0
+        self.truncate_positions = truncate_positions
         self.preds: List[Predicate] = []
         self.tree: List[Tuple[str, int, int]] = []
 
@@ -81,19 +148,18 @@ class _Parser:
 
     def p_unary(self) -> int:
         self.ws()
-        m = _CLAUSE.match(self.s, self.i)
-        if m:
-            self.i = m.end()
-            thr = float(m.group("thr"))
-            slope = float(m.group("m")) if m.group("m") is not None else 0.0
-            icpt = float(m.group("c")) * (-1.0 if m.group("sgn") == "-" else 1.0) if m.group("c") is not None else 0.0
-            t0, t1 = float(m.group("t0")), float(m.group("t1"))
-            a, b = float(m.group("a")), float(m.group("b"))
+        hit = _match_clause(self.s, self.i)
+        if hit:
+            self.i, c = hit
+            t0, t1, a, b = c["t0"], c["t1"], c["a"], c["b"]
+            if self.truncate_positions:
+                # the reference reads the position interval as int(float(.)) (eval_script.py:341): truncation towards zero
+                a, b = float(int(a)), float(int(b))
             if t1 < t0 or b < a:
-                raise SstlError(f"sstl: reversed interval in {m.group(0).strip()!r}")
+                raise SstlError(f"sstl: reversed interval in {c['text']!r}")
             label = chr(ord("A") + len(self.preds)) if len(self.preds) < 26 else f"P{len(self.preds)}"
             # u - (m x + c) REL thr   <=>   u - (m x + c + thr) REL 0
-            self.preds.append(Predicate(a, b, _rel(m.group("rel")), slope, icpt + thr, m.group("top"), t0, t1, label))
+            self.preds.append(Predicate(a, b, c["rel"], c["slope"], c["icpt"] + c["thr"], c["top"], t0, t1, label))
             self.tree.append(("leaf", len(self.preds) - 1, 0))
             return len(self.tree) - 1
         if self.i < len(self.s) and self.s[self.i] == "(":
@@ -107,12 +173,15 @@ class _Parser:
         raise SstlError(f"sstl: cannot read a clause at {self.s[self.i:self.i + 60]!r}")
 
 
-def parse_sstl(latex: str):
-    """-> (predicates, tree); labels A, B, C ... in order of appearance, as the reference's programs name them."""
+def parse_sstl(latex: str, truncate_positions: bool = False):
+    """-> (predicates, tree); labels A, B, C ... in order of appearance, as the reference's programs name them.
+
+    truncate_positions: read the ends of every position interval as int(float(.)), the rule of the reference's
+    parse_clause (eval_script.py:341); off by default because the programs carry the untruncated numbers."""
     if not isinstance(latex, str) or not latex.strip():
         raise SstlError("sstl is empty")
     text = latex.replace("\\left", "").replace("\\right", "").replace("$", "")
-    p = _Parser(text)
+    p = _Parser(text, truncate_positions)
     root = p.p_or()
     p.ws()
     if p.i != len(p.s):
@@ -138,10 +207,13 @@ def _canon_tree(tree, n_leaf_map=None):
     return build(len(tree) - 1)
 
 
-def cross_check(problem: Problem, latex: str, rtol: float = 1e-9, atol: float = 1e-12) -> List[str]:
-    """Mismatches between the program's clauses / formula and the LaTeX specification (empty list = consistent)."""
+def cross_check(problem: Problem, latex: str, rtol: float = 1e-9, atol: float = 1e-12,
+                truncate_positions: bool = False) -> List[str]:
+    """Mismatches between the program's clauses / formula and the LaTeX specification (empty list = consistent).
+    truncate_positions compares the position intervals as the reference's parse_clause reads them: int(float(.)) on
+    both sides."""
     try:
-        preds, tree = parse_sstl(latex)
+        preds, tree = parse_sstl(latex, truncate_positions)
     except SstlError as e:
         return [str(e)]
     out = []
@@ -157,7 +229,8 @@ def cross_check(problem: Problem, latex: str, rtol: float = 1e-9, atol: float = 
             out.append(f"{name}: temporal operator {p.top} vs {q.top}")
         if p.rel != q.rel:
             out.append(f"{name}: relation {p.rel!r} vs {q.rel!r}")
-        for what, x, y in (("t_lo", p.t_lo, q.t_lo), ("t_hi", p.t_hi, q.t_hi), ("x_lo", p.x_lo, q.x_lo), ("x_hi", p.x_hi, q.x_hi),
+        pxl, pxh = (float(int(p.x_lo)), float(int(p.x_hi))) if truncate_positions else (p.x_lo, p.x_hi)
+        for what, x, y in (("t_lo", p.t_lo, q.t_lo), ("t_hi", p.t_hi, q.t_hi), ("x_lo", pxl, q.x_lo), ("x_hi", pxh, q.x_hi),
                            ("slope", p.m, q.m), ("intercept", p.b, q.b)):
             if not close(float(x), float(y)):
                 out.append(f"{name}: {what} {x!r} vs {y!r}")

@@ -90,3 +90,21 @@ def test_device_code_eight_clauses(emu, oracle_lib, wl):
     assert rel_err(rob, ref, b).max() <= TOL64
     live = (np.arange(b.pmax)[:, None] < b.n_pred) & (ref_st == 0)
     assert np.allclose(cl[:, :b.n][live], ref_cl[:, :b.n][live], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("wl", ["heat", "wave"])
+@pytest.mark.parametrize("bad", [np.inf, np.nan])
+def test_device_code_flags_a_state_that_turns_nonfinite_inside_a_window(emu, oracle_lib, wl, bad):
+    """inf / NaN at the LAST control knot: the trajectory is finite for most of the run and turns non-finite inside
+    clause 0's window; the running maxima drop NaN margins, the sticky state test must not (advisor, round 1)."""
+    conv = default_conventions()
+    b = synth.make_batch(128, wl, seed=21)
+    hit = np.arange(b.n) % 2 == 0
+    for s in np.nonzero(hit)[0]:
+        b.knot_y[b.n_knots[s] - 1, s] = bad
+        b.pred_tlo[0, s], b.pred_thi[0, s] = 0.0, b.T[s]
+    ref, ref_st = oracle_lib.eval_batch(b, conv)
+    rob, st, _ = run_emu(emu, b, conv)
+    assert (ref_st[hit] == 2).all() and (st == ref_st).all() and (rob[hit] == -100.0).all()
+    from parity import rel_err
+    assert rel_err(rob, ref, b)[~hit].max() <= TOL64

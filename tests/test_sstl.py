@@ -128,3 +128,86 @@ def test_fuzzed_latex_and_cspec_parse_or_raise_their_own_error_only():
 
     run_latex()
     run_cspec()
+
+
+# ---- the clause spellings of the reference's parse_clause (eval_script.py:331-382) --------------------------------
+# (spelling of the part behind "u(x)", expected slope, expected intercept + threshold, expected relation, reference pattern)
+_HEAD = "G_[[0.5, 2.25]] (\\forall x \\in [12.7, 40.2]  (u(x)"
+SPELLINGS = [
+    (" - (0.25 \\cdot x + 290.5) > 0))", 0.25, 290.5, ">", 1),
+    (" - (-2e-05 \\cdot x + -1.7281) < 0))", -2e-05, -1.7281, "<", 1),
+    (" - (0.25 \\cdot x + 290.5) \\leq 3))", 0.25, 293.5, "<", 1),
+    (" - (0.25 \\cdot x + 290.5) \\geq -2.5))", 0.25, 288.0, ">", 1),
+    (" - (0.25 \\cdot x + 290.5) != 0))", 0.25, 290.5, "!=", 1),
+    (" > 300))", 0.0, 300.0, ">", 1),                                   # no profile at all: the "- (...)" part is optional
+    (" - (x/(4) + 290.5) > 0))", 0.25, 290.5, ">", 2),
+    (" - (-x/8 - 3) <= 0))", -0.125, -3.0, "<", 2),
+    (" - (x \\cdot 0.25 + 290.5) > 0))", 0.25, 290.5, ">", 3),
+    (" - (-x \\cdot 0.5 - 2) >= 0))", -0.5, -2.0, ">", 3),
+    (" - (x \\cdot (0.25) + 290.5) < 0))", 0.25, 290.5, "<", 4),
+    (" - (x \\cdot (-0.5) + 1) > 0))", -0.5, 1.0, ">", 4),
+    (" - (0.25x + 290.5) = 0))", 0.25, 290.5, "=", 5),
+    (" - (3x - 7) > 1))", 3.0, -6.0, ">", 5),
+]
+NEAR_MISSES = [
+    " - (0.25 \\cdot y + 290.5) > 0))",          # not a profile in x
+    " - (0.25 \\cdot x \\cdot x + 290.5) > 0))",  # not affine
+    " - (x/(0) + 1) > 0))",                       # division by zero
+    " - (x \\cdot \\cdot 3 + 1) > 0))",
+    " - (0.25 \\cdot x + 290.5) >> 0))",
+    " - 0.25 \\cdot x + 290.5 > 0))",             # profile without its parentheses
+    " - (0.25 \\cdot x + 290.5) > ))",            # no threshold
+]
+
+
+@pytest.mark.parametrize("tail,slope,icpt,rel,pattern", SPELLINGS, ids=[f"p{s[4]}:{s[0].strip()[:28]}" for s in SPELLINGS])
+def test_clause_spellings_of_the_reference_grammar(tail, slope, icpt, rel, pattern):
+    preds, tree = parse_sstl(_HEAD + tail)
+    (q,) = preds
+    assert (q.top, q.t_lo, q.t_hi, q.x_lo, q.x_hi, q.rel) == ("G", 0.5, 2.25, 12.7, 40.2, rel)
+    assert q.m == pytest.approx(slope, rel=1e-15) and q.b == pytest.approx(icpt, rel=1e-15)
+    assert tree == [("leaf", 0, 0)]
+    # the reference reads position intervals as int(float(.)) (eval_script.py:341): a flag here
+    (t,) = parse_sstl(_HEAD + tail, truncate_positions=True)[0]
+    assert (t.x_lo, t.x_hi) == (12.0, 40.0)
+
+
+@pytest.mark.parametrize("tail", NEAR_MISSES)
+def test_near_misses_are_reported_not_guessed(tail):
+    with pytest.raises(SstlError):
+        parse_sstl(_HEAD + tail)
+
+
+def test_truncation_flag_in_the_cross_check():
+    p = Problem("heat", 30, 100.0, 0.05, 5.0, 300.0, 20.0, 60.0, 1.0, 1.0, 1.0, 1.0,
+                [Predicate(12.7, 40.2, ">", 0.25, 290.5, "G", 0.5, 2.25, "A")], [("leaf", 0, 0)])
+    latex_trunc = "G_[[0.5, 2.25]] (\\forall x \\in [12, 40]  (u(x) - (0.25 \\cdot x + 290.5) > 0))"
+    assert cross_check(p, latex_trunc) != []
+    assert cross_check(p, latex_trunc, truncate_positions=True) == []
+    assert any("relation" in m for m in cross_check(p, latex_trunc.replace("> 0", "!= 0"), truncate_positions=True))
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/test/PDEcontrol/evaluation/eval/eval_script.py"),
+                    reason="the reference tree only exists in the build container")
+def test_spellings_against_the_references_own_regexes():
+    """pattern1..pattern5 are read out of the reference's source at test time (nothing of it is copied here): every
+    spelling above must be accepted by the pattern it is listed under with the same operator and threshold, and every
+    spelling the reference accepts must be accepted here."""
+    import re
+    src = open("/root/reference/test/PDEcontrol/evaluation/eval/eval_script.py").read()
+    pats = {}
+    for m in re.finditer(r"^\s*pattern(\d)\s*=\s*r'(.*)'\s*$", src, flags=re.M):
+        pats[int(m.group(1))] = re.compile(m.group(2))
+    assert sorted(pats) == [1, 2, 3, 4, 5]
+    ops = {"\\leq": "<", "<=": "<", "\\geq": ">", ">=": ">"}
+    for tail, slope, icpt, rel, k in SPELLINGS:
+        text = _HEAD + tail
+        hits = [i for i in sorted(pats) if pats[i].search(text)]
+        assert hits, text                                   # the reference accepts it ...
+        assert k in hits, (text, hits)                      # ... under the pattern it is listed for
+        m = pats[k].search(text)
+        op, thr = (m.group(3), m.group(4)) if k < 5 else (m.group(2), m.group(3))
+        (q,) = parse_sstl(text)[0]
+        assert ops.get(op, op) == q.rel
+        assert q.b == pytest.approx(icpt)
+        assert float(thr) == pytest.approx(q.b - (icpt - float(thr)))
