@@ -38,6 +38,15 @@ DEFAULT_BATCH = {"heat": 65536, "wave": 65536, "mixed": 65536, "heat_refined": 4
                  "controls_wave": 1048576}
 
 
+L2_NOTE = "GPU arm: flushed (256 MiB write) between timed steps; CPU arm: not applicable"
+
+
+def common_config(args, world):
+    """The `config` object is THE SAME in both arms (same keys, same values): what the driver compares."""
+    return {"workload": WORKLOAD_TEXT[args.workload], "batch_per_gpu": args.batch, "global_batch": args.batch * world,
+            "precision": args.precision, "seed": args.seed, "l2": L2_NOTE}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -136,6 +145,7 @@ def run_reference(args, rank, world):
     from pde_controller_b200 import synth
     oracle.build()
     nthreads = os.cpu_count() or 1
+    cfg = common_config(args, world)          # before the bounded sample below may shrink args.batch
     sample_note = f"{args.batch} samples per step"
     if args.workload.startswith("controls_"):
         # bounded sample of the same workload: the first 65,536 candidate controls of rank 0 for the same specification
@@ -163,10 +173,13 @@ def run_reference(args, rank, world):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "impl": "reference",
-        "config": {"workload": WORKLOAD_TEXT[args.workload], "batch": args.batch, "seed": args.seed,
-                   "note": "reference femformal (Python 2 + Gurobi) is absent from the snapshot; this is the CPU oracle port"},
+        "config": cfg,
+        "detail": {"note": "reference femformal (Python 2 + Gurobi) is absent from the snapshot; this is the CPU oracle port "
+                           "(oracle/pde_oracle.c, OpenMP over samples); like the kernels it simulates up to the last "
+                           "observed step of each sample: both arms do the same stepping work",
+                   "samples_per_step": args.batch},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port",
-                         "sample": f"{sample_note}, {len(times)} steps, OpenMP over samples"},
+                         "sample": f"{sample_note}, {len(times)} steps, OpenMP over samples, stops at the last observed step"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -185,7 +198,8 @@ def cpu_baseline(args, batch):
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     out = {"value": batch.n / best, "unit": UNIT, "cores": nthreads, "kind": "port",
-           "sample": f"the same {batch.n}-sample batch, best of 2 passes, C oracle -O3 + OpenMP over samples"}
+           "sample": f"the same {batch.n}-sample batch, best of 2 passes, C oracle -O3 + OpenMP over samples, each sample "
+                     "simulated up to its last observed step (the work the kernels do)"}
     out["context"] = cpu_context(batch, nthreads)
     return out
 
@@ -331,8 +345,8 @@ def run_controls(args, rank, local_rank, world):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": kms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD_TEXT[args.workload], "candidates_per_gpu": m, "knots": nk, "sim_steps": steps_sim,
-                       "n_pred": int(spec.n_pred[s]), "seed": args.seed, "l2": "flushed (256 MiB write) between timed steps",
+            "config": common_config(args, world),
+            "detail": {"candidates_per_gpu": m, "knots": nk, "sim_steps": steps_sim, "n_pred": int(spec.n_pred[s]),
                        "e2e_overlap": "two halves of the candidates on two streams, one host thread each",
                        "wall_s_timed_region": wall1 - wall0},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(8 * nk * m), "d2h_bytes_per_step": int(12 * m)},
@@ -364,8 +378,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-block", type=int, default=65536, help="samples per block of the end-to-end pipeline")
     ap.add_argument("--explicit-knots", action="store_true", help="carry per-sample knot times instead of uniform knots")
-    ap.add_argument("--e2e-planar", action="store_true",
-                    help="end-to-end path moves the plane-major slab instead of the packed transfer form (PdebPackedBatch)")
+    ap.add_argument("--no-text", action="store_true", help="skip the text-level end-to-end leg (e2e_text)")
+    ap.add_argument("--text-programs", type=int, default=8192, help="programs of the text-level leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the device-timed rates of the other BASELINE configs")
     args = ap.parse_args()
     if args.batch is None:
         args.batch = DEFAULT_BATCH[args.workload]
@@ -454,48 +469,103 @@ def main():
     value = total * args.steps / (total_ms * 1e-3)
 
     # ---- end to end through the public API with HOST buffers ("e2e") ----
-    # every step: the whole batch goes pinned host -> H2D (packed transfer form) -> unpack + plan -> kernels -> D2H
-    # (robustness + status) as
-    # args.e2e_block-sample blocks, E2E_DEPTH generations of buffers on as many streams (native.BlockPipeline); run() returns after the
-    # last byte of the results is back in host memory
+    # The caller holds a PdebBatch (include/pdeb200.h) in page-locked host memory.  Every step the whole batch goes
+    # host -> H2D -> plan -> kernels -> D2H (robustness + status) as args.e2e_block-sample blocks, E2E_DEPTH generations
+    # of buffers on as many streams (native.BlockPipeline); a step ends when the last byte of its results is in host memory.
+    #   e2e            PLANAR route: the PdebBatch slab itself crosses PCIe (one copy per block), nothing is prepared
+    #                  outside the timed region.  This is the headline: what a caller of pdeb_resident_upload pays.
+    #   e2e_packed     packed transfer form WITH its host-side producer (pdeb_pack_batch) inside the timed region
+    #   e2e_prepacked  packed transfer form produced OUTSIDE the timed region (a producer that writes PdebPackedBatch
+    #                  itself, e.g. a data-set loader): the PCIe-lean route, reported for the multi-GPU curve only
     E2E_DEPTH = 3
-    pipe = native.BlockPipeline(src.n, src.kmax, src.pmax, src.tmax, block=args.e2e_block, device=dev, depth=E2E_DEPTH,
-                                uniform_knots=uk, packed=not args.e2e_planar)
-    for g in range(E2E_DEPTH):
-        pipe.fill(src, g)
 
-    def e2e_loop(depth):
-        """K steps; depth 1 = wait for every step before the next, depth d = steps i+1 .. i+d-1 are enqueued while step i
-        runs (their buffers are the other generations), which is how a sweep over many batches uses the API: the
-        host->device copy engine never waits for the host."""
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            g = i % depth
-            if i >= depth:
-                pipe.wait(g)                      # results of step i-depth are in host memory: they are read here
-            pipe.submit(g, args.precision)
-        for g in range(depth):
-            pipe.wait(g)
-        torch.cuda.synchronize()
-        dt_ = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(dt_, op=dist.ReduceOp.MAX)
-        return total * args.steps / float(dt_.item())
+    def e2e_route(packed, pack_inside):
+        pipe = native.BlockPipeline(src.n, src.kmax, src.pmax, src.tmax, block=args.e2e_block, device=dev, depth=E2E_DEPTH,
+                                    uniform_knots=uk, packed=packed)
+        for g in range(E2E_DEPTH):
+            pipe.fill(src, g)
 
-    for g in range(E2E_DEPTH):                    # every generation of buffers once (also: results valid for the check below)
-        pipe.run(args.precision, gen=g)
-    e2e_sync = e2e_loop(1)
-    e2e_value = e2e_loop(E2E_DEPTH)
+        def loop(depth):
+            """K steps; depth 1 = wait for every step before the next, depth d = steps i+1 .. i+d-1 are enqueued while
+            step i runs (their buffers are the other generations): the host->device copy engine never waits for the host."""
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                g = i % depth
+                if i >= depth:
+                    pipe.wait(g)                      # results of step i-depth are in host memory: they are read here
+                pipe.submit(g, args.precision, pack=pack_inside)
+            for g in range(depth):
+                pipe.wait(g)
+            torch.cuda.synchronize()
+            dt_ = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(dt_, op=dist.ReduceOp.MAX)
+            return total * args.steps / float(dt_.item()), float(dt_.item())
+
+        for g in range(E2E_DEPTH):                    # every generation of buffers once (also: results for the check below)
+            pipe.run(args.precision, gen=g)
+        v1, _ = loop(1)
+        vd, secs = loop(E2E_DEPTH)
+        ok = all(np.array_equal(pipe.robustness[g], out_host["robustness"]) for g in range(E2E_DEPTH))
+        out = {"value": vd, "unit": UNIT, "h2d_bytes_per_step": int(pipe.h2d_bytes), "d2h_bytes_per_step": int(12 * host.n),
+               "depth1_value": v1, "h2d_gbs_per_rank": pipe.h2d_bytes * args.steps / secs / 1e9}
+        pipe.close()
+        return out, ok
+
     res.eval(args.precision, stream=stream)
     res.fetch(stream=stream, out=out_host)
-    if not all(np.array_equal(pipe.robustness[g], out_host["robustness"]) for g in range(E2E_DEPTH)):
+    e2e, ok_a = e2e_route(packed=False, pack_inside=False)
+    e2e["route"] = "planar PdebBatch slab, one H2D copy per block; nothing prepared outside the timed region"
+    e2e_packed, ok_b = e2e_route(packed=True, pack_inside=True)
+    e2e_packed["route"] = "pdeb_pack_batch (host, inside the timed region) -> packed H2D -> device-side unpack"
+    e2e_prepacked, ok_c = e2e_route(packed=True, pack_inside=False)
+    e2e_prepacked["route"] = "PdebPackedBatch produced outside the timed region -> packed H2D -> device-side unpack"
+    if not (ok_a and ok_b and ok_c):
         raise SystemExit("bench: pipelined end-to-end results differ from the resident evaluation")
-    h2d_bytes = pipe.h2d_bytes
-    pipe.close()
 
     st = out_host["status"]
     n_fail = int((st != 0).sum())
+
+    # ---- the reference's real call surface: program TEXT in, robustness out (eval_script.py:43-79) ----
+    e2e_text = None
+    if rank == 0 and not args.no_text:
+        from pde_controller_b200 import eval_script as es
+        from pde_controller_b200.frontend import render_program
+        m = min(args.text_programs, src.n)
+        probs, ctrls = zip(*(src.get_problem(i) for i in range(m)))
+        texts = [render_program(p) for p in probs]
+        es.configure(device=dev, precision=args.precision)
+        es.eval_robustness_batch(texts[:64], controls=list(ctrls[:64]))            # warm-up: imports, regex compilation
+        t0 = time.perf_counter()
+        rob_text, _ = es.eval_robustness_batch(texts, controls=list(ctrls))
+        secs = time.perf_counter() - t0
+        if not np.array_equal(np.array(rob_text), out_host["robustness"][:m]):
+            raise SystemExit("bench: text-level results differ from the resident evaluation")
+        e2e_text = {"value": m / secs, "unit": "programs/s", "programs": m, "cores": os.cpu_count(),
+                    "route": "eval_robustness_batch(program strings, given controls): parse (worker processes) -> "
+                             "PdebBatch -> pdeb_eval_batch -> robustness list"}
+
+    # ---- the other single-GPU configurations of BASELINE.json, device-timed like `value` (configs 3, 5, 4) ----
+    configs = {}
+    if not args.no_configs and args.workload == "heat":
+        for name, wl, nb, steps_c in (("configs[2] wave 65536", "wave", 65536, 5), ("configs[4] mixed 65536 per GPU", "mixed", 65536, 5),
+                                      ("configs[3] refined heat 1024x10000, 4096 per GPU", "heat_refined", 4096, 2)):
+            bsrc = synth.make_batch(nb, wl, seed=args.seed, start=rank * nb, total=nb * world, uniform_knots=True,
+                                    kind_slice=(rank, world) if wl == "mixed" and world > 1 else None)
+            r2 = native.ResidentBatch(bsrc, device=dev, stream=stream)
+            r2.eval(64, stream=stream, timing=True)
+            ms = 0.0
+            for _ in range(steps_c):
+                flush.zero_()
+                ms += r2.eval(64, stream=stream, timing=True).kernel_ms
+            r2.close()
+            t2 = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            configs[name] = {"value": nb * world * steps_c / (float(t2.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(t2.item()) / steps_c,
+                             "batch_per_gpu": nb, "steps": steps_c, "dtype": "f64",
+                             "timing": "CUDA events inside pdeb_resident_eval, inputs resident, L2 flushed, max over ranks"}
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -509,13 +579,11 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64" if args.precision == 64 else "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD_TEXT[args.workload], "batch_per_gpu": args.batch, "global_batch": total,
-                       "precision": args.precision, "seed": args.seed, "l2": "flushed (256 MiB write) between timed steps",
-                       "gather": bool(rob_t is not None), "failed_samples": n_fail, "knots": "uniform (formed on device)" if uk else "explicit", "e2e_block": args.e2e_block, "e2e_pipeline_depth": E2E_DEPTH,
-                       "e2e_format": "planar slab" if args.e2e_planar else "packed transfer form (ragged lists, unpacked on the device)", "e2e_value_depth1": e2e_sync,
-                       "wall_s_timed_region": wall1 - wall0},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
-                    "d2h_bytes_per_step": int(12 * host.n)},
+            "config": common_config(args, world),
+            "detail": {"gather": bool(rob_t is not None), "failed_samples": n_fail,
+                       "knots": "uniform (formed on device)" if uk else "explicit", "e2e_block": args.e2e_block,
+                       "e2e_pipeline_depth": E2E_DEPTH, "wall_s_timed_region": wall1 - wall0},
+            "e2e": e2e, "e2e_packed": e2e_packed, "e2e_prepacked": e2e_prepacked,
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -524,6 +592,10 @@ def main():
                          "note": "fused kernel is FP64-issue bound by design (state never leaves registers); see DESIGN.md"},
             "roofline_fp64": fp64,
         }
+        if e2e_text is not None:
+            line["e2e_text"] = e2e_text
+        if configs:
+            line["configs"] = configs
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, src)
         print(json.dumps(line), flush=True)

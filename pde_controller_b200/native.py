@@ -324,11 +324,15 @@ class BlockPipeline:
             if pk is not None:
                 pk.pack(blk)
 
-    def submit(self, gen: int = 0, precision: int = 64, conv=None):
-        """Enqueue upload + plan + kernels + download of every block of generation `gen`; does not wait."""
+    def submit(self, gen: int = 0, precision: int = 64, conv=None, pack: bool = False):
+        """Enqueue upload + plan + kernels + download of every block of generation `gen`; does not wait.
+        pack (packed pipelines only): run the host-side producer of the packed form (PackedBatch.pack ->
+        pdeb_pack_batch) on each block's plane-major batch first, i.e. inside whatever region the caller is timing."""
         for blk, pk, (res, si), out in zip(self.blocks[gen], self.packs[gen], self.residents[gen], self._outs[gen]):
             st = self.streams[si]
             if pk is not None:
+                if pack:
+                    pk.pack(blk)
                 res.upload_packed(pk, stream=st)
             else:
                 res.upload(blk, stream=st)
