@@ -89,8 +89,11 @@ struct PdebResident {
     int device = 0;
     int64_t n = 0, stride = 0, host_stride = 0;
     int kmax = 0, pmax = 0, tmax = 0;
-    unsigned char* slab = nullptr;   /* inputs */
+    unsigned char* slab = nullptr;   /* inputs as uploaded: the caller's order (and, with a host slab, the caller's layout) */
     size_t slab_bytes = 0;
+    unsigned char* img = nullptr;    /* the same inputs in PLAN ORDER: what the kernels read (dimg); formed by pdeb_permute
+                                        after every plan, so consecutive lanes read consecutive addresses */
+    PdebDevBatch dimg{};
     unsigned char* outs = nullptr;   /* robustness | clause | status */
     PdebDevBatch dev{};
     PdebDevOut out{};
@@ -136,6 +139,7 @@ extern "C" void pdeb_resident_destroy(PdebResident* r) {
     DeviceGuard g(r->device);
     for (auto& e : r->ev) if (e) cudaEventDestroy(e);
     if (r->slab) cudaFree(r->slab);
+    if (r->img) cudaFree(r->img);
     if (r->outs) cudaFree(r->outs);
     if (r->plan) cudaFree(r->plan);
     if (r->pstage) cudaFree(r->pstage);
@@ -201,7 +205,8 @@ static int upload(PdebResident* r, const PdebBatch* in, int64_t lo, int64_t hi, 
 
 /* a contiguous range of the resident batch seen as a batch of its own (pointer offsets, same plane stride) */
 struct RangeView {
-    PdebDevBatch dev;
+    PdebDevBatch dev;      /* as uploaded */
+    PdebDevBatch dimg;     /* plan order */
     PdebDevOut out;
     PdebPlanBuffers pb;
     int32_t vsc[2 * PDEB_NUM_VARIANTS];
@@ -211,7 +216,9 @@ static RangeView view_of(const PdebResident* r, int64_t lo, int64_t hi, int chun
     RangeView v;
     v.dev = r->dev;
     v.dev.n = hi - lo;
-#define OFF(f) v.dev.f = r->dev.f + lo
+    v.dimg = r->dimg;
+    v.dimg.n = hi - lo;
+#define OFF(f) v.dev.f = r->dev.f + lo; v.dimg.f = r->dimg.f + lo
     OFF(kind); OFF(n_elem); OFF(L); OFF(dt); OFF(T); OFF(g0); OFF(x_a); OFF(x_b); OFF(rho_in); OFF(rho_out); OFF(E_in);
     OFF(E_out); OFF(n_knots); if (r->dev.knot_t) { OFF(knot_t); } OFF(knot_y); OFF(n_pred); OFF(pred_xlo); OFF(pred_xhi); OFF(pred_m); OFF(pred_b);
     OFF(pred_tlo); OFF(pred_thi); OFF(pred_rel); OFF(pred_top); OFF(n_tree); OFF(tree_op); OFF(tree_lhs); OFF(tree_rhs);
@@ -274,7 +281,12 @@ static int plan_view(PdebResident* r, const RangeView& v, const int32_t* vsc, cu
     for (int q = 0; q < PDEB_NUM_VARIANTS; ++q) if (vsc[2 * q + 1] > 0) live |= 1u << q;
     int rc = pdeb_plan(v.dev, cv, v.out, v.pb, live, stream, &nl, keys_done);
     if (rc) return fail(PDEB_E_CUDA, "plan launch", (cudaError_t)rc);
-    r->plan_launches = nl;
+    /* the image the kernels read, in the order just formed (samples no variant covers are not part of it) */
+    int64_t ordered = 0;
+    for (int q = 0; q < PDEB_NUM_VARIANTS; ++q) ordered += vsc[2 * q + 1];
+    rc = pdeb_permute(v.dev, v.dimg, v.pb.order, ordered, false, stream);
+    if (rc) return fail(PDEB_E_CUDA, "permute launch", (cudaError_t)rc);
+    r->plan_launches = nl + (ordered > 0 ? 1 : 0);
     return 0;
 }
 
@@ -328,11 +340,19 @@ static int resident_alloc(const PdebBatch* in, int device, PdebResident** outp) 
         }
     }
     r->slab_bytes = total;
+    /* the plan-ordered image: always the compact layout */
+    size_t ioff[NF];
+    size_t itotal = 0;
+    for (int f = 0; f < NF; ++f) {
+        ioff[f] = itotal;
+        itotal = align_up(itotal + elem[f] * (size_t)(n > 0 ? n : 1) * planes[f], 256);
+    }
     const size_t out_rob = 0;
     const size_t out_clause = align_up(out_rob + 8 * (size_t)(n > 0 ? n : 1), 256);
     const size_t out_status = align_up(out_clause + 8 * (size_t)(n > 0 ? n : 1) * in->pmax, 256);
     const size_t out_total = align_up(out_status + 4 * (size_t)(n > 0 ? n : 1), 256);
     cudaError_t ce = cudaMalloc((void**)&r->slab, total > 0 ? total : 256);
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&r->img, itotal > 0 ? itotal : 256);
     if (ce == cudaSuccess) ce = cudaMalloc((void**)&r->outs, out_total);
     const size_t n1 = (size_t)(n > 0 ? n : 1);
     const size_t plan_keys = 0, plan_order = align_up(4 * n1, 256), plan_hist = plan_order + align_up(4 * n1, 256);
@@ -367,6 +387,25 @@ static int resident_alloc(const PdebBatch* in, int device, PdebResident** outp) 
     d.pred_rel = (const uint8_t*)(s + off[22]);   d.pred_top = (const uint8_t*)(s + off[23]);
     d.n_tree = (const int32_t*)(s + off[24]);     d.tree_op = (const uint8_t*)(s + off[25]);
     d.tree_lhs = (const int8_t*)(s + off[26]);    d.tree_rhs = (const int8_t*)(s + off[27]);
+    {
+        PdebDevBatch& g = r->dimg;
+        unsigned char* q = r->img;
+        g = d;
+        g.kind = (const uint8_t*)(q + ioff[0]);        g.n_elem = (const int32_t*)(q + ioff[1]);
+        g.L = (const double*)(q + ioff[2]);            g.dt = (const double*)(q + ioff[3]);
+        g.T = (const double*)(q + ioff[4]);            g.g0 = (const double*)(q + ioff[5]);
+        g.x_a = (const double*)(q + ioff[6]);          g.x_b = (const double*)(q + ioff[7]);
+        g.rho_in = (const double*)(q + ioff[8]);       g.rho_out = (const double*)(q + ioff[9]);
+        g.E_in = (const double*)(q + ioff[10]);        g.E_out = (const double*)(q + ioff[11]);
+        g.n_knots = (const int32_t*)(q + ioff[12]);    g.knot_t = in->knot_t ? (const double*)(q + ioff[13]) : nullptr;
+        g.knot_y = (const double*)(q + ioff[14]);      g.n_pred = (const int32_t*)(q + ioff[15]);
+        g.pred_xlo = (const double*)(q + ioff[16]);    g.pred_xhi = (const double*)(q + ioff[17]);
+        g.pred_m = (const double*)(q + ioff[18]);      g.pred_b = (const double*)(q + ioff[19]);
+        g.pred_tlo = (const double*)(q + ioff[20]);    g.pred_thi = (const double*)(q + ioff[21]);
+        g.pred_rel = (const uint8_t*)(q + ioff[22]);   g.pred_top = (const uint8_t*)(q + ioff[23]);
+        g.n_tree = (const int32_t*)(q + ioff[24]);     g.tree_op = (const uint8_t*)(q + ioff[25]);
+        g.tree_lhs = (const int8_t*)(q + ioff[26]);    g.tree_rhs = (const int8_t*)(q + ioff[27]);
+    }
     r->out.robustness = (double*)(r->outs + out_rob);
     r->out.clause = (double*)(r->outs + out_clause);
     r->out.status = (int32_t*)(r->outs + out_status);
@@ -756,7 +795,21 @@ extern "C" int pdeb_resident_set_knots(PdebResident* r, const double* knot_t, co
     PdebBatch in{};
     in.n = r->n; in.stride = r->host_stride; in.kmax = r->kmax; in.pmax = r->pmax; in.tmax = r->tmax;
     in.knot_t = knot_t; in.knot_y = knot_y; in.n_knots = n_knots;
-    return upload(r, &in, 0, r->n, (cudaStream_t)stream_, true);
+    int rc = upload(r, &in, 0, r->n, (cudaStream_t)stream_, true);
+    if (rc) return rc;
+    /* the knots move into the plan-ordered image under the current order (the order depends on windows and steps, not
+     * on the control) */
+    if (r->plan_stale) {
+        rc = plan_view(r, view_of(r, 0, r->n, 0), r->vsc_host, (cudaStream_t)stream_);
+        if (rc) return rc;
+        r->plan_stale = false;
+        return 0;                            /* the plan has just permuted everything */
+    }
+    int64_t ordered = 0;
+    for (int q = 0; q < PDEB_NUM_VARIANTS; ++q) ordered += r->vsc_host[2 * q + 1];
+    rc = pdeb_permute(r->dev, r->dimg, r->pb.order, ordered, true, (cudaStream_t)stream_);
+    if (rc) return fail(PDEB_E_CUDA, "permute launch", (cudaError_t)rc);
+    return 0;
 }
 
 extern "C" int pdeb_resident_eval(PdebResident* r, int precision, const PdebConventions* conv, void* stream_,
@@ -778,7 +831,7 @@ extern "C" int pdeb_resident_eval(PdebResident* r, int precision, const PdebConv
         r->plan_stale = false;
     }
     if (timing) CK(cudaEventRecord(r->ev[0], stream));
-    int rc = pdeb_launch_all(r->dev, cv, r->out, r->pb, r->vsc_host, precision, stream, &launches);
+    int rc = pdeb_launch_all(r->dimg, cv, r->out, r->pb, r->vsc_host, precision, stream, &launches);
     if (rc) return fail(PDEB_E_CUDA, "kernel launch", (cudaError_t)rc);
     if (timing) {
         CK(cudaEventRecord(r->ev[1], stream));
@@ -914,7 +967,7 @@ extern "C" int pdeb_resident_run(PdebResident* r, const PdebBatch* in, int preci
         rc = plan_view(r, v, v.vsc, st, false, &cv);
         if (rc) return rc;
         int nl = 0;
-        const int lrc = pdeb_launch_all(v.dev, cv, v.out, v.pb, v.vsc, precision, st, &nl);
+        const int lrc = pdeb_launch_all(v.dimg, cv, v.out, v.pb, v.vsc, precision, st, &nl);
         if (lrc) return fail(PDEB_E_CUDA, "kernel launch", (cudaError_t)lrc);
         launches += nl + r->plan_launches;
         rc = fetch_range(r, lo, hi, robustness_out, clause_out, status_out, st);

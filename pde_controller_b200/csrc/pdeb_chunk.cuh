@@ -110,7 +110,8 @@ pdeb_chunk_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t t = (int64_t)blockIdx.x * PDEB_CHUNK_WARPS + warp;
     if (t >= count) return;                                   /* whole warp */
-    const int64_t s = order[first + t];
+    const int64_t s = first + t;                              /* position in the plan-ordered input image */
+    const int64_t so = order[first + t];                      /* the sample's index in the caller's order: outputs */
     const int64_t st = b.stride;
     double* tab = reinterpret_cast<double*>(pdeb_smem) + (size_t)warp * G::WARP_REALS;
 
@@ -639,11 +640,11 @@ pdeb_chunk_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant_
         }
     }
     if (lane == 0) {
-        out.robustness[s] = (status == PDEB_OK) ? rob : PDEB_FAILED_ROBUSTNESS;
-        if (out.status) out.status[s] = status;
+        out.robustness[so] = (status == PDEB_OK) ? rob : PDEB_FAILED_ROBUSTNESS;
+        if (out.status) out.status[so] = status;
     }
     if (out.clause && lane < b.pmax)
-        out.clause[(int64_t)lane * st + s] = (status == PDEB_OK && lane < np) ? c_acc : PDEB_FAILED_ROBUSTNESS;
+        out.clause[(int64_t)lane * st + so] = (status == PDEB_OK && lane < np) ? c_acc : PDEB_FAILED_ROBUSTNESS;
 }
 
 template <int R>

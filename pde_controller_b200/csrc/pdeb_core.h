@@ -56,6 +56,17 @@
 #ifndef PDEB_C_SMEM
 #define PDEB_C_SMEM 0
 #endif
+/* A/B switches of tools/variant_bench.py (defaults = what measured faster on B200, profiles/r02_*):
+ *   PDEB_LOAD_SEQ   1: the input as an incrementally updated scaled load sequence (PdebLoadStaged), 0: evaluated from
+ *                   the segment every step (PdebPwlStaged)
+ *   PDEB_EVENT_LIST 1: window events from a presorted per-lane list (one word per event), 0: every event re-scans the
+ *                   windows of all clauses */
+#ifndef PDEB_LOAD_SEQ
+#define PDEB_LOAD_SEQ 0
+#endif
+#ifndef PDEB_EVENT_LIST
+#define PDEB_EVENT_LIST 1
+#endif
 
 /* device view of a batch: the PdebBatch arrays, on the device */
 struct PdebDevBatch {
@@ -88,7 +99,11 @@ struct PdebDevOut {
  *        relation-transformed margin; turned into the clause value (G: -A, F: A, + eq_eps for the band rule) once,
  *        after the time loop
  *   3, 4 xi of the two interval end points inside their elements (interpolated end points only)
- *   5 { nmask (bit i: node i inside [x_lo,x_hi]), info }      6 { klo, khi } window steps
+ *   5 { nmask (bit i: node i inside [x_lo,x_hi]), info }
+ *   6 two words of the lane's WINDOW-EVENT LIST: the steps at which the set of open windows changes, ascending, each
+ *     as  step << 9 | last << 8 | open mask  (bit j: clause j's window holds that step; PDEB_MAX_STEPS < 2^23 and
+ *     PDEB_MAX_PRED = 8 make it one word).  A clause contributes two boundaries (k_lo, k_hi + 1), so the 2 pmax words
+ *     of the pmax cells always suffice.  The time loop reads ONE word per event instead of re-scanning every window.
  *   info: bits 0-1 rel, bit 2 top, bit 3 needs the interpolated end points (general form),
  *         bits 4-8 / 9-13 element of end point 0 / 1, bit 14 interval inside ONE element (nmask then holds that
  *         element's two nodes)
@@ -102,7 +117,9 @@ struct PdebClauseSlots {
     PDEB_HD unsigned char* cell(int p, int f) const { return base + (size_t)((p * PDEB_SLOT_CELLS + f) * STRIDE) * 8; }
     PDEB_HD real& R(int p, int f) const { return *reinterpret_cast<real*>(cell(p, f)); }
     PDEB_HD PdebU2& NI(int p) const { return *reinterpret_cast<PdebU2*>(cell(p, 5)); }     /* { nmask, info } */
-    PDEB_HD PdebU2& WIN(int p) const { return *reinterpret_cast<PdebU2*>(cell(p, 6)); }    /* { klo, khi } */
+    /* cell 6 of clause p holds event words 2p and 2p + 1 of the lane's window-event list (below) */
+    PDEB_HD uint32_t& EV(int e) const { return *reinterpret_cast<uint32_t*>(cell(e >> 1, 6) + (e & 1) * 4); }
+    PDEB_HD PdebU2& WIN(int p) const { return *reinterpret_cast<PdebU2*>(cell(p, 6)); }    /* { klo, khi } (PDEB_EVENT_LIST 0) */
 };
 
 template <typename real>
@@ -209,6 +226,137 @@ struct PdebPwl {
 };
 
 /*
+ * The same input for the register family, as the SCALED LOAD SEQUENCE the time loop consumes, with the next knot staged
+ * in shared memory.
+ *
+ * What a step needs is g_k = scale * f(k dt) (scale = s_N: the load enters row N of the scaled system).  Inside one
+ * segment of the piecewise-linear input that is an arithmetic sequence, so a step costs ONE add (g += dg) and an integer
+ * compare against the step at which the next knot is crossed; the earlier form evaluated  y0 + slope (k dt - t0)  from
+ * scratch every step (int-to-double conversion, two multiplies, an add, an FMA and a 64-bit compare: 11 % of the heat
+ * kernel's warp time went into the input of a 30-row solve).  At a crossing the value is re-formed EXACTLY from the knots
+ * (same arithmetic and same "t >= knot" rule as PdebPwl / the oracle), so the increments never accumulate over more than
+ * one segment (~20 steps: a relative drift of ~2e-15).
+ *
+ * In this family the lanes of a warp cross their knots at different steps, so a warp runs the crossing code in about
+ * half of its steps, and a knot fetched into a register there would stall the whole warp for a global-memory latency.
+ * The crossing reads the knot from a per-thread shared-memory slot (two doubles: value, time) and refills the slot with
+ * an ASYNCHRONOUS copy (cp.async, global -> shared, no register destination) that has the ~20 steps until the next
+ * crossing to land.
+ */
+template <typename real, int STRIDE>
+struct PdebLoadStaged {
+    double t1;            /* end of the current segment (+inf on the last) */
+    real y1;              /* input value at t1 */
+    real g, dg;           /* scaled load at the current step; its increment per step inside the current segment */
+    real f_exact;         /* UNscaled input at the last exact evaluation (set-up: f(0), which the wave start needs) */
+    int32_t kx;           /* first step k with k dt >= t1 (0x7fffffff: the segment never ends) */
+    int nk, j;            /* j: index of the knot at t1 */
+    double ustep, uT;     /* uniform knots, as in PdebPwl */
+    double rstep;         /* uniform knots: 1 / ustep */
+    double dt, rdt;       /* time step and its reciprocal */
+    real scale;
+    /* shared, + tid: slot[0] value of knot j+1, slot[STRIDE] its time (explicit knot times only) */
+#if defined(__CUDA_ARCH__)
+    uint32_t slot;        /* shared-window address */
+#else
+    double* slot;
+#endif
+
+    PDEB_HD double knot_time(const double* kt, int q, int64_t stride) const {
+        if (kt) return kt[(int64_t)q * stride];
+        return (q == nk - 1 && nk > 1) ? uT : (double)q * ustep;
+    }
+    /* start the copy of knot q into the slot */
+    PDEB_HD void stage(const double* kt, const double* ky, int q, int64_t stride) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(slot), "l"(ky + (int64_t)q * stride) : "memory");
+        if (kt)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(slot + (uint32_t)(STRIDE * sizeof(double))),
+                         "l"(kt + (int64_t)q * stride) : "memory");
+#else
+        slot[0] = ky[(int64_t)q * stride];
+        if (kt) slot[STRIDE] = kt[(int64_t)q * stride];
+#endif
+    }
+    /* staged value (which = 0) or time (which = 1), once the copy has landed */
+    PDEB_HD double staged(int which) const {
+#if defined(__CUDA_ARCH__)
+        double v;
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(slot + (uint32_t)(which * STRIDE * sizeof(double))) : "memory");
+        return v;
+#else
+        return slot[which * STRIDE];
+#endif
+    }
+    /* first step k with (double)k * dt >= t: the rule `t_k >= knot` of PdebPwl / the oracle, as an integer */
+    PDEB_HD int32_t first_step_at(double t) const {
+        if (!(t < 4.0e9 * dt)) return 0x7fffffff;
+        double q = ceil(t * rdt);
+        if (!(q >= 0.0)) q = 0.0;
+        int32_t k = (int32_t)q;
+        while ((double)k * dt < t) ++k;                          /* the product with 1/dt may be an ulp off either way */
+        while (k > 0 && (double)(k - 1) * dt >= t) --k;
+        return k;
+    }
+    /*
+     * Step kn has reached the end of the current segment: move to the segment that holds t = kn dt (several knots may
+     * lie inside one step), re-form the scaled load there exactly, and its increment and next crossing step.
+     */
+    PDEB_HD void cross(int32_t kn, const double* kt, const double* ky, int64_t stride) {
+        const double t = (double)kn * dt;
+        real t0 = 0, y0 = 0, slope = 0;
+        while (t >= t1) {
+            t0 = (real)t1; y0 = y1;
+            double tn = INFINITY;
+            real yn = 0;
+            if (j + 1 < nk) {
+                yn = (real)staged(0);
+                tn = kt ? staged(1) : knot_time(nullptr, j + 1, 0);
+            }
+            if (tn < INFINITY) {
+                slope = (real)(((double)yn - (double)y1) * (kt ? pdeb_rcp(tn - t1) : rstep));
+                t1 = tn; y1 = yn;
+                ++j;
+                if (j + 1 < nk) stage(kt, ky, j + 1, stride);
+            } else { slope = 0; t1 = INFINITY; }
+        }
+        f_exact = fma(slope, (real)(t - (double)t0), y0);
+        g = scale * f_exact;
+        dg = scale * (slope * (real)dt);
+        kx = first_step_at(t1);
+    }
+    /* set-up: the load at step 0.  scale_ = s_N (known after the factorisation). */
+    PDEB_HD void init(const double* kt, const double* ky, int nk_, int64_t stride, double T, double dt_, real scale_, double* slot_) {
+        nk = nk_; j = 0;
+#if defined(__CUDA_ARCH__)
+        slot = (uint32_t)__cvta_generic_to_shared(slot_);
+#else
+        slot = slot_;
+#endif
+        dt = dt_; rdt = 1.0 / dt_; scale = scale_;
+        uT = T; ustep = (nk > 1) ? T / (double)(nk - 1) : 0.0;
+        rstep = (nk > 1) ? pdeb_rcp(ustep) : 0.0;
+        y1 = 0; g = 0; dg = 0; f_exact = 0; t1 = INFINITY; kx = 0x7fffffff;
+        if (nk >= 1) {
+            y1 = (real)ky[0];
+            t1 = knot_time(kt, 0, stride);
+            f_exact = y1;
+            g = scale * y1;                          /* held at the first value before the first knot */
+            kx = first_step_at(t1);
+            if (nk >= 2) stage(kt, ky, 1, stride);
+            if (kx <= 0) cross(0, kt, ky, stride);
+        }
+    }
+    /* advance from step kn - 1 to step kn: returns g_kn (the scaled load at step kn) */
+    PDEB_HD real advance(int32_t kn, const double* kt, const double* ky, int64_t stride) {
+        if (kn >= kx) cross(kn, kt, ky, stride);
+        else g += dg;
+        return g;
+    }
+};
+#if !PDEB_LOAD_SEQ
+/*
  * The same input for the register family, with the NEXT knot staged in shared memory.
  * In that family the lanes of a warp cross their knots at different steps, so a warp runs the crossing code in about
  * half of its steps, and a knot fetched into a register there stalls the whole warp for a global-memory latency: the
@@ -290,6 +438,7 @@ struct PdebPwlStaged {
         return fma(slope, (real)(t - (double)t0), y0);
     }
 };
+#endif
 #define PDEB_PWL_SLOT_BYTES (2 * sizeof(double))   /* per thread */
 
 struct alignas(16) PdebD2 { double x, y; };
@@ -767,8 +916,9 @@ PDEB_HD PdebClauseData pdeb_clause_data(double m, double bb, double xlo, double 
 }
 
 /*
- * Whole trajectory of sample s.  `slots` is this thread's clause column in shared memory,
- * `table` its row table.  Writes robustness / clause / status.
+ * Whole trajectory of the sample at position s of the input image; results go to index so of the outputs (the image
+ * the kernels read is in plan order, the outputs in the caller's).  `slots` is this thread's clause column in shared
+ * memory, `table` its row table.  Writes robustness / clause / status.
  *
  * Time loop, per step k:  (1) clauses whose window is open are reduced on the state w^k (a warp
  * runs as many reduction passes as its busiest lane has open clauses, usually one),
@@ -777,7 +927,7 @@ PDEB_HD PdebClauseData pdeb_clause_data(double m, double bb, double xlo, double 
  * ordered by step count, so that is a handful of steps): their observations are switched off.
  */
 template <int KIND, int N, typename real, int STRIDE>
-PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out, int64_t s,
+PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out, int64_t s, int64_t so,
                           typename PdebVec2<real>::type* table, real* stab, PdebClauseSlots<real, STRIDE> slots, bool live,
                           double* pwl_slot, real* ctab = nullptr) {
     /* `live` is false for padding lanes of a partially filled warp: they run the loop with S = 0 */
@@ -794,8 +944,16 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
 #if PDEB_C_SMEM
     tr.ctab = ctab;
 #endif
+#if PDEB_LOAD_SEQ
+    PdebLoadStaged<real, STRIDE> in;
+    in.init(nullptr, nullptr, 0, 0, 0.0, 1.0, (real)0, pwl_slot);
+#else
     PdebPwlStaged<real, STRIDE> in;
     in.init(nullptr, nullptr, 0, 0, 0.0, pwl_slot);
+#endif
+    uint32_t evw = 0x100u;     /* the NEXT window event of this lane (clause-slot cell 6); none yet */
+    int32_t next_ev = 0x7fffffff;
+    int evi = 0;
     const double* kt = b.knot_t ? b.knot_t + (live ? s : 0) : nullptr;     /* NULL: uniform knots */
     const double* ky = b.knot_y + (live ? s : 0);
     PDEB_UNROLL
@@ -833,14 +991,20 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
             const double cR = (1.0 - cv.theta) * dt;
             const bool ok = tr.setup(L, x_a, x_b, rho_in, rho_out, E_in, E_out, lumped, cv.material_sampling, cA, cR);
             if (!ok) status = PDEB_ST_NONFINITE;
+#if PDEB_LOAD_SEQ
+            if (ok) in.init(kt, ky, nk, st, T, dt, tr.sN, pwl_slot);
+            if (KIND == PDEB_KIND_WAVE && ok) tr.wave_init(h, g0, (double)in.f_exact, rho_in, rho_out, E_in, E_out, lumped);
+#else
             in.init(kt, ky, nk, st, T, pwl_slot);
             if (KIND == PDEB_KIND_WAVE && ok) {
                 const double f0 = (double)in.eval(0.0, kt, ky, st);
                 tr.wave_init(h, g0, f0, rho_in, rho_out, E_in, E_out, lumped);
             }
+#endif
         }
         if (status != PDEB_OK) { S = 0; np = 0; }
         int32_t k_end = 0;         /* last step any clause observes: nothing after it can change the result */
+        int32_t wlo[PDEB_MAX_PRED], whi[PDEB_MAX_PRED];    /* window steps of the clauses (set-up only) */
         /* clause slots */
         for (int j = 0; j < np; ++j) {
             const double m = b.pred_m[(int64_t)j * st + s], bb = b.pred_b[(int64_t)j * st + s];
@@ -853,9 +1017,7 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
             slots.R(j, 2) = (real)(-INFINITY);
             slots.R(j, 3) = (real)cd.xi[0];
             slots.R(j, 4) = (real)cd.xi[1];
-            PdebU2 win;
-            win.x = (uint32_t)cd.klo; win.y = (uint32_t)cd.khi;
-            slots.WIN(j) = win;
+            wlo[j] = cd.klo; whi[j] = cd.khi;
             uint32_t nm = cd.nmask, info = cd.info;
 #ifndef PDEB_NO_INEL   /* A/B switch of tools/variant_bench.py */
             if ((info & 8u) && nm == 0u && ((info >> 4) & 31u) == ((info >> 9) & 31u))
@@ -875,10 +1037,36 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
             if (a1 > k_end) k_end = a1;
         }
         S32 = k_end;
+        /* window-event list: the distinct boundaries k_lo, k_hi + 1 of all clauses in ascending order, each with the set
+         * of windows open from that step on (selection by repeated minimum: at most 16 boundaries, set-up only) */
+        int ne = 0;
+        int32_t prev = -1;
+        for (;;) {
+            int32_t nxt = 0x7fffffff;
+            for (int j = 0; j < np; ++j) {
+                if (wlo[j] > prev && wlo[j] < nxt) nxt = wlo[j];
+                if (whi[j] + 1 > prev && whi[j] + 1 < nxt) nxt = whi[j] + 1;
+            }
+            if (nxt == 0x7fffffff) break;
+            uint32_t m = 0;
+            for (int j = 0; j < np; ++j) if (nxt >= wlo[j] && nxt <= whi[j]) m |= 1u << j;
+            slots.EV(ne++) = ((uint32_t)nxt << 9) | m;
+            prev = nxt;
+        }
+        if (ne > 0) {
+            slots.EV(ne - 1) |= 0x100u;
+            evw = slots.EV(0);
+            next_ev = (int32_t)(evw >> 9);
+        }
+#if !PDEB_EVENT_LIST
+        for (int j = 0; j < np; ++j) { PdebU2 win; win.x = (uint32_t)wlo[j]; win.y = (uint32_t)whi[j]; slots.WIN(j) = win; }
+        next_ev = 0;
+#endif
     }
 
+#if !PDEB_LOAD_SEQ
     real f_prev = in.eval(0.0, kt, ky, st);
-    int32_t next_ev = 0;      /* next step at which the set of open windows may change (every window closes by S32 + 1) */
+#endif
     uint32_t open = 0;        /* bit j: step k is inside clause j's window */
     int cur = 0;              /* lowest open clause (0 when none is open) */
     /* what this lane needs from the pass of the current step: bit 0 a clause is open, bit 1 more than one is,
@@ -894,6 +1082,7 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
     const real eq_shift = (cv.eq_rule == 1) ? (real)cv.eq_eps : (real)0;
 
     /* window events of step k: which clauses are open from here on, and what the pass needs to know about them */
+#if !PDEB_EVENT_LIST
     auto window_events = [&](int32_t k) {
         if (k == next_ev) {
             open = 0;
@@ -912,6 +1101,22 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
             }
         }
     };
+    (void)evw; (void)evi;
+#else
+    auto window_events = [&](int32_t k) {
+        if (k == next_ev) {
+            open = evw & 0xffu;
+            cur = open ? __builtin_ffs((int)open) - 1 : 0;
+            flags = 0;
+            if (open) {
+                const uint32_t info = slots.NI(cur).y;
+                flags = 1u | ((open & (open - 1u)) ? 2u : 0u) | (((info >> 14) & 1u) << 2) | (info & 8u);
+            }
+            if (evw & 0x100u) next_ev = 0x7fffffff;                     /* that was the lane's last event */
+            else { evw = slots.EV(++evi); next_ev = (int32_t)(evw >> 9); }
+        }
+    };
+#endif
     const int32_t Smax = PDEB_WARP_MAX(S32);     /* the warp steps until its longest lane is done */
     window_events(0);
     uint32_t wf = PDEB_WARP_OR(flags);
@@ -986,13 +1191,22 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
         wf = PDEB_WARP_OR(flags);
         /* ---- (2) advance to step k+1 (lanes that are done keep stepping; nobody looks at them) ---- */
         {
+#if PDEB_LOAD_SEQ
+            const real g_prev = in.g;                                       /* s_N f(t_k) */
+            const real g_next = in.advance(k + 1, kt, ky, st);              /* s_N f(t_k+1) */
+#else
             const real f_next = in.eval((double)(k + 1) * dt, kt, ky, st);
+#endif
             if (KIND == PDEB_KIND_HEAT) {
                 const real th_dt = (real)(cv.theta * dt);
-                const real fb = fma((real)dt - th_dt, f_prev, th_dt * f_next);
+#if PDEB_LOAD_SEQ
+                const real fb = fma((real)dt - th_dt, g_prev, th_dt * g_next);
+#else
+                const real fb = tr.sN * fma((real)dt - th_dt, f_prev, th_dt * f_next);
+#endif
                 real z[N + 2];
                 z[0] = 0; z[N + 1] = 0;
-                tr.step_solve(tr.w, tr.sN * fb, z);
+                tr.step_solve(tr.w, fb, z);
                 PDEB_UNROLL
                 for (int i = 1; i <= N; ++i) tr.w[i] = z[i];
             } else {
@@ -1004,7 +1218,11 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
                     tr.w[i] = fma(cw2, tr.a[i], fma(cw1, tr.v[i], tr.w[i]));   /* predictor d~ */
                     tr.v[i] = fma(cw3, tr.a[i], tr.v[i]);                       /* predictor v~ */
                 }
-                tr.step_solve(tr.w, tr.sN * f_next, tr.a);                      /* a' = A^-1 (f' e_N - K d~), scaled */
+#if PDEB_LOAD_SEQ
+                tr.step_solve(tr.w, g_next, tr.a);                              /* a' = A^-1 (f' e_N - K d~), scaled */
+#else
+                tr.step_solve(tr.w, tr.sN * f_next, tr.a);
+#endif
                 const real cw4 = (real)(cv.newmark_beta * dt * dt);
                 const real cw5 = (real)(cv.newmark_gamma * dt);
                 PDEB_UNROLL
@@ -1013,7 +1231,9 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
                     tr.v[i] = fma(cw5, tr.a[i], tr.v[i]);
                 }
             }
+#if !PDEB_LOAD_SEQ
             f_prev = f_next;
+#endif
         }
     }
 
@@ -1048,11 +1268,12 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
             for (int j = 0; j < np; ++j) if (!isfinite((double)slots.R(j, 2))) status = PDEB_ST_NONFINITE;
         }
     }
-    out.robustness[s] = (status == PDEB_OK) ? rob : PDEB_FAILED_ROBUSTNESS;
-    if (out.status) out.status[s] = status;
+    /* s is the sample's position in the (plan-ordered) input image, so its index in the caller's order */
+    out.robustness[so] = (status == PDEB_OK) ? rob : PDEB_FAILED_ROBUSTNESS;
+    if (out.status) out.status[so] = status;
     if (out.clause) {
         for (int j = 0; j < b.pmax; ++j)
-            out.clause[(int64_t)j * st + s] = (status == PDEB_OK && j < np) ? (double)slots.R(j, 2) : PDEB_FAILED_ROBUSTNESS;
+            out.clause[(int64_t)j * st + so] = (status == PDEB_OK && j < np) ? (double)slots.R(j, 2) : PDEB_FAILED_ROBUSTNESS;
     }
 }
 

@@ -25,7 +25,10 @@ pdeb_reg_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant__ 
     extern __shared__ __align__(16) unsigned char pdeb_smem[];
     const int64_t t = (int64_t)blockIdx.x * PDEB_REG_THREADS + threadIdx.x;
     const bool live = t < count;                      /* padding lanes of the last warp idle through the loop */
-    const int64_t s = live ? (int64_t)order[first + t] : 0;
+    /* `b` is the PLAN-ORDERED image: thread t of this launch reads position first + t of every array (consecutive lanes,
+     * consecutive addresses) and writes its results to the sample's own index order[first + t] */
+    const int64_t s = live ? first + t : 0;
+    const int64_t so = live ? (int64_t)order[first + t] : 0;
     typedef typename PdebVec2<real>::type real2;
     real2* table = reinterpret_cast<real2*>(pdeb_smem) + threadIdx.x;
     PdebClauseSlots<real, PDEB_REG_THREADS> slots = pdeb_clause_slots<real, PDEB_REG_THREADS>(
@@ -39,7 +42,7 @@ pdeb_reg_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant__ 
      * every area before it is a multiple of 8 bytes per thread) */
     double* pwl_slot = reinterpret_cast<double*>(pdeb_smem + pdeb_table_smem_bytes<real>(PDEB_REG_THREADS, N, KIND) +
                                                  pdeb_clause_smem_bytes<real>(PDEB_REG_THREADS, b.pmax)) + threadIdx.x;
-    pdeb_run_reg<KIND, N, real, PDEB_REG_THREADS>(b, cv, out, s, table, stab, slots, live, pwl_slot, ctab);
+    pdeb_run_reg<KIND, N, real, PDEB_REG_THREADS>(b, cv, out, s, so, table, stab, slots, live, pwl_slot, ctab);
 }
 
 /*
@@ -105,6 +108,61 @@ __global__ void pdeb_plan_scatter_kernel(int64_t n, const int32_t* __restrict__ 
     const int key = keys[s];
     if (key < 0) return;
     order[atomicAdd(&cursor[key], 1)] = (int32_t)s;
+}
+
+/*
+ * Permutation of the resident image into PLAN ORDER: position p of `dst` receives sample order[p] of `src` (the image as
+ * uploaded: the caller's order).  One thread per position; the reads are gathers from an image that has just been
+ * written (L2), the writes are coalesced, and from then on every kernel launch reads its per-sample parameters as
+ * consecutive lanes -> consecutive addresses.  Only the list entries a sample uses are moved.  knots_only: the refill
+ * of pdeb_resident_set_knots.
+ */
+__global__ void pdeb_permute_kernel(const __grid_constant__ PdebDevBatch src, const __grid_constant__ PdebDevBatch dst,
+                                    const int32_t* __restrict__ order, int64_t count, int knots_only) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= count) return;
+    const int64_t s = order[p], ss = src.stride, ds = dst.stride;
+    int nk = src.n_knots[s];
+    ((int32_t*)dst.n_knots)[p] = nk;
+    if (nk > src.kmax) nk = src.kmax;                  /* counts beyond the planes are flagged by the kernels */
+    for (int j = 0; j < nk; ++j) {
+        ((double*)dst.knot_y)[(int64_t)j * ds + p] = src.knot_y[(int64_t)j * ss + s];
+        if (src.knot_t) ((double*)dst.knot_t)[(int64_t)j * ds + p] = src.knot_t[(int64_t)j * ss + s];
+    }
+    if (knots_only) return;
+    ((uint8_t*)dst.kind)[p] = src.kind[s];
+    ((int32_t*)dst.n_elem)[p] = src.n_elem[s];
+    ((double*)dst.L)[p] = src.L[s];             ((double*)dst.dt)[p] = src.dt[s];
+    ((double*)dst.T)[p] = src.T[s];             ((double*)dst.g0)[p] = src.g0[s];
+    ((double*)dst.x_a)[p] = src.x_a[s];         ((double*)dst.x_b)[p] = src.x_b[s];
+    ((double*)dst.rho_in)[p] = src.rho_in[s];   ((double*)dst.rho_out)[p] = src.rho_out[s];
+    ((double*)dst.E_in)[p] = src.E_in[s];       ((double*)dst.E_out)[p] = src.E_out[s];
+    int np = src.n_pred[s], nt = src.n_tree[s];
+    ((int32_t*)dst.n_pred)[p] = np;
+    ((int32_t*)dst.n_tree)[p] = nt;
+    if (np > src.pmax) np = src.pmax;
+    if (nt > src.tmax) nt = src.tmax;
+    for (int j = 0; j < np; ++j) {
+        const int64_t a = (int64_t)j * ss + s, d = (int64_t)j * ds + p;
+        ((double*)dst.pred_xlo)[d] = src.pred_xlo[a];   ((double*)dst.pred_xhi)[d] = src.pred_xhi[a];
+        ((double*)dst.pred_m)[d] = src.pred_m[a];       ((double*)dst.pred_b)[d] = src.pred_b[a];
+        ((double*)dst.pred_tlo)[d] = src.pred_tlo[a];   ((double*)dst.pred_thi)[d] = src.pred_thi[a];
+        ((uint8_t*)dst.pred_rel)[d] = src.pred_rel[a];  ((uint8_t*)dst.pred_top)[d] = src.pred_top[a];
+    }
+    for (int j = 0; j < nt; ++j) {
+        const int64_t a = (int64_t)j * ss + s, d = (int64_t)j * ds + p;
+        ((uint8_t*)dst.tree_op)[d] = src.tree_op[a];
+        ((int8_t*)dst.tree_lhs)[d] = src.tree_lhs[a];
+        ((int8_t*)dst.tree_rhs)[d] = src.tree_rhs[a];
+    }
+}
+
+int pdeb_permute(const PdebDevBatch& src, const PdebDevBatch& dst, const int32_t* order, int64_t count, bool knots_only,
+                 cudaStream_t stream) {
+    if (count <= 0) return 0;
+    pdeb_permute_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(src, dst, order, count, knots_only ? 1 : 0);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
 }
 
 int pdeb_plan(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out, const PdebPlanBuffers& pb,

@@ -129,7 +129,11 @@ struct PdebPlanBuffers {
 int pdeb_plan(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out, const PdebPlanBuffers& pb,
               uint32_t live_variants, cudaStream_t stream, int* launches, bool keys_done = false);
 
-/* enqueue the compute kernels of every non-empty variant; returns 0 or a cudaError_t value */
+/* dst[p] <- src[order[p]], p < count: the resident image in plan order (see pdeb_permute_kernel) */
+int pdeb_permute(const PdebDevBatch& src, const PdebDevBatch& dst, const int32_t* order, int64_t count, bool knots_only,
+                 cudaStream_t stream);
+
+/* enqueue the compute kernels of every non-empty variant over the PLAN-ORDERED image `b`; returns 0 or a cudaError_t value */
 int pdeb_launch_all(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out, const PdebPlanBuffers& pb,
                     const int32_t* vstart_count_host, int precision, cudaStream_t stream, int* launches);
 

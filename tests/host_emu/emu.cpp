@@ -17,7 +17,7 @@ static void run_one(const PdebDevBatch& b, const PdebConventions& cv, const Pdeb
     std::vector<real> scales(2 * N + 2), mult(N + 1);
     PdebClauseSlots<real, 1> slots = pdeb_clause_slots<real, 1>(smem.data(), b.pmax, 0);
     double pwl_slot[2] = {0.0, 0.0};
-    pdeb_run_reg<KIND, N, real, 1>(b, cv, out, s, table.data(), scales.data(), slots, true, pwl_slot, mult.data());
+    pdeb_run_reg<KIND, N, real, 1>(b, cv, out, s, s, table.data(), scales.data(), slots, true, pwl_slot, mult.data());
 }
 
 extern "C" int emu_eval_batch(const PdebBatch* in, const PdebConventions* conv, int precision, double* rob,
