@@ -239,7 +239,7 @@ static RangeView view_of(const PdebResident* r, int64_t lo, int64_t hi, int chun
  * The device-side plan orders the samples; because the variant of a sample depends on (kind, mesh) only,
  * the host knows every variant's place inside that order without reading anything back.
  */
-static void host_variant_counts(const PdebBatch* in, int64_t lo, int64_t hi, int32_t* vsc) {
+static void host_variant_counts(const PdebBatch* in, int64_t lo, int64_t hi, int32_t* vsc, int flags) {
     int32_t cnt[PDEB_NUM_VARIANTS] = {0};
     int last_kind = -1, last_ne = -1, last_v = -1;      /* the variant is looked up only where (kind, mesh) changes */
     int64_t len = 0;
@@ -249,7 +249,7 @@ static void host_variant_counts(const PdebBatch* in, int64_t lo, int64_t hi, int
             if (last_v >= 0) cnt[last_v] += (int32_t)len;
             len = 0;
             last_kind = k; last_ne = ne;
-            last_v = pdeb_variant_of(k, ne);
+            last_v = pdeb_variant_of(k, ne, flags);
         }
         ++len;
     }
@@ -310,7 +310,8 @@ static int resident_alloc(const PdebBatch* in, int device, PdebResident** outp) 
     const bool slab = in->slab_base && in->slab_bytes > 0 && in->stride == n;
     r->stride = n;
     PdebDevBatch& d = r->dev;
-    d.n = n; d.stride = r->stride; d.kmax = in->kmax; d.pmax = in->pmax; d.tmax = in->tmax; d.pad = 0;
+    d.n = n; d.stride = r->stride; d.kmax = in->kmax; d.pmax = in->pmax; d.tmax = in->tmax;
+    { const char* e = getenv("PDEB_CTA"); d.pad = (e && e[0] == '1') ? PDEB_FLAG_CTA : 0; }   /* opt-in kernel family (pdeb_launch.h) */
     const void* hostp[] = {in->kind, in->n_elem, in->L, in->dt, in->T, in->g0, in->x_a, in->x_b, in->rho_in, in->rho_out,
                            in->E_in, in->E_out, in->n_knots, in->knot_t, in->knot_y, in->n_pred, in->pred_xlo, in->pred_xhi,
                            in->pred_m, in->pred_b, in->pred_tlo, in->pred_thi, in->pred_rel, in->pred_top, in->n_tree,
@@ -420,7 +421,7 @@ extern "C" int pdeb_resident_create(const PdebBatch* in, int device, void* strea
     if (rc) return rc;
     DeviceGuard g(device);
     rc = upload(r, in, 0, r->n, (cudaStream_t)stream_, false);
-    if (rc == 0) { host_variant_counts(in, 0, r->n, r->vsc_host); rc = plan_view(r, view_of(r, 0, r->n, 0), r->vsc_host, (cudaStream_t)stream_); }
+    if (rc == 0) { host_variant_counts(in, 0, r->n, r->vsc_host, r->dev.pad); rc = plan_view(r, view_of(r, 0, r->n, 0), r->vsc_host, (cudaStream_t)stream_); }
     if (rc) { pdeb_resident_destroy(r); return rc; }
     *outp = r;
     return 0;
@@ -437,7 +438,7 @@ extern "C" int pdeb_resident_upload(PdebResident* r, const PdebBatch* in, void* 
         return fail(PDEB_E_ARG, "batch slab layout differs from the resident image");
     DeviceGuard g(r->device);
     rc = upload(r, in, 0, r->n, (cudaStream_t)stream_, false);
-    if (rc == 0) { host_variant_counts(in, 0, r->n, r->vsc_host); rc = plan_view(r, view_of(r, 0, r->n, 0), r->vsc_host, (cudaStream_t)stream_); }
+    if (rc == 0) { host_variant_counts(in, 0, r->n, r->vsc_host, r->dev.pad); rc = plan_view(r, view_of(r, 0, r->n, 0), r->vsc_host, (cudaStream_t)stream_); }
     return rc;
 }
 
@@ -743,7 +744,7 @@ extern "C" int pdeb_resident_upload_packed(PdebResident* r, const PdebPackedBatc
                 if (last_v >= 0) cnt[last_v] += (int32_t)run;
                 run = 0;
                 last_kind = k; last_ne = ne;
-                last_v = pdeb_variant_of(k, ne);
+                last_v = pdeb_variant_of(k, ne, r->dev.pad);
             }
             ++run;
         }
@@ -950,7 +951,7 @@ extern "C" int pdeb_resident_run(PdebResident* r, const PdebBatch* in, int preci
     int launches = 0;
     {
         int32_t vall[2 * PDEB_NUM_VARIANTS];
-        host_variant_counts(in, 0, n, vall);
+        host_variant_counts(in, 0, n, vall, r->dev.pad);
         rc = check_precision(precision, vall);
         if (rc) return rc;
     }
@@ -963,7 +964,7 @@ extern "C" int pdeb_resident_run(PdebResident* r, const PdebBatch* in, int preci
         rc = upload(r, in, lo, hi, st, false);
         if (rc) return rc;
         RangeView v = view_of(r, lo, hi, c);
-        host_variant_counts(in, lo, hi, v.vsc);
+        host_variant_counts(in, lo, hi, v.vsc, r->dev.pad);
         rc = plan_view(r, v, v.vsc, st, false, &cv);
         if (rc) return rc;
         int nl = 0;
@@ -981,7 +982,7 @@ extern "C" int pdeb_resident_run(PdebResident* r, const PdebBatch* in, int preci
     CK(cudaStreamSynchronize(user));
     CK(cudaGetLastError());
     /* the whole-batch order and counts are stale now (each chunk was planned on its own): rebuild lazily */
-    host_variant_counts(in, 0, n, r->vsc_host);
+    host_variant_counts(in, 0, n, r->vsc_host, r->dev.pad);
     r->plan_stale = nch > 1;
     if (timing) {
         memset(timing, 0, sizeof *timing);

@@ -114,3 +114,22 @@ def test_refined_mesh_accuracy_on_a_larger_sample(oracle_lib):
     assert (got["status"] == ref_st).all()
     assert rel_err(got["robustness"], ref, b).max() <= 1e-10
 
+
+
+@pytest.mark.parametrize("N", [543, 700, 1024, 1054])
+def test_cta_family_opt_in(oracle_lib, N, monkeypatch):
+    """The block-per-trajectory mapping of the north star (pdeb_cta.cuh: 128 threads, 8 rows per lane, two-level
+    substructuring with one barrier per step).  Opt-in (PDEB_CTA=1 when the image is created): on B200 it is slower than
+    the warp-per-trajectory family it would replace (profiles/r02_cta_refined_summary.txt); parity is the same."""
+    monkeypatch.setenv("PDEB_CTA", "1")
+    b = with_mesh("heat", 24, N, seed=N)
+    b.pred_xhi[0, :4] = b.pred_xlo[0, :4] + 0.01          # interpolated end points (published through shared memory)
+    b.pred_thi[0, 4:8] = b.T[4:8]
+    b.n_knots[8:10] = 0
+    got, ref = check(b, oracle_lib)
+    for kw in (dict(theta=1.0), dict(mass_heat=1), dict(region_rule=1, window_rule=1, steps_rule=1),
+               dict(eq_rule=1, eq_eps=0.25, material_sampling=2)):
+        check(with_mesh("heat", 8, N, seed=N + 1), oracle_lib, conv=default_conventions(**kw))
+    monkeypatch.delenv("PDEB_CTA")
+    again = native.evaluate_batch(b)                      # the default family on the same batch
+    assert rel_err(again["robustness"], got["robustness"], b).max() <= 1e-11
