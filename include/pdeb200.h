@@ -180,10 +180,16 @@ int pdeb_eval_batch(const PdebBatch* in, int device, int precision, const PdebCo
                     void* stream, PdebTiming* timing);
 
 /*
- * Same over several devices of one box: contiguous shards [floor(r n/R), floor((r+1) n/R)),
- * one host thread and one stream per device, no inter-device traffic.
- * devices == NULL means 0..ndev-1.
+ * Same over several devices of one box: contiguous shards of equal COST (time steps x mesh rows, x 1.5 for waves:
+ * SURVEY.md section 8e; pdeb_shard_bounds gives the cut points), one host thread and one stream per device, every shard
+ * through its device's page-locked staging mirror (one H2D copy), results written straight to the samples' own indices
+ * of the caller's arrays: no inter-device traffic, nothing to gather.  devices == NULL means 0..ndev-1.
+ * Replaces the process pool of evaluate_future (simulate_gt.py:62-89 of the reference).
  */
+int pdeb_shard_bounds(const PdebBatch* in, int ndev, const PdebConventions* conv, int64_t* bounds /* [ndev + 1] */);
+/* one-shot calls keep small resident images per device and shape (no allocation on the next call of that shape);
+   this frees them */
+void pdeb_cache_clear(void);
 int pdeb_eval_batch_multi(const PdebBatch* in, int ndev, const int* devices, int precision,
                           const PdebConventions* conv, double* robustness_out, double* clause_out,
                           int32_t* status_out, PdebTiming* timing_per_device);

@@ -153,6 +153,8 @@ EXPORTS = [
     "pdeb_default_conventions",
     "pdeb_eval_batch",
     "pdeb_eval_batch_multi",
+    "pdeb_shard_bounds",
+    "pdeb_cache_clear",
     "pdeb_resident_create",
     "pdeb_resident_upload",
     "pdeb_resident_upload_packed",

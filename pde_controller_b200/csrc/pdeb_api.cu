@@ -10,7 +10,9 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -109,6 +111,10 @@ struct PdebResident {
                                                         last observed step and where windows open: the plan's keys) */
     unsigned char* pstage = nullptr; /* packed uploads: the transferred block | list offsets | block sums (lazy) */
     size_t pstage_cap = 0, pstage_off = 0;
+    size_t soff[28] = {0};           /* byte offset of every input array inside `slab` */
+    unsigned char* hstage = nullptr; /* page-locked host mirror of `slab` (compact layout): batches that are not one pinned slab
+                                        of this shape (shards, pageable memory, strided views) are gathered here, so that an
+                                        upload is ONE asynchronous copy whatever the caller's layout (lazy) */
     cudaStream_t pipe[2] = {nullptr, nullptr};        /* internal streams of the pipelined run */
     cudaEvent_t pev[3] = {nullptr, nullptr, nullptr};
 };
@@ -143,6 +149,7 @@ extern "C" void pdeb_resident_destroy(PdebResident* r) {
     if (r->outs) cudaFree(r->outs);
     if (r->plan) cudaFree(r->plan);
     if (r->pstage) cudaFree(r->pstage);
+    if (r->hstage) cudaFreeHost(r->hstage);
     for (auto& st : r->pipe) if (st) cudaStreamDestroy(st);
     for (auto& e : r->pev) if (e) cudaEventDestroy(e);
     delete r;
@@ -200,6 +207,45 @@ static int upload(PdebResident* r, const PdebBatch* in, int64_t lo, int64_t hi, 
     CK(copy(d.tree_op, in->tree_op, 1, r->tmax));
     CK(copy(d.tree_lhs, in->tree_lhs, 1, r->tmax));
     CK(copy(d.tree_rhs, in->tree_rhs, 1, r->tmax));
+    return 0;
+}
+
+/* is this host pointer page-locked (cudaHostAlloc / cudaHostRegister)?  Pageable memory cannot be copied asynchronously. */
+static bool host_is_pinned(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+/*
+ * Upload of samples [lo, hi) of ANY host batch (a shard, pageable memory, a strided view) into a resident image of the
+ * compact layout with n = hi - lo: the arrays are gathered into the image's page-locked host mirror (plain memcpy, one per
+ * array and plane) and cross PCIe as ONE asynchronous copy, instead of 28 strided copies from pageable memory.
+ */
+static int upload_staged(PdebResident* r, const PdebBatch* in, int64_t lo, int64_t hi, cudaStream_t stream) {
+    const int64_t n = hi - lo;
+    if (n != r->n || r->host_slab) return fail(PDEB_E_ARG, "staged upload needs a compact image of the shard's size");
+    if (n <= 0) return 0;
+    if ((in->knot_t != nullptr) != (r->dev.knot_t != nullptr)) return fail(PDEB_E_ARG, "knot_t must be given (or NULL) as at creation");
+    if (!r->hstage) {
+        cudaError_t ce = cudaHostAlloc((void**)&r->hstage, r->slab_bytes, cudaHostAllocDefault);
+        if (ce != cudaSuccess) { r->hstage = nullptr; return fail(PDEB_E_NOMEM, "page-locked staging buffer", ce); }
+    }
+    const void* hostp[] = {in->kind, in->n_elem, in->L, in->dt, in->T, in->g0, in->x_a, in->x_b, in->rho_in, in->rho_out,
+                           in->E_in, in->E_out, in->n_knots, in->knot_t, in->knot_y, in->n_pred, in->pred_xlo, in->pred_xhi,
+                           in->pred_m, in->pred_b, in->pred_tlo, in->pred_thi, in->pred_rel, in->pred_top, in->n_tree,
+                           in->tree_op, in->tree_lhs, in->tree_rhs};
+    const size_t elem[] = {1, 4, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 4, 8, 8, 4, 8, 8, 8, 8, 8, 8, 1, 1, 4, 1, 1, 1};
+    const int planes[] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, in->knot_t ? r->kmax : 0, r->kmax, 1, r->pmax, r->pmax, r->pmax,
+                          r->pmax, r->pmax, r->pmax, r->pmax, r->pmax, 1, r->tmax, r->tmax, r->tmax};
+    for (int f = 0; f < 28; ++f) {
+        if (!hostp[f]) continue;
+        for (int p = 0; p < planes[f]; ++p)
+            memcpy(r->hstage + r->soff[f] + elem[f] * (size_t)n * p,
+                   (const unsigned char*)hostp[f] + elem[f] * ((size_t)p * (size_t)in->stride + (size_t)lo), elem[f] * (size_t)n);
+    }
+    CK(cudaMemcpyAsync(r->slab, r->hstage, r->slab_bytes, cudaMemcpyHostToDevice, stream));
     return 0;
 }
 
@@ -291,7 +337,7 @@ static int plan_view(PdebResident* r, const RangeView& v, const int32_t* vsc, cu
 }
 
 /* allocate the device image of `in` (no copy yet) */
-static int resident_alloc(const PdebBatch* in, int device, PdebResident** outp) {
+static int resident_alloc(const PdebBatch* in, int device, PdebResident** outp, bool force_compact = false) {
     if (!outp) return fail(PDEB_E_ARG, "out is NULL");
     *outp = nullptr;
     int rc = check_batch(in);
@@ -307,7 +353,7 @@ static int resident_alloc(const PdebBatch* in, int device, PdebResident** outp) 
     const int64_t n = in->n;
 
     /* device layout: the host slab verbatim when there is one, else a compact slab with stride n */
-    const bool slab = in->slab_base && in->slab_bytes > 0 && in->stride == n;
+    const bool slab = !force_compact && in->slab_base && in->slab_bytes > 0 && in->stride == n;
     r->stride = n;
     PdebDevBatch& d = r->dev;
     d.n = n; d.stride = r->stride; d.kmax = in->kmax; d.pmax = in->pmax; d.tmax = in->tmax;
@@ -341,6 +387,7 @@ static int resident_alloc(const PdebBatch* in, int device, PdebResident** outp) 
         }
     }
     r->slab_bytes = total;
+    for (int f = 0; f < NF; ++f) r->soff[f] = off[f];
     /* the plan-ordered image: always the compact layout */
     size_t ioff[NF];
     size_t itotal = 0;
@@ -994,32 +1041,192 @@ extern "C" int pdeb_resident_run(PdebResident* r, const PdebBatch* in, int preci
 
 /* ---- one-shot ------------------------------------------------------------ */
 
+/*
+ * Resident images of recent one-shot calls, kept per device and keyed by shape, so that a caller that evaluates batch
+ * after batch of one shape (the per-sample helpers of the reference's call surface: eval_robustness_helper evaluates
+ * ONE program per call) does not pay three cudaMalloc, two streams and seven events every time.  Small images only
+ * (PDEB_CACHE_MAX_BYTES of device memory each, PDEB_CACHE_ENTRIES per device, least recently used out); an image in
+ * use by another thread is never shared: that caller gets a private one.  pdeb_cache_clear() frees them.
+ */
+#define PDEB_CACHE_ENTRIES 8
+#define PDEB_CACHE_MAX_BYTES ((size_t)256 << 20)
+#define PDEB_API_MAX_DEVICES 64
+struct CacheKey {
+    int64_t n;
+    int kmax, pmax, tmax, has_kt, slab;
+    size_t slab_bytes, sig0, sig1;
+    bool operator==(const CacheKey& o) const {
+        return n == o.n && kmax == o.kmax && pmax == o.pmax && tmax == o.tmax && has_kt == o.has_kt && slab == o.slab &&
+               slab_bytes == o.slab_bytes && sig0 == o.sig0 && sig1 == o.sig1;
+    }
+};
+struct CacheEntry { CacheKey key; PdebResident* r; bool busy; uint64_t stamp; };
+static std::mutex g_cache_mu;
+static std::vector<CacheEntry> g_cache[PDEB_API_MAX_DEVICES];
+static uint64_t g_cache_stamp = 0;
+
+static int cache_acquire(const PdebBatch* view, const CacheKey& key, int device, bool compact, PdebResident** outp, bool* cached) {
+    *cached = false;
+    if (device >= 0 && device < PDEB_API_MAX_DEVICES) {
+        std::lock_guard<std::mutex> lock(g_cache_mu);
+        for (CacheEntry& e : g_cache[device])
+            if (!e.busy && e.key == key) { e.busy = true; e.stamp = ++g_cache_stamp; *outp = e.r; *cached = true; return 0; }
+    }
+    PdebResident* r = nullptr;
+    int rc = resident_alloc(view, device, &r, compact);
+    if (rc) return rc;
+    *outp = r;
+    const size_t bytes = 2 * r->slab_bytes + (size_t)r->n * (20 + 8 * (size_t)r->pmax);
+    if (device >= 0 && device < PDEB_API_MAX_DEVICES && bytes <= PDEB_CACHE_MAX_BYTES) {
+        PdebResident* evict = nullptr;
+        {
+            std::lock_guard<std::mutex> lock(g_cache_mu);
+            std::vector<CacheEntry>& v = g_cache[device];
+            if (v.size() >= PDEB_CACHE_ENTRIES) {
+                int lru = -1;
+                for (int i = 0; i < (int)v.size(); ++i) if (!v[i].busy && (lru < 0 || v[i].stamp < v[lru].stamp)) lru = i;
+                if (lru >= 0) { evict = v[lru].r; v.erase(v.begin() + lru); }
+            }
+            if (v.size() < PDEB_CACHE_ENTRIES) { v.push_back({key, r, true, ++g_cache_stamp}); *cached = true; }
+        }
+        if (evict) pdeb_resident_destroy(evict);
+    }
+    return 0;
+}
+
+static void cache_release(PdebResident* r, bool cached) {
+    if (!cached) { pdeb_resident_destroy(r); return; }
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    for (CacheEntry& e : g_cache[r->device]) if (e.r == r) { e.busy = false; return; }
+}
+
+extern "C" void pdeb_cache_clear(void) {
+    std::vector<PdebResident*> dead;
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mu);
+        for (auto& v : g_cache) {
+            for (size_t i = 0; i < v.size();) {
+                if (!v[i].busy) { dead.push_back(v[i].r); v.erase(v.begin() + i); } else ++i;
+            }
+        }
+    }
+    for (PdebResident* r : dead) pdeb_resident_destroy(r);
+}
+
+/*
+ * Samples [lo, hi) of a host batch on one device: H2D (one copy), plan, kernels, D2H into the caller's arrays at the
+ * samples' own indices; synchronises.  A batch that is one page-locked slab of exactly this range goes across as it
+ * lies; anything else (a shard, pageable memory, a strided view) through the image's page-locked mirror (upload_staged).
+ */
+static int run_range(const PdebBatch* in, int64_t lo, int64_t hi, int device, int precision, const PdebConventions* conv,
+                     double* robustness_out, double* clause_out, int32_t* status_out, cudaStream_t user, PdebTiming* timing) {
+    const int64_t n = hi - lo;
+    if (timing) memset(timing, 0, sizeof *timing);
+    if (n <= 0) return 0;
+    const bool whole = lo == 0 && hi == in->n;
+    const bool slab = whole && in->slab_base && in->slab_bytes > 0 && in->stride == in->n && host_is_pinned(in->slab_base);
+    PdebBatch view = *in;                       /* shape of the image: n samples */
+    view.n = n;
+    if (!slab) { view.slab_base = nullptr; view.slab_bytes = 0; }
+    CacheKey key{n, in->kmax, in->pmax, in->tmax, in->knot_t ? 1 : 0, slab ? 1 : 0, 0, 0, 0};
+    if (slab) {
+        key.slab_bytes = (size_t)in->slab_bytes;
+        key.sig0 = (size_t)((const unsigned char*)in->L - (const unsigned char*)in->slab_base);
+        key.sig1 = (size_t)((const unsigned char*)in->tree_rhs - (const unsigned char*)in->slab_base);
+    }
+    PdebResident* r = nullptr;
+    bool cached = false;
+    int rc = cache_acquire(&view, key, device, !slab, &r, &cached);
+    if (rc) return rc;
+    r->host_stride = in->stride;
+    if (slab) {
+        rc = pdeb_resident_run(r, in, precision, conv, robustness_out, clause_out, status_out, user, timing);
+        cache_release(r, cached);
+        return rc;
+    }
+    DeviceGuard g(device);
+    PdebConventions cv;
+    if (conv) cv = *conv; else pdeb_default_conventions(&cv);
+    auto done = [&](int code) { cache_release(r, cached); return code; };
+    if (timing) { cudaError_t ce = cudaEventRecord(r->ev[0], user); if (ce != cudaSuccess) return done(fail(PDEB_E_CUDA, "event record", ce)); }
+    rc = upload_staged(r, in, lo, hi, user);
+    if (rc) return done(rc);
+    {
+        /* variants of the shard: the counting pass reads the caller's arrays at their own indices */
+        host_variant_counts(in, lo, hi, r->vsc_host, r->dev.pad);
+        rc = check_precision(precision, r->vsc_host);
+        if (rc) return done(rc);
+        rc = plan_view(r, view_of(r, 0, n, 0), r->vsc_host, user, false, &cv);
+        if (rc) return done(rc);
+        r->plan_stale = false;
+    }
+    int launches = 0;
+    const int lrc = pdeb_launch_all(r->dimg, cv, r->out, r->pb, r->vsc_host, precision, user, &launches);
+    if (lrc) return done(fail(PDEB_E_CUDA, "kernel launch", (cudaError_t)lrc));
+    {
+        cudaError_t ce = cudaMemcpyAsync(robustness_out + lo, r->out.robustness, 8 * (size_t)n, cudaMemcpyDeviceToHost, user);
+        if (ce == cudaSuccess && status_out) ce = cudaMemcpyAsync(status_out + lo, r->out.status, 4 * (size_t)n, cudaMemcpyDeviceToHost, user);
+        if (ce == cudaSuccess && clause_out)
+            ce = cudaMemcpy2DAsync(clause_out + lo, 8 * (size_t)in->stride, r->out.clause, 8 * (size_t)r->stride, 8 * (size_t)n,
+                                   r->pmax, cudaMemcpyDeviceToHost, user);
+        if (ce == cudaSuccess && timing) ce = cudaEventRecord(r->ev[3], user);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(user);
+        if (ce == cudaSuccess) ce = cudaGetLastError();
+        if (ce != cudaSuccess) return done(fail(PDEB_E_CUDA, "download", ce));
+    }
+    if (timing) {
+        cudaEventElapsedTime(&timing->total_ms, r->ev[0], r->ev[3]);
+        timing->launches = launches + r->plan_launches;
+    }
+    return done(0);
+}
+
 extern "C" int pdeb_eval_batch(const PdebBatch* in, int device, int precision, const PdebConventions* conv,
                                double* robustness_out, double* clause_out, int32_t* status_out, void* stream_,
                                PdebTiming* timing) {
     if (!robustness_out) return fail(PDEB_E_ARG, "robustness_out is NULL");
     if (precision != 64 && precision != 32) return fail(PDEB_E_ARG, "precision must be 64 or 32");
-    PdebResident* r = nullptr;
-    int rc = resident_alloc(in, device, &r);
+    int rc = check_batch(in);
     if (rc) return rc;
-    rc = pdeb_resident_run(r, in, precision, conv, robustness_out, clause_out, status_out, stream_, timing);
-    pdeb_resident_destroy(r);
-    return rc;
+    if (device < 0 || device >= pdeb_device_count()) return fail(PDEB_E_NODEVICE, "no such CUDA device");
+    return run_range(in, 0, in->n, device, precision, conv, robustness_out, clause_out, status_out, (cudaStream_t)stream_, timing);
 }
 
-/* ---- several devices of one box: contiguous shards, no inter-device traffic ---- */
+/* ---- several devices of one box: contiguous shards balanced by cost, no inter-device traffic ---- */
 
-static PdebBatch shard_of(const PdebBatch* in, int64_t lo, int64_t hi) {
-    PdebBatch s = *in;
-    s.n = hi - lo;
-    s.slab_base = nullptr;
-    s.slab_bytes = 0;
-#define OFF(f) s.f = in->f + lo
-    OFF(kind); OFF(n_elem); OFF(L); OFF(dt); OFF(T); OFF(g0); OFF(x_a); OFF(x_b); OFF(rho_in); OFF(rho_out); OFF(E_in);
-    OFF(E_out); OFF(n_knots); if (in->knot_t) { OFF(knot_t); } OFF(knot_y); OFF(n_pred); OFF(pred_xlo); OFF(pred_xhi); OFF(pred_m); OFF(pred_b);
-    OFF(pred_tlo); OFF(pred_thi); OFF(pred_rel); OFF(pred_top); OFF(n_tree); OFF(tree_op); OFF(tree_lhs); OFF(tree_rhs);
-#undef OFF
-    return s;
+/*
+ * Cut points of `ndev` contiguous shards carrying equal COST ("for mixed batches balance by estimated
+ * cost S n rather than by count"): cost of a sample = time steps x mesh rows (x 1.5 for waves: three state vectors).
+ * bounds[r] .. bounds[r+1] is shard r.  pdeb_shard_bounds exports the rule (the Python mirror is sharding.cost_balanced_bounds).
+ */
+extern "C" int pdeb_shard_bounds(const PdebBatch* in, int ndev, const PdebConventions* conv, int64_t* bounds) {
+    int rc = check_batch(in);
+    if (rc) return rc;
+    if (ndev < 1 || !bounds) return fail(PDEB_E_ARG, "bad ndev / bounds");
+    PdebConventions cv;
+    if (conv) cv = *conv; else pdeb_default_conventions(&cv);
+    const int64_t n = in->n;
+    std::vector<double> acc((size_t)n + 1, 0.0);
+    for (int64_t s = 0; s < n; ++s) {
+        const double T = in->T[s], dt = in->dt[s];
+        double c = 1.0;
+        if (T > 0 && dt > 0 && std::isfinite(T) && std::isfinite(dt)) {
+            const double steps = (double)pdeb_step_count(T, dt, cv.steps_rule);
+            const int ne = in->n_elem[s] > 0 ? in->n_elem[s] : 1;
+            c = steps * (double)ne * (in->kind[s] == PDEB_KIND_WAVE ? 1.5 : 1.0);
+        }
+        acc[(size_t)s + 1] = acc[(size_t)s] + c;
+    }
+    const double total = acc[(size_t)n];
+    bounds[0] = 0;
+    int64_t cut = 0;
+    for (int r = 1; r < ndev; ++r) {
+        const double want = total * (double)r / (double)ndev;
+        while (cut < n && acc[(size_t)cut + 1] < want) ++cut;   /* the sample whose inclusion reaches the target opens the next shard */
+        bounds[r] = cut;
+    }
+    bounds[ndev] = n;
+    return 0;
 }
 
 extern "C" int pdeb_eval_batch_multi(const PdebBatch* in, int ndev, const int* devices, int precision,
@@ -1027,25 +1234,40 @@ extern "C" int pdeb_eval_batch_multi(const PdebBatch* in, int ndev, const int* d
                                      int32_t* status_out, PdebTiming* timing_per_device) {
     int rc = check_batch(in);
     if (rc) return rc;
-    if (ndev < 1 || ndev > pdeb_device_count()) return fail(PDEB_E_NODEVICE, "ndev exceeds the visible devices");
+    {
+        /* devices == NULL: shard r on device r; an explicit list may name a device more than once (its shards then run
+         * concurrently on that device, each on an image of its own) */
+        const int have = pdeb_device_count();
+        if (ndev < 1 || ndev > 1024) return fail(PDEB_E_ARG, "bad ndev");
+        if (!devices && ndev > have) return fail(PDEB_E_NODEVICE, "ndev exceeds the visible devices");
+        for (int r = 0; devices && r < ndev; ++r)
+            if (devices[r] < 0 || devices[r] >= have) return fail(PDEB_E_NODEVICE, "no such CUDA device in the device list");
+    }
     if (!robustness_out) return fail(PDEB_E_ARG, "robustness_out is NULL");
+    if (precision != 64 && precision != 32) return fail(PDEB_E_ARG, "precision must be 64 or 32");
+    std::vector<int64_t> bounds((size_t)ndev + 1);
+    rc = pdeb_shard_bounds(in, ndev, conv, bounds.data());
+    if (rc) return rc;
     std::vector<int> rcs(ndev, 0);
     std::vector<std::string> errs(ndev);
     std::vector<std::thread> th;
     for (int r = 0; r < ndev; ++r) {
         th.emplace_back([&, r]() {
-            const int64_t lo = in->n * r / ndev, hi = in->n * (r + 1) / ndev;
-            if (hi <= lo) { if (timing_per_device) memset(&timing_per_device[r], 0, sizeof(PdebTiming)); return; }
-            PdebBatch s = shard_of(in, lo, hi);
+            const int64_t lo = bounds[(size_t)r], hi = bounds[(size_t)r + 1];
+            if (timing_per_device) memset(&timing_per_device[r], 0, sizeof(PdebTiming));
+            if (hi <= lo) return;
             const int dev = devices ? devices[r] : r;
             cudaStream_t stream = nullptr;
-            cudaSetDevice(dev);
-            cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
-            rcs[r] = pdeb_eval_batch(&s, dev, precision, conv, robustness_out + lo, clause_out ? clause_out + lo : nullptr,
-                                     status_out ? status_out + lo : nullptr, stream,
-                                     timing_per_device ? &timing_per_device[r] : nullptr);
+            if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) {
+                cudaGetLastError();
+                rcs[r] = PDEB_E_NODEVICE; errs[r] = "cannot use the device";
+                return;
+            }
+            /* the shard goes through its device's page-locked mirror: one H2D copy, results straight into the caller's arrays */
+            rcs[r] = run_range(in, lo, hi, dev, precision, conv, robustness_out, clause_out, status_out, stream,
+                               timing_per_device ? &timing_per_device[r] : nullptr);
             if (rcs[r]) errs[r] = g_err;
-            if (stream) cudaStreamDestroy(stream);
+            cudaStreamDestroy(stream);
         });
     }
     for (auto& t : th) t.join();

@@ -45,6 +45,10 @@ def lib():
         L.pdeb_eval_batch_multi.restype = C.c_int
         L.pdeb_eval_batch_multi.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pdeb_shard_bounds.restype = C.c_int
+        L.pdeb_shard_bounds.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.pdeb_cache_clear.restype = None
+        L.pdeb_cache_clear.argtypes = []
         L.pdeb_resident_create.restype = C.c_int
         L.pdeb_resident_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.pdeb_resident_upload.restype = C.c_int
@@ -182,6 +186,19 @@ def evaluate_batch_multi(batch: ProblemBatch, ndev: int, devices=None, precision
     if want_clauses:
         out["clause"] = cl[:, : batch.n]
     return out
+
+
+def shard_bounds(batch: ProblemBatch, ndev: int, conv=None) -> np.ndarray:
+    """Cut points of the cost-balanced contiguous shards pdeb_eval_batch_multi uses (host-side rule, no device)."""
+    cb = batch.as_c()
+    out = np.zeros(ndev + 1, dtype=np.int64)
+    _check(lib().pdeb_shard_bounds(C.addressof(cb), ndev, _conv_ptr(conv), _ptr(out)), "pdeb_shard_bounds")
+    return out
+
+
+def cache_clear():
+    """Free the resident images one-shot calls keep per device and shape."""
+    lib().pdeb_cache_clear()
 
 
 class ResidentBatch:

@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported(so):
 def test_every_pointer_taking_export_has_argtypes():
     """ctypes passes an undeclared argument as a C int: a 64-bit pointer would be truncated (a crash on the GPU box)."""
     L = native.lib()
-    no_args = {"pdeb_version", "pdeb_device_count", "pdeb_last_error"}
+    no_args = {"pdeb_version", "pdeb_device_count", "pdeb_last_error", "pdeb_cache_clear"}
     for name in abi.EXPORTS:
         if name in no_args:
             continue
@@ -154,3 +154,20 @@ def test_native_packer_equals_numpy_packer():
     big.n_elem[2] = 70000                                  # does not fit u16
     with pytest.raises(ValueError):
         PackedBatch(big.n, big.kmax, big.pmax, big.tmax).pack(big, use_native=True)
+
+
+def test_cost_balanced_shard_bounds_match_the_python_rule():
+    """pdeb_shard_bounds (host-only): contiguous shards of equal cost (steps x rows, x 1.5 for waves: SURVEY.md 8e),
+    the same cut points as sharding.cost_balanced_bounds."""
+    import numpy as np
+    from pde_controller_b200 import sharding, synth
+    b = synth.make_batch(6000, "mixed", seed=2)            # first half heat, second half waves (3x the cost each)
+    for ndev in (1, 2, 3, 8):
+        got = native.shard_bounds(b, ndev)
+        want = sharding.cost_balanced_bounds(sharding.batch_cost(b), ndev)
+        assert got[0] == 0 and got[-1] == b.n and (np.diff(got) >= 0).all()
+        assert [(int(got[r]), int(got[r + 1])) for r in range(ndev)] == want
+        cost = sharding.batch_cost(b)
+        per = np.array([cost[got[r]:got[r + 1]].sum() for r in range(ndev)])
+        assert per.max() <= per.mean() * 1.02 + cost.max()
+    assert list(native.shard_bounds(b, 2)) != [0, b.n // 2, b.n]      # by cost, not by count
