@@ -93,9 +93,13 @@ struct PdebResident {
     int kmax = 0, pmax = 0, tmax = 0;
     unsigned char* slab = nullptr;   /* inputs as uploaded: the caller's order (and, with a host slab, the caller's layout) */
     size_t slab_bytes = 0;
-    unsigned char* img = nullptr;    /* the same inputs in PLAN ORDER: what the kernels read (dimg); formed by pdeb_permute
-                                        after every plan, so consecutive lanes read consecutive addresses */
+    unsigned char* img = nullptr;    /* the same inputs in PLAN ORDER (dimg): consecutive lanes read consecutive addresses.
+                                        Formed by pdeb_permute when an upload is evaluated a SECOND time (the permutation costs
+                                        more than the gathers of one evaluation: a batch that passes through once is read where
+                                        it lies, a resident batch that is evaluated again and again is permuted once) */
     PdebDevBatch dimg{};
+    bool img_valid = false;          /* dimg holds the current upload in the current order */
+    int evals_since_upload = 0;
     unsigned char* outs = nullptr;   /* robustness | clause | status */
     PdebDevBatch dev{};
     PdebDevOut out{};
@@ -327,12 +331,18 @@ static int plan_view(PdebResident* r, const RangeView& v, const int32_t* vsc, cu
     for (int q = 0; q < PDEB_NUM_VARIANTS; ++q) if (vsc[2 * q + 1] > 0) live |= 1u << q;
     int rc = pdeb_plan(v.dev, cv, v.out, v.pb, live, stream, &nl, keys_done);
     if (rc) return fail(PDEB_E_CUDA, "plan launch", (cudaError_t)rc);
-    /* the image the kernels read, in the order just formed (samples no variant covers are not part of it) */
+    r->plan_launches = nl;
+    r->img_valid = false;                    /* a new order (and usually a new upload): the plan-ordered image is stale */
+    r->evals_since_upload = 0;
+    return 0;
+}
+
+/* the plan-ordered image of the whole batch, formed on demand (samples no variant covers are not part of it) */
+static int permute_image(PdebResident* r, bool knots_only, cudaStream_t stream) {
     int64_t ordered = 0;
-    for (int q = 0; q < PDEB_NUM_VARIANTS; ++q) ordered += vsc[2 * q + 1];
-    rc = pdeb_permute(v.dev, v.dimg, v.pb.order, ordered, false, stream);
+    for (int q = 0; q < PDEB_NUM_VARIANTS; ++q) ordered += r->vsc_host[2 * q + 1];
+    const int rc = pdeb_permute(r->dev, r->dimg, r->pb.order, ordered, knots_only, stream);
     if (rc) return fail(PDEB_E_CUDA, "permute launch", (cudaError_t)rc);
-    r->plan_launches = nl + (ordered > 0 ? 1 : 0);
     return 0;
 }
 
@@ -851,12 +861,9 @@ extern "C" int pdeb_resident_set_knots(PdebResident* r, const double* knot_t, co
         rc = plan_view(r, view_of(r, 0, r->n, 0), r->vsc_host, (cudaStream_t)stream_);
         if (rc) return rc;
         r->plan_stale = false;
-        return 0;                            /* the plan has just permuted everything */
+        return 0;
     }
-    int64_t ordered = 0;
-    for (int q = 0; q < PDEB_NUM_VARIANTS; ++q) ordered += r->vsc_host[2 * q + 1];
-    rc = pdeb_permute(r->dev, r->dimg, r->pb.order, ordered, true, (cudaStream_t)stream_);
-    if (rc) return fail(PDEB_E_CUDA, "permute launch", (cudaError_t)rc);
+    if (r->img_valid) return permute_image(r, true, (cudaStream_t)stream_);
     return 0;
 }
 
@@ -878,8 +885,14 @@ extern "C" int pdeb_resident_eval(PdebResident* r, int precision, const PdebConv
         if (prc) return prc;
         r->plan_stale = false;
     }
+    if (!r->img_valid && r->evals_since_upload >= 1) {
+        int prc = permute_image(r, false, stream);      /* evaluated again: from now on the kernels read coalesced */
+        if (prc) return prc;
+        r->img_valid = true;
+    }
+    ++r->evals_since_upload;
     if (timing) CK(cudaEventRecord(r->ev[0], stream));
-    int rc = pdeb_launch_all(r->dimg, cv, r->out, r->pb, r->vsc_host, precision, stream, &launches);
+    int rc = pdeb_launch_all(r->img_valid ? r->dimg : r->dev, cv, r->out, r->pb, r->vsc_host, precision, r->img_valid ? 0 : 1, stream, &launches);
     if (rc) return fail(PDEB_E_CUDA, "kernel launch", (cudaError_t)rc);
     if (timing) {
         CK(cudaEventRecord(r->ev[1], stream));
@@ -1015,7 +1028,7 @@ extern "C" int pdeb_resident_run(PdebResident* r, const PdebBatch* in, int preci
         rc = plan_view(r, v, v.vsc, st, false, &cv);
         if (rc) return rc;
         int nl = 0;
-        const int lrc = pdeb_launch_all(v.dimg, cv, v.out, v.pb, v.vsc, precision, st, &nl);
+        const int lrc = pdeb_launch_all(v.dev, cv, v.out, v.pb, v.vsc, precision, 1, st, &nl);
         if (lrc) return fail(PDEB_E_CUDA, "kernel launch", (cudaError_t)lrc);
         launches += nl + r->plan_launches;
         rc = fetch_range(r, lo, hi, robustness_out, clause_out, status_out, st);
@@ -1161,7 +1174,7 @@ static int run_range(const PdebBatch* in, int64_t lo, int64_t hi, int device, in
         r->plan_stale = false;
     }
     int launches = 0;
-    const int lrc = pdeb_launch_all(r->dimg, cv, r->out, r->pb, r->vsc_host, precision, user, &launches);
+    const int lrc = pdeb_launch_all(r->dev, cv, r->out, r->pb, r->vsc_host, precision, 1, user, &launches);
     if (lrc) return done(fail(PDEB_E_CUDA, "kernel launch", (cudaError_t)lrc));
     {
         cudaError_t ce = cudaMemcpyAsync(robustness_out + lo, r->out.robustness, 8 * (size_t)n, cudaMemcpyDeviceToHost, user);

@@ -104,14 +104,15 @@ struct PdebChunkGeom {
 template <int KIND, int R>
 __global__ void __launch_bounds__(32 * PDEB_CHUNK_WARPS, PDEB_CHUNK_MINBLOCKS)
 pdeb_chunk_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant__ PdebConventions cv,
-                  const __grid_constant__ PdebDevOut out, const int32_t* __restrict__ order, int64_t first, int64_t count) {
+                  const __grid_constant__ PdebDevOut out, const int32_t* __restrict__ order, int64_t first, int64_t count,
+                  int gather) {
     typedef PdebChunkGeom<R> G;
     extern __shared__ __align__(16) unsigned char pdeb_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t t = (int64_t)blockIdx.x * PDEB_CHUNK_WARPS + warp;
     if (t >= count) return;                                   /* whole warp */
-    const int64_t s = first + t;                              /* position in the plan-ordered input image */
     const int64_t so = order[first + t];                      /* the sample's index in the caller's order: outputs */
+    const int64_t s = gather ? so : first + t;                /* inputs: the image as uploaded, or the plan-ordered image */
     const int64_t st = b.stride;
     double* tab = reinterpret_cast<double*>(pdeb_smem) + (size_t)warp * G::WARP_REALS;
 

@@ -4,7 +4,7 @@
 
 template <int R>
 static cudaError_t launch(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out, const int32_t* order,
-                          int64_t first, int64_t count, cudaStream_t stream) {
+                          int64_t first, int64_t count, int gather, cudaStream_t stream) {
     const size_t smem = pdeb_chunk_smem_bytes<R>();
     auto kern = pdeb_chunk_kernel<PDEB_KIND_WAVE, R>;
     if (smem > 48 * 1024) {
@@ -12,18 +12,18 @@ static cudaError_t launch(const PdebDevBatch& b, const PdebConventions& cv, cons
         if (e != cudaSuccess) return e;
     }
     const int64_t blocks = (count + PDEB_CHUNK_WARPS - 1) / PDEB_CHUNK_WARPS;
-    kern<<<(unsigned)blocks, 32 * PDEB_CHUNK_WARPS, smem, stream>>>(b, cv, out, order, first, count);
+    kern<<<(unsigned)blocks, 32 * PDEB_CHUNK_WARPS, smem, stream>>>(b, cv, out, order, first, count, gather);
     return cudaGetLastError();
 }
 
 cudaError_t pdeb_launch_chunk_wave(int R, const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out,
-                                   const int32_t* order, int64_t first, int64_t count, cudaStream_t stream) {
+                                   const int32_t* order, int64_t first, int64_t count, int gather, cudaStream_t stream) {
     switch (R) {
-    case 1: return launch<1>(b, cv, out, order, first, count, stream);
-    case 2: return launch<2>(b, cv, out, order, first, count, stream);
-    case 4: return launch<4>(b, cv, out, order, first, count, stream);
-    case 8: return launch<8>(b, cv, out, order, first, count, stream);
-    case 16: return launch<16>(b, cv, out, order, first, count, stream);
+    case 1: return launch<1>(b, cv, out, order, first, count, gather, stream);
+    case 2: return launch<2>(b, cv, out, order, first, count, gather, stream);
+    case 4: return launch<4>(b, cv, out, order, first, count, gather, stream);
+    case 8: return launch<8>(b, cv, out, order, first, count, gather, stream);
+    case 16: return launch<16>(b, cv, out, order, first, count, gather, stream);
     default: return cudaErrorInvalidValue;
     }
 }

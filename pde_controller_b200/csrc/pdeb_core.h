@@ -56,17 +56,13 @@
 #ifndef PDEB_C_SMEM
 #define PDEB_C_SMEM 0
 #endif
-/* A/B switches of tools/variant_bench.py (defaults = what measured faster on B200, profiles/r02_*):
- *   PDEB_LOAD_SEQ   1: the input as an incrementally updated scaled load sequence (PdebLoadStaged), 0: evaluated from
- *                   the segment every step (PdebPwlStaged)
+/* A/B switch of tools/variant_bench.py (default = what measured faster on B200):
  *   PDEB_EVENT_LIST 1: window events from a presorted per-lane list (one word per event), 0: every event re-scans the
  *                   windows of all clauses */
-#ifndef PDEB_LOAD_SEQ
-#define PDEB_LOAD_SEQ 0
-#endif
 #ifndef PDEB_EVENT_LIST
 #define PDEB_EVENT_LIST 1
 #endif
+
 
 /* device view of a batch: the PdebBatch arrays, on the device */
 struct PdebDevBatch {
@@ -226,137 +222,6 @@ struct PdebPwl {
 };
 
 /*
- * The same input for the register family, as the SCALED LOAD SEQUENCE the time loop consumes, with the next knot staged
- * in shared memory.
- *
- * What a step needs is g_k = scale * f(k dt) (scale = s_N: the load enters row N of the scaled system).  Inside one
- * segment of the piecewise-linear input that is an arithmetic sequence, so a step costs ONE add (g += dg) and an integer
- * compare against the step at which the next knot is crossed; the earlier form evaluated  y0 + slope (k dt - t0)  from
- * scratch every step (int-to-double conversion, two multiplies, an add, an FMA and a 64-bit compare: 11 % of the heat
- * kernel's warp time went into the input of a 30-row solve).  At a crossing the value is re-formed EXACTLY from the knots
- * (same arithmetic and same "t >= knot" rule as PdebPwl / the oracle), so the increments never accumulate over more than
- * one segment (~20 steps: a relative drift of ~2e-15).
- *
- * In this family the lanes of a warp cross their knots at different steps, so a warp runs the crossing code in about
- * half of its steps, and a knot fetched into a register there would stall the whole warp for a global-memory latency.
- * The crossing reads the knot from a per-thread shared-memory slot (two doubles: value, time) and refills the slot with
- * an ASYNCHRONOUS copy (cp.async, global -> shared, no register destination) that has the ~20 steps until the next
- * crossing to land.
- */
-template <typename real, int STRIDE>
-struct PdebLoadStaged {
-    double t1;            /* end of the current segment (+inf on the last) */
-    real y1;              /* input value at t1 */
-    real g, dg;           /* scaled load at the current step; its increment per step inside the current segment */
-    real f_exact;         /* UNscaled input at the last exact evaluation (set-up: f(0), which the wave start needs) */
-    int32_t kx;           /* first step k with k dt >= t1 (0x7fffffff: the segment never ends) */
-    int nk, j;            /* j: index of the knot at t1 */
-    double ustep, uT;     /* uniform knots, as in PdebPwl */
-    double rstep;         /* uniform knots: 1 / ustep */
-    double dt, rdt;       /* time step and its reciprocal */
-    real scale;
-    /* shared, + tid: slot[0] value of knot j+1, slot[STRIDE] its time (explicit knot times only) */
-#if defined(__CUDA_ARCH__)
-    uint32_t slot;        /* shared-window address */
-#else
-    double* slot;
-#endif
-
-    PDEB_HD double knot_time(const double* kt, int q, int64_t stride) const {
-        if (kt) return kt[(int64_t)q * stride];
-        return (q == nk - 1 && nk > 1) ? uT : (double)q * ustep;
-    }
-    /* start the copy of knot q into the slot */
-    PDEB_HD void stage(const double* kt, const double* ky, int q, int64_t stride) {
-#if defined(__CUDA_ARCH__)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(slot), "l"(ky + (int64_t)q * stride) : "memory");
-        if (kt)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(slot + (uint32_t)(STRIDE * sizeof(double))),
-                         "l"(kt + (int64_t)q * stride) : "memory");
-#else
-        slot[0] = ky[(int64_t)q * stride];
-        if (kt) slot[STRIDE] = kt[(int64_t)q * stride];
-#endif
-    }
-    /* staged value (which = 0) or time (which = 1), once the copy has landed */
-    PDEB_HD double staged(int which) const {
-#if defined(__CUDA_ARCH__)
-        double v;
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(slot + (uint32_t)(which * STRIDE * sizeof(double))) : "memory");
-        return v;
-#else
-        return slot[which * STRIDE];
-#endif
-    }
-    /* first step k with (double)k * dt >= t: the rule `t_k >= knot` of PdebPwl / the oracle, as an integer */
-    PDEB_HD int32_t first_step_at(double t) const {
-        if (!(t < 4.0e9 * dt)) return 0x7fffffff;
-        double q = ceil(t * rdt);
-        if (!(q >= 0.0)) q = 0.0;
-        int32_t k = (int32_t)q;
-        while ((double)k * dt < t) ++k;                          /* the product with 1/dt may be an ulp off either way */
-        while (k > 0 && (double)(k - 1) * dt >= t) --k;
-        return k;
-    }
-    /*
-     * Step kn has reached the end of the current segment: move to the segment that holds t = kn dt (several knots may
-     * lie inside one step), re-form the scaled load there exactly, and its increment and next crossing step.
-     */
-    PDEB_HD void cross(int32_t kn, const double* kt, const double* ky, int64_t stride) {
-        const double t = (double)kn * dt;
-        real t0 = 0, y0 = 0, slope = 0;
-        while (t >= t1) {
-            t0 = (real)t1; y0 = y1;
-            double tn = INFINITY;
-            real yn = 0;
-            if (j + 1 < nk) {
-                yn = (real)staged(0);
-                tn = kt ? staged(1) : knot_time(nullptr, j + 1, 0);
-            }
-            if (tn < INFINITY) {
-                slope = (real)(((double)yn - (double)y1) * (kt ? pdeb_rcp(tn - t1) : rstep));
-                t1 = tn; y1 = yn;
-                ++j;
-                if (j + 1 < nk) stage(kt, ky, j + 1, stride);
-            } else { slope = 0; t1 = INFINITY; }
-        }
-        f_exact = fma(slope, (real)(t - (double)t0), y0);
-        g = scale * f_exact;
-        dg = scale * (slope * (real)dt);
-        kx = first_step_at(t1);
-    }
-    /* set-up: the load at step 0.  scale_ = s_N (known after the factorisation). */
-    PDEB_HD void init(const double* kt, const double* ky, int nk_, int64_t stride, double T, double dt_, real scale_, double* slot_) {
-        nk = nk_; j = 0;
-#if defined(__CUDA_ARCH__)
-        slot = (uint32_t)__cvta_generic_to_shared(slot_);
-#else
-        slot = slot_;
-#endif
-        dt = dt_; rdt = 1.0 / dt_; scale = scale_;
-        uT = T; ustep = (nk > 1) ? T / (double)(nk - 1) : 0.0;
-        rstep = (nk > 1) ? pdeb_rcp(ustep) : 0.0;
-        y1 = 0; g = 0; dg = 0; f_exact = 0; t1 = INFINITY; kx = 0x7fffffff;
-        if (nk >= 1) {
-            y1 = (real)ky[0];
-            t1 = knot_time(kt, 0, stride);
-            f_exact = y1;
-            g = scale * y1;                          /* held at the first value before the first knot */
-            kx = first_step_at(t1);
-            if (nk >= 2) stage(kt, ky, 1, stride);
-            if (kx <= 0) cross(0, kt, ky, stride);
-        }
-    }
-    /* advance from step kn - 1 to step kn: returns g_kn (the scaled load at step kn) */
-    PDEB_HD real advance(int32_t kn, const double* kt, const double* ky, int64_t stride) {
-        if (kn >= kx) cross(kn, kt, ky, stride);
-        else g += dg;
-        return g;
-    }
-};
-#if !PDEB_LOAD_SEQ
-/*
  * The same input for the register family, with the NEXT knot staged in shared memory.
  * In that family the lanes of a warp cross their knots at different steps, so a warp runs the crossing code in about
  * half of its steps, and a knot fetched into a register there stalls the whole warp for a global-memory latency: the
@@ -438,7 +303,6 @@ struct PdebPwlStaged {
         return fma(slope, (real)(t - (double)t0), y0);
     }
 };
-#endif
 #define PDEB_PWL_SLOT_BYTES (2 * sizeof(double))   /* per thread */
 
 struct alignas(16) PdebD2 { double x, y; };
@@ -944,13 +808,8 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
 #if PDEB_C_SMEM
     tr.ctab = ctab;
 #endif
-#if PDEB_LOAD_SEQ
-    PdebLoadStaged<real, STRIDE> in;
-    in.init(nullptr, nullptr, 0, 0, 0.0, 1.0, (real)0, pwl_slot);
-#else
     PdebPwlStaged<real, STRIDE> in;
     in.init(nullptr, nullptr, 0, 0, 0.0, pwl_slot);
-#endif
     uint32_t evw = 0x100u;     /* the NEXT window event of this lane (clause-slot cell 6); none yet */
     int32_t next_ev = 0x7fffffff;
     int evi = 0;
@@ -991,16 +850,11 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
             const double cR = (1.0 - cv.theta) * dt;
             const bool ok = tr.setup(L, x_a, x_b, rho_in, rho_out, E_in, E_out, lumped, cv.material_sampling, cA, cR);
             if (!ok) status = PDEB_ST_NONFINITE;
-#if PDEB_LOAD_SEQ
-            if (ok) in.init(kt, ky, nk, st, T, dt, tr.sN, pwl_slot);
-            if (KIND == PDEB_KIND_WAVE && ok) tr.wave_init(h, g0, (double)in.f_exact, rho_in, rho_out, E_in, E_out, lumped);
-#else
             in.init(kt, ky, nk, st, T, pwl_slot);
             if (KIND == PDEB_KIND_WAVE && ok) {
                 const double f0 = (double)in.eval(0.0, kt, ky, st);
                 tr.wave_init(h, g0, f0, rho_in, rho_out, E_in, E_out, lumped);
             }
-#endif
         }
         if (status != PDEB_OK) { S = 0; np = 0; }
         int32_t k_end = 0;         /* last step any clause observes: nothing after it can change the result */
@@ -1064,9 +918,7 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
 #endif
     }
 
-#if !PDEB_LOAD_SEQ
     real f_prev = in.eval(0.0, kt, ky, st);
-#endif
     uint32_t open = 0;        /* bit j: step k is inside clause j's window */
     int cur = 0;              /* lowest open clause (0 when none is open) */
     /* what this lane needs from the pass of the current step: bit 0 a clause is open, bit 1 more than one is,
@@ -1191,19 +1043,10 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
         wf = PDEB_WARP_OR(flags);
         /* ---- (2) advance to step k+1 (lanes that are done keep stepping; nobody looks at them) ---- */
         {
-#if PDEB_LOAD_SEQ
-            const real g_prev = in.g;                                       /* s_N f(t_k) */
-            const real g_next = in.advance(k + 1, kt, ky, st);              /* s_N f(t_k+1) */
-#else
             const real f_next = in.eval((double)(k + 1) * dt, kt, ky, st);
-#endif
             if (KIND == PDEB_KIND_HEAT) {
                 const real th_dt = (real)(cv.theta * dt);
-#if PDEB_LOAD_SEQ
-                const real fb = fma((real)dt - th_dt, g_prev, th_dt * g_next);
-#else
                 const real fb = tr.sN * fma((real)dt - th_dt, f_prev, th_dt * f_next);
-#endif
                 real z[N + 2];
                 z[0] = 0; z[N + 1] = 0;
                 tr.step_solve(tr.w, fb, z);
@@ -1218,11 +1061,7 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
                     tr.w[i] = fma(cw2, tr.a[i], fma(cw1, tr.v[i], tr.w[i]));   /* predictor d~ */
                     tr.v[i] = fma(cw3, tr.a[i], tr.v[i]);                       /* predictor v~ */
                 }
-#if PDEB_LOAD_SEQ
-                tr.step_solve(tr.w, g_next, tr.a);                              /* a' = A^-1 (f' e_N - K d~), scaled */
-#else
-                tr.step_solve(tr.w, tr.sN * f_next, tr.a);
-#endif
+                tr.step_solve(tr.w, tr.sN * f_next, tr.a);                      /* a' = A^-1 (f' e_N - K d~), scaled */
                 const real cw4 = (real)(cv.newmark_beta * dt * dt);
                 const real cw5 = (real)(cv.newmark_gamma * dt);
                 PDEB_UNROLL
@@ -1231,9 +1070,7 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
                     tr.v[i] = fma(cw5, tr.a[i], tr.v[i]);
                 }
             }
-#if !PDEB_LOAD_SEQ
             f_prev = f_next;
-#endif
         }
     }
 

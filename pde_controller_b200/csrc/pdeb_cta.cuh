@@ -67,15 +67,16 @@ struct PdebCtaShared {
 template <int KIND>
 __global__ void __launch_bounds__(PDEB_CTA_THREADS, PDEB_CTA_MINBLOCKS)
 pdeb_cta_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant__ PdebConventions cv,
-                const __grid_constant__ PdebDevOut out, const int32_t* __restrict__ order, int64_t first, int64_t count) {
+                const __grid_constant__ PdebDevOut out, const int32_t* __restrict__ order, int64_t first, int64_t count,
+                  int gather) {
     static_assert(KIND == PDEB_KIND_HEAT, "the CTA family is instantiated for the heat equation");
     constexpr int R = PDEB_CTA_R, NT = PDEB_CTA_THREADS, CAP = PDEB_CTA_CAP, M = R / 2;
     __shared__ PdebCtaShared sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t t = blockIdx.x;
     if (t >= count) return;
-    const int64_t s = first + t;                   /* position in the plan-ordered input image */
     const int64_t so = order[first + t];           /* the sample's index in the caller's order: outputs */
+    const int64_t s = gather ? so : first + t;     /* inputs: the image as uploaded, or the plan-ordered image */
     const int64_t st = b.stride;
 
     /* ---- parameters (block-uniform) ---- */

@@ -21,14 +21,17 @@
 template <int KIND, int N, typename real>
 __global__ void PDEB_REG_BOUNDS
 pdeb_reg_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant__ PdebConventions cv,
-                const __grid_constant__ PdebDevOut out, const int32_t* __restrict__ order, int64_t first, int64_t count) {
+                const __grid_constant__ PdebDevOut out, const int32_t* __restrict__ order, int64_t first, int64_t count,
+                int gather) {
     extern __shared__ __align__(16) unsigned char pdeb_smem[];
     const int64_t t = (int64_t)blockIdx.x * PDEB_REG_THREADS + threadIdx.x;
     const bool live = t < count;                      /* padding lanes of the last warp idle through the loop */
-    /* `b` is the PLAN-ORDERED image: thread t of this launch reads position first + t of every array (consecutive lanes,
-     * consecutive addresses) and writes its results to the sample's own index order[first + t] */
-    const int64_t s = live ? first + t : 0;
+    /* gather = 0: `b` is the PLAN-ORDERED image: thread t of this launch reads position first + t of every array
+     * (consecutive lanes, consecutive addresses); gather = 1: `b` is the image as uploaded and the thread reads its
+     * sample's own index (a batch that is evaluated once is not worth permuting).  Results always go to the sample's own
+     * index order[first + t]. */
     const int64_t so = live ? (int64_t)order[first + t] : 0;
+    const int64_t s = live ? (gather ? so : first + t) : 0;
     typedef typename PdebVec2<real>::type real2;
     real2* table = reinterpret_cast<real2*>(pdeb_smem) + threadIdx.x;
     PdebClauseSlots<real, PDEB_REG_THREADS> slots = pdeb_clause_slots<real, PDEB_REG_THREADS>(
@@ -185,7 +188,7 @@ int pdeb_plan(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut
 
 template <int KIND, int N, typename real>
 static cudaError_t launch_reg(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out,
-                              const int32_t* order, int64_t first, int64_t count, cudaStream_t stream) {
+                              const int32_t* order, int64_t first, int64_t count, int gather, cudaStream_t stream) {
     if (count <= 0) return cudaSuccess;
     const size_t smem = pdeb_table_smem_bytes<real>(PDEB_REG_THREADS, N, KIND) + pdeb_clause_smem_bytes<real>(PDEB_REG_THREADS, b.pmax) +
                         PDEB_PWL_SLOT_BYTES * PDEB_REG_THREADS;
@@ -195,7 +198,7 @@ static cudaError_t launch_reg(const PdebDevBatch& b, const PdebConventions& cv, 
         if (e != cudaSuccess) return e;
     }
     const int64_t blocks = (count + PDEB_REG_THREADS - 1) / PDEB_REG_THREADS;
-    kern<<<(unsigned)blocks, PDEB_REG_THREADS, smem, stream>>>(b, cv, out, order, first, count);
+    kern<<<(unsigned)blocks, PDEB_REG_THREADS, smem, stream>>>(b, cv, out, order, first, count, gather);
     return cudaGetLastError();
 }
 
@@ -233,24 +236,24 @@ static PdebSidePool* side_pool() {
 }
 
 static cudaError_t launch_variant(int v, const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out,
-                                  const PdebPlanBuffers& pb, int64_t first, int64_t count, int precision, cudaStream_t stream) {
+                                  const PdebPlanBuffers& pb, int64_t first, int64_t count, int precision, int gather, cudaStream_t stream) {
     switch (v) {
     case 0:
-        return (precision == 32) ? launch_reg<PDEB_KIND_HEAT, 30, float>(b, cv, out, pb.order, first, count, stream)
-                                 : launch_reg<PDEB_KIND_HEAT, 30, double>(b, cv, out, pb.order, first, count, stream);
+        return (precision == 32) ? launch_reg<PDEB_KIND_HEAT, 30, float>(b, cv, out, pb.order, first, count, gather, stream)
+                                 : launch_reg<PDEB_KIND_HEAT, 30, double>(b, cv, out, pb.order, first, count, gather, stream);
     case 1:
-        return (precision == 32) ? launch_reg<PDEB_KIND_WAVE, 20, float>(b, cv, out, pb.order, first, count, stream)
-                                 : launch_reg<PDEB_KIND_WAVE, 20, double>(b, cv, out, pb.order, first, count, stream);
+        return (precision == 32) ? launch_reg<PDEB_KIND_WAVE, 20, float>(b, cv, out, pb.order, first, count, gather, stream)
+                                 : launch_reg<PDEB_KIND_WAVE, 20, double>(b, cv, out, pb.order, first, count, gather, stream);
     default:
-        if (v >= 2 && v <= 7) return pdeb_launch_chunk_heat(1 << (v - 2), b, cv, out, pb.order, first, count, stream);
-        if (v >= 8 && v <= 12) return pdeb_launch_chunk_wave(1 << (v - 8), b, cv, out, pb.order, first, count, stream);
-        if (v == PDEB_VARIANT_CTA_HEAT) return pdeb_launch_cta_heat(b, cv, out, pb.order, first, count, stream);
+        if (v >= 2 && v <= 7) return pdeb_launch_chunk_heat(1 << (v - 2), b, cv, out, pb.order, first, count, gather, stream);
+        if (v >= 8 && v <= 12) return pdeb_launch_chunk_wave(1 << (v - 8), b, cv, out, pb.order, first, count, gather, stream);
+        if (v == PDEB_VARIANT_CTA_HEAT) return pdeb_launch_cta_heat(b, cv, out, pb.order, first, count, gather, stream);
         return cudaSuccess;
     }
 }
 
 int pdeb_launch_all(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out, const PdebPlanBuffers& pb,
-                    const int32_t* vstart_count_host, int precision, cudaStream_t stream, int* launches) {
+                    const int32_t* vstart_count_host, int precision, int gather, cudaStream_t stream, int* launches) {
     int live[PDEB_NUM_VARIANTS], nlive = 0;
     for (int v = 0; v < PDEB_NUM_VARIANTS; ++v) if (vstart_count_host[2 * v + 1] > 0) live[nlive++] = v;
     /* a stream that is being captured into a graph cannot be forked this way: keep those on one stream */
@@ -275,7 +278,7 @@ int pdeb_launch_all(const PdebDevBatch& b, const PdebConventions& cv, const Pdeb
             e = cudaStreamWaitEvent(st, pool->fork, 0);
             if (e != cudaSuccess) break;
         }
-        e = launch_variant(v, b, cv, out, pb, first, count, precision, st);
+        e = launch_variant(v, b, cv, out, pb, first, count, precision, gather, st);
         if (st != stream && e == cudaSuccess) {
             e = cudaEventRecord(pool->join[used], st);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, pool->join[used], 0);

@@ -119,12 +119,14 @@ __device__ __forceinline__ void pdeb_plan_count(const PdebDevBatch& b, const Pde
 }
 #endif
 
+/* gather: 0 = `b` is the plan-ordered image (thread t reads position first + t), 1 = `b` is the image as uploaded
+ * (thread t reads its sample's own index order[first + t]) */
 cudaError_t pdeb_launch_chunk_heat(int R, const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out,
-                                   const int32_t* order, int64_t first, int64_t count, cudaStream_t stream);
+                                   const int32_t* order, int64_t first, int64_t count, int gather, cudaStream_t stream);
 cudaError_t pdeb_launch_cta_heat(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out,
-                                 const int32_t* order, int64_t first, int64_t count, cudaStream_t stream);
+                                 const int32_t* order, int64_t first, int64_t count, int gather, cudaStream_t stream);
 cudaError_t pdeb_launch_chunk_wave(int R, const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out,
-                                   const int32_t* order, int64_t first, int64_t count, cudaStream_t stream);
+                                   const int32_t* order, int64_t first, int64_t count, int gather, cudaStream_t stream);
 
 /* device scratch of the plan (owned by the resident batch) */
 struct PdebPlanBuffers {
@@ -144,8 +146,8 @@ int pdeb_plan(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut
 int pdeb_permute(const PdebDevBatch& src, const PdebDevBatch& dst, const int32_t* order, int64_t count, bool knots_only,
                  cudaStream_t stream);
 
-/* enqueue the compute kernels of every non-empty variant over the PLAN-ORDERED image `b`; returns 0 or a cudaError_t value */
+/* enqueue the compute kernels of every non-empty variant over the image `b` (gather: see above); returns 0 or a cudaError_t value */
 int pdeb_launch_all(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out, const PdebPlanBuffers& pb,
-                    const int32_t* vstart_count_host, int precision, cudaStream_t stream, int* launches);
+                    const int32_t* vstart_count_host, int precision, int gather, cudaStream_t stream, int* launches);
 
 #endif
