@@ -502,8 +502,10 @@ def _fast_regex():
 _FAST = _fast_regex()
 # an integer literal with a leading zero ("02298576") is a SyntaxError for Python (2 and 3 alike; "0123.5", "1e-06" and
 # "00" are fine): the template matcher must not accept what the interpreter of the dialect rejects
+_ZERO_DIGIT = re.compile(r"[^\w.]0\d")
 _LEADING_ZERO_INT = re.compile(r"(?<![\w.])(?<![eE][-+])0\d*[1-9]\d*(?![\d.eE])")
 _FAST_APC = re.compile(rf"apc(\d) = logic\.APCont\(\[({_RE_NUM}), ({_RE_NUM})\], \"([<>=])\", lambda x: ({_RE_NUM}) \* x \+ ({_RE_NUM}), lambda x: {_RE_NUM}\)")
+_FAST_JOIN = re.compile(r"\)\) ([&|]) \(")
 _FAST_CLAUSE = re.compile(rf"\(([GF])_\[({_RE_NUM}), ({_RE_NUM})\] \(([A-H])\)\)")
 
 
@@ -512,7 +514,11 @@ def _parse_fast(src: str) -> Optional[Problem]:
     if len(src) > 8192:
         return None
     m = _FAST.fullmatch(src)
-    if m is None or _LEADING_ZERO_INT.search(src):
+    if m is None:
+        return None
+    # leading-zero integers: the lookbehind scan costs more than the template match, so it only runs on texts that hold
+    # a zero followed by a digit after a non-digit at all (a cheap necessary condition)
+    if _ZERO_DIGIT.search(src) and _LEADING_ZERO_INT.search(src):
         return None
     heat = m["sys"].startswith("fosys")
     if m["imod"] is not None and (m["imod"] == "heatlinfem") != heat:
@@ -540,11 +546,16 @@ def _parse_fast(src: str) -> Optional[Problem]:
     if len(cl) != P or "".join(c[3] for c in cl) != labels:
         return None
     parts = [f"({c[0]}_[{c[1]}, {c[2]}] ({c[3]}))" for c in cl]
+    # the joins, in order; the structure is then CHECKED by rebuilding the text: left-nested with those operators
+    # ((A op B) op C), or flat with "&" only -- the spelling of the reference's records: ((A) & (B) & (C)), ((A))
+    ops = _FAST_JOIN.findall(spec)
+    if len(ops) != P - 1:
+        return None
     nested = parts[0]
-    for q in parts[1:]:
-        nested = f"({nested} & {q})"
-    flat = "(" + " & ".join(parts) + ")"          # the spelling of the reference's records: ((A) & (B) & (C)), ((A))
-    if spec != nested and spec != flat:
+    for q, op in zip(parts[1:], ops):
+        nested = f"({nested} {op} {q})"
+    flat = "(" + " & ".join(parts) + ")"
+    if spec != nested and not (spec == flat and all(op == "&" for op in ops)):
         return None
     preds, tree = [], []
     for j, (a, c) in enumerate(zip(apcs, cl)):
@@ -554,7 +565,7 @@ def _parse_fast(src: str) -> Optional[Problem]:
         preds.append(Predicate(x_lo, x_hi, a[3], f(a[4]), f(a[5]), c[0], t_lo, t_hi, labels[j]))
         tree.append(("leaf", j, 0))
         if j >= 1:
-            tree.append(("and", 0 if j == 1 else len(tree) - 2, len(tree) - 1))
+            tree.append(("and" if ops[j - 1] == "&" else "or", 0 if j == 1 else len(tree) - 2, len(tree) - 1))
     return Problem("heat" if heat else "wave", N, L, dt, T, g0, x_a, x_b, rho_in, rho_out, E_in, E_out, preds, tree)
 
 
@@ -580,7 +591,9 @@ def _parse_program(text: str, fast: Optional[bool] = None) -> Problem:
     only; True = template matcher only (ParseError if the text is not the template; used by the tests)."""
     if not isinstance(text, str):
         raise ParseError("program is not text")
-    src = textwrap.dedent(text.replace("\x00", "")).strip()
+    src = text.replace("\x00", "") if "\x00" in text else text
+    # common leading whitespace is removed only where there is any (dedent is a quarter of the template route's time)
+    src = (textwrap.dedent(src) if (src[:1] in " \t" or "\n " in src or "\n\t" in src) else src).strip()
     if fast is None or fast:
         p = _parse_fast(src)
         if p is not None:

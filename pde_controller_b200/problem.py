@@ -73,6 +73,7 @@ def default_knot_times(p: Problem) -> np.ndarray:
     return np.linspace(0.0, p.T, k)
 
 
+_F8 = np.dtype(np.float64)      # native float64 arrays share this dtype object: an identity test, not a comparison
 _F64 = ["L", "dt", "T", "g0", "x_a", "x_b", "rho_in", "rho_out", "E_in", "E_out"]
 _PRED_F64 = ["pred_xlo", "pred_xhi", "pred_m", "pred_b", "pred_tlo", "pred_thi"]
 _PLANAR = set(["knot_t", "knot_y", "pred_rel", "pred_top", "tree_op", "tree_lhs", "tree_rhs"] + _PRED_F64)
@@ -165,8 +166,10 @@ class ProblemBatch:
                 ctrl.append((np.zeros(0), np.zeros(0)))
             else:
                 t, y = c
-                t = np.asarray(t, dtype=np.float64).ravel()
-                y = np.asarray(y, dtype=np.float64).ravel()
+                if not (type(t) is np.ndarray and type(y) is np.ndarray and t.dtype is _F8 and y.dtype is _F8
+                        and t.ndim == 1 and y.ndim == 1):
+                    t = np.asarray(t, dtype=np.float64).ravel()
+                    y = np.asarray(y, dtype=np.float64).ravel()
                 if t.shape != y.shape:
                     raise ValueError("control knot times and values differ in length")
                 ctrl.append((t, y))
@@ -177,8 +180,47 @@ class ProblemBatch:
         tmax = max([len(p.tree) if p.tree else 2 * len(p.predicates) - 1 for p in problems] + [1])
         tmax = max(tmax, 2 * pmax - 1)
         b = cls(n, kmax, pmax, tmax)
-        for s, p in enumerate(problems):
-            b.set_problem(s, p, ctrl[s])
+        if n < 64:
+            for s, p in enumerate(problems):
+                b.set_problem(s, p, ctrl[s])
+            return b
+        # long lists: whole columns at a time (the per-sample route costs ~17 us a sample in the interpreter, which
+        # would put the batch assembly, not the parser workers, on the critical path of eval_robustness_batch)
+        b.kind[:] = [abi.KIND_HEAT if p.kind == "heat" else abi.KIND_WAVE for p in problems]
+        b.n_elem[:] = [p.n_elem for p in problems]
+        import operator
+        for f in _F64:
+            getattr(b, f)[:] = np.fromiter(map(operator.attrgetter(f), problems), dtype=np.float64, count=n)
+        preds = [p.predicates for p in problems]
+        cnt = np.fromiter(map(len, preds), dtype=np.int64, count=n)
+        if cnt.max(initial=0) > pmax:
+            raise ValueError("too many predicates for this batch")
+        b.n_pred[:] = cnt
+        flat = [q for ps in preds for q in ps]                       # sample-major, the order a [n, pmax] mask walks
+        m = np.arange(pmax)[None, :] < cnt[:, None]
+        tot = len(flat)
+        for name, attr in (("pred_xlo", "x_lo"), ("pred_xhi", "x_hi"), ("pred_m", "m"), ("pred_b", "b"),
+                           ("pred_tlo", "t_lo"), ("pred_thi", "t_hi")):
+            getattr(b, name).T[m] = np.fromiter(map(operator.attrgetter(attr), flat), dtype=np.float64, count=tot)
+        b.pred_rel.T[m] = np.fromiter((abi.REL_CODE[q.rel] for q in flat), dtype=np.uint8, count=tot)
+        b.pred_top.T[m] = np.fromiter((abi.TOP_CODE[q.top] for q in flat), dtype=np.uint8, count=tot)
+        trees = [p.tree if p.tree else p.default_tree() for p in problems]
+        tcnt = np.fromiter(map(len, trees), dtype=np.int64, count=n)
+        if tcnt.max(initial=0) > tmax:
+            raise ValueError("formula tree too large for this batch")
+        b.n_tree[:] = tcnt
+        tm = np.arange(tmax)[None, :] < tcnt[:, None]
+        tflat = [t for tr in trees for t in tr]
+        ttot = len(tflat)
+        b.tree_op.T[tm] = np.fromiter((_TREE_OPS[t[0]] for t in tflat), dtype=np.uint8, count=ttot)
+        b.tree_lhs.T[tm] = np.fromiter((t[1] for t in tflat), dtype=np.int8, count=ttot)
+        b.tree_rhs.T[tm] = np.fromiter((t[2] for t in tflat), dtype=np.int8, count=ttot)
+        kcnt = np.fromiter((len(t) for t, _ in ctrl), dtype=np.int64, count=n)
+        b.n_knots[:] = kcnt
+        if kcnt.sum() > 0:
+            km = np.arange(kmax)[None, :] < kcnt[:, None]
+            b.knot_t.T[km] = np.concatenate([t for t, _ in ctrl])
+            b.knot_y.T[km] = np.concatenate([y for _, y in ctrl])
         return b
 
     def set_problem(self, s: int, p: Problem, control=None):
