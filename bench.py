@@ -381,6 +381,7 @@ def main():
     ap.add_argument("--no-text", action="store_true", help="skip the text-level end-to-end leg (e2e_text)")
     ap.add_argument("--text-programs", type=int, default=8192, help="programs of the text-level leg")
     ap.add_argument("--no-configs", action="store_true", help="skip the device-timed rates of the other BASELINE configs")
+    ap.add_argument("--e2e-planar-only", action="store_true", help="skip the two packed end-to-end legs (long-running workloads)")
     args = ap.parse_args()
     if args.batch is None:
         args.batch = DEFAULT_BATCH[args.workload]
@@ -517,10 +518,12 @@ def main():
     res.fetch(stream=stream, out=out_host)
     e2e, ok_a = e2e_route(packed=False, pack_inside=False)
     e2e["route"] = "planar PdebBatch slab, one H2D copy per block; nothing prepared outside the timed region"
-    e2e_packed, ok_b = e2e_route(packed=True, pack_inside=True)
-    e2e_packed["route"] = "pdeb_pack_batch (host, inside the timed region) -> packed H2D -> device-side unpack"
-    e2e_prepacked, ok_c = e2e_route(packed=True, pack_inside=False)
-    e2e_prepacked["route"] = "PdebPackedBatch produced outside the timed region -> packed H2D -> device-side unpack"
+    e2e_packed, e2e_prepacked, ok_b, ok_c = None, None, True, True
+    if not args.e2e_planar_only:
+        e2e_packed, ok_b = e2e_route(packed=True, pack_inside=True)
+        e2e_packed["route"] = "pdeb_pack_batch (host, inside the timed region) -> packed H2D -> device-side unpack"
+        e2e_prepacked, ok_c = e2e_route(packed=True, pack_inside=False)
+        e2e_prepacked["route"] = "PdebPackedBatch produced outside the timed region -> packed H2D -> device-side unpack"
     if not (ok_a and ok_b and ok_c):
         raise SystemExit("bench: pipelined end-to-end results differ from the resident evaluation")
 
@@ -583,7 +586,7 @@ def main():
             "detail": {"gather": bool(rob_t is not None), "failed_samples": n_fail,
                        "knots": "uniform (formed on device)" if uk else "explicit", "e2e_block": args.e2e_block,
                        "e2e_pipeline_depth": E2E_DEPTH, "wall_s_timed_region": wall1 - wall0},
-            "e2e": e2e, "e2e_packed": e2e_packed, "e2e_prepacked": e2e_prepacked,
+            "e2e": e2e,
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -592,6 +595,8 @@ def main():
                          "note": "fused kernel is FP64-issue bound by design (state never leaves registers); see DESIGN.md"},
             "roofline_fp64": fp64,
         }
+        if e2e_packed is not None:
+            line["e2e_packed"], line["e2e_prepacked"] = e2e_packed, e2e_prepacked
         if e2e_text is not None:
             line["e2e_text"] = e2e_text
         if configs:
