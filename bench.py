@@ -379,7 +379,7 @@ def main():
     ap.add_argument("--e2e-block", type=int, default=65536, help="samples per block of the end-to-end pipeline")
     ap.add_argument("--explicit-knots", action="store_true", help="carry per-sample knot times instead of uniform knots")
     ap.add_argument("--no-text", action="store_true", help="skip the text-level end-to-end leg (e2e_text)")
-    ap.add_argument("--text-programs", type=int, default=8192, help="programs of the text-level leg")
+    ap.add_argument("--text-programs", type=int, default=32768, help="programs of the text-level leg")
     ap.add_argument("--no-configs", action="store_true", help="skip the device-timed rates of the other BASELINE configs")
     ap.add_argument("--e2e-planar-only", action="store_true", help="skip the two packed end-to-end legs (long-running workloads)")
     args = ap.parse_args()
@@ -546,8 +546,9 @@ def main():
         if not np.array_equal(np.array(rob_text), out_host["robustness"][:m]):
             raise SystemExit("bench: text-level results differ from the resident evaluation")
         e2e_text = {"value": m / secs, "unit": "programs/s", "programs": m, "cores": os.cpu_count(),
-                    "route": "eval_robustness_batch(program strings, given controls): parse (worker processes) -> "
-                             "PdebBatch -> pdeb_eval_batch -> robustness list"}
+                    "route": "eval_robustness_batch(program strings, given controls): native template matcher "
+                             "(pdeb_parse_programs, host threads; anything else -> Python front-end) -> PdebBatch -> "
+                             "pdeb_eval_batch -> robustness list"}
 
     # ---- the other single-GPU configurations of BASELINE.json, device-timed like `value` (configs 3, 5, 4) ----
     configs = {}

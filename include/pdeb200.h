@@ -297,6 +297,18 @@ int  pdeb_controls_eval(PdebControls* h, int64_t m, const double* knot_y, double
                         int32_t* status_out, int64_t* best_index, double* best_value, void* stream, PdebTiming* timing);
 void pdeb_controls_destroy(PdebControls* h);
 
+/*
+ * Native front-end for the CANONICAL program template (host only).  The reference's call surface is program TEXT
+ * (eval_robustness_helper(program, nl), eval/eval_script.py:43-79), and every program of its records is the same dozen
+ * lines with different numbers (utils/few_shot_prompts/examples/one_d_heat/examples.jsonl:1-3, ...).  Program i of `texts`
+ * (`lengths[i]` bytes, need not be NUL-terminated) that IS that template is parsed, never executed, straight into sample
+ * first + i of `out` (the PdebBatch arrays must be writable host memory; n_knots / knot_* are not touched: the control
+ * input is the caller's) and accepted[i] = 1; any other text leaves accepted[i] = 0 and is the business of the general
+ * front-end (pde_controller_b200/frontend.py), which this matcher never contradicts.  nthreads <= 0: all host threads.
+ */
+int  pdeb_parse_programs(const char* const* texts, const int64_t* lengths, int64_t n, const PdebBatch* out, int64_t first,
+                         uint8_t* accepted, int nthreads);
+
 /* pinned host memory for batches that are uploaded every step */
 void* pdeb_host_alloc(int64_t bytes);
 void  pdeb_host_free(void* p);

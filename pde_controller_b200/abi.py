@@ -154,6 +154,7 @@ EXPORTS = [
     "pdeb_eval_batch",
     "pdeb_eval_batch_multi",
     "pdeb_shard_bounds",
+    "pdeb_parse_programs",
     "pdeb_cache_clear",
     "pdeb_resident_create",
     "pdeb_resident_upload",

@@ -96,26 +96,75 @@ def eval_robustness_batch(programs: Sequence[str], natural_language: Optional[Se
         raise ValueError("controls must have one entry per program")
     dev = _DEVICE if device is None else device
     conv = conventions if conventions is not None else _CONV
-    problems: List[Optional[Problem]] = []
     status = np.zeros(n, dtype=np.int32)
-    for i, (prob, _msg) in enumerate(parse_many(programs, workers=parse_workers)):
-        problems.append(prob)
-        if prob is None:
-            status[i] = abi.ST_PARSE
-    live = [i for i in range(n) if problems[i] is not None]
     rob = np.full(n, abi.FAILED_ROBUSTNESS, dtype=np.float64)
-    if live:
-        need = [i for i in live if controls[i] is None]
+    # ---- front-end: the native template matcher takes what is the canonical template (every record of the reference,
+    # ~1 us per program, no Python object), the Python front-end the rest (frontend.parse_many: worker processes)
+    from . import frontend as _fe
+    try:
+        wide, accepted = _fe.parse_native(programs)
+    except (native.NativeError, OSError):
+        wide, accepted = None, np.zeros(n, dtype=bool)
+    rest = np.nonzero(~accepted)[0]
+    rest_problems: List[Optional[Problem]] = []
+    if rest.size:
+        for prob, _msg in parse_many([programs[i] for i in rest], workers=parse_workers):
+            rest_problems.append(prob)
+    bad = [int(i) for i, p in zip(rest, rest_problems) if p is None]
+    status[bad] = abi.ST_PARSE
+    ok_rest = [(int(i), p) for i, p in zip(rest, rest_problems) if p is not None]
+    live = np.ones(n, dtype=bool)
+    live[bad] = False
+    if live.any():
+        # ---- one batch of all n samples (a program that did not parse keeps a place and is masked out afterwards) ----
+        pmax = int(max([int(wide.n_pred[accepted].max(initial=1)) if wide is not None else 1] + [len(p.predicates) for _, p in ok_rest] + [1]))
+        tmax = int(max([2 * pmax - 1] + [len(p.tree) for _, p in ok_rest]))
+        ctrl = [None] * n
+        need = []
+        for i in range(n):
+            c = controls[i]
+            if c is not None:
+                t, y = c
+                ctrl[i] = (np.asarray(t, dtype=np.float64).ravel(), np.asarray(y, dtype=np.float64).ravel())
+                if ctrl[i][0].shape != ctrl[i][1].shape:
+                    raise ValueError("control knot times and values differ in length")
+            elif live[i]:
+                need.append(i)
         if need and mode == "search":
             from . import search as _search
-            found = _search.search_controls([problems[i] for i in need], device=dev, conv=conv, **{**_SEARCH, **(search or {})})
+            by_index = dict(ok_rest)
+            probs = [by_index[i] if i in by_index else wide.get_problem(i)[0] for i in need]
+            found = _search.search_controls(probs, device=dev, conv=conv, **{**_SEARCH, **(search or {})})
             for i, f in zip(need, found):
-                controls[i] = (f["knot_t"], f["knot_y"]) if f["knot_y"] is not None else None
+                if f["knot_y"] is not None:
+                    ctrl[i] = (np.asarray(f["knot_t"], dtype=np.float64), np.asarray(f["knot_y"], dtype=np.float64))
+                    controls[i] = ctrl[i]
+        kmax = max([len(c[0]) for c in ctrl if c is not None] + [1])
+        batch = ProblemBatch(n, kmax, pmax, tmax)
+        if wide is not None:
+            for name in batch._names:
+                if name in ("knot_t", "knot_y", "n_knots"):
+                    continue
+                src, dst = getattr(wide, name), getattr(batch, name)
+                if src.ndim == 1:
+                    dst[:] = src
+                else:
+                    dst[...] = src[: dst.shape[0]]
+        for i, p in ok_rest:
+            batch.set_problem(i, p, None)
+        # a program that did not parse: a harmless place-holder (its results are overwritten below)
+        for i in bad:
+            batch.n_pred[i] = 0
+        cnt = np.fromiter((0 if c is None else len(c[0]) for c in ctrl), dtype=np.int64, count=n)
+        batch.n_knots[:] = cnt
+        if cnt.sum() > 0:
+            km = np.arange(kmax)[None, :] < cnt[:, None]
+            batch.knot_t.T[km] = np.concatenate([c[0] for c in ctrl if c is not None])
+            batch.knot_y.T[km] = np.concatenate([c[1] for c in ctrl if c is not None])
         # the number returned is ALWAYS the batch kernels' robustness under the control in `controls` (found or given)
-        batch = ProblemBatch.from_problems([problems[i] for i in live], [controls[i] for i in live])
         out = native.evaluate_batch(batch, device=dev, precision=_PRECISION if precision is None else precision, conv=conv)
-        rob[live] = out["robustness"]
-        status[live] = out["status"]
+        rob[live] = out["robustness"][live]
+        status[live] = out["status"][live]
     runtime = (time.perf_counter() - t0) / max(n, 1)
     res = ([float(r) for r in rob], [runtime] * n)
     if return_status:

@@ -47,6 +47,8 @@ def lib():
                                             C.c_void_p, C.c_void_p, C.c_void_p]
         L.pdeb_shard_bounds.restype = C.c_int
         L.pdeb_shard_bounds.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.pdeb_parse_programs.restype = C.c_int
+        L.pdeb_parse_programs.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
         L.pdeb_cache_clear.restype = None
         L.pdeb_cache_clear.argtypes = []
         L.pdeb_resident_create.restype = C.c_int

@@ -1,0 +1,147 @@
+"""Native template matcher (pdeb_parse_programs, csrc/pdeb_frontend.cpp) against the Python front-end.
+
+Contract under test: whatever the native matcher ACCEPTS, the Python template matcher accepts with identical values;
+what it declines is left to the Python front-end (never an error).  Host-only: no GPU needed."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+from pde_controller_b200 import synth
+from pde_controller_b200.frontend import ParseError, parse_native, parse_program, render_program
+from test_frontend import HEAT as _HEAT
+
+REF = "/root/reference"
+# test_frontend.HEAT spells one intercept as a sum ("+ -2.5e+2 + 560"): valid for the interpreter, not the template
+HEAT = _HEAT.replace("-2.5e+2 + 560", "310.0")
+assert parse_program(HEAT, fast=True) == parse_program(_HEAT)
+
+
+def native_problem(batch, i):
+    p, _ = batch.get_problem(i)
+    return p
+
+
+def same_problem(a, b):
+    """Problem equality up to the clause labels (the batch form does not carry them; get_problem names them A, B, ...)."""
+    return a == b
+
+
+def test_rendered_programs_are_accepted_and_read_identically():
+    texts = []
+    for wl, seed in (("heat", 2), ("wave", 3), ("mixed", 4)):
+        b = synth.make_batch(700, wl, seed=seed)
+        texts += [render_program(b.get_problem(s)[0]) for s in range(b.n)]
+    batch, acc = parse_native(texts, nthreads=4)
+    assert acc.all()
+    for i in range(0, len(texts), 7):
+        assert same_problem(native_problem(batch, i), parse_program(texts[i], fast=True)), i
+    # threads do not change the result
+    b1, a1 = parse_native(texts, nthreads=1)
+    assert np.array_equal(b1.slab, batch.slab) and np.array_equal(a1, acc)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference tree only exists in the build container")
+def test_every_reference_record_is_the_template():
+    texts = []
+    for f in sorted(glob.glob(os.path.join(REF, "utils/few_shot_prompts/examples/*/examples.jsonl"))):
+        for line in open(f):
+            rec = json.loads(line)
+            texts += [rec[k] for k in sorted(rec) if "python" in k]
+    assert len(texts) == 14
+    batch, acc = parse_native(texts)
+    assert acc.all()
+    for i, t in enumerate(texts):
+        assert same_problem(native_problem(batch, i), parse_program(t))
+
+
+@pytest.mark.parametrize("mutate", [
+    lambda t: t.replace("N = 30", "N = 030"),                         # leading-zero integer: SyntaxError for the interpreter
+    lambda t: t.replace("L = 140", "L = 0140"),
+    lambda t: t.replace("[11, 40]", "[011, 40]"),
+    lambda t: t.replace("T = 9", "T = 9\x00"),
+    lambda t: t.replace("\n", "\r\n"),
+    lambda t: "\n".join("    " + l for l in t.strip().split("\n")),   # indented: dedent is the Python route's job
+    lambda t: t.replace("N = 30", "N = 15 * 2"),
+    lambda t: t.replace('"A" : apc0', '"A":apc0'),
+    lambda t: t.replace("x < 21 or x > 77 else 1420000", "x < 22 or x > 77 else 1420000"),   # E thresholds differ from rho's
+    lambda t: t.replace("(A)) &", "(B)) &"),
+    lambda t: t.replace("dt = .05", "dt = 0"),
+    lambda t: t.replace("[11, 40]", "[40, 11]"),
+    lambda t: t.replace("N = 30", "N = 1"),
+    lambda t: t.replace("apc1 = ", "apc2 = "),
+    lambda t: t + "\nprint(1)",
+    lambda t: t.replace("fosys = heatlinfem.heatlinfem_mix", "sosys = mechlinfem.mechlinfem"),   # import says heat
+    lambda t: "",
+    lambda t: "x" * 20000,
+])
+def test_near_misses_are_declined_not_guessed(mutate):
+    text = mutate(HEAT)
+    batch, acc = parse_native([HEAT, text, HEAT])
+    assert list(acc) == [True, False, True]
+    assert same_problem(native_problem(batch, 2), parse_program(HEAT))
+
+
+def test_spellings_the_template_allows():
+    variants = [HEAT, HEAT.strip(), "\n\n" + HEAT + "\n\n  ", HEAT.replace("\n\n", "\n\n\n"),
+                HEAT.replace("from femformal.core.fem import heatlinfem as heatlinfem\n", ""),
+                HEAT.replace('cspec = "((F_[0.5, 2.25] (A)) & (G_[4.125, 7.5] (B)))"', 'cspec = "((F_[0.5, 2.25] (A)) | (G_[4.125, 7.5] (B)))"'),
+                HEAT.replace("L = 140", "L = 1.4e2").replace("g = [305, None]", "g = [+305., None]").replace("dt = .05", "dt = 5E-2")]
+    batch, acc = parse_native(variants)
+    assert acc.all()
+    for i, t in enumerate(variants):
+        assert same_problem(native_problem(batch, i), parse_program(t, fast=True)), i
+    assert native_problem(batch, 5).tree[-1][0] == "or"
+
+
+def test_more_clauses_than_the_batch_has_planes_are_declined():
+    p = synth.make_batch(1, "heat", seed=1).get_problem(0)[0]
+    while len(p.predicates) < 3:
+        p.predicates.append(p.predicates[0])
+    p.tree = p.default_tree()
+    t = render_program(p)
+    assert parse_native([t], pmax=8)[1].all()
+    assert not parse_native([t], pmax=2)[1].any()
+
+
+def test_fuzz_native_never_accepts_what_python_declines_or_reads_differently():
+    from hypothesis import HealthCheck, given, settings, strategies as st
+    wave = render_program(synth.make_batch(1, "wave", seed=3).get_problem(0)[0])
+    heat3 = render_program(synth.make_batch(40, "heat", seed=5).get_problem(17)[0])
+    alphabet = "0123456789.eE+-*/()[]{}<>=:,\"' \nxlambdaNLTgdtorifelsenp_GF&|AB#\\\x00\t\r"
+
+    @st.composite
+    def mutated(draw):
+        text = draw(st.sampled_from([HEAT, wave, heat3]))
+        for _ in range(draw(st.integers(0, 4))):
+            kind = draw(st.integers(0, 3))
+            i = draw(st.integers(0, max(len(text) - 1, 0)))
+            if kind == 0:
+                text = text[:i] + text[i + draw(st.integers(1, 6)):]
+            elif kind == 1:
+                text = text[:i] + draw(st.text(alphabet, max_size=6)) + text[i:]
+            elif kind == 2:
+                # rewrite one number: the commonest way two readers of the same text disagree
+                num = draw(st.sampled_from(["0", "00", "007", "1.", ".5", "1e3", "1E-2", "-2.5", "+3", "1e", "1e+", "0x10", "1_0",
+                                            "9" * 30, "1e999", "-0.0", "0.50", "05", "5e05", "٣"]))
+                j = text.find(" ", i)
+                text = text[:i] + num + (text[j:] if j >= 0 else "")
+            else:
+                lines = text.split("\n")
+                a, b = draw(st.integers(0, len(lines) - 1)), draw(st.integers(0, len(lines) - 1))
+                lines[a], lines[b] = lines[b], lines[a]
+                text = "\n".join(lines)
+        return text
+
+    @settings(max_examples=600, deadline=2000, suppress_health_check=[HealthCheck.too_slow])
+    @given(mutated())
+    def run(text):
+        batch, acc = parse_native([text])
+        if not acc[0]:
+            return
+        want = parse_program(text, fast=True)          # must not raise: the Python template matcher accepts it too
+        assert same_problem(native_problem(batch, 0), want)
+
+    run()
