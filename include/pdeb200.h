@@ -309,6 +309,34 @@ void pdeb_controls_destroy(PdebControls* h);
 int  pdeb_parse_programs(const char* const* texts, const int64_t* lengths, int64_t n, const PdebBatch* out, int64_t first,
                          uint8_t* accepted, int nthreads);
 
+/*
+ * Boolean grids of the reference's IoU metric between two sSTL formulas (eval_IOU, eval/eval_script.py:233-281;
+ * check_conditions :437-487; G_array / F_array :159-219), batched: for every clause and every linear test profile
+ * u(t) = m t + b, the bit per time step the reference's bit array holds.  The caller (pde_controller_b200/iou.py) parses
+ * the formulas, forms the time / position grids with the reference's own numpy calls and combines the clauses' arrays;
+ * this entry evaluates the ~1.4 M cells per clause, which the reference does with one Python eval() each.
+ *   clauses   one record per clause; `item` selects the grid set (one per formula pair)
+ *   tgrid     [n_items][2][tmax]  times: direction 0 = forwards (G clauses), 1 = backwards (F clauses), in iteration order
+ *   xgrid     [n_items][2][xmax]  positions, likewise
+ *   ngrid     [n_items][4]        lengths { nt forwards, nt backwards, nx forwards, nx backwards };  tmax <= 64
+ *   m_vals, b_vals                the profile grid; profile index = im * nb + ib  (itertools.product(m, b))
+ *   bits_out  [n_clauses][nm * nb][tmax]  0/1 per profile and time, times ASCENDING for both clause types
+ * Bit-exact with the reference: IEEE double operations in Python's order, no contraction.
+ */
+typedef struct PdebIouClause {
+    double t0, t1;          /* time interval of the clause */
+    double p0, p1;          /* position interval (the reference truncates its ends to integers) */
+    double coef, c, thr;    /* expr(x) = coef * x + c (PDEB_IOU_MUL) or x / coef + c (PDEB_IOU_DIV); no profile: coef = c = 0 */
+    int32_t item;
+    uint8_t kind, neg, op, backwards;   /* neg: x enters negated ("-x / 8"); op: PDEB_IOU_*; backwards: 1 for F clauses */
+} PdebIouClause;
+#define PDEB_IOU_MUL 0
+#define PDEB_IOU_DIV 1
+enum { PDEB_IOU_LE = 0, PDEB_IOU_LT, PDEB_IOU_GE, PDEB_IOU_GT, PDEB_IOU_EQ, PDEB_IOU_NE };
+int  pdeb_iou_grids(const PdebIouClause* clauses, int64_t n_clauses, const double* tgrid, const double* xgrid,
+                    const int32_t* ngrid, int64_t n_items, int32_t tmax, int32_t xmax, const double* m_vals, int32_t nm,
+                    const double* b_vals, int32_t nb, uint8_t* bits_out, int device, void* stream, PdebTiming* timing);
+
 /* pinned host memory for batches that are uploaded every step */
 void* pdeb_host_alloc(int64_t bytes);
 void  pdeb_host_free(void* p);

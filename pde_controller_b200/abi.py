@@ -146,6 +146,16 @@ class PdebTiming(C.Structure):
 
 
 # every symbol include/pdeb200.h declares (checked by tests/test_abi_symbols.py)
+class PdebIouClause(C.Structure):
+    """One clause of an IoU comparison (include/pdeb200.h)."""
+    _fields_ = [("t0", C.c_double), ("t1", C.c_double), ("p0", C.c_double), ("p1", C.c_double), ("coef", C.c_double),
+                ("c", C.c_double), ("thr", C.c_double), ("item", C.c_int32), ("kind", C.c_uint8), ("neg", C.c_uint8),
+                ("op", C.c_uint8), ("backwards", C.c_uint8)]
+
+
+IOU_MUL, IOU_DIV = 0, 1
+IOU_OP = {"<=": 0, "<": 1, ">=": 2, ">": 3, "=": 4, "!=": 5}
+
 EXPORTS = [
     "pdeb_version",
     "pdeb_device_count",
@@ -155,6 +165,7 @@ EXPORTS = [
     "pdeb_eval_batch_multi",
     "pdeb_shard_bounds",
     "pdeb_parse_programs",
+    "pdeb_iou_grids",
     "pdeb_cache_clear",
     "pdeb_resident_create",
     "pdeb_resident_upload",

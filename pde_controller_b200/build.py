@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libpdeb200.so")
-SOURCES = ["pdeb_api.cu", "pdeb_kernels.cu", "pdeb_chunk_heat.cu", "pdeb_chunk_wave.cu", "pdeb_cta_heat.cu", "pdeb_controls.cu", "pdeb_frontend.cpp"]
+SOURCES = ["pdeb_api.cu", "pdeb_kernels.cu", "pdeb_chunk_heat.cu", "pdeb_chunk_wave.cu", "pdeb_cta_heat.cu", "pdeb_controls.cu", "pdeb_iou.cu", "pdeb_frontend.cpp"]
 HEADERS = ["pdeb_core.h", "pdeb_launch.h", "pdeb_chunk.cuh", "pdeb_cta.cuh", os.path.join("..", "..", "include", "pdeb200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread"]

@@ -29,6 +29,7 @@ import numpy as np
 
 from . import abi, native
 from .frontend import ParseError, parse_many, parse_program  # noqa: F401
+from .iou import eval_IOU, eval_IOU_DPO, eval_IOU_batch  # noqa: F401  (eval_script.py:229-281 of the reference, on the GPU)
 from .problem import Problem, ProblemBatch
 
 _DEVICE = 0

@@ -49,6 +49,9 @@ def lib():
         L.pdeb_shard_bounds.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.pdeb_parse_programs.restype = C.c_int
         L.pdeb_parse_programs.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
+        L.pdeb_iou_grids.restype = C.c_int
+        L.pdeb_iou_grids.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.pdeb_cache_clear.restype = None
         L.pdeb_cache_clear.argtypes = []
         L.pdeb_resident_create.restype = C.c_int

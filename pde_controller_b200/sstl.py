@@ -65,6 +65,7 @@ def _match_clause(s: str, i: int):
         return None
     j = h.end()
     slope, icpt = 0.0, 0.0
+    form = ("mul", 0.0, False, 0.0)          # (kind, coefficient, x negated, constant): expr(x) as the text spells it
     if j < len(s) and s[j] == "-":
         # u(x) - ( PROFILE )
         k = j + 1
@@ -95,12 +96,17 @@ def _match_clause(s: str, i: int):
             slope = -slope
         if g.get("c") is not None:
             icpt = float(g["c"]) * (-1.0 if g["sgn"] == "-" else 1.0)
+        if g.get("d") is not None:
+            form = ("div", float(g["d"]), g.get("xs") == "-", icpt)
+        else:
+            form = ("mul", float(g["m"]), g.get("xs") == "-", icpt)
         j = hit.end() + 1
     r = _REL.match(s, j)
     if not r:
         return None
     out = {"top": h.group("top"), "t0": float(h.group("t0")), "t1": float(h.group("t1")), "a": float(h.group("a")),
            "b": float(h.group("b")), "slope": slope, "icpt": icpt, "rel": _rel(r.group("rel")), "thr": float(r.group("thr")),
+           "form": form, "op_raw": {"\\leq": "<=", "\\geq": ">=", "\\neq": "!="}.get(r.group("rel"), r.group("rel")),
            "text": s[i:r.end()].strip()}
     return r.end(), out
 
