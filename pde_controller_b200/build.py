@@ -29,7 +29,8 @@ def build(force=False, verbose=False, defines=(), out=None):
     for s in srcs:
         o = os.path.splitext(s)[0] + (".o" if out is None else "." + os.path.basename(out) + ".o")
         objs.append(o)
-        cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        # NVCC_EXTRA: extra compiler flags of an experimental variant (tools/variant_bench.py), e.g. "-Xptxas --opt-level=4"
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("NVCC_EXTRA", "").split() + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:
         out, _ = p.communicate()
