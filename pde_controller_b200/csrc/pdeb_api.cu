@@ -367,7 +367,7 @@ static int resident_alloc(const PdebBatch* in, int device, PdebResident** outp, 
     r->stride = n;
     PdebDevBatch& d = r->dev;
     d.n = n; d.stride = r->stride; d.kmax = in->kmax; d.pmax = in->pmax; d.tmax = in->tmax;
-    { const char* e = getenv("PDEB_CTA"); d.pad = (e && e[0] == '1') ? PDEB_FLAG_CTA : 0; }   /* opt-in kernel family (pdeb_launch.h) */
+    { const char* e = getenv("PDEB_CTA"); d.pad = (e && e[0] == '1') ? PDEB_FLAG_CTA : ((e && e[0] == '2') ? PDEB_FLAG_CTA2 : 0); }   /* opt-in kernel family (pdeb_launch.h) */
     const void* hostp[] = {in->kind, in->n_elem, in->L, in->dt, in->T, in->g0, in->x_a, in->x_b, in->rho_in, in->rho_out,
                            in->E_in, in->E_out, in->n_knots, in->knot_t, in->knot_y, in->n_pred, in->pred_xlo, in->pred_xhi,
                            in->pred_m, in->pred_b, in->pred_tlo, in->pred_thi, in->pred_rel, in->pred_top, in->n_tree,

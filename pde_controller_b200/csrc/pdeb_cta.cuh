@@ -25,8 +25,9 @@
  *   3. B0..B2 satisfy a 3 x 3 system whose inverse is precomputed; its right-hand side needs three numbers from every
  *      warp, exchanged through shared memory behind THE ONE block barrier of the step (double-buffered slots);
  *   4. interiors are corrected with the two spike vectors (2 FMA per row).
- * Values a lane needs from the neighbouring WARP between barriers (the separator in front of lane 0, the first row
- * behind lane 31) are kept as ghost copies that are advanced with the owner's own arithmetic, so they agree bit for bit.
+ * Between barriers a lane needs two things from the neighbouring WARP: the separator in front of lane 0 (kept as a ghost
+ * copy that is advanced with the owner's own arithmetic, so it agrees bit for bit) and, in the level-2 row of lane 31, the
+ * first row behind it (that term is contributed by its owner through the same exchange).
  *
  * STL: G clauses accumulate a per-lane running maximum over steps AND nodes (max is associative), reduced across the
  * block once, after the time loop; F clauses need the block-wide maximum of every step, which rides on the step's
@@ -39,23 +40,33 @@
 
 #include "pdeb_chunk.cuh"
 
-#define PDEB_CTA_THREADS 128
-#define PDEB_CTA_R 8
 #ifndef PDEB_CTA_MINBLOCKS
-#define PDEB_CTA_MINBLOCKS 3
+#define PDEB_CTA_MINBLOCKS 2      /* 4 x 8 shape: no register cap */
 #endif
-#define PDEB_CTA_CAP (PDEB_CTA_THREADS * (PDEB_CTA_R + 1) - 1)     /* positions: 1151 */
+#ifndef PDEB_CTA2_MINBLOCKS
+#define PDEB_CTA2_MINBLOCKS 4     /* 2 x 16 shape, 64 threads: no register cap (a 168-register build spills and is 1.6x slower) */
+#endif
 
+/*
+ * Shared memory of one block.  WARPS x R is the shape of the mapping: 4 x 8 (128 threads, every table in registers) or
+ * 2 x 16 (64 threads; the spike vectors and flux coefficients then live in per-lane columns of shared memory, TAB = true:
+ * 16 rows of them do not fit the register file next to the state and the factors; class-shared tables for ALL per-row
+ * constants, as in the chunk family, were measured slower: 87 against 69 ms, the factors sit on the dependent chain).
+ */
+template <int WARPS, int R, bool TAB>
 struct PdebCtaShared {
-    double ex[2][4][4];                    /* per step, double-buffered: [warp]{ y[0] of lane 0, tau of lane 0, level-2 piece of lane 31 } */
-    double fx[2][4][PDEB_MAX_PRED];        /* per step: warp maxima of the open F clauses */
-    double G[3][3];                        /* inverse of the level-2 matrix */
+    static constexpr int NT = 32 * WARPS;
+    double ex[2][WARPS][4];                /* per step, double-buffered: [warp]{ y[0] of lane 0, tau of lane 0, level-2 piece of lane 31 } */
+    double fx[2][WARPS][PDEB_MAX_PRED];    /* per step: warp maxima of the open F clauses */
+    double G[3][3];                        /* inverse of the level-2 matrix (WARPS - 1 unknowns) */
     double afn[3], supB[3];                /* a_first_next and Sup of the level-2 separators */
-    double P0[4], Q0[4];                   /* P, Q of lane 0 of every warp */
+    double rsr[WARPS];                     /* flux coefficient right of every warp's last separator */
     double scr[16];                        /* set-up and rare-path scratch */
-    double set[4][8];                      /* set-up exchange: per warp { P0, Q0, P30, Q30, SloB, SdiB, SupB, afn } */
-    double nb[PDEB_CTA_THREADS + 1];       /* set-up: neighbour exchange */
-    double gacc[PDEB_MAX_PRED][PDEB_CTA_THREADS];   /* per-lane running maxima of the G clauses */
+    double set[WARPS][8];                  /* set-up exchange: per warp { P0, Q0, P30, Q30, SloB, SdiB, SupB, afn } */
+    double nb[NT + 1];                     /* set-up: neighbour exchange */
+    double gacc[PDEB_MAX_PRED][NT];        /* per-lane running maxima of the G clauses */
+    PdebD2 vw[TAB ? R : 1][NT];            /* TAB: { v_l, w_l } spikes, one column per lane (conflict-free) */
+    double kqs[TAB ? R + 1 : 1][NT];       /* TAB: flux coefficients, one column per lane */
     double cval[PDEB_MAX_PRED];            /* clause values for the formula tree */
     /* clause data (block-uniform, written by thread j at set-up) */
     double c_mh[PDEB_MAX_PRED], c_c0[PDEB_MAX_PRED], c_acc[PDEB_MAX_PRED];
@@ -64,14 +75,16 @@ struct PdebCtaShared {
     int32_t flag;
 };
 
-template <int KIND>
-__global__ void __launch_bounds__(PDEB_CTA_THREADS, PDEB_CTA_MINBLOCKS)
+template <int KIND, int WARPS, int R, int MINB>
+__global__ void __launch_bounds__(32 * WARPS, MINB)
 pdeb_cta_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant__ PdebConventions cv,
                 const __grid_constant__ PdebDevOut out, const int32_t* __restrict__ order, int64_t first, int64_t count,
                   int gather) {
     static_assert(KIND == PDEB_KIND_HEAT, "the CTA family is instantiated for the heat equation");
-    constexpr int R = PDEB_CTA_R, NT = PDEB_CTA_THREADS, CAP = PDEB_CTA_CAP, M = R / 2;
-    __shared__ PdebCtaShared sm;
+    constexpr int NT = 32 * WARPS, CAP = NT * (R + 1) - 1, M = R / 2, NB = WARPS - 1;   /* NB: level-2 unknowns */
+    constexpr bool TAB = R > 8;
+    static_assert(WARPS >= 2 && WARPS <= 4 && R <= 32, "two to four warps per trajectory");
+    __shared__ PdebCtaShared<WARPS, R, TAB> sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t t = blockIdx.x;
     if (t >= count) return;
@@ -178,42 +191,42 @@ pdeb_cta_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant__ 
             dinv[M] = dm;
         }
     }
-    /* twisted solve of the interior block for a full right-hand side */
-    auto local_solve = [&](const double (&r)[R], double (&z)[R]) {
+    /* twisted solve of the interior block IN PLACE: z holds the right-hand side on entry, the solution on return */
+    auto solve_with = [&](double (&z)[R], auto E, auto DI) {
         double zt = 0.0, zb = 0.0;
 #pragma unroll
         for (int j = 0; j < R; ++j) {
             const int it = j, ib = R - 1 - j;
             if (it < M) {
-                const double q = (it > 0) ? fma(-e[it - 1], zt, r[it]) : r[it];
+                const double q = (it > 0) ? fma(-E(it - 1), zt, z[it]) : z[it];
                 zt = q;
-                z[it] = q * dinv[it];
+                z[it] = q * DI(it);
             }
             if (ib > M) {
-                const double q = (ib < R - 1) ? fma(-e[ib], zb, r[ib]) : r[ib];
+                const double q = (ib < R - 1) ? fma(-E(ib), zb, z[ib]) : z[ib];
                 zb = q;
-                z[ib] = q * dinv[ib];
+                z[ib] = q * DI(ib);
             }
         }
         {
-            double q = r[M];
-            if (M > 0) q = fma(-e[M - 1], zt, q);
-            if (M < R - 1) q = fma(-e[M], zb, q);
-            z[M] = q * dinv[M];
+            double q = z[M];
+            if (M > 0) q = fma(-E(M - 1), zt, q);
+            if (M < R - 1) q = fma(-E(M), zb, q);
+            z[M] = q * DI(M);
         }
 #pragma unroll
-        for (int l = M - 1; l >= 0; --l) z[l] = fma(-e[l], z[l + 1], z[l]);
+        for (int l = M - 1; l >= 0; --l) z[l] = fma(-E(l), z[l + 1], z[l]);
 #pragma unroll
-        for (int l = M + 1; l < R; ++l) z[l] = fma(-e[l - 1], z[l - 1], z[l]);
+        for (int l = M + 1; l < R; ++l) z[l] = fma(-E(l - 1), z[l - 1], z[l]);
     };
+    auto local_solve = [&](double (&z)[R]) { solve_with(z, [&](int l) { return e[l]; }, [&](int l) { return dinv[l]; }); };
     {
-        double r[R];
 #pragma unroll
-        for (int l = 0; l < R; ++l) r[l] = (l == 0) ? a_first : 0.0;
-        local_solve(r, v);
+        for (int l = 0; l < R; ++l) v[l] = (l == 0) ? a_first : 0.0;
+        local_solve(v);
 #pragma unroll
-        for (int l = 0; l < R; ++l) r[l] = (l == R - 1) ? a_last : 0.0;
-        local_solve(r, w);
+        for (int l = 0; l < R; ++l) w[l] = (l == R - 1) ? a_last : 0.0;
+        local_solve(w);
     }
     /* neighbour exchange through shared memory (set-up only): value of thread tid + d (0 outside the block) */
     auto from_tid = [&](double val, int d) {
@@ -238,6 +251,15 @@ pdeb_cta_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant__ 
     /* the Dirichlet node (row 0) is an identity row that receives the flux of element 0: its increment must stay 0 */
 #pragma unroll
     for (int l = 0; l < R; ++l) if (g_first + l == 0) dinv[l] = 0.0;
+    if (TAB) {
+        /* 16 rows per lane: spikes and flux coefficients go to per-lane columns of shared memory (conflict-free: consecutive
+         * lanes, consecutive addresses); from here on the register copies are dead */
+#pragma unroll
+        for (int l = 0; l < R; ++l) { PdebD2 p2; p2.x = v[l]; p2.y = w[l]; sm.vw[TAB ? l : 0][tid] = p2; }
+#pragma unroll
+        for (int l = 0; l <= R; ++l) sm.kqs[TAB ? l : 0][tid] = kq[l];
+    }
+    auto KQ = [&](int l) -> double { if (TAB) return sm.kqs[TAB ? l : 0][tid]; return kq[l]; };
     const bool sep_is_dirichlet = (g_sep == 0);
     /* level 1 / level 2 split: lane 31 of every warp is a level-2 unknown (an identity row inside the warp's system) */
     const double Slo0 = Slo, Sup0 = Sup, Sdi0 = Sdi;
@@ -278,7 +300,7 @@ pdeb_cta_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant__ 
     __syncthreads();
     if (lane == 0) { sm.set[warp][0] = P; sm.set[warp][1] = Q; }
     if (lane == 30) { sm.set[warp][2] = P; sm.set[warp][3] = Q; }
-    if (lane == 31) { sm.set[warp][4] = Slo0; sm.set[warp][5] = Sdi0; sm.set[warp][6] = Sup0; sm.set[warp][7] = a_first_next; }
+    if (lane == 31) { sm.set[warp][4] = Slo0; sm.set[warp][5] = Sdi0; sm.set[warp][6] = Sup0; sm.set[warp][7] = a_first_next; sm.rsr[warp] = rs_r; }
     {
         const bool bad = !ok;
         if (tid == 0) sm.flag = 0;
@@ -287,45 +309,48 @@ pdeb_cta_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant__ 
     }
     __syncthreads();
     if (tid == 0) {
-        double m2[3][3];
-        for (int j = 0; j < 3; ++j) {
+        double m2[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, inv[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+        for (int j = 0; j < NB; ++j) {
             const double sl = sm.set[j][4], sd = sm.set[j][5], su = sm.set[j][6];
-            double dl = 0.0, dd = sd, du = 0.0;
             /* sigma(lane 30 of warp j) = tau - B_{j-1} P_j[30] - B_j Q_j[30];  sigma(lane 0 of warp j+1) = tau - B_j P_{j+1}[0] - B_{j+1} Q_{j+1}[0] */
-            dl -= sl * sm.set[j][2];
-            dd -= sl * sm.set[j][3];
-            dd -= su * sm.set[j + 1][0];
-            du -= su * sm.set[j + 1][1];
             m2[j][0] = m2[j][1] = m2[j][2] = 0.0;
-            if (j > 0) m2[j][j - 1] = dl;
-            m2[j][j] = dd;
-            if (j < 2) m2[j][j + 1] = du;
+            if (j > 0) m2[j][j - 1] = -sl * sm.set[j][2];
+            m2[j][j] = sd - sl * sm.set[j][3] - su * sm.set[j + 1][0];
+            if (j + 1 < NB) m2[j][j + 1] = -su * sm.set[j + 1][1];
             sm.afn[j] = sm.set[j][7];
             sm.supB[j] = su;
-            if (sm.set[j][5] == 1.0 && sl == 0.0 && su == 0.0) { /* padding separator: identity */ }
         }
-        /* a Dirichlet node that falls onto a level-2 separator keeps its increment at 0: identity row, zero right-hand side */
-        const double c00 = m2[1][1] * m2[2][2] - m2[1][2] * m2[2][1];
-        const double c01 = m2[1][0] * m2[2][2] - m2[1][2] * m2[2][0];
-        const double c02 = m2[1][0] * m2[2][1] - m2[1][1] * m2[2][0];
-        const double det = m2[0][0] * c00 - m2[0][1] * c01 + m2[0][2] * c02;
-        const double id = 1.0 / det;
-        if (!isfinite(id) || det == 0.0) sm.flag = 1;
-        sm.G[0][0] = c00 * id;
-        sm.G[0][1] = -(m2[0][1] * m2[2][2] - m2[0][2] * m2[2][1]) * id;
-        sm.G[0][2] = (m2[0][1] * m2[1][2] - m2[0][2] * m2[1][1]) * id;
-        sm.G[1][0] = -c01 * id;
-        sm.G[1][1] = (m2[0][0] * m2[2][2] - m2[0][2] * m2[2][0]) * id;
-        sm.G[1][2] = -(m2[0][0] * m2[1][2] - m2[0][2] * m2[1][0]) * id;
-        sm.G[2][0] = c02 * id;
-        sm.G[2][1] = -(m2[0][0] * m2[2][1] - m2[0][1] * m2[2][0]) * id;
-        sm.G[2][2] = (m2[0][0] * m2[1][1] - m2[0][1] * m2[1][0]) * id;
-        for (int q = 0; q < 4; ++q) { sm.P0[q] = sm.set[q][0]; sm.Q0[q] = sm.set[q][1]; }
+        for (int j = NB; j < 3; ++j) { sm.afn[j] = 0.0; sm.supB[j] = 0.0; }
+        /* inverse of the (at most 3 x 3, tridiagonal, diagonally dominant) level-2 matrix by Gauss-Jordan without pivoting */
+        bool bad = false;
+        for (int c = 0; c < NB; ++c) {
+            const double piv = m2[c][c];
+            if (!(piv != 0.0) || !isfinite(piv)) { bad = true; break; }
+            const double ip = 1.0 / piv;
+            for (int q = 0; q < 3; ++q) { m2[c][q] *= ip; inv[c][q] *= ip; }
+            for (int r2 = 0; r2 < NB; ++r2) {
+                if (r2 == c) continue;
+                const double f = m2[r2][c];
+                for (int q = 0; q < 3; ++q) { m2[r2][q] -= f * m2[c][q]; inv[r2][q] -= f * inv[c][q]; }
+            }
+        }
+        for (int r2 = 0; r2 < 3; ++r2) for (int q = 0; q < 3; ++q) { sm.G[r2][q] = (r2 < NB && q < NB) ? inv[r2][q] : 0.0; if (!isfinite(sm.G[r2][q])) bad = true; }
+        if (bad) sm.flag = 1;
     }
     __syncthreads();
     if (sm.flag && status == PDEB_OK) { status = PDEB_ST_NONFINITE; S = 0; np = 0; }
-    /* a level-2 separator that is the Dirichlet node: its increment is forced to 0 by zeroing its row of G */
-    const int dirichlet_b = (shift % (R + 1) == 0 && (shift / (R + 1) - 1) % 32 == 31) ? (shift / (R + 1) - 1) / 32 : -1;
+    /* level-2 constants of this warp in registers: rows of G for the separator in front of the warp (gp) and its own (go),
+     * and, for lane 0, the couplings of the PREVIOUS warp's level-2 row to this lane (a_first_next, Sup, flux coefficient) */
+    double gp[3] = {0.0, 0.0, 0.0}, go[3] = {0.0, 0.0, 0.0};
+    /* (a level-2 separator that is the Dirichlet node keeps its increment at 0: its row of G is taken as zero) */
+    const int dirichlet_b0 = (shift % (R + 1) == 0 && (shift / (R + 1) - 1) % 32 == 31) ? (shift / (R + 1) - 1) / 32 : -1;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+        if (warp >= 1 && warp - 1 < NB && warp - 1 != dirichlet_b0) gp[j] = sm.G[warp - 1][j];
+        if (warp < NB && warp != dirichlet_b0) go[j] = sm.G[warp][j];
+    }
+    const double pv_afn = (warp >= 1) ? sm.afn[warp - 1] : 0.0, pv_supB = (warp >= 1) ? sm.supB[warp - 1] : 0.0;
+    const double pv_rsr = (warp >= 1) ? sm.rsr[warp - 1] : 0.0;
 
     PdebPwl<double> in;
     in.init(kt, ky, (status == PDEB_OK) ? nk : 0, st, T);
@@ -377,7 +402,7 @@ pdeb_cta_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant__ 
 #pragma unroll
     for (int l = 0; l < R; ++l) { x[l] = 0.0; y[l] = 0.0; }
     double xs = 0.0;                              /* own separator */
-    double xsp = 0.0, xnf = 0.0;                  /* ghosts: separator in front of lane 0, first row behind lane 31 */
+    double xsp = 0.0;                             /* ghost of the neighbouring warp's separator in front of lane 0 */
     bool bad_state = false;                       /* sticky: state not finite at an observed step */
     uint32_t open = 0;
     int32_t next_ev = 0;
@@ -491,7 +516,7 @@ pdeb_cta_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant__ 
                     todo &= todo - 1u;
                     const uint32_t info = sm.c_info[j];
                     double gm = sm.fx[buf][0][j];
-                    for (int q = 1; q < 4; ++q) gm = sm.fx[buf][q][j] > gm ? sm.fx[buf][q][j] : gm;
+                    for (int q = 1; q < WARPS; ++q) gm = sm.fx[buf][q][j] > gm ? sm.fx[buf][q][j] : gm;
                     double r = ((info & 3u) == PDEB_REL_EQ) ? eq_eps - gm : -gm;
                     if (sm.c_ilo[j] > sm.c_ihi[j]) r = INFINITY;
                     if (info & 8u) { const double re = sm.scr[8 + j]; if (re < r || re != re) r = re; }
@@ -507,57 +532,50 @@ pdeb_cta_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant__ 
         {
             const double xs_up = __shfl_up_sync(PDEB_FULL, xs, 1), x0_dn = __shfl_down_sync(PDEB_FULL, x[0], 1);
             const double xs_prev = (lane == 0) ? xsp : xs_up;             /* warp 0: the ghost stays 0 */
-            const double x_nf = (lane == 31) ? xnf : x0_dn;
-            /* right-hand side in ELEMENT-FLUX form (see pdeb_chunk.cuh): Q_e = kq_e (x_{e+1} - x_e), row i gets Q_i - Q_{i-1} */
-            double r[R];
+            /* right-hand side in ELEMENT-FLUX form (see pdeb_chunk.cuh): Q_e = kq_e (x_{e+1} - x_e), row i gets Q_i - Q_{i-1};
+             * formed straight into y, which the solve then overwrites with the increment */
             {
-                double q_prev = kq[0] * (x[0] - xs_prev);
+                double q_prev = KQ(0) * (x[0] - xs_prev);
 #pragma unroll
                 for (int l = 0; l < R - 1; ++l) {
-                    const double q = kq[l + 1] * (x[l + 1] - x[l]);
-                    r[l] = q - q_prev;
+                    const double q = KQ(l + 1) * (x[l + 1] - x[l]);
+                    y[l] = q - q_prev;
                     q_prev = q;
                 }
-                const double q_sep = kq[R] * (xs - x[R - 1]);
-                r[R - 1] = q_sep - q_prev + ((tid == NT - 1) ? fN : 0.0);
-                /* separator row */
-                const double rsep = rs_r * (x_nf - xs) - q_sep;
-                local_solve(r, y);
+                const double q_sep = KQ(R) * (xs - x[R - 1]);
+                y[R - 1] = q_sep - q_prev + ((tid == NT - 1) ? fN : 0.0);
+                /* separator row: rs_r (x_nf - xs) - q_sep.  For the level-2 separator (lane 31) x_nf belongs to the next warp:
+                 * that warp's lane 0 carries the term rs_r x_nf in what it publishes (c2 below), so no ghost copy is needed */
+                const double rsep = (lane == 31) ? fma(-rs_r, xs, -q_sep) : fma(rs_r, x0_dn - xs, -q_sep);
+                const double x0_own = x[0];
+                local_solve(y);
                 const double y0_dn = __shfl_down_sync(PDEB_FULL, y[0], 1);
                 /* level-1 Schur right-hand side (lanes 0..30) and the warp's PCR: tau */
                 const double sh = (lane == 31) ? 0.0 : fma(-a_last, y[R - 1], fma(-a_first_next, y0_dn, rsep));
                 const double tau = pcr_apply(sh);
                 const double tau30 = __shfl_sync(PDEB_FULL, tau, 30);
-                if (lane == 0) { sm.ex[buf][warp][0] = y[0]; sm.ex[buf][warp][1] = tau; }
-                if (lane == 31) sm.ex[buf][warp][2] = fma(-a_last, y[R - 1], rsep) - Slo0 * tau30;     /* level-2 piece */
+                /* what the level-2 right-hand side needs from this warp: lane 31 its own row's piece, lane 0 the terms of the
+                 * PREVIOUS warp's level-2 row that live here (constants of that row were exchanged at set-up) */
+                if (lane == 31) sm.ex[buf][warp][2] = fma(-a_last, y[R - 1], rsep) - Slo0 * tau30;
+                if (lane == 0) sm.ex[buf][warp][0] = fma(pv_afn, y[0], fma(pv_supB, tau, -pv_rsr * x0_own));
                 __syncthreads();                                                              /* THE barrier of the step */
-                /* level 2: beta_j = piece_j - afn_j y0_{j+1} - SupB_j tau0_{j+1};  B = G beta */
-                double beta[3];
+                /* level 2: beta_j = piece_j - c2_{j+1};  B = G beta (G rows of this warp's two neighbours are in registers) */
+                double beta[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-                for (int j = 0; j < 3; ++j)
-                    beta[j] = fma(-sm.supB[j], sm.ex[buf][j + 1][1], fma(-sm.afn[j], sm.ex[buf][j + 1][0], sm.ex[buf][j][2]));
-                double B[4];
+                for (int j = 0; j < NB; ++j) beta[j] = sm.ex[buf][j][2] - sm.ex[buf][j + 1][0];
+                double Bp = 0.0, Bo = 0.0;                 /* B of the separator in front of this warp, and of its own */
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    B[j] = fma(sm.G[j][2], beta[2], fma(sm.G[j][1], beta[1], sm.G[j][0] * beta[0]));
-                    if (j == dirichlet_b) B[j] = 0.0;
-                }
-                B[3] = 0.0;
-                const double Bp = (warp == 0) ? 0.0 : ((warp == 1) ? B[0] : ((warp == 2) ? B[1] : B[2]));
-                const double Bo = (warp == 0) ? B[0] : ((warp == 1) ? B[1] : ((warp == 2) ? B[2] : 0.0));
-                const double Bn = (warp == 0) ? B[1] : ((warp == 1) ? B[2] : 0.0);            /* B of the next warp */
+                for (int j = 0; j < NB; ++j) { Bp = fma(gp[j], beta[j], Bp); Bo = fma(go[j], beta[j], Bo); }
                 const double xs_new = (lane == 31) ? Bo : fma(-Bo, Q, fma(-Bp, P, tau));
                 const double xn_up = __shfl_up_sync(PDEB_FULL, xs_new, 1);
                 const double xs_new_prev = (lane == 0) ? Bp : xn_up;
-                /* ghosts of the neighbouring warp, advanced with the owner's arithmetic */
-                if (lane == 31 && warp < 3) {
-                    const double y_nf = sm.ex[buf][warp + 1][0];
-                    const double xs_new_next = fma(-Bn, sm.Q0[warp + 1], fma(-Bo, sm.P0[warp + 1], sm.ex[buf][warp + 1][1]));
-                    xnf += fma(-v0n, xs_new, fma(-w0n, xs_new_next, y_nf));
-                }
-                if (lane == 0) xsp += Bp;
+                xsp += Bp;                                 /* ghost of the separator in front of lane 0 (used by lane 0 only) */
 #pragma unroll
-                for (int l = 0; l < R; ++l) x[l] += fma(-v[l], xs_new_prev, fma(-w[l], xs_new, y[l]));   /* the solve returned the increment */
+                for (int l = 0; l < R; ++l) {
+                    double vl, wl;
+                    if (TAB) { const PdebD2 p2 = sm.vw[TAB ? l : 0][tid]; vl = p2.x; wl = p2.y; } else { vl = v[l]; wl = w[l]; }
+                    x[l] += fma(-vl, xs_new_prev, fma(-wl, xs_new, y[l]));                       /* the solve returned the increment */
+                }
                 xs += xs_new;
             }
         }
@@ -569,7 +587,7 @@ pdeb_cta_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant__ 
                 todo &= todo - 1u;
                 const uint32_t info = sm.c_info[j];
                 double gm = sm.fx[buf][0][j];
-                for (int q = 1; q < 4; ++q) gm = sm.fx[buf][q][j] > gm ? sm.fx[buf][q][j] : gm;
+                for (int q = 1; q < WARPS; ++q) gm = sm.fx[buf][q][j] > gm ? sm.fx[buf][q][j] : gm;
                 double r = ((info & 3u) == PDEB_REL_EQ) ? eq_eps - gm : -gm;
                 if (sm.c_ilo[j] > sm.c_ihi[j]) r = INFINITY;
                 if (info & 8u) { const double re = sm.scr[8 + j]; if (re < r || re != re) r = re; }
@@ -598,7 +616,7 @@ pdeb_cta_kernel(const __grid_constant__ PdebDevBatch b, const __grid_constant__ 
             const uint32_t info = sm.c_info[j];
             if (((info >> 2) & 1u) == PDEB_TOP_G) {
                 double gm = sm.fx[0][0][j];
-                for (int q = 1; q < 4; ++q) gm = sm.fx[0][q][j] > gm ? sm.fx[0][q][j] : gm;
+                for (int q = 1; q < WARPS; ++q) gm = sm.fx[0][q][j] > gm ? sm.fx[0][q][j] : gm;
                 double r = ((info & 3u) == PDEB_REL_EQ) ? eq_eps - gm : -gm;
                 if (sm.c_ilo[j] > sm.c_ihi[j]) r = INFINITY;
                 const double re = sm.c_acc[j];                 /* end-point margins (INFINITY when there are none) */

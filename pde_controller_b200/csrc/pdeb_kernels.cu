@@ -247,7 +247,8 @@ static cudaError_t launch_variant(int v, const PdebDevBatch& b, const PdebConven
     default:
         if (v >= 2 && v <= 7) return pdeb_launch_chunk_heat(1 << (v - 2), b, cv, out, pb.order, first, count, gather, stream);
         if (v >= 8 && v <= 12) return pdeb_launch_chunk_wave(1 << (v - 8), b, cv, out, pb.order, first, count, gather, stream);
-        if (v == PDEB_VARIANT_CTA_HEAT) return pdeb_launch_cta_heat(b, cv, out, pb.order, first, count, gather, stream);
+        if (v == PDEB_VARIANT_CTA_HEAT) return pdeb_launch_cta_heat(0, b, cv, out, pb.order, first, count, gather, stream);
+        if (v == PDEB_VARIANT_CTA2_HEAT) return pdeb_launch_cta_heat(1, b, cv, out, pb.order, first, count, gather, stream);
         return cudaSuccess;
     }
 }

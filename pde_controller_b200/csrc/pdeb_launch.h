@@ -21,21 +21,24 @@ void pdeb_set_last_error(const char* msg);
  * 2..7: chunk family heat with R = 1,2,4,8,16,32 rows per lane; 8..12: chunk family wave, R = 1..16.
  * A mesh of N elements needs 32 R + 30 >= N.
  */
-#define PDEB_NUM_VARIANTS 14
+#define PDEB_NUM_VARIANTS 15
 #define PDEB_VARIANT_SLOTS 16
 /* 13: CTA family (one block of 128 threads per trajectory, 8 rows per lane, two-level substructuring; pdeb_cta.cuh), heat
- * meshes beyond 542 elements (BASELINE.json configs[3]).  Measured on B200 it is 1.7x SLOWER than the chunk family at
- * R = 32 on that configuration (profiles/r02_cta_refined_summary.txt: the per-step fixed cost -- cyclic reduction, exchange,
- * barrier, clause pass -- is paid by four warps instead of one), so it is an OPT-IN: PDEB_FLAG_CTA in the image's flags
- * (environment PDEB_CTA=1 when the resident image is created).  Kept because it is the mapping the north star names and
- * the parity tests cover it. */
-#define PDEB_VARIANT_CTA_HEAT 13
-#define PDEB_FLAG_CTA 1            /* PdebDevBatch.pad: refined heat meshes go to the CTA family */
+ * meshes beyond 542 elements (BASELINE.json configs[3]).  Measured on B200 it is SLOWER than the chunk family at R = 32 on
+ * that configuration (62.8 ms chunk, 68.4 ms 2 x 16, 91.9 ms 4 x 8; profiles/r02_cta_refined_summary.txt: the per-step fixed
+ * cost -- cyclic reduction, exchange, barrier, clause pass -- is paid by every warp of the block), so it is an OPT-IN:
+ * PDEB_FLAG_CTA / PDEB_FLAG_CTA2 in the image's flags (environment PDEB_CTA=1 / 2 when the resident image is created).  Kept
+ * because it is the mapping the north star names and the parity tests cover it. */
+#define PDEB_VARIANT_CTA_HEAT 13   /* 4 warps x 8 rows per lane */
+#define PDEB_VARIANT_CTA2_HEAT 14  /* 2 warps x 16 rows per lane */
+#define PDEB_FLAG_CTA 1            /* PdebDevBatch.pad: refined heat meshes go to the CTA family, 4 x 8 shape (PDEB_CTA=1) */
+#define PDEB_FLAG_CTA2 2           /* ... 2 x 16 shape (PDEB_CTA=2) */
 PDEB_HD int pdeb_variant_of(int kind, int n_elem, int flags = 0) {
     if (n_elem < 1) return -1;
     if (kind == PDEB_KIND_HEAT) {
         if (n_elem == 30) return 0;
         if ((flags & PDEB_FLAG_CTA) && n_elem > 32 * 16 + 30 && n_elem <= PDEB_MAX_ELEM) return PDEB_VARIANT_CTA_HEAT;
+        if ((flags & PDEB_FLAG_CTA2) && n_elem > 32 * 16 + 30 && n_elem <= PDEB_MAX_ELEM) return PDEB_VARIANT_CTA2_HEAT;
         for (int q = 0; q < 6; ++q) if (n_elem <= 32 * (1 << q) + 30) return 2 + q;
         return -1;
     }
@@ -123,7 +126,7 @@ __device__ __forceinline__ void pdeb_plan_count(const PdebDevBatch& b, const Pde
  * (thread t reads its sample's own index order[first + t]) */
 cudaError_t pdeb_launch_chunk_heat(int R, const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out,
                                    const int32_t* order, int64_t first, int64_t count, int gather, cudaStream_t stream);
-cudaError_t pdeb_launch_cta_heat(const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out,
+cudaError_t pdeb_launch_cta_heat(int shape, const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out,
                                  const int32_t* order, int64_t first, int64_t count, int gather, cudaStream_t stream);
 cudaError_t pdeb_launch_chunk_wave(int R, const PdebDevBatch& b, const PdebConventions& cv, const PdebDevOut& out,
                                    const int32_t* order, int64_t first, int64_t count, int gather, cudaStream_t stream);

@@ -116,12 +116,14 @@ def test_refined_mesh_accuracy_on_a_larger_sample(oracle_lib):
 
 
 
+@pytest.mark.parametrize("shape", ["1", "2"])
 @pytest.mark.parametrize("N", [543, 700, 1024, 1054])
-def test_cta_family_opt_in(oracle_lib, N, monkeypatch):
+def test_cta_family_opt_in(oracle_lib, N, shape, monkeypatch):
     """The block-per-trajectory mapping of the north star (pdeb_cta.cuh: 128 threads, 8 rows per lane, two-level
-    substructuring with one barrier per step).  Opt-in (PDEB_CTA=1 when the image is created): on B200 it is slower than
-    the warp-per-trajectory family it would replace (profiles/r02_cta_refined_summary.txt); parity is the same."""
-    monkeypatch.setenv("PDEB_CTA", "1")
+    substructuring with one barrier per step; PDEB_CTA=2: 64 threads, 16 rows per lane, spikes and flux coefficients in
+    shared-memory columns).  Opt-in (PDEB_CTA when the image is created): on B200 it is slower than the warp-per-trajectory
+    family it would replace (profiles/r02_cta_refined_summary.txt); parity is the same."""
+    monkeypatch.setenv("PDEB_CTA", shape)
     b = with_mesh("heat", 24, N, seed=N)
     b.pred_xhi[0, :4] = b.pred_xlo[0, :4] + 0.01          # interpolated end points (published through shared memory)
     b.pred_thi[0, 4:8] = b.T[4:8]
