@@ -238,6 +238,41 @@ def test_resident_api_matches_one_shot(oracle_lib):
     r.close()
 
 
+@pytest.mark.parametrize("wl", ["heat", "wave", "mixed"])
+def test_plan_ordered_image_and_knot_refills(oracle_lib, wl):
+    """A resident batch is read where it lies on its first evaluation and from the plan-ordered image from the second on;
+    knot refills must reach whichever image the next evaluation reads; a re-plan (other conventions) starts over."""
+    b = synth.make_batch(2500, wl, seed=17)
+    r = native.ResidentBatch(b)
+    first = None
+    for _ in range(3):                                    # 1: as uploaded (gather), 2: permutes, 3: ordered image
+        r.eval()
+        got = r.fetch(want_clauses=True)
+        if first is None:
+            first = got
+        assert np.array_equal(got["robustness"], first["robustness"]) and np.array_equal(got["status"], first["status"])
+    ref, ref_st = oracle_lib.eval_batch(b)
+    assert (first["status"] == ref_st).all() and rel_err(first["robustness"], ref, b).max() <= TOL_FP64
+    rng = np.random.default_rng(3)
+    for rep in range(2):                                  # refill while the ordered image is valid
+        b.knot_y[...] = rng.uniform(-1.0, 1.0, b.knot_y.shape) * np.where(b.kind == 0, 1e6, 5e3)
+        r.set_knots(b.knot_t, b.knot_y, b.n_knots)
+        r.eval()
+        got = r.fetch()
+        ref, ref_st = oracle_lib.eval_batch(b)
+        assert (got["status"] == ref_st).all() and rel_err(got["robustness"], ref, b).max() <= TOL_FP64
+    conv = default_conventions(steps_rule=1, window_rule=1)   # re-plan: back to the image as uploaded, then ordered again
+    for _ in range(2):
+        r.eval(64, conv)
+        got = r.fetch()
+        ref, ref_st = oracle_lib.eval_batch(b, conv)
+        assert (got["status"] == ref_st).all() and rel_err(got["robustness"], ref, b).max() <= TOL_FP64
+    r.upload(b)                                           # a fresh upload invalidates the ordered image
+    r.eval()
+    assert np.array_equal(r.fetch()["robustness"], native.evaluate_batch(b)["robustness"])
+    r.close()
+
+
 def test_shard_views_and_multi_entry(oracle_lib):
     b = synth.make_batch(5000, "wave", seed=13)
     full = native.evaluate_batch(b)["robustness"]
