@@ -394,6 +394,7 @@ def main():
     ap.add_argument("--text-programs", type=int, default=32768, help="programs of the text-level leg")
     ap.add_argument("--no-configs", action="store_true", help="skip the device-timed rates of the other BASELINE configs")
     ap.add_argument("--e2e-planar-only", action="store_true", help="skip the two packed end-to-end legs (long-running workloads)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="leave the placement of this rank's host thread and page-locked buffers to the OS")
     args = ap.parse_args()
     if args.batch is None:
         args.batch = DEFAULT_BATCH[args.workload]
@@ -421,6 +422,11 @@ def main():
         return
     torch.cuda.set_device(local_rank)
     dev = local_rank
+    # one process per GPU: run on the CPUs of the NUMA node the GPU hangs off BEFORE any page-locked buffer is allocated,
+    # so that this rank's host -> device copies stay off the socket interconnect (native.bind_host_near); the text-level and CPU legs
+    # below get the original CPU set back
+    all_cpus = os.sched_getaffinity(0)
+    numa = {"bound": False, "note": "--no-numa-bind"} if args.no_numa_bind else native.bind_host_near(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stream = torch.cuda.current_stream().cuda_stream
@@ -541,6 +547,11 @@ def main():
 
     st = out_host["status"]
     n_fail = int((st != 0).sum())
+    os.sched_setaffinity(0, all_cpus)
+    if world > 1:
+        nb_ = torch.tensor([1.0 if numa.get("bound") else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(nb_, op=dist.ReduceOp.SUM)
+        numa["ranks_bound"] = int(nb_.item())
 
     # ---- the reference's real call surface: program TEXT in, robustness out (eval_script.py:43-79) ----
     e2e_text = None
@@ -613,7 +624,7 @@ def main():
             "config": common_config(args, world),
             "detail": {"gather": bool(rob_t is not None), "failed_samples": n_fail,
                        "knots": "uniform (formed on device)" if uk else "explicit", "e2e_block": args.e2e_block,
-                       "e2e_pipeline_depth": E2E_DEPTH, "wall_s_timed_region": wall1 - wall0},
+                       "e2e_pipeline_depth": E2E_DEPTH, "wall_s_timed_region": wall1 - wall0, "numa": numa},
             "e2e": e2e,
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,

@@ -164,6 +164,10 @@ typedef struct PdebTiming {
 int  pdeb_version(void);
 int  pdeb_device_count(void);
 const char* pdeb_last_error(void);       /* thread-local, valid until the next call on this thread */
+/* "dddd:bb:dd.f" of a device (cudaDeviceGetPCIBusId), so that a host process can place itself and its page-locked
+   buffers on the NUMA node the device hangs off (native.bind_host_near; the reference's process pool,
+   simulate_gt.py:62-89, leaves placement to the OS).  len >= 13. */
+int  pdeb_device_pci_bus_id(int device, char* buf, int len);
 void pdeb_default_conventions(PdebConventions* out);
 
 /*

@@ -159,6 +159,7 @@ IOU_OP = {"<=": 0, "<": 1, ">=": 2, ">": 3, "=": 4, "!=": 5}
 EXPORTS = [
     "pdeb_version",
     "pdeb_device_count",
+    "pdeb_device_pci_bus_id",
     "pdeb_last_error",
     "pdeb_default_conventions",
     "pdeb_eval_batch",

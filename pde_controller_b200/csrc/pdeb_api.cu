@@ -59,6 +59,14 @@ extern "C" int pdeb_device_count(void) {
 
 extern "C" const char* pdeb_last_error(void) { return g_err.c_str(); }
 
+extern "C" int pdeb_device_pci_bus_id(int device, char* buf, int len) {
+    if (!buf || len < 13) return fail(PDEB_E_ARG, "pdeb_device_pci_bus_id: buffer of at least 13 bytes wanted");
+    if (device < 0 || device >= pdeb_device_count()) return fail(PDEB_E_NODEVICE, "no such CUDA device");
+    const cudaError_t e = cudaDeviceGetPCIBusId(buf, len, device);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(PDEB_E_CUDA, cudaGetErrorString(e)); }
+    return 0;
+}
+
 extern "C" void pdeb_default_conventions(PdebConventions* c) {
     if (!c) return;
     memset(c, 0, sizeof *c);

@@ -59,6 +59,48 @@
 /* A/B switch of tools/variant_bench.py (default = what measured faster on B200):
  *   PDEB_EVENT_LIST 1: window events from a presorted per-lane list (one word per event), 0: every event re-scans the
  *                   windows of all clauses */
+/*
+ * Software pipelining across the basic blocks of a step (round 2; ptxas schedules inside a block only, and the step
+ * is cut into blocks by the window events, the knot crossing and the pass): per kind (H heat, W wave)
+ *   PDEB_PRE_TAB_x    rows per chain whose { R~_ii, 1/pivot } are loaded BEFORE the events / crossing blocks, so the solve
+ *                     starts on operands that have arrived instead of on its own first loads;
+ *   PDEB_PRE_SLOTS_x  the clause slots of the next pass are loaded behind the solve, not at the top of the pass;
+ *   PDEB_PRE_TIME_x   the time of the next step is formed behind the solve of the current one.
+ */
+#ifndef PDEB_PRE_TAB_H
+#define PDEB_PRE_TAB_H 3
+#endif
+#ifndef PDEB_PRE_TAB_W
+#define PDEB_PRE_TAB_W 2
+#endif
+#ifndef PDEB_PRE_SLOTS_H
+#define PDEB_PRE_SLOTS_H 1
+#endif
+#ifndef PDEB_PRE_SLOTS_W
+#define PDEB_PRE_SLOTS_W 1
+#endif
+#ifndef PDEB_PRE_TIME_H
+#define PDEB_PRE_TIME_H 1
+#endif
+#ifndef PDEB_PRE_TIME_W
+#define PDEB_PRE_TIME_W 1
+#endif
+#define PDEB_PRE_TAB_MAX 8
+/*   PDEB_ROTATE            the loop is rotated: the pass over step k+1 closes the iteration that advanced to it (the
+ *                          unrotated form tests "last step?" between pass and advance: one more branch per step);
+ *   PDEB_ENDPOINTS_MERGED  one warp-wide test skips both interpolated-end-point forms of the pass, and the in-element
+ *                          form is a select instead of a divergent branch.
+ * Measured on B200, 65,536 heat samples (tools/variant_bench.py): 0.3645 ms without any of these, 0.3535 with the three
+ * prefetches, 0.3463 with all five; waves 1.108 -> 1.086 ms. */
+#ifndef PDEB_PWL_SELECT
+#define PDEB_PWL_SELECT 1
+#endif
+#ifndef PDEB_ROTATE
+#define PDEB_ROTATE 1
+#endif
+#ifndef PDEB_ENDPOINTS_MERGED
+#define PDEB_ENDPOINTS_MERGED 1
+#endif
 #ifndef PDEB_EVENT_LIST
 #define PDEB_EVENT_LIST 1
 #endif
@@ -262,10 +304,10 @@ struct PdebPwlStaged {
 #endif
     }
     /* staged value (which = 0) or time (which = 1), once the copy has landed */
-    PDEB_HD double staged(int which) const {
+    PDEB_HD double staged(int which, bool wait = true) const {
 #if defined(__CUDA_ARCH__)
         double v;
-        asm volatile("cp.async.wait_all;" ::: "memory");
+        if (wait) asm volatile("cp.async.wait_all;" ::: "memory");
         asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(slot + (uint32_t)(which * STRIDE * sizeof(double))) : "memory");
         return v;
 #else
@@ -290,8 +332,16 @@ struct PdebPwlStaged {
             double tn = INFINITY;
             real yn = 0;
             if (j + 1 < nk) {
+#if PDEB_PWL_SELECT
+                /* both forms of the knot time, then a select: no branch on the (batch-wide) kind of knots */
+                const double tu = knot_time(nullptr, j + 1, 0);
+                yn = (real)staged(0);
+                const double ts = staged(1, false);
+                tn = kt ? ts : tu;
+#else
                 yn = (real)staged(0);
                 tn = kt ? staged(1) : knot_time(nullptr, j + 1, 0);
+#endif
             }
             if (tn < INFINITY) {
                 slope = (real)(((double)yn - (double)y1) * pdeb_rcp(tn - t1));
@@ -371,7 +421,8 @@ struct PdebTrajReg {
      * z[1..N] <- A~^-1 (R~ x + fNs e_N), fNs = s_N f, the two chains interleaved row by row.
      * x and z may not alias (x is read at i-1, i, i+1); x[0] must be 0.
      */
-    PDEB_HD void step_solve(const real* x, real fNs, real* z) const {
+    template <int PRE = 0>
+    PDEB_HD void step_solve(const real* x, real fNs, real* z, const real2* pre_t = nullptr, const real2* pre_b = nullptr) const {
         /* right-hand side + forward elimination; z[i] leaves this loop already divided by its pivot */
         real zt = 0, zb = 0;    /* undivided value of the last row of each chain */
         PDEB_UNROLL
@@ -379,7 +430,7 @@ struct PdebTrajReg {
             /* top row it = 1 + j (while it < M), bottom row ib = N - j (while ib > M) */
             const int it = 1 + j, ib = N - j;
             if (it < M) {
-                const real2 t = tab[(it - 1) * tstride];
+                const real2 t = (j < PRE) ? pre_t[j < PRE ? j : 0] : tab[(it - 1) * tstride];
                 real r = x[it - 1] + x[it + 1];
                 if (DD) r = fma(ltab[(it - 1) * tstride], x[it], r);
                 r = fma(t.x, x[it], r);
@@ -388,7 +439,7 @@ struct PdebTrajReg {
                 z[it] = r * t.y;
             }
             if (ib > M) {
-                const real2 t = tab[(ib - 1) * tstride];
+                const real2 t = (j < PRE) ? pre_b[j < PRE ? j : 0] : tab[(ib - 1) * tstride];
                 real r = x[ib - 1] + ((ib == N) ? fNs : x[ib + 1]);
                 if (DD) r = fma(ltab[(ib - 1) * tstride], x[ib], r);
                 r = fma(t.x, x[ib], r);
@@ -972,14 +1023,20 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
     const int32_t Smax = PDEB_WARP_MAX(S32);     /* the warp steps until its longest lane is done */
     window_events(0);
     uint32_t wf = PDEB_WARP_OR(flags);
+    constexpr int PRE_TAB = (KIND == PDEB_KIND_HEAT) ? PDEB_PRE_TAB_H : PDEB_PRE_TAB_W;
+    constexpr bool PRE_SLOTS = (KIND == PDEB_KIND_HEAT) ? PDEB_PRE_SLOTS_H : PDEB_PRE_SLOTS_W;
+    constexpr bool PRE_TIME = (KIND == PDEB_KIND_HEAT) ? PDEB_PRE_TIME_H : PDEB_PRE_TIME_W;
+    static_assert(PRE_TAB >= 0 && PRE_TAB <= PDEB_PRE_TAB_MAX && PRE_TAB < (N + 1) / 2 - 1, "prefetched rows lie inside the two chains");
+    real p_mh = slots.R(cur, 0), p_c0 = slots.R(cur, 1), p_A = slots.R(cur, 2);
+    PdebU2 p_ni = slots.NI(cur);
+    double t_nx = dt;
 
-    for (int32_t k = 0;; ++k) {
-        /* ---- (1) reduce the open clauses on the state of step k ---- */
-        if (wf & 1u) {
+    /* ---- (1) reduce the open clauses on the state of the current step ---- */
+    auto clause_pass = [&]() {
             /* every lane runs the pass on its clause `cur`; a lane without an open clause does so with an empty mask */
             const bool has = flags & 1u;
-            const real mh = slots.R(cur, 0), c0 = slots.R(cur, 1), A = slots.R(cur, 2);
-            const PdebU2 ni = slots.NI(cur);
+            const real mh = PRE_SLOTS ? p_mh : slots.R(cur, 0), c0 = PRE_SLOTS ? p_c0 : slots.R(cur, 1), A = PRE_SLOTS ? p_A : slots.R(cur, 2);
+            const PdebU2 ni = PRE_SLOTS ? p_ni : slots.NI(cur);
             const uint32_t nm = has ? ni.x : 0u, info = ni.y;
             const uint32_t rel = info & 3u;
             const uint32_t and_mask = (rel == PDEB_REL_EQ) ? 0x7fffffffu : 0xffffffffu;
@@ -988,6 +1045,23 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
             real hi[PDEB_MARGIN_ACC];
             pdeb_clause_partials<N, real, STRIDE>(tr.w, tr.stab, mh, c0, nm, inel ? 0xffffffffu : and_mask, inel ? 0u : xor_mask, hi);
             real gmax = pdeb_partials_max<real>(hi);
+#if PDEB_ENDPOINTS_MERGED
+            /* interpolated end points: ONE warp-wide test skips both forms (two thirds of the passes see neither) */
+            if (wf & 12u) {
+                if (wf & 4u) {
+                    /* every lane runs the few selects; only the lanes whose interval lies inside one element keep the result */
+                    const real gi = pdeb_inelement_gmax<real>(hi, (info >> 4) & 31u, slots.R(cur, 3), slots.R(cur, 4), and_mask, xor_mask);
+                    gmax = inel ? gi : gmax;
+                }
+                if (wf & 8u) {
+                    if (flags & 8u) {
+                        const real ge = pdeb_endpoint_gmax<N, real, STRIDE>(tr.w, tr.stab, mh, c0, info, slots.R(cur, 3), slots.R(cur, 4),
+                                                                            and_mask, xor_mask);
+                        if (ge > gmax) gmax = ge;
+                    }
+                }
+            }
+#else
             if (wf & 4u) {
                 if (inel) gmax = pdeb_inelement_gmax<real>(hi, (info >> 4) & 31u, slots.R(cur, 3), slots.R(cur, 4), and_mask, xor_mask);
             }
@@ -998,6 +1072,7 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
                     if (ge > gmax) gmax = ge;
                 }
             }
+#endif
             /* G: min over steps of -gmax = -(max gmax); F: max over steps of -gmax: one running max either way */
             const real v = (((info >> 2) & 1u) == PDEB_TOP_G) ? gmax : -gmax;
             if (has && v > A) slots.R(cur, 2) = v;
@@ -1036,20 +1111,31 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
                     if (has2 && v2 > slots.R(j, 2)) slots.R(j, 2) = v2;
                 }
             }
-        }
+            };
+#if PDEB_ROTATE
+    /* rotated loop: the pass of step k+1 closes the iteration that advanced to it (one branch per step less) */
+    if (wf & 1u) clause_pass();
+    for (int32_t k = 0; k < Smax; ++k) {
+#else
+    for (int32_t k = 0;; ++k) {
+        if (wf & 1u) clause_pass();
         if (k >= Smax) break;
+#endif
+        typename PdebTrajReg<KIND, N, real, STRIDE>::real2 pre_t[PDEB_PRE_TAB_MAX], pre_b[PDEB_PRE_TAB_MAX];
+        PDEB_UNROLL
+        for (int q = 0; q < PRE_TAB; ++q) { pre_t[q] = tr.tab[q * STRIDE]; pre_b[q] = tr.tab[(N - 1 - q) * STRIDE]; }
         /* the windows of step k+1 are settled before the solve, which hides the latency of the warp-wide OR */
         window_events(k + 1);
         wf = PDEB_WARP_OR(flags);
         /* ---- (2) advance to step k+1 (lanes that are done keep stepping; nobody looks at them) ---- */
         {
-            const real f_next = in.eval((double)(k + 1) * dt, kt, ky, st);
+            const real f_next = in.eval(PRE_TIME ? t_nx : (double)(k + 1) * dt, kt, ky, st);
             if (KIND == PDEB_KIND_HEAT) {
                 const real th_dt = (real)(cv.theta * dt);
                 const real fb = tr.sN * fma((real)dt - th_dt, f_prev, th_dt * f_next);
                 real z[N + 2];
                 z[0] = 0; z[N + 1] = 0;
-                tr.step_solve(tr.w, fb, z);
+                tr.template step_solve<PRE_TAB>(tr.w, fb, z, pre_t, pre_b);
                 PDEB_UNROLL
                 for (int i = 1; i <= N; ++i) tr.w[i] = z[i];
             } else {
@@ -1061,7 +1147,7 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
                     tr.w[i] = fma(cw2, tr.a[i], fma(cw1, tr.v[i], tr.w[i]));   /* predictor d~ */
                     tr.v[i] = fma(cw3, tr.a[i], tr.v[i]);                       /* predictor v~ */
                 }
-                tr.step_solve(tr.w, tr.sN * f_next, tr.a);                      /* a' = A^-1 (f' e_N - K d~), scaled */
+                tr.template step_solve<PRE_TAB>(tr.w, tr.sN * f_next, tr.a, pre_t, pre_b);   /* a' = A^-1 (f' e_N - K d~), scaled */
                 const real cw4 = (real)(cv.newmark_beta * dt * dt);
                 const real cw5 = (real)(cv.newmark_gamma * dt);
                 PDEB_UNROLL
@@ -1072,6 +1158,11 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
             }
             f_prev = f_next;
         }
+        if (PRE_SLOTS) { p_mh = slots.R(cur, 0); p_c0 = slots.R(cur, 1); p_A = slots.R(cur, 2); p_ni = slots.NI(cur); }
+        if (PRE_TIME) t_nx = (double)(k + 2) * dt;
+#if PDEB_ROTATE
+        if (wf & 1u) clause_pass();
+#endif
     }
 
     if (!live) return;

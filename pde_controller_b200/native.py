@@ -35,6 +35,8 @@ def lib():
         L.pdeb_version.restype = C.c_int
         L.pdeb_device_count.restype = C.c_int
         L.pdeb_last_error.restype = C.c_char_p
+        L.pdeb_device_pci_bus_id.restype = C.c_int
+        L.pdeb_device_pci_bus_id.argtypes = [C.c_int, C.c_char_p, C.c_int]
         L.pdeb_default_conventions.argtypes = [C.c_void_p]
         L.pdeb_host_alloc.restype = C.c_void_p
         L.pdeb_host_alloc.argtypes = [C.c_int64]
@@ -104,6 +106,69 @@ def _check(rc, what):
 
 def device_count() -> int:
     return int(lib().pdeb_device_count())
+
+
+def device_pci_bus_id(device: int) -> str:
+    buf = C.create_string_buffer(32)
+    _check(lib().pdeb_device_pci_bus_id(int(device), buf, 32), "pdeb_device_pci_bus_id")
+    return buf.value.decode().lower()
+
+
+def _cpulist(text: str) -> set:
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def _nvml_cpu_affinity(bus_id: str) -> set:
+    """The driver's ideal CPU set of the device at `bus_id` (what `nvidia-smi topo -m` prints), empty if NVML is not there."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus_id.encode())
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(os.cpu_count() or 1, 1) + 63) // 64)
+            return {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        finally:
+            pynvml.nvmlShutdown()
+    except Exception:
+        return set()
+
+
+def bind_host_near(device: int, sysfs: str = "/sys") -> dict:
+    """Run the calling thread (and the threads it starts later) on the CPUs of the NUMA node `device` hangs off.
+
+    Page-locked buffers allocated afterwards (`pdeb_host_alloc`, the staging mirrors of the one-shot calls) are placed on
+    that node by the kernel's local allocation policy, so host -> device copies do not cross the socket interconnect: on a box with
+    one process per GPU that is what keeps eight concurrent uploads from sharing one socket's links.  Returns what was
+    done: {"bus_id", "node", "cpus", "bound"}; on a box without NUMA information (node -1, containers that hide sysfs)
+    nothing changes and "bound" is False.  Undo with os.sched_setaffinity(0, previous).
+    """
+    info = {"bus_id": None, "node": None, "cpus": 0, "bound": False}
+    try:
+        bus = device_pci_bus_id(device)
+        info["bus_id"] = bus
+        with open(f"{sysfs}/bus/pci/devices/{bus}/numa_node") as fh:
+            node = int(fh.read().strip())
+        info["node"] = node
+        if node < 0:
+            cpus = _nvml_cpu_affinity(bus) & os.sched_getaffinity(0)     # virtual machines: sysfs says -1, the driver may still know
+            if not cpus or cpus == os.sched_getaffinity(0):
+                return info
+        else:
+            with open(f"{sysfs}/devices/system/node/node{node}/cpulist") as fh:
+                cpus = _cpulist(fh.read()) & os.sched_getaffinity(0)
+        info["cpus"] = len(cpus)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info["bound"] = True
+    except (OSError, ValueError, NativeError):
+        pass
+    return info
 
 
 def _ptr(a: Optional[np.ndarray]):

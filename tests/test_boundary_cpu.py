@@ -36,3 +36,35 @@ def test_wrapper_without_a_device_fails_loudly_and_prints_nothing_on_stdout():
     assert p.returncode != 0 and p.stdout == "" and "NativeError" in p.stderr
     p = subprocess.run([sys.executable, exe], capture_output=True, text=True, timeout=300)
     assert p.returncode == 2 and p.stdout == ""
+
+
+def test_bind_host_near_uses_the_gpu_numa_node(tmp_path, monkeypatch):
+    """native.bind_host_near: PCI bus id -> sysfs numa_node -> cpulist of that node -> sched_setaffinity; nothing changes
+    on boxes that hide the information (node -1, no sysfs entry, no device)."""
+    import os
+    from pde_controller_b200 import native
+
+    assert native._cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert native._cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    keep = sorted(before)[: max(1, len(before) // 2)]
+    bus = "0000:1b:00.0"
+    dev_dir = tmp_path / "bus" / "pci" / "devices" / bus
+    dev_dir.mkdir(parents=True)
+    node_dir = tmp_path / "devices" / "system" / "node" / "node1"
+    node_dir.mkdir(parents=True)
+    (node_dir / "cpulist").write_text(",".join(str(c) for c in keep) + ",4093-4095\n")    # CPUs outside the process's set are dropped
+    monkeypatch.setattr(native, "device_pci_bus_id", lambda device: bus)
+    try:
+        (dev_dir / "numa_node").write_text("-1\n")
+        info = native.bind_host_near(0, sysfs=str(tmp_path))
+        assert info == {"bus_id": bus, "node": -1, "cpus": 0, "bound": False} and os.sched_getaffinity(0) == before
+        (dev_dir / "numa_node").write_text("1\n")
+        info = native.bind_host_near(0, sysfs=str(tmp_path))
+        assert info["bound"] and info["node"] == 1 and info["cpus"] == len(keep)
+        assert os.sched_getaffinity(0) == set(keep)
+        os.sched_setaffinity(0, before)
+        info = native.bind_host_near(0, sysfs=str(tmp_path / "absent"))
+        assert not info["bound"] and os.sched_getaffinity(0) == before
+    finally:
+        os.sched_setaffinity(0, before)

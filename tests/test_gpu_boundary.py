@@ -153,3 +153,24 @@ def test_block_pipeline_packed_matches_planar():
         if packed:
             assert pipe.h2d_bytes < 0.8 * sum(x.slab_bytes for x in pipe.blocks[0])
         pipe.close()
+
+
+@pytest.mark.gpu
+def test_device_pci_bus_id_and_host_binding():
+    """pdeb_device_pci_bus_id names the device the way sysfs does; bind_host_near never leaves the process without CPUs."""
+    import os
+    import re
+    from pde_controller_b200 import native
+
+    bus = native.device_pci_bus_id(0)
+    assert re.fullmatch(r"[0-9a-f]{4,8}:[0-9a-f]{2}:[0-9a-f]{2}\.[0-9a-f]", bus), bus
+    with pytest.raises(native.NativeError):
+        native.device_pci_bus_id(native.device_count())
+    before = os.sched_getaffinity(0)
+    try:
+        info = native.bind_host_near(0)
+        assert info["bus_id"] == bus
+        now = os.sched_getaffinity(0)
+        assert now and now <= before and (info["bound"] or now == before)
+    finally:
+        os.sched_setaffinity(0, before)
