@@ -1124,12 +1124,14 @@ PDEB_HD void pdeb_run_reg(const PdebDevBatch& b, const PdebConventions& cv, cons
         typename PdebTrajReg<KIND, N, real, STRIDE>::real2 pre_t[PDEB_PRE_TAB_MAX], pre_b[PDEB_PRE_TAB_MAX];
         PDEB_UNROLL
         for (int q = 0; q < PRE_TAB; ++q) { pre_t[q] = tr.tab[q * STRIDE]; pre_b[q] = tr.tab[(N - 1 - q) * STRIDE]; }
-        /* the windows of step k+1 are settled before the solve, which hides the latency of the warp-wide OR */
+        /* the windows of step k+1 are settled before the solve */
         window_events(k + 1);
-        wf = PDEB_WARP_OR(flags);
         /* ---- (2) advance to step k+1 (lanes that are done keep stepping; nobody looks at them) ---- */
         {
             const real f_next = in.eval(PRE_TIME ? t_nx : (double)(k + 1) * dt, kt, ky, st);
+            /* the warp-wide OR opens the block of the solve, whose length hides its latency (between the events and the
+             * crossing it ended a short block, and the copy of its result out of the uniform register stalled there) */
+            wf = PDEB_WARP_OR(flags);
             if (KIND == PDEB_KIND_HEAT) {
                 const real th_dt = (real)(cv.theta * dt);
                 const real fb = tr.sN * fma((real)dt - th_dt, f_prev, th_dt * f_next);
