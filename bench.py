@@ -562,13 +562,20 @@ def main():
         probs, ctrls = zip(*(src.get_problem(i) for i in range(m)))
         texts = [render_program(p) for p in probs]
         es.configure(device=dev, precision=args.precision)
-        es.eval_robustness_batch(texts[:64], controls=list(ctrls[:64]))            # warm-up: imports, regex compilation
+        ctrls = list(ctrls)
+        es.eval_robustness_batch(texts[:64], controls=ctrls[:64])                  # imports, regex compilation
         t0 = time.perf_counter()
-        rob_text, _ = es.eval_robustness_batch(texts, controls=list(ctrls))
-        secs = time.perf_counter() - t0
+        rob_text, _ = es.eval_robustness_batch(texts, controls=ctrls)              # first call of this size: page-locked mirror,
+        first = time.perf_counter() - t0                                           # device image and host pages are allocated here
         if not np.array_equal(np.array(rob_text), out_host["robustness"][:m]):
             raise SystemExit("bench: text-level results differ from the resident evaluation")
-        e2e_text = {"value": m / secs, "unit": "programs/s", "programs": m, "cores": os.cpu_count(),
+        reps = 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            es.eval_robustness_batch(texts, controls=ctrls)
+        secs = (time.perf_counter() - t0) / reps
+        e2e_text = {"value": m / secs, "unit": "programs/s", "programs": m, "cores": os.cpu_count(), "calls_timed": reps,
+                    "first_call_value": m / first,
                     "route": "eval_robustness_batch(program strings, given controls): native template matcher "
                              "(pdeb_parse_programs, host threads; anything else -> Python front-end) -> PdebBatch -> "
                              "pdeb_eval_batch -> robustness list"}

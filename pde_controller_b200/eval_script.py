@@ -22,6 +22,7 @@ Differences that are deliberate and documented in INTEGRATION.md:
 from __future__ import annotations
 
 import json
+import operator
 import time
 from typing import List, Optional, Sequence, Tuple
 
@@ -120,17 +121,10 @@ def eval_robustness_batch(programs: Sequence[str], natural_language: Optional[Se
         # ---- one batch of all n samples (a program that did not parse keeps a place and is masked out afterwards) ----
         pmax = int(max([int(wide.n_pred[accepted].max(initial=1)) if wide is not None else 1] + [len(p.predicates) for _, p in ok_rest] + [1]))
         tmax = int(max([2 * pmax - 1] + [len(p.tree) for _, p in ok_rest]))
-        ctrl = [None] * n
-        need = []
-        for i in range(n):
-            c = controls[i]
-            if c is not None:
-                t, y = c
-                ctrl[i] = (np.asarray(t, dtype=np.float64).ravel(), np.asarray(y, dtype=np.float64).ravel())
-                if ctrl[i][0].shape != ctrl[i][1].shape:
-                    raise ValueError("control knot times and values differ in length")
-            elif live[i]:
-                need.append(i)
+        # controls: no per-sample numpy call (a list of n (times, values) pairs goes through two concatenations)
+        given = (np.fromiter((c is not None for c in controls), dtype=bool, count=n) if None in controls
+                 else np.ones(n, dtype=bool))
+        need = np.nonzero(~given & live)[0].tolist()
         if need and mode == "search":
             from . import search as _search
             by_index = dict(ok_rest)
@@ -138,9 +132,36 @@ def eval_robustness_batch(programs: Sequence[str], natural_language: Optional[Se
             found = _search.search_controls(probs, device=dev, conv=conv, **{**_SEARCH, **(search or {})})
             for i, f in zip(need, found):
                 if f["knot_y"] is not None:
-                    ctrl[i] = (np.asarray(f["knot_t"], dtype=np.float64), np.asarray(f["knot_y"], dtype=np.float64))
-                    controls[i] = ctrl[i]
-        kmax = max([len(c[0]) for c in ctrl if c is not None] + [1])
+                    controls[i] = (np.asarray(f["knot_t"], dtype=np.float64), np.asarray(f["knot_y"], dtype=np.float64))
+                    given[i] = True
+        have = np.nonzero(given)[0]
+        cnt = np.zeros(n, dtype=np.int64)
+        flat_t = flat_y = None
+        if have.size:
+            sel = controls if have.size == n else [controls[i] for i in have.tolist()]
+            ts = list(map(operator.itemgetter(0), sel))
+            ys = list(map(operator.itemgetter(1), sel))
+            try:
+                len_t, len_y = list(map(len, ts)), list(map(len, ys))
+                same = len_t == len_y
+                len_t = np.array(len_t, dtype=np.int64)
+                len_y = len_t if same else np.array(len_y, dtype=np.int64)
+                flat_t = np.concatenate(ts, dtype=np.float64) if len_t.sum() else np.zeros(0)
+                flat_y = np.concatenate(ys, dtype=np.float64) if len_y.sum() else np.zeros(0)
+                if flat_t.ndim != 1 or flat_y.ndim != 1:
+                    raise ValueError("multi-dimensional entries")
+            except (TypeError, ValueError):
+                # scalars, nested or multi-dimensional entries: the slow, forgiving route
+                ts = [np.asarray(t, dtype=np.float64).ravel() for t in ts]
+                ys = [np.asarray(y, dtype=np.float64).ravel() for y in ys]
+                len_t = np.array([t.size for t in ts], dtype=np.int64)
+                len_y = np.array([y.size for y in ys], dtype=np.int64)
+                flat_t = np.concatenate(ts) if ts else np.zeros(0)
+                flat_y = np.concatenate(ys) if ys else np.zeros(0)
+            if not np.array_equal(len_t, len_y):
+                raise ValueError("control knot times and values differ in length")
+            cnt[have] = len_t
+        kmax = int(max(cnt.max(initial=0), 1))
         batch = ProblemBatch(n, kmax, pmax, tmax)
         if wide is not None:
             for name in batch._names:
@@ -156,18 +177,17 @@ def eval_robustness_batch(programs: Sequence[str], natural_language: Optional[Se
         # a program that did not parse: a harmless place-holder (its results are overwritten below)
         for i in bad:
             batch.n_pred[i] = 0
-        cnt = np.fromiter((0 if c is None else len(c[0]) for c in ctrl), dtype=np.int64, count=n)
         batch.n_knots[:] = cnt
-        if cnt.sum() > 0:
+        if flat_t is not None and flat_t.size:
             km = np.arange(kmax)[None, :] < cnt[:, None]
-            batch.knot_t.T[km] = np.concatenate([c[0] for c in ctrl if c is not None])
-            batch.knot_y.T[km] = np.concatenate([c[1] for c in ctrl if c is not None])
+            batch.knot_t.T[km] = flat_t
+            batch.knot_y.T[km] = flat_y
         # the number returned is ALWAYS the batch kernels' robustness under the control in `controls` (found or given)
         out = native.evaluate_batch(batch, device=dev, precision=_PRECISION if precision is None else precision, conv=conv)
         rob[live] = out["robustness"][live]
         status[live] = out["status"][live]
     runtime = (time.perf_counter() - t0) / max(n, 1)
-    res = ([float(r) for r in rob], [runtime] * n)
+    res = (rob.tolist(), [runtime] * n)
     if return_status:
         res = res + (status,)
     if return_controls:

@@ -738,9 +738,28 @@ def parse_native(texts, pmax: int = abi.MAX_PRED, nthreads: int = 0):
     accepted = np.zeros(n, dtype=np.uint8)
     if n == 0:
         return batch, accepted.astype(bool)
-    enc = [t.encode("utf-8", "surrogatepass") if isinstance(t, str) else b"" for t in texts]
-    ptrs = (C.c_char_p * n)(*enc)
-    lens = np.fromiter(map(len, enc), dtype=np.int64, count=n)
+    # ONE byte buffer for the whole list (a join and an encode at memcpy speed) and a pointer table formed in numpy; the
+    # per-text route below (one bytes object and one ctypes conversion per program) cost more than the parse itself
+    blob, lens = None, None
+    try:
+        joined = "\0".join(texts)
+        if joined.isascii():
+            lens = np.fromiter(map(len, texts), dtype=np.int64, count=n)          # characters == bytes
+            if int(lens.sum()) + n - 1 == len(joined):
+                blob = joined.encode("ascii")
+    except TypeError:                                                              # an entry that is not a str
+        blob = None
+    if blob is not None:
+        starts = np.zeros(n, dtype=np.int64)
+        np.cumsum(lens[:-1] + 1, out=starts[1:])
+        base = C.cast(C.c_char_p(blob), C.c_void_p).value or 0
+        table = (starts + base).astype(np.uint64)
+        ptrs = table.ctypes.data
+    else:
+        enc = [t.encode("utf-8", "surrogatepass") if isinstance(t, str) else b"" for t in texts]
+        keep = (C.c_char_p * n)(*enc)
+        ptrs = C.cast(keep, C.c_void_p).value
+        lens = np.fromiter(map(len, enc), dtype=np.int64, count=n)
     cb = batch.as_c()
     rc = L.pdeb_parse_programs(ptrs, lens.ctypes.data, n, C.addressof(cb), 0, accepted.ctypes.data, int(nthreads))
     if rc != 0:

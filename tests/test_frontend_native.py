@@ -145,3 +145,56 @@ def test_fuzz_native_never_accepts_what_python_declines_or_reads_differently():
         assert same_problem(native_problem(batch, 0), want)
 
     run()
+
+
+def test_blob_route_and_per_text_route_agree():
+    """parse_native hands the whole list over as ONE byte buffer when every text is ASCII and falls back to one buffer per
+    text otherwise (a non-ASCII character, an entry that is not a str): same numbers, same accepted mask."""
+    src = synth.make_batch(64, "heat", seed=11)
+    texts = [render_program(src.get_problem(i)[0]) for i in range(64)]
+    a, acc_a = parse_native(texts)
+    assert acc_a.all()
+    mixed = list(texts)
+    mixed[5] = mixed[5] + "# café\n"            # not ASCII: the per-text route for the whole list
+    mixed[9] = None                                  # not a str: declined, never an exception
+    b, acc_b = parse_native(mixed)
+    assert not acc_b[9] and acc_b[[i for i in range(64) if i not in (5, 9)]].all()
+    for name in ("L", "T", "dt", "E_in", "rho_out", "pred_m", "pred_tlo", "pred_rel", "tree_op"):
+        x, y = getattr(a, name), getattr(b, name)
+        keep = np.array([i for i in range(64) if acc_b[i]])
+        assert np.array_equal(x[..., keep], y[..., keep]), name
+    c, acc_c = parse_native(["", "x = 1", texts[0]])
+    assert acc_c.tolist() == [False, False, True]
+
+
+def test_eval_robustness_batch_assembles_controls_without_a_device(monkeypatch):
+    """Host side of eval_robustness_batch: given controls of every accepted shape land in the batch's knot planes, a
+    missing one follows the mode, mismatched lengths raise; the device call is replaced by a recorder."""
+    from pde_controller_b200 import abi, eval_script as es, native
+
+    src = synth.make_batch(6, "heat", seed=3)
+    texts = [render_program(src.get_problem(i)[0]) for i in range(6)]
+    seen = {}
+
+    def fake(batch, **kw):
+        seen["batch"] = batch
+        return {"robustness": np.arange(batch.n, dtype=np.float64), "status": np.zeros(batch.n, np.int32), "clause": None}
+
+    monkeypatch.setattr(native, "evaluate_batch", fake)
+    ctrl = [(np.array([0.0, 1.0, 2.0]), np.array([5.0, 6.0, 7.0])),          # arrays
+            ([0.0, 4.0], [1.0, 2.0]),                                          # lists
+            None,                                                              # mode "zero": no knots
+            (np.array([[0.0, 1.0]]), np.array([[3.0], [4.0]])),                # odd shapes are flattened
+            ((0.0,), (9.0,)),
+            (np.zeros(0), np.zeros(0))]
+    monkeypatch.setattr(es, "_CONTROL_MODE", "zero")      # a missing control means zero input here (the default mode searches on the GPU)
+    rob, rt, st = es.eval_robustness_batch(texts + ["not a program"], controls=ctrl + [None], return_status=True)
+    b = seen["batch"]
+    assert b.n == 7 and b.n_knots.tolist() == [3, 2, 0, 2, 1, 0, 0]
+    assert b.knot_t[:3, 0].tolist() == [0.0, 1.0, 2.0] and b.knot_y[:3, 0].tolist() == [5.0, 6.0, 7.0]
+    assert b.knot_t[:2, 1].tolist() == [0.0, 4.0] and b.knot_y[:2, 3].tolist() == [3.0, 4.0] and b.knot_y[0, 4] == 9.0
+    assert rob[:6] == [0.0, 1.0, 2.0, 3.0, 4.0, 5.0] and rob[6] == abi.FAILED_ROBUSTNESS and st[6] == abi.ST_PARSE
+    with pytest.raises(ValueError):
+        es.eval_robustness_batch(texts[:2], controls=[([0.0, 1.0], [1.0]), ([0.0], [1.0, 2.0])])
+    with pytest.raises(ValueError):
+        es.eval_robustness_batch(texts[:2], controls=[None])
