@@ -300,6 +300,38 @@ int  pdeb_controls_create(const PdebBatch* spec, int64_t sample, int64_t capacit
 int  pdeb_controls_eval(PdebControls* h, int64_t m, const double* knot_y, double* robustness_out, double* clause_out,
                         int32_t* status_out, int64_t* best_index, double* best_value, void* stream, PdebTiming* timing);
 void pdeb_controls_destroy(PdebControls* h);
+/* point an existing handle at another specification of the family (heat N=30 / wave N=20, up to 32 knots): no allocation,
+   the candidates on the device stay.  What a sweep over many programs calls between searches. */
+int  pdeb_controls_respec(PdebControls* h, const PdebBatch* spec, int64_t sample, int32_t n_knots, const double* knot_t,
+                          const PdebConventions* conv);
+/*
+ * The whole cross-entropy search for the handle's specification on the device (the sampling surrogate of the reference's
+ * control synthesis, eval_robustness_wrapper.py:16): `generations` times { draw `population` candidates
+ * y = clip(mean + std z, lo, hi) from a counter-based generator (generation 0: uniform over [lo, hi], plus the zero input
+ * and both bounds; the incumbent is always candidate 0) -> their robustness -> the elite_frac best re-centre mean / std }.
+ * Three launches per generation, nothing crosses PCIe in between, deterministic for a given seed.
+ *   best_y_out [n_knots], best_value_out, found_out (0: no candidate had status 0; then best_value = -100),
+ *   history_out [generations] best robustness after each generation (never decreases), mean_out / std_out [n_knots]
+ *   the final sampling distribution: all optional.  Synchronises `stream` before returning.
+ */
+int  pdeb_controls_search(PdebControls* h, int64_t population, int32_t generations, double elite_frac, double lo, double hi,
+                          uint64_t seed, double* best_y_out, double* best_value_out, int32_t* found_out, double* history_out,
+                          double* mean_out, double* std_out, void* stream, PdebTiming* timing);
+/*
+ * pdeb_controls_search for MANY specifications: samples[0..n_samples) of `in` (NULL = every sample), `nthreads` host threads
+ * (<= 0: all, at most 32) with one stream and one controls handle each.  Knot TIMES are the batch's own (n_knots, knot_t;
+ * knot_t == NULL: linspace(0, T, n_knots)), the knot VALUES found are written to knot_y_out in the batch's plane-major
+ * layout [kmax][stride] (it may BE in->knot_y), best_out [n] / found_out [n] per sample.  bounds = { heat lo, heat hi, wave lo,
+ * wave hi }.  Sample s draws from the generator stream mix(seed, s): the result does not depend on the thread count.
+ * A sample outside the controls family (or with more than 32 knots) is left with found = 0 for the caller to handle.
+ * Replaces one femformal + Gurobi process per sample (simulate_gt.py:62-89 -> eval_robustness_wrapper.py:16).
+ */
+int  pdeb_controls_search_batch(const PdebBatch* in, const int64_t* samples, int64_t n_samples, int64_t population,
+                                int32_t generations, double elite_frac, const double* bounds, uint64_t seed, int device,
+                                const PdebConventions* conv, int nthreads, double* knot_y_out, double* best_out,
+                                int32_t* found_out, PdebTiming* timing);
+/* the candidates currently on the device, host [n_knots][m] plane-major (diagnostics, tests) */
+int  pdeb_controls_fetch_knots(PdebControls* h, int64_t m, double* knot_y_out, void* stream);
 
 /*
  * Native front-end for the CANONICAL program template (host only).  The reference's call surface is program TEXT

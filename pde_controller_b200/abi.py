@@ -180,6 +180,10 @@ EXPORTS = [
     "pdeb_controls_create",
     "pdeb_controls_eval",
     "pdeb_controls_destroy",
+    "pdeb_controls_respec",
+    "pdeb_controls_search",
+    "pdeb_controls_search_batch",
+    "pdeb_controls_fetch_knots",
     "pdeb_resident_fetch",
     "pdeb_resident_fetch_async",
     "pdeb_stream_create",

@@ -20,7 +20,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pdeb200.h"
@@ -336,6 +339,185 @@ __global__ void pdeb_argmax_partial_kernel(const double* __restrict__ r, const i
     if (threadIdx.x == 0) { pv[blockIdx.x] = sv[0]; pi[blockIdx.x] = si[0]; }
 }
 
+
+/* ---- device-resident cross-entropy search over the candidates of one specification ------------------------------
+ * The host-driven search (pde_controller_b200/search.py, round 1) drew every generation with numpy, uploaded it,
+ * fetched every robustness and ranked them on the host: ~4 ms of host work per program around ~0.7 ms of kernels.
+ * Here a generation is three launches and nothing crosses PCIe until the search is over:
+ *   pdeb_cem_sample_kernel   candidates  y = clip(mean + std * z)  from a counter-based generator (generation 0:
+ *                            uniform over the bounds, plus the zero input and the two bounds; the incumbent is
+ *                            always candidate 0),
+ *   pdeb_controls_kernel     their robustness (the kernel above, unchanged),
+ *   pdeb_cem_update_kernel   ONE block: radix select of the elite (largest robustness, ties by lowest index),
+ *                            mean / standard deviation of the elite's knot values, incumbent, history.
+ * Deterministic for a given seed (fixed reduction trees, no atomics on floating-point values). */
+#define PDEB_CEM_MAX_GEN 64
+#define PDEB_CEM_MAX_ELITE 8192
+#define PDEB_CEM_THREADS 1024
+struct PdebCemState {
+    double mean[PDEB_CTL_KMAX], std[PDEB_CTL_KMAX], best_y[PDEB_CTL_KMAX];
+    double history[PDEB_CEM_MAX_GEN];
+    double best_r;
+    int32_t has_best, n_valid_last;
+};
+
+__host__ __device__ __forceinline__ uint64_t pdeb_mix64(uint64_t z) {     /* splitmix64 finaliser */
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+/* uniform in (0, 1): one 64-bit word per (seed, generation, knot, candidate, which) */
+__device__ __forceinline__ double pdeb_cem_uniform(uint64_t seed, int gen, int j, int64_t i, int which) {
+    const uint64_t k = pdeb_mix64(pdeb_mix64(seed ^ pdeb_mix64(((uint64_t)gen << 32) | (uint64_t)(uint32_t)j)) + 2ull * (uint64_t)i + (uint64_t)which);
+    return ((double)(k >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+__global__ void pdeb_cem_sample_kernel(double* __restrict__ ky, int64_t stride, int nk, int64_t P, const PdebCemState* __restrict__ st,
+                                       int gen, uint64_t seed, double lo, double hi) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const bool has_best = st->has_best != 0;
+    for (int j = 0; j < nk; ++j) {
+        double y;
+        if (gen == 0) {
+            y = lo + (hi - lo) * pdeb_cem_uniform(seed, gen, j, i, 0);
+            if (i == 1) y = fmin(fmax(0.0, lo), hi);       /* the zero input competes from the start */
+            if (i == 2) y = lo;
+            if (i == 3) y = hi;
+        } else {
+            const double u1 = pdeb_cem_uniform(seed, gen, j, i, 0), u2 = pdeb_cem_uniform(seed, gen, j, i, 1);
+            const double z = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+            y = fmin(fmax(fma(st->std[j], z, st->mean[j]), lo), hi);
+        }
+        if (i == 0 && has_best) y = st->best_y[j];         /* the incumbent stays in the population */
+        ky[(int64_t)j * stride + i] = y;
+    }
+}
+
+/* larger robustness <-> larger key; 0 is reserved for candidates that do not count (status != 0, non-finite) */
+__device__ __forceinline__ uint64_t pdeb_cem_key(const double* __restrict__ rob, const int32_t* __restrict__ status, int64_t i) {
+    const double r = rob[i];
+    if (status[i] != PDEB_OK || !isfinite(r)) return 0ull;
+    const uint64_t u = (uint64_t)__double_as_longlong(r);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+
+__global__ void __launch_bounds__(PDEB_CEM_THREADS)
+pdeb_cem_update_kernel(const double* __restrict__ rob, const int32_t* __restrict__ status, const double* __restrict__ ky, int64_t stride,
+                       int64_t P, int nk, int n_elite, double std_floor, PdebCemState* __restrict__ st, int gen) {
+    __shared__ unsigned hist[256];
+    __shared__ int32_t elist[PDEB_CEM_MAX_ELITE];
+    __shared__ uint64_t s_prefix;
+    __shared__ unsigned long long s_best;       /* packed arg-max, see below */
+    __shared__ uint64_t s_bestkey;
+    __shared__ int s_need, s_k, s_woff[32], s_eoff, s_goff;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    /* ---- how many candidates count, and the best of them (largest key, lowest index) ---- */
+    if (tid < 256) hist[tid] = 0;
+    if (tid == 0) { s_bestkey = 0ull; s_best = ~0ull; }
+    __syncthreads();
+    unsigned nv_local = 0;
+    uint64_t bk = 0ull; int64_t bi = -1;
+    for (int64_t i = tid; i < P; i += PDEB_CEM_THREADS) {
+        const uint64_t k = pdeb_cem_key(rob, status, i);
+        if (k) { ++nv_local; if (k > bk) { bk = k; bi = i; } }        /* ascending i per thread: first of equal keys */
+    }
+    atomicAdd(&hist[0], nv_local);
+    atomicMax((unsigned long long*)&s_bestkey, (unsigned long long)bk);
+    __syncthreads();
+    const int nv = (int)hist[0];
+    if (bk == s_bestkey && bi >= 0) atomicMin(&s_best, (unsigned long long)bi);
+    __syncthreads();
+    const int64_t best_i = (s_bestkey != 0ull) ? (int64_t)s_best : -1;
+    const int k_el = nv < n_elite ? nv : n_elite;
+
+    /* ---- radix select of the k_el-th largest key ---- */
+    if (tid == 0) { s_prefix = 0ull; s_need = k_el; }
+    __syncthreads();
+    if (k_el >= 2) {
+        for (int b = 7; b >= 0; --b) {
+            if (tid < 256) hist[tid] = 0;
+            __syncthreads();
+            const uint64_t prefix = s_prefix;
+            for (int64_t i = tid; i < P; i += PDEB_CEM_THREADS) {
+                const uint64_t k = pdeb_cem_key(rob, status, i);
+                if (k && (b == 7 || (k >> (8 * (b + 1))) == prefix)) atomicAdd(&hist[(unsigned)(k >> (8 * b)) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int need = s_need, bin = 255;
+                for (; bin > 0; --bin) { if ((int)hist[bin] >= need) break; need -= (int)hist[bin]; }
+                s_need = need;                         /* still to take among the keys of this bin */
+                s_prefix = (prefix << 8) | (uint64_t)bin;
+            }
+            __syncthreads();
+        }
+        /* ---- the elite in index order: every key above the threshold, and the first s_need of those equal to it ---- */
+        const uint64_t thr = s_prefix;
+        const int need_eq = s_need;
+        if (tid == 0) { s_eoff = 0; s_goff = 0; }
+        __syncthreads();
+        for (int64_t base = 0; base < P; base += PDEB_CEM_THREADS) {
+            const int64_t i = base + tid;
+            const uint64_t k = (i < P) ? pdeb_cem_key(rob, status, i) : 0ull;
+            const bool eq = k != 0ull && k == thr;
+            /* rank of this thread among the equal keys of the chunk */
+            const unsigned beq = __ballot_sync(0xffffffffu, eq);
+            if (lane == 0) s_woff[warp] = __popc(beq);
+            __syncthreads();
+            int eq_before = s_eoff;
+            for (int w = 0; w < warp; ++w) eq_before += s_woff[w];
+            eq_before += __popc(beq & ((1u << lane) - 1u));
+            int eq_total = 0;
+            for (int w = 0; w < 32; ++w) eq_total += s_woff[w];
+            __syncthreads();
+            const bool take = k != 0ull && (k > thr || (eq && eq_before < need_eq));
+            const unsigned bt = __ballot_sync(0xffffffffu, take);
+            if (lane == 0) s_woff[warp] = __popc(bt);
+            __syncthreads();
+            int pos = s_goff;
+            for (int w = 0; w < warp; ++w) pos += s_woff[w];
+            pos += __popc(bt & ((1u << lane) - 1u));
+            if (take && pos < PDEB_CEM_MAX_ELITE) elist[pos] = (int32_t)i;
+            int tk_total = 0;
+            for (int w = 0; w < 32; ++w) tk_total += s_woff[w];
+            __syncthreads();
+            if (tid == 0) { s_eoff += eq_total; s_goff += tk_total; }
+            __syncthreads();
+        }
+        if (tid == 0) s_k = s_goff < PDEB_CEM_MAX_ELITE ? s_goff : PDEB_CEM_MAX_ELITE;
+        __syncthreads();
+        /* ---- mean and standard deviation of the elite per knot: warp w takes the knots w, w + 32, .. ---- */
+        const int ke = s_k;
+        for (int j = warp; j < nk; j += 32) {
+            const double* col = ky + (int64_t)j * stride;
+            double sum = 0.0;
+            for (int q = lane; q < ke; q += 32) sum += col[elist[q]];
+            for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const double mean = sum / (double)ke;
+            double var = 0.0;
+            for (int q = lane; q < ke; q += 32) { const double d = col[elist[q]] - mean; var = fma(d, d, var); }
+            for (int o = 16; o >= 1; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+            if (lane == 0) { st->mean[j] = mean; st->std[j] = fmax(sqrt(var / (double)ke), std_floor); }
+        }
+    }
+    /* ---- incumbent ---- */
+    __syncthreads();
+    const bool better = best_i >= 0 && (!st->has_best || rob[best_i] > st->best_r);
+    __syncthreads();
+    if (better) {
+        for (int j = tid; j < nk; j += PDEB_CEM_THREADS) st->best_y[j] = ky[(int64_t)j * stride + best_i];
+        if (tid == 0) { st->best_r = rob[best_i]; st->has_best = 1; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        st->history[gen] = st->has_best ? st->best_r : -INFINITY;
+        st->n_valid_last = nv;
+    }
+}
+
 /* ---- host side ------------------------------------------------------------------------------------------------ */
 static int cfail(int code, const char* what, cudaError_t ce = cudaSuccess) {
     char buf[512];
@@ -360,6 +542,8 @@ struct PdebControls {
     int64_t* d_pi = nullptr;
     double* h_pv = nullptr;       /* pinned */
     int64_t* h_pi = nullptr;
+    struct PdebCemState* d_cem = nullptr;   /* state of the device-resident search (pdeb_controls_search) */
+    struct PdebCemState* h_cem = nullptr;   /* pinned mirror */
     cudaEvent_t ev[2] = {nullptr, nullptr};
 };
 #define PDEB_ARGMAX_BLOCKS 128
@@ -446,10 +630,30 @@ extern "C" void pdeb_controls_destroy(PdebControls* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaFree(h->d_y); cudaFree(h->d_rob); cudaFree(h->d_clause); cudaFree(h->d_status); cudaFree(h->d_pv); cudaFree(h->d_pi);
+    cudaFree(h->d_cem);
     if (h->h_pv) cudaFreeHost(h->h_pv);
     if (h->h_pi) cudaFreeHost(h->h_pi);
+    if (h->h_cem) cudaFreeHost(h->h_cem);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     delete h;
+}
+
+/* (re)build the specification of a handle; the device buffers are sized for the family's maxima and stay */
+static int controls_set_spec(PdebControls* h, const PdebBatch* spec, int64_t sample, int32_t n_knots, const double* knot_t,
+                             const PdebConventions* conv) {
+    if (!spec || sample < 0 || sample >= spec->n || n_knots < 0 || (n_knots > 0 && !knot_t))
+        return cfail(PDEB_E_ARG, "controls: bad specification arguments");
+    if (n_knots > PDEB_CTL_KMAX) return cfail(PDEB_E_ARG, "controls: more knots than PDEB_CTL_KMAX (32)");
+    PdebConventions cv;
+    if (conv) cv = *conv; else pdeb_default_conventions(&cv);
+    const int kind = spec->kind[sample], N = spec->n_elem[sample];
+    if (!((kind == PDEB_KIND_HEAT && N == 30) || (kind == PDEB_KIND_WAVE && N == 20)))
+        return cfail(PDEB_E_ARG, "controls family covers the default meshes (heat N=30, wave N=20); use the batch path for other meshes");
+    h->kind = kind; h->n_elem = N; h->nk = n_knots; h->pmax = spec->n_pred[sample];
+    h->spec_status = (kind == PDEB_KIND_HEAT) ? build_spec<PDEB_KIND_HEAT, 30>(spec, sample, cv, n_knots, knot_t, h->heat)
+                                              : build_spec<PDEB_KIND_WAVE, 20>(spec, sample, cv, n_knots, knot_t, h->wave);
+    if (h->pmax < 1 || h->pmax > PDEB_MAX_PRED) h->pmax = 1;
+    return PDEB_E_OK;
 }
 
 extern "C" int pdeb_controls_create(const PdebBatch* spec, int64_t sample, int64_t capacity, int32_t n_knots, const double* knot_t,
@@ -459,30 +663,33 @@ extern "C" int pdeb_controls_create(const PdebBatch* spec, int64_t sample, int64
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return cfail(PDEB_E_NODEVICE, "no CUDA device (this library has no CPU path)"); }
     if (device < 0 || device >= ndev) return cfail(PDEB_E_ARG, "bad device");
-    PdebConventions cv;
-    if (conv) cv = *conv; else pdeb_default_conventions(&cv);
-    const int kind = spec->kind[sample], N = spec->n_elem[sample];
-    if (!((kind == PDEB_KIND_HEAT && N == 30) || (kind == PDEB_KIND_WAVE && N == 20)))
-        return cfail(PDEB_E_ARG, "controls family covers the default meshes (heat N=30, wave N=20); use the batch path for other meshes");
     PdebControls* h = new PdebControls;
-    h->device = device; h->kind = kind; h->n_elem = N; h->capacity = capacity; h->nk = n_knots; h->pmax = spec->n_pred[sample];
-    h->spec_status = (kind == PDEB_KIND_HEAT) ? build_spec<PDEB_KIND_HEAT, 30>(spec, sample, cv, n_knots, knot_t, h->heat)
-                                              : build_spec<PDEB_KIND_WAVE, 20>(spec, sample, cv, n_knots, knot_t, h->wave);
-    if (h->pmax < 1 || h->pmax > PDEB_MAX_PRED) h->pmax = 1;
+    h->device = device; h->capacity = capacity;
+    const int rc = controls_set_spec(h, spec, sample, n_knots, knot_t, conv);
+    if (rc != PDEB_E_OK) { delete h; return rc; }
+    /* sized for ANY specification of the family (PDEB_CTL_KMAX knots, PDEB_MAX_PRED clauses), so that
+     * pdeb_controls_respec can point the handle at the next program without touching the allocator */
     cudaError_t e = cudaSetDevice(device);
-    const int nkp = n_knots > 0 ? n_knots : 1;
-    if (e == cudaSuccess) e = cudaMalloc(&h->d_y, sizeof(double) * (size_t)nkp * capacity);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_y, sizeof(double) * (size_t)PDEB_CTL_KMAX * capacity);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_rob, sizeof(double) * (size_t)capacity);
-    if (e == cudaSuccess) e = cudaMalloc(&h->d_clause, sizeof(double) * (size_t)h->pmax * capacity);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_clause, sizeof(double) * (size_t)PDEB_MAX_PRED * capacity);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_status, sizeof(int32_t) * (size_t)capacity);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_pv, sizeof(double) * PDEB_ARGMAX_BLOCKS);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_pi, sizeof(int64_t) * PDEB_ARGMAX_BLOCKS);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_cem, sizeof(PdebCemState));
     if (e == cudaSuccess) e = cudaHostAlloc(&h->h_pv, sizeof(double) * PDEB_ARGMAX_BLOCKS, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc(&h->h_pi, sizeof(int64_t) * PDEB_ARGMAX_BLOCKS, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc(&h->h_cem, sizeof(PdebCemState), cudaHostAllocDefault);
     for (auto& ev : h->ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
     if (e != cudaSuccess) { pdeb_controls_destroy(h); return cfail(PDEB_E_CUDA, "pdeb_controls_create", e); }
     *out = h;
     return PDEB_E_OK;
+}
+
+extern "C" int pdeb_controls_respec(PdebControls* h, const PdebBatch* spec, int64_t sample, int32_t n_knots, const double* knot_t,
+                                    const PdebConventions* conv) {
+    if (!h) return cfail(PDEB_E_ARG, "pdeb_controls_respec: NULL handle");
+    return controls_set_spec(h, spec, sample, n_knots, knot_t, conv);
 }
 
 template <int KIND, int N>
@@ -556,6 +763,167 @@ extern "C" int pdeb_controls_eval(PdebControls* h, int64_t m, const double* knot
         float ms = 0;
         CCK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
         timing->kernel_ms = ms; timing->total_ms = ms; timing->launches = launches;
+    }
+    return PDEB_E_OK;
+}
+
+/* the candidates currently on the device (the last generation of a search, or what pdeb_controls_eval uploaded) */
+extern "C" int pdeb_controls_fetch_knots(PdebControls* h, int64_t m, double* knot_y_out, void* stream_) {
+    if (!h || !knot_y_out || m < 1 || m > h->capacity) return cfail(PDEB_E_ARG, "pdeb_controls_fetch_knots: bad arguments");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CCK(cudaSetDevice(h->device));
+    if (h->nk > 0) CCK(cudaMemcpyAsync(knot_y_out, h->d_y, sizeof(double) * (size_t)h->nk * m, cudaMemcpyDeviceToHost, stream));
+    CCK(cudaStreamSynchronize(stream));
+    return PDEB_E_OK;
+}
+
+extern "C" int pdeb_controls_search(PdebControls* h, int64_t population, int32_t generations, double elite_frac, double lo, double hi,
+                                    uint64_t seed, double* best_y_out, double* best_value_out, int32_t* found_out, double* history_out,
+                                    double* mean_out, double* std_out, void* stream_, PdebTiming* timing) {
+    if (!h || population < 4 || population > h->capacity || generations < 1 || generations > PDEB_CEM_MAX_GEN || !(hi >= lo) ||
+        !(elite_frac > 0.0 && elite_frac <= 1.0))
+        return cfail(PDEB_E_ARG, "pdeb_controls_search: bad arguments (population 4..capacity, generations 1..64, lo <= hi, 0 < elite_frac <= 1)");
+    int64_t n_elite = (int64_t)llround(elite_frac * (double)population);
+    if (n_elite < 2) n_elite = 2;
+    if (n_elite > PDEB_CEM_MAX_ELITE) return cfail(PDEB_E_ARG, "pdeb_controls_search: more than 8192 elite candidates");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CCK(cudaSetDevice(h->device));
+    if (timing) memset(timing, 0, sizeof *timing);
+    const int nk = h->nk;
+    if (h->spec_status != PDEB_OK) {
+        /* the specification itself is unusable: nothing to search (never raises per sample) */
+        if (found_out) *found_out = 0;
+        if (best_value_out) *best_value_out = PDEB_FAILED_ROBUSTNESS;
+        if (history_out) for (int g = 0; g < generations; ++g) history_out[g] = PDEB_FAILED_ROBUSTNESS;
+        return PDEB_E_OK;
+    }
+    PdebCemState* hs = h->h_cem;
+    memset(hs, 0, sizeof *hs);
+    for (int j = 0; j < PDEB_CTL_KMAX; ++j) { hs->mean[j] = 0.5 * (lo + hi); hs->std[j] = 0.5 * (hi - lo); }
+    hs->best_r = -INFINITY;
+    CCK(cudaMemcpyAsync(h->d_cem, hs, sizeof *hs, cudaMemcpyHostToDevice, stream));
+    PdebCtlOut out{h->d_rob, h->d_clause, h->d_status};
+    const unsigned sblocks = (unsigned)((population + 255) / 256);
+    const double std_floor = 1e-3 * (hi - lo);
+    CCK(cudaEventRecord(h->ev[0], stream));
+    for (int g = 0; g < generations; ++g) {
+        pdeb_cem_sample_kernel<<<sblocks, 256, 0, stream>>>(h->d_y, population, nk, population, h->d_cem, g, seed, lo, hi);
+        CCK(cudaGetLastError());
+        cudaError_t e = (h->kind == PDEB_KIND_HEAT)
+                            ? launch_controls<PDEB_KIND_HEAT, 30>(h->heat, h->pmax, h->d_y, population, population, out, stream)
+                            : launch_controls<PDEB_KIND_WAVE, 20>(h->wave, h->pmax, h->d_y, population, population, out, stream);
+        if (e != cudaSuccess) return cfail(PDEB_E_CUDA, "controls kernel launch", e);
+        pdeb_cem_update_kernel<<<1, PDEB_CEM_THREADS, 0, stream>>>(h->d_rob, h->d_status, h->d_y, population, population, nk, (int)n_elite,
+                                                                  std_floor, h->d_cem, g);
+        CCK(cudaGetLastError());
+    }
+    CCK(cudaEventRecord(h->ev[1], stream));
+    CCK(cudaMemcpyAsync(hs, h->d_cem, sizeof *hs, cudaMemcpyDeviceToHost, stream));
+    CCK(cudaStreamSynchronize(stream));
+    const bool found = hs->has_best != 0;
+    if (found_out) *found_out = found ? 1 : 0;
+    if (best_value_out) *best_value_out = found ? hs->best_r : PDEB_FAILED_ROBUSTNESS;
+    if (best_y_out) for (int j = 0; j < nk; ++j) best_y_out[j] = found ? hs->best_y[j] : 0.0;
+    if (history_out) for (int g = 0; g < generations; ++g) history_out[g] = hs->history[g];
+    if (mean_out) for (int j = 0; j < nk; ++j) mean_out[j] = hs->mean[j];
+    if (std_out) for (int j = 0; j < nk; ++j) std_out[j] = hs->std[j];
+    if (timing) {
+        float ms = 0;
+        CCK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+        timing->kernel_ms = ms; timing->total_ms = ms; timing->launches = 3 * generations;
+    }
+    return PDEB_E_OK;
+}
+
+/*
+ * The search for MANY specifications: host threads, each with its own stream and ONE controls handle that it points at
+ * sample after sample (no allocation per program, nothing per program in the caller's language).  The knot TIMES are the
+ * batch's (knot_t == NULL: linspace(0, T, n_knots), convention C11); the knot VALUES found go to knot_y_out in the batch's
+ * own plane-major layout, so a caller can hand in the batch's knot_y array and evaluate the batch right after.
+ */
+extern "C" int pdeb_controls_search_batch(const PdebBatch* in, const int64_t* samples, int64_t n_samples, int64_t population,
+                                          int32_t generations, double elite_frac, const double* bounds, uint64_t seed, int device,
+                                          const PdebConventions* conv, int nthreads, double* knot_y_out, double* best_out,
+                                          int32_t* found_out, PdebTiming* timing) {
+    if (!in || !bounds || !knot_y_out || !best_out || !found_out || n_samples < 0 || (samples == nullptr && n_samples != in->n))
+        return cfail(PDEB_E_ARG, "pdeb_controls_search_batch: bad arguments (samples == NULL means all: n_samples == n)");
+    if (population < 4 || generations < 1 || generations > PDEB_CEM_MAX_GEN || !(elite_frac > 0.0 && elite_frac <= 1.0))
+        return cfail(PDEB_E_ARG, "pdeb_controls_search_batch: bad search budget");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return cfail(PDEB_E_NODEVICE, "no CUDA device (this library has no CPU path)"); }
+    if (device < 0 || device >= ndev) return cfail(PDEB_E_ARG, "bad device");
+    if (timing) memset(timing, 0, sizeof *timing);
+    if (n_samples == 0) return PDEB_E_OK;
+    for (int64_t q = 0; q < n_samples; ++q)
+        if (samples && (samples[q] < 0 || samples[q] >= in->n)) return cfail(PDEB_E_ARG, "pdeb_controls_search_batch: sample index out of range");
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = nthreads > 0 ? nthreads : (int)(hw ? hw : 8);
+    if (nt > 32) nt = 32;
+    if ((int64_t)nt > n_samples) nt = (int)n_samples;
+    std::atomic<int64_t> next{0};
+    std::atomic<int> failed{0};
+    std::mutex err_mutex;
+    std::string err_text;
+    int err_code = PDEB_E_OK;
+    std::vector<float> ms((size_t)nt, 0.f);
+    std::vector<int> launches((size_t)nt, 0);
+    const int64_t st = in->stride;
+
+    auto work = [&](int w) {
+        PdebControls* h = nullptr;
+        cudaStream_t stream = nullptr;
+        int rc = PDEB_E_OK;
+        if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) {
+            cudaGetLastError();
+            rc = cfail(PDEB_E_CUDA, "pdeb_controls_search_batch: stream");
+        }
+        while (rc == PDEB_E_OK && !failed.load(std::memory_order_relaxed)) {
+            const int64_t q = next.fetch_add(1);
+            if (q >= n_samples) break;
+            const int64_t s = samples ? samples[q] : q;
+            found_out[s] = 0;
+            best_out[s] = PDEB_FAILED_ROBUSTNESS;
+            const int kind = in->kind[s], N = in->n_elem[s];
+            int nk = in->n_knots[s];
+            if (!((kind == PDEB_KIND_HEAT && N == 30) || (kind == PDEB_KIND_WAVE && N == 20)) || nk < 0 || nk > PDEB_CTL_KMAX || nk > in->kmax)
+                continue;                                   /* not this family's: the caller searches it another way */
+            double kt[PDEB_CTL_KMAX], by[PDEB_CTL_KMAX];
+            for (int j = 0; j < nk; ++j)
+                kt[j] = in->knot_t ? in->knot_t[(int64_t)j * st + s]
+                                   : ((j == nk - 1 && nk > 1) ? in->T[s] : (nk > 1 ? (double)j * (in->T[s] / (double)(nk - 1)) : 0.0));
+            if (!h) rc = pdeb_controls_create(in, s, population, nk, kt, device, conv, &h);
+            else rc = pdeb_controls_respec(h, in, s, nk, kt, conv);
+            if (rc != PDEB_E_OK) break;
+            const double lo = bounds[kind == PDEB_KIND_HEAT ? 0 : 2], hi = bounds[kind == PDEB_KIND_HEAT ? 1 : 3];
+            /* one generator stream per sample, whatever thread takes it */
+            const uint64_t seed_s = pdeb_mix64(seed ^ pdeb_mix64((uint64_t)s));
+            double best = 0.0;
+            int32_t found = 0;
+            PdebTiming tm;
+            rc = pdeb_controls_search(h, population, generations, elite_frac, lo, hi, seed_s, by, &best, &found, nullptr, nullptr, nullptr,
+                                      (void*)stream, &tm);
+            if (rc != PDEB_E_OK) break;
+            ms[(size_t)w] += tm.kernel_ms; launches[(size_t)w] += tm.launches;
+            found_out[s] = found;
+            best_out[s] = best;
+            if (found) for (int j = 0; j < nk; ++j) knot_y_out[(int64_t)j * st + s] = by[j];
+        }
+        if (rc != PDEB_E_OK) {
+            std::lock_guard<std::mutex> lock(err_mutex);
+            if (err_code == PDEB_E_OK) { err_code = rc; err_text = pdeb_last_error(); }
+            failed.store(1);
+        }
+        if (h) pdeb_controls_destroy(h);
+        if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
+    };
+    std::vector<std::thread> pool;
+    for (int w = 1; w < nt; ++w) pool.emplace_back(work, w);
+    work(0);
+    for (auto& t : pool) t.join();
+    if (err_code != PDEB_E_OK) { pdeb_set_last_error(err_text.c_str()); return err_code; }
+    if (timing) {
+        for (int w = 0; w < nt; ++w) { timing->kernel_ms += ms[(size_t)w]; timing->launches += launches[(size_t)w]; }
+        timing->total_ms = timing->kernel_ms;      /* sum over the threads' own streams (they overlap on the device) */
     }
     return PDEB_E_OK;
 }

@@ -124,16 +124,20 @@ def eval_robustness_batch(programs: Sequence[str], natural_language: Optional[Se
         # controls: no per-sample numpy call (a list of n (times, values) pairs goes through two concatenations)
         given = (np.fromiter((c is not None for c in controls), dtype=bool, count=n) if None in controls
                  else np.ones(n, dtype=bool))
-        need = np.nonzero(~given & live)[0].tolist()
-        if need and mode == "search":
-            from . import search as _search
-            by_index = dict(ok_rest)
-            probs = [by_index[i] if i in by_index else wide.get_problem(i)[0] for i in need]
-            found = _search.search_controls(probs, device=dev, conv=conv, **{**_SEARCH, **(search or {})})
-            for i, f in zip(need, found):
-                if f["knot_y"] is not None:
-                    controls[i] = (np.asarray(f["knot_t"], dtype=np.float64), np.asarray(f["knot_y"], dtype=np.float64))
-                    given[i] = True
+        need = np.nonzero(~given & live)[0]
+        searching = need.size > 0 and mode == "search"
+        k_need = np.zeros(0, dtype=np.int64)
+        if searching:
+            # default knots (C11) of the samples that will be searched: they size the batch's knot planes
+            from .problem import default_knot_counts
+            kind_all = wide.kind.copy() if wide is not None else np.zeros(n, dtype=np.uint8)
+            T_all = wide.T.copy() if wide is not None else np.zeros(n)
+            for i, p in ok_rest:
+                kind_all[i], T_all[i] = (abi.KIND_HEAT if p.kind == "heat" else abi.KIND_WAVE), p.T
+            k_need = default_knot_counts(kind_all[need], T_all[need])
+            # more default knots than the controls family takes (a horizon beyond 31 time units): not searched, the sample
+            # is evaluated without a control and reports its own status
+            k_need = np.where(k_need <= 32, k_need, 0)
         have = np.nonzero(given)[0]
         cnt = np.zeros(n, dtype=np.int64)
         flat_t = flat_y = None
@@ -161,7 +165,7 @@ def eval_robustness_batch(programs: Sequence[str], natural_language: Optional[Se
             if not np.array_equal(len_t, len_y):
                 raise ValueError("control knot times and values differ in length")
             cnt[have] = len_t
-        kmax = int(max(cnt.max(initial=0), 1))
+        kmax = int(max(cnt.max(initial=0), k_need.max(initial=0), 1))
         batch = ProblemBatch(n, kmax, pmax, tmax)
         if wide is not None:
             for name in batch._names:
@@ -182,6 +186,44 @@ def eval_robustness_batch(programs: Sequence[str], natural_language: Optional[Se
             km = np.arange(kmax)[None, :] < cnt[:, None]
             batch.knot_t.T[km] = flat_t
             batch.knot_y.T[km] = flat_y
+        if searching:
+            # the sampling surrogate of the reference's synthesis, for every sample without a control: ONE library call
+            # (pdeb_controls_search_batch) writes the inputs it finds straight into the batch's knot planes
+            from . import search as _search
+            from .problem import fill_default_knot_times
+            budget = {**_SEARCH, **(search or {})}
+            engine = budget.pop("engine", "device")
+            b2 = budget.pop("bounds", None)
+            b4 = list(_search.DEFAULT_BOUNDS["heat"]) + list(_search.DEFAULT_BOUNDS["wave"]) if b2 is None else [b2[0], b2[1], b2[0], b2[1]]
+            fill_default_knot_times(batch, need, k_need)
+            fam = (((batch.kind[need] == abi.KIND_HEAT) & (batch.n_elem[need] == 30)) |
+                   ((batch.kind[need] == abi.KIND_WAVE) & (batch.n_elem[need] == 20))) & (k_need >= 2)
+            done = k_need < 2
+            if engine == "device" and fam.any():
+                sr = native.search_batch(batch, samples=need[fam], population=budget.get("population", 4096),
+                                         generations=budget.get("generations", 6), elite_frac=budget.get("elite_frac", 0.02),
+                                         bounds=b4, seed=_search._seed64(budget.get("seed", 0)), device=dev, conv=conv,
+                                         nthreads=budget.get("workers", 0))
+                done[fam] = True
+                lost = need[fam][~sr["found"][need[fam]]]
+                batch.n_knots[lost] = 0                  # nothing found (an unusable specification): its own status is reported
+            rest_i = need[~done]
+            if rest_i.size:                              # other meshes, or the host engine on request: problem by problem
+                probs = [batch.get_problem(int(i))[0] for i in rest_i]
+                kw = {k: v for k, v in budget.items() if k in ("population", "generations", "elite_frac", "seed", "workers")}
+                found = _search.search_controls(probs, device=dev, conv=conv, bounds=b2, engine=engine, **kw)
+                for i, f in zip(rest_i.tolist(), found):
+                    if f["knot_y"] is None:
+                        batch.n_knots[i] = 0
+                    else:
+                        k = len(f["knot_t"])
+                        batch.n_knots[i] = k
+                        batch.knot_t[:k, i], batch.knot_y[:k, i] = f["knot_t"], f["knot_y"]
+            if return_controls:
+                for i in need.tolist():
+                    k = int(batch.n_knots[i])
+                    if k > 0:
+                        controls[i] = (batch.knot_t[:k, i].copy(), batch.knot_y[:k, i].copy())
         # the number returned is ALWAYS the batch kernels' robustness under the control in `controls` (found or given)
         out = native.evaluate_batch(batch, device=dev, precision=_PRECISION if precision is None else precision, conv=conv)
         rob[live] = out["robustness"][live]

@@ -93,6 +93,18 @@ def lib():
         L.pdeb_controls_eval.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p]
         L.pdeb_controls_destroy.argtypes = [C.c_void_p]
+        L.pdeb_controls_respec.restype = C.c_int
+        L.pdeb_controls_respec.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
+        L.pdeb_controls_search.restype = C.c_int
+        L.pdeb_controls_search.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_uint64,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p]
+        L.pdeb_controls_search_batch.restype = C.c_int
+        L.pdeb_controls_search_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_double, C.c_void_p,
+                                                 C.c_uint64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.c_void_p]
+        L.pdeb_controls_fetch_knots.restype = C.c_int
+        L.pdeb_controls_fetch_knots.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         if L.pdeb_version() != abi.ABI_VERSION:
             raise NativeError("libpdeb200.so ABI version mismatch: rebuild it")
         _lib = L
@@ -463,6 +475,32 @@ class BlockPipeline:
             pass
 
 
+def search_batch(batch: ProblemBatch, samples=None, population: int = 4096, generations: int = 6, elite_frac: float = 0.02,
+                 bounds=(0.0, 1.0e6, -5.0e3, 5.0e3), seed: int = 0, device: int = 0, conv=None, nthreads: int = 0, knot_y_out=None):
+    """pdeb_controls_search_batch: the device-resident search for many samples of `batch` in one call (host threads inside
+    the library, nothing per sample in Python).  The knot times are the batch's (`n_knots`, `knot_t`; a uniform-knots batch:
+    linspace(0, T, n_knots)); the values found are written into `knot_y_out` (default: batch.knot_y itself, so the batch
+    can be evaluated right away).  -> dict(best f64[n], found bool[n], kernel_ms, launches); entries of samples that were
+    not asked for, or that are outside the controls family, have found False."""
+    n = batch.n
+    idx = None if samples is None else np.ascontiguousarray(samples, dtype=np.int64)
+    ky = batch.knot_y if knot_y_out is None else knot_y_out
+    if ky.dtype != np.float64 or not ky.flags.c_contiguous or ky.shape != batch.knot_y.shape:
+        raise ValueError("knot_y_out must look like batch.knot_y")
+    best = np.full(n, abi.FAILED_ROBUSTNESS, dtype=np.float64)
+    found = np.zeros(n, dtype=np.int32)
+    b4 = np.ascontiguousarray(bounds, dtype=np.float64)
+    if b4.shape != (4,):
+        raise ValueError("bounds = (heat lo, heat hi, wave lo, wave hi)")
+    tm = abi.PdebTiming()
+    cb = batch.as_c()
+    _check(lib().pdeb_controls_search_batch(C.addressof(cb), _ptr(idx), n if idx is None else int(idx.size), int(population),
+                                            int(generations), float(elite_frac), _ptr(b4), C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF),
+                                            int(device), _conv_ptr(conv), int(nthreads), _ptr(ky), _ptr(best), _ptr(found),
+                                            C.addressof(tm)), "pdeb_controls_search_batch")
+    return {"best": best, "found": found.astype(bool), "kernel_ms": float(tm.kernel_ms), "launches": int(tm.launches)}
+
+
 class ControlsEvaluator:
     """One specification against many candidate controls (pdeb_controls_*).
 
@@ -509,6 +547,39 @@ class ControlsEvaluator:
         if want_clauses:
             res["clause"] = cl
         return res
+
+    def respec(self, batch: ProblemBatch, knot_t, sample: int = 0, conv=None):
+        """Point the evaluator at another specification of the family (no allocation: what a sweep over many programs
+        calls between searches).  Up to 32 knots; the capacity stays."""
+        self.knot_t = np.ascontiguousarray(knot_t, dtype=np.float64).ravel()
+        self.nk = int(self.knot_t.size)
+        self.n_pred = int(batch.n_pred[sample])
+        cb = batch.as_c()
+        _check(self._L.pdeb_controls_respec(self._h, C.addressof(cb), sample, self.nk, _ptr(self.knot_t), _conv_ptr(conv)),
+               "pdeb_controls_respec")
+
+    def search(self, population: int, generations: int, elite_frac: float, lo: float, hi: float, seed: int = 0, stream: int = 0):
+        """The whole cross-entropy search on the device (pdeb_controls_search): three launches per generation, nothing
+        crosses PCIe until it is over.  -> dict(knot_y [n_knots] or None, robustness, history [generations], mean, std,
+        kernel_ms, launches)."""
+        nk = self.nk
+        best = np.zeros(max(nk, 1), dtype=np.float64)
+        mean, std = np.zeros(max(nk, 1), dtype=np.float64), np.zeros(max(nk, 1), dtype=np.float64)
+        hist = np.zeros(int(generations), dtype=np.float64)
+        bv, found, tm = C.c_double(0.0), C.c_int32(0), abi.PdebTiming()
+        _check(self._L.pdeb_controls_search(self._h, int(population), int(generations), float(elite_frac), float(lo), float(hi),
+                                            C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), _ptr(best), C.addressof(bv), C.addressof(found),
+                                            _ptr(hist), _ptr(mean), _ptr(std), stream or None, C.addressof(tm)), "pdeb_controls_search")
+        ok = bool(found.value)
+        return {"knot_y": best[:nk].copy() if ok else None, "robustness": float(bv.value) if ok else -np.inf,
+                "history": hist.tolist(), "mean": mean[:nk], "std": std[:nk], "kernel_ms": float(tm.kernel_ms),
+                "launches": int(tm.launches)}
+
+    def fetch_knots(self, m: int, stream: int = 0) -> np.ndarray:
+        """The candidates currently on the device, [n_knots, m]."""
+        out = np.zeros((max(self.nk, 1), int(m)), dtype=np.float64)
+        _check(self._L.pdeb_controls_fetch_knots(self._h, int(m), _ptr(out), stream or None), "pdeb_controls_fetch_knots")
+        return out[: self.nk]
 
     def close(self):
         if self._h:

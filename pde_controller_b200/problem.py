@@ -73,6 +73,35 @@ def default_knot_times(p: Problem) -> np.ndarray:
     return np.linspace(0.0, p.T, k)
 
 
+def default_knot_counts(kind: np.ndarray, T: np.ndarray) -> np.ndarray:
+    """default_knot_times' K for arrays of samples (kind codes of abi.py): round(T)+1 for heat (round half to even, like
+    Python's round), 5 for waves, at least 2."""
+    with np.errstate(invalid="ignore"):
+        k_heat = np.where(np.isfinite(T), np.rint(np.clip(np.nan_to_num(T), -1e9, 1e9)), 0.0).astype(np.int64) + 1
+    return np.maximum(np.where(kind == abi.KIND_HEAT, k_heat, 5), 2)
+
+
+def fill_default_knot_times(batch: "ProblemBatch", samples, counts: Optional[np.ndarray] = None) -> np.ndarray:
+    """n_knots / knot_t of `samples` <- the C11 default knots linspace(0, T, K) (vectorised default_knot_times); the knot
+    values of those samples are zeroed.  -> K per sample of `samples`.  K is clipped to the batch's kmax."""
+    idx = np.asarray(samples, dtype=np.int64)
+    if idx.size == 0:
+        return np.zeros(0, dtype=np.int64)
+    T = batch.T[idx]
+    K = default_knot_counts(batch.kind[idx], T) if counts is None else np.asarray(counts, dtype=np.int64)
+    K = np.minimum(K, batch.kmax)
+    batch.n_knots[idx] = K
+    j = np.arange(batch.kmax, dtype=np.float64)[:, None]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        kt = j * (T / np.maximum(K - 1, 1))[None, :]
+    kt = np.where(j == (K - 1)[None, :], T[None, :], kt)
+    kt = np.where(j < K[None, :], kt, 0.0)
+    if not batch.uniform_knots:
+        batch.knot_t[:, idx] = kt
+    batch.knot_y[:, idx] = 0.0
+    return K
+
+
 _F8 = np.dtype(np.float64)      # native float64 arrays share this dtype object: an identity test, not a comparison
 _F64 = ["L", "dt", "T", "g0", "x_a", "x_b", "rho_in", "rho_out", "E_in", "E_out"]
 _PRED_F64 = ["pred_xlo", "pred_xhi", "pred_m", "pred_b", "pred_tlo", "pred_thi"]

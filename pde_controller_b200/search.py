@@ -60,15 +60,53 @@ class _BatchScorer:
         pass
 
 
+ENGINES = ("device", "host")
+_MAX_DEVICE_KNOTS = 32          # PDEB_CTL_KMAX
+_MAX_DEVICE_ELITE = 8192        # PDEB_CEM_MAX_ELITE
+_MAX_DEVICE_GENERATIONS = 64    # PDEB_CEM_MAX_GEN
+
+
+_M64 = (1 << 64) - 1
+
+
+def _mix64(z: int) -> int:
+    """splitmix64 finaliser: pdeb_mix64 of csrc/pdeb_controls.cu."""
+    z = (z + 0x9E3779B97F4A7C15) & _M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    return z ^ (z >> 31)
+
+
+def _seed64(seed) -> int:
+    """An integer seed IS the 64-bit generator seed; anything else goes through numpy's SeedSequence."""
+    if isinstance(seed, (int, np.integer)):
+        return int(seed) & _M64
+    return int(np.random.SeedSequence(seed).generate_state(1, dtype=np.uint64)[0])
+
+
+def sample_seed(seed, i: int) -> int:
+    """Generator seed of problem i of a sweep: what pdeb_controls_search_batch derives for sample i."""
+    return _mix64(_seed64(seed) ^ _mix64(int(i)))
+
+
 def search_control(problem: Problem, knot_t: Optional[np.ndarray] = None, bounds: Optional[Tuple[float, float]] = None,
                    population: int = 16384, generations: int = 8, elite_frac: float = 0.02, seed=0, device: int = 0,
-                   conv=None, stream: int = 0):
+                   conv=None, stream: int = 0, engine: str = "device", evaluator=None):
     """Best-found PWL control for `problem`.
 
     Returns dict(knot_t, knot_y, robustness, history, evaluations, kernel_ms): `history` is the best robustness after
     every generation; it never decreases because the incumbent is re-evaluated with each generation.  The first
     generation always holds the ZERO input (clipped into the bounds), so the result is never worse than it.
-    Deterministic for a given seed."""
+    Deterministic for a given seed.
+
+    engine: "device" (default) runs the whole search in ONE library call (pdeb_controls_search: candidates drawn, scored
+    and ranked on the GPU, three launches per generation); "host" draws and ranks with numpy and calls the device once per
+    generation (the round-1 form; also what meshes outside the controls family use, whatever `engine` says).  The two
+    draw different candidates (different generators), so their results differ like two seeds do.
+    evaluator: a ControlsEvaluator of capacity >= population to re-target (`respec`) instead of creating one: a sweep over
+    many programs keeps one per thread (search_controls)."""
+    if engine not in ENGINES:
+        raise ValueError(f"engine must be one of {ENGINES}")
     if knot_t is None:
         knot_t = default_knot_times(problem)
     knot_t = np.asarray(knot_t, dtype=np.float64)
@@ -76,7 +114,22 @@ def search_control(problem: Problem, knot_t: Optional[np.ndarray] = None, bounds
     nk = knot_t.size
     population = max(int(population), 4)
     spec = ProblemBatch.from_problems([problem], kmax=max(nk, 1))
-    if problem.n_elem == _DEFAULT_MESH.get(problem.kind):
+    family = problem.n_elem == _DEFAULT_MESH.get(problem.kind)
+    n_elite = max(2, int(round(elite_frac * population)))
+    if (engine == "device" and family and nk <= _MAX_DEVICE_KNOTS and n_elite <= _MAX_DEVICE_ELITE
+            and 1 <= generations <= _MAX_DEVICE_GENERATIONS):
+        own = evaluator is None
+        ev = native.ControlsEvaluator(spec, knot_t, capacity=population, device=device, conv=conv) if own else evaluator
+        try:
+            if not own:
+                ev.respec(spec, knot_t, conv=conv)
+            res = ev.search(population, generations, elite_frac, lo, hi, seed=_seed64(seed), stream=stream)
+        finally:
+            if own:
+                ev.close()
+        return {"knot_t": knot_t, "knot_y": res["knot_y"], "robustness": res["robustness"], "history": res["history"],
+                "evaluations": population * generations, "kernel_ms": res["kernel_ms"], "engine": "device"}
+    if family:
         ev = native.ControlsEvaluator(spec, knot_t, capacity=population, device=device, conv=conv)
     else:
         ev = _BatchScorer(spec, knot_t, device, conv)
@@ -85,7 +138,6 @@ def search_control(problem: Problem, knot_t: Optional[np.ndarray] = None, bounds
     std = np.full(nk, 0.5 * (hi - lo))
     best_y, best_r = None, -np.inf
     history, kernel_ms = [], 0.0
-    n_elite = max(2, int(round(elite_frac * population)))
     try:
         for g in range(generations):
             if g == 0:
@@ -111,32 +163,72 @@ def search_control(problem: Problem, knot_t: Optional[np.ndarray] = None, bounds
     finally:
         ev.close()
     return {"knot_t": knot_t, "knot_y": best_y, "robustness": best_r, "history": history,
-            "evaluations": population * generations, "kernel_ms": kernel_ms}
+            "evaluations": population * generations, "kernel_ms": kernel_ms, "engine": "host"}
 
 
 def search_controls(problems: Sequence[Problem], population: int = 4096, generations: int = 6, elite_frac: float = 0.02,
                     seed: int = 0, device: int = 0, conv=None, bounds: Optional[Tuple[float, float]] = None,
-                    workers: int = 4) -> List[dict]:
-    """search_control for every problem of a list; problem i uses the seed (seed, i), so the result does not depend
-    on the number of workers.  A problem the search cannot run for (a specification the controls set-up rejects)
-    yields knot_y None and robustness -inf: the caller evaluates it as it would without a control and reports that
-    sample's own status."""
+                    workers: int = 0, engine: str = "device") -> List[dict]:
+    """search_control for every problem of a list; problem i uses the seed sample_seed(seed, i), so the result does not
+    depend on the number of workers and equals `search_control(problems[i], seed=sample_seed(seed, i))`.  A problem the
+    search cannot run for (a specification the controls set-up rejects) yields knot_y None and robustness -inf: the
+    caller evaluates it as it would without a control and reports that sample's own status.
+
+    engine "device": ONE library call for the whole list (pdeb_controls_search_batch: `workers` host threads inside the
+    library, 0 = all, each with a stream and a controls handle it re-targets from program to program; nothing per program
+    in Python), then the per-problem route below for whatever is outside the controls family.  engine "host": the
+    per-problem route for everything (Python threads, numpy draws; at most 8 workers)."""
     n = len(problems)
     out: List[Optional[dict]] = [None] * n
     if n == 0:
         return []
+    if engine not in ENGINES:
+        raise ValueError(f"engine must be one of {ENGINES}")
     L = native.lib()
-    workers = max(1, min(int(workers), n))
+    todo = list(range(n))
+    population = max(int(population), 4)
+    n_elite = max(2, int(round(elite_frac * population)))
+    if engine == "device" and n_elite <= _MAX_DEVICE_ELITE and 1 <= generations <= _MAX_DEVICE_GENERATIONS:
+        from .problem import default_knot_counts, fill_default_knot_times
+        spec = ProblemBatch.from_problems(list(problems), kmax=1)
+        K = default_knot_counts(spec.kind, spec.T)
+        fam = np.array([p.n_elem == _DEFAULT_MESH.get(p.kind) for p in problems]) & (K <= _MAX_DEVICE_KNOTS)
+        idx = np.nonzero(fam)[0]
+        if idx.size:
+            wide = ProblemBatch(n, int(K[idx].max()), spec.pmax, spec.tmax)
+            for name in wide._names:
+                if name in ("knot_t", "knot_y", "n_knots"):
+                    continue
+                src, dst = getattr(spec, name), getattr(wide, name)
+                dst[...] = src
+            fill_default_knot_times(wide, idx, K[idx])
+            b4 = list(DEFAULT_BOUNDS["heat"]) + list(DEFAULT_BOUNDS["wave"])
+            if bounds is not None:
+                b4 = [bounds[0], bounds[1], bounds[0], bounds[1]]
+            res = native.search_batch(wide, samples=idx, population=population, generations=generations, elite_frac=elite_frac,
+                                      bounds=b4, seed=_seed64(seed), device=device, conv=conv, nthreads=workers)
+            per = res["kernel_ms"] / idx.size
+            for i in idx.tolist():
+                k = int(wide.n_knots[i])
+                ok = bool(res["found"][i])
+                r = float(res["best"][i]) if ok else -np.inf
+                out[i] = {"knot_t": wide.knot_t[:k, i].copy(), "knot_y": wide.knot_y[:k, i].copy() if ok else None,
+                          "robustness": r, "history": [r], "evaluations": population * generations, "kernel_ms": per,
+                          "engine": "device"}
+            todo = [i for i in todo if out[i] is None]
+    if not todo:
+        return out  # type: ignore[return-value]
+    workers = max(1, min(int(workers) if workers > 0 else 4, 8, len(todo)))
     errors: List[BaseException] = []
 
     def work(w):
         stream = L.pdeb_stream_create(device) if workers > 1 else 0
         try:
-            for i in range(w, n, workers):
+            for i in todo[w::workers]:
                 try:
                     out[i] = search_control(problems[i], bounds=bounds, population=population, generations=generations,
-                                            elite_frac=elite_frac, seed=(seed, i), device=device, conv=conv,
-                                            stream=stream or 0)
+                                            elite_frac=elite_frac, seed=sample_seed(seed, i), device=device, conv=conv,
+                                            stream=stream or 0, engine=engine)
                 except native.NativeError as e:
                     if native.device_count() < 1:
                         raise

@@ -195,3 +195,128 @@ def test_plan_orders_by_the_callers_conventions(kw):
     last = np.minimum(np.where(live, a1, 0).max(axis=0), S).astype(np.int64)
     bucket = np.maximum(last, 1)[order] // 8
     assert (np.diff(bucket) <= 0).all()                  # non-increasing buckets along the order
+
+
+def _spec_of(p):
+    from pde_controller_b200 import default_knot_times
+    kt = default_knot_times(p)
+    return ProblemBatch.from_problems([p], kmax=max(kt.size, 1)), kt
+
+
+@pytest.mark.parametrize("rec", [0, 9])
+def test_device_search_one_generation_equals_numpy_ranking(rec):
+    """pdeb_cem_update_kernel against numpy on the very candidates the device drew: elite = the n best (ties by lowest
+    index), mean / standard deviation of their knot values, incumbent = first best candidate."""
+    p = problem_of(GOLD[rec])
+    spec, kt = _spec_of(p)
+    lo, hi = (0.0, 1.0e6) if p.kind == "heat" else (-5.0e3, 5.0e3)
+    P, frac = 3000, 0.05
+    ev = native.ControlsEvaluator(spec, kt, capacity=4096)
+    try:
+        res = ev.search(P, 1, frac, lo, hi, seed=77)
+        y = ev.fetch_knots(P)                                    # generation 0, as drawn on the device
+        out = ev.eval(None, m=P)                                 # the same candidates scored again
+    finally:
+        ev.close()
+    assert y.shape == (kt.size, P) and (y >= lo).all() and (y <= hi).all()
+    assert (y[:, 1] == min(max(0.0, lo), hi)).all() and (y[:, 2] == lo).all() and (y[:, 3] == hi).all()
+    r = np.where((out["status"] == 0) & np.isfinite(out["robustness"]), out["robustness"], -np.inf)
+    n_el = max(2, int(round(frac * P)))
+    order = np.lexsort((np.arange(P), -r))[:n_el]                # value descending, index ascending
+    order = order[np.isfinite(r[order])]
+    assert order.size >= 2
+    mean, std = y[:, order].mean(axis=1), np.maximum(y[:, order].std(axis=1), 1e-3 * (hi - lo))
+    assert np.allclose(res["mean"], mean, rtol=1e-12, atol=0) and np.allclose(res["std"], std, rtol=1e-10, atol=0)
+    bi = int(np.argmax(r))
+    assert res["robustness"] == r[bi] and np.array_equal(res["knot_y"], y[:, bi]) and res["history"] == [r[bi]]
+    assert res["launches"] == 3
+    # uniform draws: every knot's sample mean is near the middle of the bounds
+    assert np.all(np.abs(y[:, 4:].mean(axis=1) - 0.5 * (lo + hi)) < 0.05 * (hi - lo))
+
+
+def test_device_search_properties_on_the_reference_records(oracle_lib):
+    """Never below the zero input, deterministic for a seed, monotone history, and the number returned is the oracle's
+    robustness under the input returned with it."""
+    from pde_controller_b200 import search
+    probs = [problem_of(r) for r in GOLD]
+    kw = dict(population=2048, generations=5, elite_frac=0.03)
+    a = search.search_controls(probs, seed=3, workers=4, **kw)
+    b = search.search_controls(probs, seed=3, workers=1, **kw)
+    c = search.search_controls(probs, seed=4, workers=4, **kw)
+    single = search.search_control(probs[5], seed=search.sample_seed(3, 5), **kw)
+    assert all(x["engine"] == "device" for x in a)
+    assert len(single["history"]) == 5 and all(h2 >= h1 for h1, h2 in zip(single["history"], single["history"][1:]))
+    assert [x["robustness"] for x in a] == [x["robustness"] for x in b]          # whatever the thread schedule
+    assert all(np.array_equal(x["knot_y"], y["knot_y"]) for x, y in zip(a, b))
+    assert single["robustness"] == a[5]["robustness"] and np.array_equal(single["knot_y"], a[5]["knot_y"])
+    assert any(x["robustness"] != y["robustness"] for x, y in zip(a, c))          # another seed, other candidates
+    ctrls = [(x["knot_t"], x["knot_y"]) for x in a]
+    batch = ProblemBatch.from_problems(probs, ctrls)
+    ref, st = oracle_lib.eval_batch(batch)
+    assert (st == 0).all()
+    assert rel_err(np.array([x["robustness"] for x in a]), ref, batch).max() <= TOL_FP64
+    zero, st0 = oracle_lib.eval_batch(ProblemBatch.from_problems(probs, [None] * len(probs)))
+    for x, z, p in zip(a, zero, probs):
+        lo, hi = search.DEFAULT_BOUNDS[p.kind]
+        assert x["robustness"] >= z - 1e-9 * max(abs(z), 1.0)
+        assert all(h2 >= h1 for h1, h2 in zip(x["history"], x["history"][1:])) and x["history"][-1] == x["robustness"]
+        assert (x["knot_y"] >= lo).all() and (x["knot_y"] <= hi).all()
+    # the device engine is as good a searcher as the host one it replaces (same budget, other candidates)
+    host = search.search_controls(probs, seed=3, workers=2, engine="host", **kw)
+    dev_r, host_r = np.array([x["robustness"] for x in a]), np.array([x["robustness"] for x in host])
+    assert all(x["engine"] == "host" for x in host)
+    scale = np.maximum(np.abs(host_r), 1.0)
+    assert np.median((dev_r - host_r) / scale) >= -0.05, (dev_r, host_r)
+
+
+def test_device_search_on_an_unusable_specification_and_bad_arguments():
+    from pde_controller_b200 import search
+    p = problem_of(GOLD[0])
+    spec, kt = _spec_of(p)
+    ev = native.ControlsEvaluator(spec, kt, capacity=512)
+    try:
+        with pytest.raises(native.NativeError):
+            ev.search(1024, 2, 0.05, 0.0, 1.0, seed=1)            # population above the capacity
+        with pytest.raises(native.NativeError):
+            ev.search(256, 0, 0.05, 0.0, 1.0, seed=1)
+        with pytest.raises(native.NativeError):
+            ev.search(256, 2, 0.05, 1.0, 0.0, seed=1)             # lo > hi
+        bad = problem_of(GOLD[0])
+        bad.T = -1.0
+        spec_bad = ProblemBatch.from_problems([bad], kmax=max(kt.size, 1))
+        ev.respec(spec_bad, kt)
+        res = ev.search(256, 2, 0.05, 0.0, 1.0e6, seed=1)
+        assert res["knot_y"] is None and res["robustness"] == -np.inf
+        ev.respec(spec, kt)                                        # and the handle is usable again
+        assert ev.search(256, 2, 0.05, 0.0, 1.0e6, seed=1)["knot_y"] is not None
+    finally:
+        ev.close()
+    out = search.search_controls([bad], population=256, generations=2)
+    assert out[0]["knot_y"] is None
+
+
+def test_search_through_the_drop_in_call_is_the_batch_search(oracle_lib):
+    """eval_robustness_batch(controls="search") = ONE pdeb_controls_search_batch call over the samples without a control;
+    sample i draws from the generator stream of index i, so the list API, the batch API and the drop-in call agree."""
+    from pde_controller_b200 import eval_script as es, search
+    src = synth.make_batch(96, "mixed", seed=8)
+    probs = [src.get_problem(i)[0] for i in range(96)]
+    texts = [render_program(p) for p in probs]
+    budget = {"population": 1024, "generations": 3, "seed": 11}
+    given = {4: (np.array([0.0, 1.0]), np.array([2.0e5, 3.0e5])), 50: ([0.0, 0.5], [10.0, -10.0])}
+    ctrl = [given.get(i) for i in range(96)]
+    rob, _, st, used = es.eval_robustness_batch(texts, controls=ctrl, return_status=True, return_controls=True, search=budget)
+    lst = search.search_controls(probs, **budget)
+    assert (st == 0).all()
+    for i in range(96):
+        if i in given:
+            assert np.array_equal(np.asarray(used[i][1], dtype=float), np.asarray(given[i][1], dtype=float))
+        else:
+            assert np.array_equal(used[i][1], lst[i]["knot_y"]) and np.array_equal(used[i][0], lst[i]["knot_t"])
+            assert abs(rob[i] - lst[i]["robustness"]) <= 1e-9 * max(abs(rob[i]), 1.0)    # controls family vs batch kernels
+    b = ProblemBatch.from_problems(probs, used)
+    ref, ref_st = oracle_lib.eval_batch(b)
+    assert (ref_st == 0).all() and rel_err(np.array(rob), ref, b).max() <= TOL_FP64
+    # the thread count of the library's pool does not change anything
+    one = search.search_controls(probs, workers=1, **budget)
+    assert [x["robustness"] for x in one] == [x["robustness"] for x in lst]
