@@ -574,7 +574,18 @@ def main():
         for _ in range(reps):
             es.eval_robustness_batch(texts, controls=ctrls)
         secs = (time.perf_counter() - t0) / reps
+        # the same call WITHOUT controls: the default mode of the drop-in helpers, a searched input per program
+        # (pdeb_controls_search_batch: 4,096 candidates x 6 generations each, drawn, scored and ranked on the device)
+        ms_ = min(2048, m)
+        es.eval_robustness_batch(texts[:64], controls="search")
+        t0 = time.perf_counter()
+        rob_s, _ = es.eval_robustness_batch(texts[:ms_], controls="search")
+        secs_s = time.perf_counter() - t0
+        search_leg = {"value": ms_ / secs_s, "unit": "programs/s", "programs": ms_, "candidates_per_program": 4096 * 6,
+                      "positive": int(sum(r > 0 for r in rob_s)),
+                      "positive_under_the_given_controls": int((out_host["robustness"][:ms_] > 0).sum())}
         e2e_text = {"value": m / secs, "unit": "programs/s", "programs": m, "cores": os.cpu_count(), "calls_timed": reps,
+                    "search_mode": search_leg,
                     "first_call_value": m / first,
                     "route": "eval_robustness_batch(program strings, given controls): native template matcher "
                              "(pdeb_parse_programs, host threads; anything else -> Python front-end) -> PdebBatch -> "

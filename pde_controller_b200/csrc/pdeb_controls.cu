@@ -158,12 +158,11 @@ __device__ __forceinline__ void pdeb_ctl_solve(const PdebSpecConst<N>& sp, const
  * consistent double-double diagonal, the momentum).  Measured deviation from the oracle: 1.0e-10 of the parity metric
  * against 2.1e-11 for the a-form on the same inputs (tolerance 1e-9).
  */
-template <int KIND, int N, int PMAX, bool MOM = false>
-__global__ void __launch_bounds__(PDEB_CTL_THREADS, (KIND == PDEB_KIND_HEAT) ? PDEB_CTL_MINBLOCKS_HEAT
-                                                    : (MOM ? PDEB_CTL_MINBLOCKS_WAVE_MOM : PDEB_CTL_MINBLOCKS_WAVE))
-pdeb_controls_kernel(const __grid_constant__ PdebSpecConst<N> sp, const double* __restrict__ ky, int64_t stride, int64_t m,
-                     const __grid_constant__ PdebCtlOut out) {
-    const int64_t t = (int64_t)blockIdx.x * PDEB_CTL_THREADS + threadIdx.x;
+/* one candidate: thread t of the launch (t >= m: a padding lane that walks along and writes nothing).  `ky` is read
+ * with plain loads: in the one-launch search below the thread that reads a value has written it in the same kernel. */
+template <int KIND, int N, int PMAX, bool MOM>
+__device__ __forceinline__ void pdeb_controls_body(const PdebSpecConst<N>& sp, const double* ky, int64_t stride, int64_t m,
+                                                   const PdebCtlOut& out, const int64_t t) {
     const bool live = t < m;
     const double* y = ky + (live ? t : 0);
 
@@ -314,6 +313,15 @@ pdeb_controls_kernel(const __grid_constant__ PdebSpecConst<N> sp, const double* 
     }
 }
 
+#define PDEB_CTL_BOUNDS(KIND, MOM) __launch_bounds__(PDEB_CTL_THREADS, ((KIND) == PDEB_KIND_HEAT) ? PDEB_CTL_MINBLOCKS_HEAT \
+                                                     : ((MOM) ? PDEB_CTL_MINBLOCKS_WAVE_MOM : PDEB_CTL_MINBLOCKS_WAVE))
+template <int KIND, int N, int PMAX, bool MOM = false>
+__global__ void PDEB_CTL_BOUNDS(KIND, MOM)
+pdeb_controls_kernel(const __grid_constant__ PdebSpecConst<N> sp, const double* __restrict__ ky, int64_t stride, int64_t m,
+                     const __grid_constant__ PdebCtlOut out) {
+    pdeb_controls_body<KIND, N, PMAX, MOM>(sp, ky, stride, m, out, (int64_t)blockIdx.x * PDEB_CTL_THREADS + threadIdx.x);
+}
+
 /* ---- arg-max of the robustness over the candidates (two tiny launches) ---- */
 __global__ void pdeb_argmax_partial_kernel(const double* __restrict__ r, const int32_t* __restrict__ status, int64_t m,
                                            double* __restrict__ pv, int64_t* __restrict__ pi) {
@@ -343,13 +351,17 @@ __global__ void pdeb_argmax_partial_kernel(const double* __restrict__ r, const i
 /* ---- device-resident cross-entropy search over the candidates of one specification ------------------------------
  * The host-driven search (pde_controller_b200/search.py, round 1) drew every generation with numpy, uploaded it,
  * fetched every robustness and ranked them on the host: ~4 ms of host work per program around ~0.7 ms of kernels.
- * Here a generation is three launches and nothing crosses PCIe until the search is over:
- *   pdeb_cem_sample_kernel   candidates  y = clip(mean + std * z)  from a counter-based generator (generation 0:
- *                            uniform over the bounds, plus the zero input and the two bounds; the incumbent is
- *                            always candidate 0),
+ * Here a generation is two launches and nothing crosses PCIe until the search is over:
+ *   pdeb_cem_sample_kernel   (once) generation 0: candidates uniform over the bounds, plus the zero input and the two
+ *                            bounds,
  *   pdeb_controls_kernel     their robustness (the kernel above, unchanged),
- *   pdeb_cem_update_kernel   ONE block: radix select of the elite (largest robustness, ties by lowest index),
- *                            mean / standard deviation of the elite's knot values, incumbent, history.
+ *   pdeb_cem_update_kernel   ONE block: radix select of the elite (largest robustness, ties by lowest index), mean /
+ *                            standard deviation of the elite's knot values, incumbent, history; then the candidates of the
+ *                            next generation  y = clip(mean + std * z)  from a counter-based generator (the incumbent is
+ *                            always candidate 0).
+ * A single cooperative launch for the whole search (grid-wide barriers between scoring and ranking) was built and measured:
+ * 1.36 ms instead of 0.95 ms per search (one 128-thread block ranks while the grid waits) and concurrent cooperative launches
+ * of different streams do not overlap: 2.8e3 programs/s instead of 4.9e3; removed.
  * Deterministic for a given seed (fixed reduction trees, no atomics on floating-point values). */
 #define PDEB_CEM_MAX_GEN 64
 #define PDEB_CEM_MAX_ELITE 8192
@@ -373,11 +385,10 @@ __device__ __forceinline__ double pdeb_cem_uniform(uint64_t seed, int gen, int j
     return ((double)(k >> 11) + 0.5) * (1.0 / 9007199254740992.0);
 }
 
-__global__ void pdeb_cem_sample_kernel(double* __restrict__ ky, int64_t stride, int nk, int64_t P, const PdebCemState* __restrict__ st,
-                                       int gen, uint64_t seed, double lo, double hi) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
-    const bool has_best = st->has_best != 0;
+/* the nk knot values of candidate i of generation `gen` */
+__device__ __forceinline__ void pdeb_cem_draw(double* ky, int64_t stride, int nk, int64_t i, const PdebCemState* st, int gen,
+                                              uint64_t seed, double lo, double hi) {
+    const bool has_best = gen > 0 && st->has_best != 0;
     for (int j = 0; j < nk; ++j) {
         double y;
         if (gen == 0) {
@@ -390,37 +401,46 @@ __global__ void pdeb_cem_sample_kernel(double* __restrict__ ky, int64_t stride, 
             const double z = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
             y = fmin(fmax(fma(st->std[j], z, st->mean[j]), lo), hi);
         }
-        if (i == 0 && has_best) y = st->best_y[j];         /* the incumbent stays in the population */
+        if (i == 0 && has_best) y = st->best_y[j];    /* the incumbent stays in the population */
         ky[(int64_t)j * stride + i] = y;
     }
 }
 
+__global__ void pdeb_cem_sample_kernel(double* __restrict__ ky, int64_t stride, int nk, int64_t P, const PdebCemState* __restrict__ st,
+                                       int gen, uint64_t seed, double lo, double hi) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P) pdeb_cem_draw(ky, stride, nk, i, st, gen, seed, lo, hi);
+}
+
 /* larger robustness <-> larger key; 0 is reserved for candidates that do not count (status != 0, non-finite) */
-__device__ __forceinline__ uint64_t pdeb_cem_key(const double* __restrict__ rob, const int32_t* __restrict__ status, int64_t i) {
+__device__ __forceinline__ uint64_t pdeb_cem_key(const double* rob, const int32_t* status, int64_t i) {
     const double r = rob[i];
-    if (status[i] != PDEB_OK || !isfinite(r)) return 0ull;
+    const int32_t st = status[i];
+    if (st != PDEB_OK || !isfinite(r)) return 0ull;
     const uint64_t u = (uint64_t)__double_as_longlong(r);
     return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
 }
 
-__global__ void __launch_bounds__(PDEB_CEM_THREADS)
-pdeb_cem_update_kernel(const double* __restrict__ rob, const int32_t* __restrict__ status, const double* __restrict__ ky, int64_t stride,
-                       int64_t P, int nk, int n_elite, double std_floor, PdebCemState* __restrict__ st, int gen) {
+/* ONE block of THREADS threads (a multiple of 32, at most 1024): elite, its statistics, the incumbent */
+template <int THREADS>
+__device__ __forceinline__ void pdeb_cem_update_body(const double* rob, const int32_t* status, const double* ky, int64_t stride, int64_t P,
+                                                     int nk, int n_elite, double std_floor, PdebCemState* st, int gen) {
+    constexpr int WARPS = THREADS / 32;
     __shared__ unsigned hist[256];
     __shared__ int32_t elist[PDEB_CEM_MAX_ELITE];
     __shared__ uint64_t s_prefix;
-    __shared__ unsigned long long s_best;       /* packed arg-max, see below */
+    __shared__ unsigned long long s_best;
     __shared__ uint64_t s_bestkey;
     __shared__ int s_need, s_k, s_woff[32], s_eoff, s_goff;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     /* ---- how many candidates count, and the best of them (largest key, lowest index) ---- */
-    if (tid < 256) hist[tid] = 0;
+    for (int q = tid; q < 256; q += THREADS) hist[q] = 0;
     if (tid == 0) { s_bestkey = 0ull; s_best = ~0ull; }
     __syncthreads();
     unsigned nv_local = 0;
     uint64_t bk = 0ull; int64_t bi = -1;
-    for (int64_t i = tid; i < P; i += PDEB_CEM_THREADS) {
+    for (int64_t i = tid; i < P; i += THREADS) {
         const uint64_t k = pdeb_cem_key(rob, status, i);
         if (k) { ++nv_local; if (k > bk) { bk = k; bi = i; } }        /* ascending i per thread: first of equal keys */
     }
@@ -438,10 +458,10 @@ pdeb_cem_update_kernel(const double* __restrict__ rob, const int32_t* __restrict
     __syncthreads();
     if (k_el >= 2) {
         for (int b = 7; b >= 0; --b) {
-            if (tid < 256) hist[tid] = 0;
+            for (int q = tid; q < 256; q += THREADS) hist[q] = 0;
             __syncthreads();
             const uint64_t prefix = s_prefix;
-            for (int64_t i = tid; i < P; i += PDEB_CEM_THREADS) {
+            for (int64_t i = tid; i < P; i += THREADS) {
                 const uint64_t k = pdeb_cem_key(rob, status, i);
                 if (k && (b == 7 || (k >> (8 * (b + 1))) == prefix)) atomicAdd(&hist[(unsigned)(k >> (8 * b)) & 255u], 1u);
             }
@@ -459,11 +479,10 @@ pdeb_cem_update_kernel(const double* __restrict__ rob, const int32_t* __restrict
         const int need_eq = s_need;
         if (tid == 0) { s_eoff = 0; s_goff = 0; }
         __syncthreads();
-        for (int64_t base = 0; base < P; base += PDEB_CEM_THREADS) {
+        for (int64_t base = 0; base < P; base += THREADS) {
             const int64_t i = base + tid;
             const uint64_t k = (i < P) ? pdeb_cem_key(rob, status, i) : 0ull;
             const bool eq = k != 0ull && k == thr;
-            /* rank of this thread among the equal keys of the chunk */
             const unsigned beq = __ballot_sync(0xffffffffu, eq);
             if (lane == 0) s_woff[warp] = __popc(beq);
             __syncthreads();
@@ -471,7 +490,7 @@ pdeb_cem_update_kernel(const double* __restrict__ rob, const int32_t* __restrict
             for (int w = 0; w < warp; ++w) eq_before += s_woff[w];
             eq_before += __popc(beq & ((1u << lane) - 1u));
             int eq_total = 0;
-            for (int w = 0; w < 32; ++w) eq_total += s_woff[w];
+            for (int w = 0; w < WARPS; ++w) eq_total += s_woff[w];
             __syncthreads();
             const bool take = k != 0ull && (k > thr || (eq && eq_before < need_eq));
             const unsigned bt = __ballot_sync(0xffffffffu, take);
@@ -482,16 +501,17 @@ pdeb_cem_update_kernel(const double* __restrict__ rob, const int32_t* __restrict
             pos += __popc(bt & ((1u << lane) - 1u));
             if (take && pos < PDEB_CEM_MAX_ELITE) elist[pos] = (int32_t)i;
             int tk_total = 0;
-            for (int w = 0; w < 32; ++w) tk_total += s_woff[w];
+            for (int w = 0; w < WARPS; ++w) tk_total += s_woff[w];
             __syncthreads();
             if (tid == 0) { s_eoff += eq_total; s_goff += tk_total; }
             __syncthreads();
         }
         if (tid == 0) s_k = s_goff < PDEB_CEM_MAX_ELITE ? s_goff : PDEB_CEM_MAX_ELITE;
         __syncthreads();
-        /* ---- mean and standard deviation of the elite per knot: warp w takes the knots w, w + 32, .. ---- */
+        /* ---- mean and standard deviation of the elite per knot: warp w takes the knots w, w + WARPS, .. (the order of
+         * the sums does not depend on the block size: lanes stride over the elite, then a butterfly) ---- */
         const int ke = s_k;
-        for (int j = warp; j < nk; j += 32) {
+        for (int j = warp; j < nk; j += WARPS) {
             const double* col = ky + (int64_t)j * stride;
             double sum = 0.0;
             for (int q = lane; q < ke; q += 32) sum += col[elist[q]];
@@ -505,16 +525,30 @@ pdeb_cem_update_kernel(const double* __restrict__ rob, const int32_t* __restrict
     }
     /* ---- incumbent ---- */
     __syncthreads();
-    const bool better = best_i >= 0 && (!st->has_best || rob[best_i] > st->best_r);
+    const double cand = best_i >= 0 ? rob[best_i] : 0.0;
+    const bool better = best_i >= 0 && (gen == 0 || !st->has_best || cand > st->best_r);
     __syncthreads();
     if (better) {
-        for (int j = tid; j < nk; j += PDEB_CEM_THREADS) st->best_y[j] = ky[(int64_t)j * stride + best_i];
-        if (tid == 0) { st->best_r = rob[best_i]; st->has_best = 1; }
+        for (int j = tid; j < nk; j += THREADS) st->best_y[j] = ky[(int64_t)j * stride + best_i];
+        if (tid == 0) { st->best_r = cand; st->has_best = 1; }
     }
     __syncthreads();
     if (tid == 0) {
+        if (gen == 0 && best_i < 0) { st->has_best = 0; st->best_r = -INFINITY; }
         st->history[gen] = st->has_best ? st->best_r : -INFINITY;
         st->n_valid_last = nv;
+    }
+}
+
+/* ranks generation `gen` and, unless it was the last, draws generation gen + 1 from the re-centred distribution: two
+ * launches per generation (the searches of a sweep are launch-rate bound: ~9e4 launches/s from 16 host threads) */
+__global__ void __launch_bounds__(PDEB_CEM_THREADS)
+pdeb_cem_update_kernel(const double* rob, const int32_t* status, double* ky, int64_t stride, int64_t P, int nk, int n_elite,
+                       double std_floor, PdebCemState* st, int gen, int generations, uint64_t seed, double lo, double hi) {
+    pdeb_cem_update_body<PDEB_CEM_THREADS>(rob, status, ky, stride, P, nk, n_elite, std_floor, st, gen);
+    if (gen + 1 < generations) {
+        __syncthreads();                       /* mean / std / incumbent of this block's own writes */
+        for (int64_t i = threadIdx.x; i < P; i += PDEB_CEM_THREADS) pdeb_cem_draw(ky, stride, nk, i, st, gen + 1, seed, lo, hi);
     }
 }
 
@@ -798,25 +832,25 @@ extern "C" int pdeb_controls_search(PdebControls* h, int64_t population, int32_t
         return PDEB_E_OK;
     }
     PdebCemState* hs = h->h_cem;
+    PdebCtlOut out{h->d_rob, h->d_clause, h->d_status};
+    const double std_floor = 1e-3 * (hi - lo);
     memset(hs, 0, sizeof *hs);
     for (int j = 0; j < PDEB_CTL_KMAX; ++j) { hs->mean[j] = 0.5 * (lo + hi); hs->std[j] = 0.5 * (hi - lo); }
     hs->best_r = -INFINITY;
     CCK(cudaMemcpyAsync(h->d_cem, hs, sizeof *hs, cudaMemcpyHostToDevice, stream));
-    PdebCtlOut out{h->d_rob, h->d_clause, h->d_status};
-    const unsigned sblocks = (unsigned)((population + 255) / 256);
-    const double std_floor = 1e-3 * (hi - lo);
     CCK(cudaEventRecord(h->ev[0], stream));
+    pdeb_cem_sample_kernel<<<(unsigned)((population + 255) / 256), 256, 0, stream>>>(h->d_y, population, nk, population, h->d_cem, 0, seed, lo, hi);
+    CCK(cudaGetLastError());
     for (int g = 0; g < generations; ++g) {
-        pdeb_cem_sample_kernel<<<sblocks, 256, 0, stream>>>(h->d_y, population, nk, population, h->d_cem, g, seed, lo, hi);
-        CCK(cudaGetLastError());
         cudaError_t e = (h->kind == PDEB_KIND_HEAT)
                             ? launch_controls<PDEB_KIND_HEAT, 30>(h->heat, h->pmax, h->d_y, population, population, out, stream)
                             : launch_controls<PDEB_KIND_WAVE, 20>(h->wave, h->pmax, h->d_y, population, population, out, stream);
         if (e != cudaSuccess) return cfail(PDEB_E_CUDA, "controls kernel launch", e);
         pdeb_cem_update_kernel<<<1, PDEB_CEM_THREADS, 0, stream>>>(h->d_rob, h->d_status, h->d_y, population, population, nk, (int)n_elite,
-                                                                  std_floor, h->d_cem, g);
+                                                                  std_floor, h->d_cem, g, generations, seed, lo, hi);
         CCK(cudaGetLastError());
     }
+    const int launches = 1 + 2 * generations;
     CCK(cudaEventRecord(h->ev[1], stream));
     CCK(cudaMemcpyAsync(hs, h->d_cem, sizeof *hs, cudaMemcpyDeviceToHost, stream));
     CCK(cudaStreamSynchronize(stream));
@@ -830,7 +864,7 @@ extern "C" int pdeb_controls_search(PdebControls* h, int64_t population, int32_t
     if (timing) {
         float ms = 0;
         CCK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
-        timing->kernel_ms = ms; timing->total_ms = ms; timing->launches = 3 * generations;
+        timing->kernel_ms = ms; timing->total_ms = ms; timing->launches = launches;
     }
     return PDEB_E_OK;
 }
@@ -856,8 +890,11 @@ extern "C" int pdeb_controls_search_batch(const PdebBatch* in, const int64_t* sa
     if (n_samples == 0) return PDEB_E_OK;
     for (int64_t q = 0; q < n_samples; ++q)
         if (samples && (samples[q] < 0 || samples[q] >= in->n)) return cfail(PDEB_E_ARG, "pdeb_controls_search_batch: sample index out of range");
+    /* default: 8 threads.  Measured on the 16-core B200 box (tools/search_workers_sweep.py): 0.8e3 programs/s with one
+     * thread, 4.7e3 with 8, no more (and erratic) beyond: a search is ~20 driver calls (13 launches, two copies, events,
+     * a synchronise) and the threads of a process share the driver's lock; a blocking synchronise does not change that */
     unsigned hw = std::thread::hardware_concurrency();
-    int nt = nthreads > 0 ? nthreads : (int)(hw ? hw : 8);
+    int nt = nthreads > 0 ? nthreads : (hw >= 8 || hw == 0 ? 8 : (int)hw);
     if (nt > 32) nt = 32;
     if ((int64_t)nt > n_samples) nt = (int)n_samples;
     std::atomic<int64_t> next{0};
