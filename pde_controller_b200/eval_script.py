@@ -34,6 +34,8 @@ from .iou import eval_IOU, eval_IOU_DPO, eval_IOU_batch  # noqa: F401  (eval_scr
 from .problem import Problem, ProblemBatch
 
 _DEVICE = 0
+_DEVICES = None           # several devices of the box for the batched call (None: the single device above)
+_MULTI_EVAL_MIN = 131072  # batches below this are evaluated on one device even when several are configured (the searches are not)
 _PRECISION = 64
 _CONV = None
 _CONTROL_MODE = "search"
@@ -42,12 +44,15 @@ CONTROL_MODES = ("search", "zero")
 
 
 def configure(device: int = 0, precision: int = 64, conventions=None, control_mode: Optional[str] = None,
-              search: Optional[dict] = None):
+              search: Optional[dict] = None, devices: Optional[Sequence[int]] = None):
     """Process-wide defaults of the helpers below: device ordinal, 64/32-bit time loop, convention flags, what a
     sample WITHOUT an explicit control is evaluated under (`control_mode`: "search" | "zero") and the search budget
-    (`search`: population, generations, seed, elite_frac, bounds)."""
-    global _DEVICE, _PRECISION, _CONV, _CONTROL_MODE, _SEARCH
+    (`search`: population, generations, seed, elite_frac, bounds).  `devices`: a list of device ordinals for the batched
+    call -- the batch is cut into cost-balanced shards (pdeb_eval_batch_multi) and the searches are dealt out over them;
+    None (the default) leaves everything on `device`."""
+    global _DEVICE, _DEVICES, _PRECISION, _CONV, _CONTROL_MODE, _SEARCH
     _DEVICE, _PRECISION, _CONV = device, precision, conventions
+    _DEVICES = [int(d) for d in devices] if devices else None
     if control_mode is not None:
         if control_mode not in CONTROL_MODES:
             raise ValueError(f"control_mode must be one of {CONTROL_MODES}")
@@ -73,7 +78,8 @@ def is_correct(pred, ans, prec=1e-3):
 def eval_robustness_batch(programs: Sequence[str], natural_language: Optional[Sequence[str]] = None,
                           controls=None, device: Optional[int] = None,
                           precision: Optional[int] = None, conventions=None, return_status: bool = False,
-                          parse_workers: Optional[int] = None, return_controls: bool = False, search: Optional[dict] = None):
+                          parse_workers: Optional[int] = None, return_controls: bool = False, search: Optional[dict] = None,
+                          devices: Optional[Sequence[int]] = None):
     """Evaluate many programs in one GPU call (long lists are parsed by worker processes: frontend.parse_many).
 
     controls: a list with one entry per program -- `(knot_times, knot_values)` or None -- or one of the mode strings
@@ -97,6 +103,9 @@ def eval_robustness_batch(programs: Sequence[str], natural_language: Optional[Se
     if len(controls) != n:
         raise ValueError("controls must have one entry per program")
     dev = _DEVICE if device is None else device
+    devs = [int(d) for d in devices] if devices else (_DEVICES if device is None else None)
+    if devs:
+        dev = devs[0]
     conv = conventions if conventions is not None else _CONV
     status = np.zeros(n, dtype=np.int32)
     rob = np.full(n, abi.FAILED_ROBUSTNESS, dtype=np.float64)
@@ -200,10 +209,32 @@ def eval_robustness_batch(programs: Sequence[str], natural_language: Optional[Se
                    ((batch.kind[need] == abi.KIND_WAVE) & (batch.n_elem[need] == 20))) & (k_need >= 2)
             done = k_need < 2
             if engine == "device" and fam.any():
-                sr = native.search_batch(batch, samples=need[fam], population=budget.get("population", 4096),
-                                         generations=budget.get("generations", 6), elite_frac=budget.get("elite_frac", 0.02),
-                                         bounds=b4, seed=_search._seed64(budget.get("seed", 0)), device=dev, conv=conv,
-                                         nthreads=budget.get("workers", 0))
+                skw = dict(population=budget.get("population", 4096), generations=budget.get("generations", 6),
+                           elite_frac=budget.get("elite_frac", 0.02), bounds=b4, seed=_search._seed64(budget.get("seed", 0)),
+                           conv=conv, nthreads=budget.get("workers", 0))
+                todo = need[fam]
+                if devs and len(devs) > 1 and todo.size >= 2 * len(devs):
+                    # one Python thread per device, each with its slice of the samples (the library call releases the GIL and
+                    # writes only its own samples' columns); a sample's generator stream depends on its index alone
+                    import threading
+                    found_all = np.zeros(n, dtype=bool)
+                    errs = []
+
+                    def _shard(d, part):
+                        try:
+                            found_all[part] = native.search_batch(batch, samples=part, device=d, **skw)["found"][part]
+                        except BaseException as e:          # surfaced on the calling thread
+                            errs.append(e)
+                    ths = [threading.Thread(target=_shard, args=(d, todo[q::len(devs)])) for q, d in enumerate(devs)]
+                    for t in ths:
+                        t.start()
+                    for t in ths:
+                        t.join()
+                    if errs:
+                        raise errs[0]
+                    sr = {"found": found_all}
+                else:
+                    sr = native.search_batch(batch, samples=todo, device=dev, **skw)
                 done[fam] = True
                 lost = need[fam][~sr["found"][need[fam]]]
                 batch.n_knots[lost] = 0                  # nothing found (an unusable specification): its own status is reported
@@ -225,7 +256,12 @@ def eval_robustness_batch(programs: Sequence[str], natural_language: Optional[Se
                     if k > 0:
                         controls[i] = (batch.knot_t[:k, i].copy(), batch.knot_y[:k, i].copy())
         # the number returned is ALWAYS the batch kernels' robustness under the control in `controls` (found or given)
-        out = native.evaluate_batch(batch, device=dev, precision=_PRECISION if precision is None else precision, conv=conv)
+        prec = _PRECISION if precision is None else precision
+        if devs and len(devs) > 1 and n >= _MULTI_EVAL_MIN:
+            # worth it for large batches only: 8,192 programs are 40 us of kernel time, less than starting the shard threads
+            out = native.evaluate_batch_multi(batch, len(devs), devices=devs, precision=prec, conv=conv)
+        else:
+            out = native.evaluate_batch(batch, device=dev, precision=prec, conv=conv)
         rob[live] = out["robustness"][live]
         status[live] = out["status"][live]
     runtime = (time.perf_counter() - t0) / max(n, 1)

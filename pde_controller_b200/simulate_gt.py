@@ -24,12 +24,14 @@ from .eval_script import eval_robustness_batch
 
 
 def evaluate_future(eval_fn, tasks, _timeout=300, python_key="python", nl_key="nl", control_key="control",
-                    control_mode=None, write_back=False, search=None):
+                    control_mode=None, write_back=False, search=None, devices=None):
     """Drop-in for simulate_gt.evaluate_future: -> (robustness tuple, time tuple, timeout_cnt).
 
     `eval_fn` is accepted for signature compatibility and ignored: the whole task list goes to the GPU at once.
     control_mode: "search" | "zero" | None (= eval_script's process-wide mode) for the records without an input of
-    their own; write_back stores the input a record was evaluated under in task[control_key].
+    their own; write_back stores the input a record was evaluated under in task[control_key]; devices: the GPUs of the
+    box to shard over (the reference's pool of cpu_count // 2 worker processes, simulate_gt.py:64-65, becomes one shard
+    per device).
     """
     from . import eval_script
     controls = []
@@ -40,17 +42,31 @@ def evaluate_future(eval_fn, tasks, _timeout=300, python_key="python", nl_key="n
     if mode not in eval_script.CONTROL_MODES:
         raise ValueError(f"control mode must be one of {eval_script.CONTROL_MODES}")
     prev = eval_script.control_mode()
-    eval_script.configure(eval_script._DEVICE, eval_script._PRECISION, eval_script._CONV, control_mode=mode)
+    eval_script.configure(eval_script._DEVICE, eval_script._PRECISION, eval_script._CONV, control_mode=mode,
+                          devices=eval_script._DEVICES)
     try:
         rob, rt, used = eval_robustness_batch([t[python_key] for t in tasks], [t.get(nl_key, "") for t in tasks], controls,
-                                              return_controls=True, search=search)
+                                              return_controls=True, search=search, devices=devices)
     finally:
-        eval_script.configure(eval_script._DEVICE, eval_script._PRECISION, eval_script._CONV, control_mode=prev)
+        eval_script.configure(eval_script._DEVICE, eval_script._PRECISION, eval_script._CONV, control_mode=prev,
+                              devices=eval_script._DEVICES)
     if write_back:
         for t, c in zip(tasks, used):
             if c is not None and control_key not in t:
                 t[control_key] = {"t": [float(x) for x in c[0]], "y": [float(x) for x in c[1]]}
     return tuple(rob), tuple(rt), 0
+
+
+def _device_list(spec):
+    """--devices: "all", a count ("4" = devices 0..3) or a comma list ("0,2,5"); None / "" = the configured device."""
+    if not spec:
+        return None
+    from . import native
+    if spec == "all":
+        return list(range(native.device_count()))
+    if "," in spec:
+        return [int(x) for x in spec.split(",") if x.strip()]
+    return list(range(int(spec)))
 
 
 def main(args):
@@ -78,7 +94,7 @@ def main(args):
     metrics = {"n_samples": len(test_data)}
     if args.eval_robustness:
         rob, times, timeouts = evaluate_future(None, test_data, control_key=args.control_key, control_mode=args.control,
-                                               write_back=True,
+                                               write_back=True, devices=_device_list(args.devices),
                                                search={"population": args.search_population, "generations": args.search_generations})
         metrics["control_mode"] = args.control
         for item, r, t in zip(test_data, rob, times):
@@ -118,6 +134,8 @@ def build_parser():
     p.add_argument("--control_key", type=str, default="control")
     p.add_argument("--control", type=str, default="search", choices=["search", "zero"],
                    help="what a record without an input of its own is evaluated under (module docstring)")
+    p.add_argument("--devices", type=str, default=None,
+                   help='GPUs of the box to shard the batch over: "all", a count, or a comma list (default: one device)')
     p.add_argument("--search_population", type=int, default=4096)
     p.add_argument("--search_generations", type=int, default=6)
     p.add_argument("--max_num_examples", type=int, default=None)

@@ -320,3 +320,41 @@ def test_search_through_the_drop_in_call_is_the_batch_search(oracle_lib):
     # the thread count of the library's pool does not change anything
     one = search.search_controls(probs, workers=1, **budget)
     assert [x["robustness"] for x in one] == [x["robustness"] for x in lst]
+
+
+def test_drop_in_call_sharded_over_devices_equals_one_device(tmp_path):
+    """eval_robustness_batch(devices=[...]) / simulate_gt --devices: cost-balanced evaluation shards (pdeb_eval_batch_multi) and
+    the searches dealt out over the devices; a sample's search depends on its index alone, so the numbers are those of one
+    device.  Two real devices when the box has them, the same device twice otherwise."""
+    from pde_controller_b200 import eval_script as es, simulate_gt
+    devs = [0, 1] if native.device_count() >= 2 else [0, 0]
+    src = synth.make_batch(80, "mixed", seed=13)
+    texts = [render_program(src.get_problem(i)[0]) for i in range(80)]
+    budget = {"population": 512, "generations": 3, "seed": 2}
+    one, _, st1, c1 = es.eval_robustness_batch(texts, controls="search", return_status=True, return_controls=True, search=budget)
+    two, _, st2, c2 = es.eval_robustness_batch(texts, controls="search", return_status=True, return_controls=True, search=budget,
+                                               devices=devs)
+    assert one == two and (st1 == st2).all()
+    assert all(np.array_equal(a[1], b[1]) for a, b in zip(c1, c2))
+    z1, _ = es.eval_robustness_batch(texts, controls="zero")
+    old_min = es._MULTI_EVAL_MIN
+    es._MULTI_EVAL_MIN = 16                     # small batches stay on one device by default: force the sharded evaluation
+    try:
+        z2, _ = es.eval_robustness_batch(texts, controls="zero", devices=devs)
+        two_b, _ = es.eval_robustness_batch(texts, controls="search", search=budget, devices=devs)
+    finally:
+        es._MULTI_EVAL_MIN = old_min
+    assert z1 == z2 and two_b == one
+    assert simulate_gt._device_list("all") == list(range(native.device_count()))
+    assert simulate_gt._device_list("0,0") == [0, 0] and simulate_gt._device_list("1") == [0] and simulate_gt._device_list(None) is None
+    d = tmp_path / "set"
+    d.mkdir()
+    with open(d / "test.jsonl", "w") as f:
+        for i, t in enumerate(texts[:24]):
+            f.write(json.dumps({"nl": f"s{i}", "sstl": "", "python": t}) + "\n")
+    base = ["--data_dir", str(d), "--max_num_examples", "24", "--eval_robustness", "--search_population", "512", "--search_generations", "3"]
+    m1 = simulate_gt.main(simulate_gt.build_parser().parse_args(base))
+    r1 = [json.loads(l)["robustness"] for l in open(str(d) + "_24/test.jsonl")]
+    m2 = simulate_gt.main(simulate_gt.build_parser().parse_args(base + ["--devices", ",".join(map(str, devs))]))
+    r2 = [json.loads(l)["robustness"] for l in open(str(d) + "_24/test.jsonl")]
+    assert r1 == r2 and m1 == m2
