@@ -319,7 +319,7 @@ int  pdeb_controls_search(PdebControls* h, int64_t population, int32_t generatio
                           double* mean_out, double* std_out, void* stream, PdebTiming* timing);
 /*
  * pdeb_controls_search for MANY specifications: samples[0..n_samples) of `in` (NULL = every sample), `nthreads` host threads
- * (<= 0: 8; at most 32) with one stream and one controls handle each.  Knot TIMES are the batch's own (n_knots, knot_t;
+ * (<= 0: one per host core, at most 16; never more than 32) with one stream and one controls handle each.  Knot TIMES are the batch's own (n_knots, knot_t;
  * knot_t == NULL: linspace(0, T, n_knots)), the knot VALUES found are written to knot_y_out in the batch's plane-major
  * layout [kmax][stride] (it may BE in->knot_y), best_out [n] / found_out [n] per sample.  bounds = { heat lo, heat hi, wave lo,
  * wave hi }.  Sample s draws from the generator stream mix(seed, s): the result does not depend on the thread count.

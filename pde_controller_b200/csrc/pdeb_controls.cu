@@ -579,6 +579,8 @@ struct PdebControls {
     struct PdebCemState* d_cem = nullptr;   /* state of the device-resident search (pdeb_controls_search) */
     struct PdebCemState* h_cem = nullptr;   /* pinned mirror */
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaEvent_t done = nullptr;   /* blocking-sync event (sweeps): a waiting host thread sleeps instead of spinning on the stream */
+    bool sleep_on_done = false;
 };
 #define PDEB_ARGMAX_BLOCKS 128
 
@@ -669,6 +671,7 @@ extern "C" void pdeb_controls_destroy(PdebControls* h) {
     if (h->h_pi) cudaFreeHost(h->h_pi);
     if (h->h_cem) cudaFreeHost(h->h_cem);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->done) cudaEventDestroy(h->done);
     delete h;
 }
 
@@ -715,6 +718,7 @@ extern "C" int pdeb_controls_create(const PdebBatch* spec, int64_t sample, int64
     if (e == cudaSuccess) e = cudaHostAlloc(&h->h_pi, sizeof(int64_t) * PDEB_ARGMAX_BLOCKS, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc(&h->h_cem, sizeof(PdebCemState), cudaHostAllocDefault);
     for (auto& ev : h->ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->done, cudaEventBlockingSync | cudaEventDisableTiming);
     if (e != cudaSuccess) { pdeb_controls_destroy(h); return cfail(PDEB_E_CUDA, "pdeb_controls_create", e); }
     *out = h;
     return PDEB_E_OK;
@@ -853,7 +857,12 @@ extern "C" int pdeb_controls_search(PdebControls* h, int64_t population, int32_t
     const int launches = 1 + 2 * generations;
     CCK(cudaEventRecord(h->ev[1], stream));
     CCK(cudaMemcpyAsync(hs, h->d_cem, sizeof *hs, cudaMemcpyDeviceToHost, stream));
-    CCK(cudaStreamSynchronize(stream));
+    if (h->sleep_on_done) {
+        CCK(cudaEventRecord(h->done, stream));
+        CCK(cudaEventSynchronize(h->done));
+    } else {
+        CCK(cudaStreamSynchronize(stream));
+    }
     const bool found = hs->has_best != 0;
     if (found_out) *found_out = found ? 1 : 0;
     if (best_value_out) *best_value_out = found ? hs->best_r : PDEB_FAILED_ROBUSTNESS;
@@ -890,13 +899,16 @@ extern "C" int pdeb_controls_search_batch(const PdebBatch* in, const int64_t* sa
     if (n_samples == 0) return PDEB_E_OK;
     for (int64_t q = 0; q < n_samples; ++q)
         if (samples && (samples[q] < 0 || samples[q] >= in->n)) return cfail(PDEB_E_ARG, "pdeb_controls_search_batch: sample index out of range");
-    /* default: 8 threads.  Measured on the 16-core B200 box (tools/search_workers_sweep.py): 0.8e3 programs/s with one
-     * thread, 4.7e3 with 8, no more (and erratic) beyond: a search is ~20 driver calls (13 launches, two copies, events,
-     * a synchronise) and the threads of a process share the driver's lock; a blocking synchronise does not change that */
+    /* default: one thread per host core, at most 16.  Measured on the 16-core B200 box (tools/search_workers_sweep.py): 0.8e3
+     * programs/s with one thread, 4.9e3 with 8, 8e3 with 16, 8-10e3 with 24 -- PROVIDED the process has more than the default 8
+     * hardware queues (CUDA_DEVICE_MAX_CONNECTIONS=32, which the Python package sets before CUDA starts: with 8, streams
+     * alias onto the same queue and 12+ threads run slower than 8) and the waiting threads sleep instead of spinning
+     * (the event below): a search is ~20 driver calls, and 16 spinning threads on 16 cores starve the ones that launch. */
     unsigned hw = std::thread::hardware_concurrency();
-    int nt = nthreads > 0 ? nthreads : (hw >= 8 || hw == 0 ? 8 : (int)hw);
+    int nt = nthreads > 0 ? nthreads : (hw == 0 ? 8 : (hw > 16 ? 16 : (int)hw));
     if (nt > 32) nt = 32;
     if ((int64_t)nt > n_samples) nt = (int)n_samples;
+    const bool sleep_wait = nt >= 8;
     std::atomic<int64_t> next{0};
     std::atomic<int> failed{0};
     std::mutex err_mutex;
@@ -928,8 +940,10 @@ extern "C" int pdeb_controls_search_batch(const PdebBatch* in, const int64_t* sa
             for (int j = 0; j < nk; ++j)
                 kt[j] = in->knot_t ? in->knot_t[(int64_t)j * st + s]
                                    : ((j == nk - 1 && nk > 1) ? in->T[s] : (nk > 1 ? (double)j * (in->T[s] / (double)(nk - 1)) : 0.0));
-            if (!h) rc = pdeb_controls_create(in, s, population, nk, kt, device, conv, &h);
-            else rc = pdeb_controls_respec(h, in, s, nk, kt, conv);
+            if (!h) {
+                rc = pdeb_controls_create(in, s, population, nk, kt, device, conv, &h);
+                if (rc == PDEB_E_OK) h->sleep_on_done = sleep_wait;
+            } else rc = pdeb_controls_respec(h, in, s, nk, kt, conv);
             if (rc != PDEB_E_OK) break;
             const double lo = bounds[kind == PDEB_KIND_HEAT ? 0 : 2], hi = bounds[kind == PDEB_KIND_HEAT ? 1 : 3];
             /* one generator stream per sample, whatever thread takes it */
