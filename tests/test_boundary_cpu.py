@@ -68,3 +68,40 @@ def test_bind_host_near_uses_the_gpu_numa_node(tmp_path, monkeypatch):
         assert not info["bound"] and os.sched_getaffinity(0) == before
     finally:
         os.sched_setaffinity(0, before)
+
+
+def test_default_knots_vectorised_equal_the_per_problem_rule():
+    """problem.fill_default_knot_times / default_knot_counts (what the batch search and eval_robustness_batch use) against
+    default_knot_times, sample by sample, including horizons that round half to even and a non-positive one."""
+    import numpy as np
+    from pde_controller_b200 import ProblemBatch, default_knot_times, synth
+    from pde_controller_b200.problem import default_knot_counts, fill_default_knot_times
+
+    for wl in ("heat", "wave"):
+        b = synth.make_batch(200, wl, seed=2)
+        b.T[:6] = [6.5, 7.5, 8.49999, 0.2, 5.5, 13.5]
+        w = ProblemBatch(200, 16, b.pmax, b.tmax)
+        for name in w._names:
+            if name not in ("knot_t", "knot_y", "n_knots"):
+                getattr(w, name)[...] = getattr(b, name)
+        w.knot_y[:] = 7.0
+        idx = np.arange(0, 200, 3)
+        K = fill_default_knot_times(w, idx)
+        for q, i in enumerate(idx):
+            kt = default_knot_times(b.get_problem(int(i))[0])
+            assert K[q] == kt.size == w.n_knots[i] and np.array_equal(w.knot_t[: kt.size, i], kt)
+            assert not w.knot_t[kt.size:, i].any() and not w.knot_y[:, i].any()
+        untouched = np.setdiff1d(np.arange(200), idx)
+        assert (w.n_knots[untouched] == 0).all() and (w.knot_y[:, untouched] == 7.0).all()
+    k = default_knot_counts(np.array([0, 0, 0, 1], dtype=np.uint8), np.array([-3.0, np.nan, 1e30, 123.0]))
+    assert k[0] == 2 and k[1] == 2 and k[2] > 32 and k[3] == 5
+
+
+def test_search_seeds_are_splitmix64():
+    """search.sample_seed mirrors pdeb_mix64 of csrc/pdeb_controls.cu: the first outputs of splitmix64 are published values."""
+    from pde_controller_b200 import search
+    assert search._mix64(0) == 0xE220A8397B1DCDAF
+    assert search._mix64(0x9E3779B97F4A7C15) == 0x6E789E6AA1B965F4          # second output of the generator seeded with 0
+    assert search._seed64(5) == 5 and search._seed64(-1) == (1 << 64) - 1 and 0 <= search._seed64((3, 4)) < (1 << 64)
+    assert search.sample_seed(7, 0) != search.sample_seed(7, 1) != search.sample_seed(8, 1)
+    assert search.sample_seed(7, 3) == search._mix64(7 ^ search._mix64(3))
