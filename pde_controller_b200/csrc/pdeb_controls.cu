@@ -406,10 +406,14 @@ __device__ __forceinline__ void pdeb_cem_draw(double* ky, int64_t stride, int nk
     }
 }
 
-__global__ void pdeb_cem_sample_kernel(double* __restrict__ ky, int64_t stride, int nk, int64_t P, const PdebCemState* __restrict__ st,
-                                       int gen, uint64_t seed, double lo, double hi) {
+/* generation 0 (the draw does not look at the state) and the state's initial values: no host -> device copy per search */
+__global__ void pdeb_cem_sample_kernel(double* __restrict__ ky, int64_t stride, int nk, int64_t P, PdebCemState* __restrict__ st,
+                                       uint64_t seed, double lo, double hi) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < P) pdeb_cem_draw(ky, stride, nk, i, st, gen, seed, lo, hi);
+    if (i < PDEB_CTL_KMAX) { st->mean[i] = 0.5 * (lo + hi); st->std[i] = 0.5 * (hi - lo); st->best_y[i] = 0.0; }
+    if (i < PDEB_CEM_MAX_GEN) st->history[i] = 0.0;
+    if (i == 0) { st->best_r = -INFINITY; st->has_best = 0; st->n_valid_last = 0; }
+    if (i < P) pdeb_cem_draw(ky, stride, nk, i, st, 0, seed, lo, hi);
 }
 
 /* larger robustness <-> larger key; 0 is reserved for candidates that do not count (status != 0, non-finite) */
@@ -838,12 +842,8 @@ extern "C" int pdeb_controls_search(PdebControls* h, int64_t population, int32_t
     PdebCemState* hs = h->h_cem;
     PdebCtlOut out{h->d_rob, h->d_clause, h->d_status};
     const double std_floor = 1e-3 * (hi - lo);
-    memset(hs, 0, sizeof *hs);
-    for (int j = 0; j < PDEB_CTL_KMAX; ++j) { hs->mean[j] = 0.5 * (lo + hi); hs->std[j] = 0.5 * (hi - lo); }
-    hs->best_r = -INFINITY;
-    CCK(cudaMemcpyAsync(h->d_cem, hs, sizeof *hs, cudaMemcpyHostToDevice, stream));
-    CCK(cudaEventRecord(h->ev[0], stream));
-    pdeb_cem_sample_kernel<<<(unsigned)((population + 255) / 256), 256, 0, stream>>>(h->d_y, population, nk, population, h->d_cem, 0, seed, lo, hi);
+    if (timing) CCK(cudaEventRecord(h->ev[0], stream));
+    pdeb_cem_sample_kernel<<<(unsigned)((population + 255) / 256), 256, 0, stream>>>(h->d_y, population, nk, population, h->d_cem, seed, lo, hi);
     CCK(cudaGetLastError());
     for (int g = 0; g < generations; ++g) {
         cudaError_t e = (h->kind == PDEB_KIND_HEAT)
@@ -855,7 +855,7 @@ extern "C" int pdeb_controls_search(PdebControls* h, int64_t population, int32_t
         CCK(cudaGetLastError());
     }
     const int launches = 1 + 2 * generations;
-    CCK(cudaEventRecord(h->ev[1], stream));
+    if (timing) CCK(cudaEventRecord(h->ev[1], stream));
     CCK(cudaMemcpyAsync(hs, h->d_cem, sizeof *hs, cudaMemcpyDeviceToHost, stream));
     if (h->sleep_on_done) {
         CCK(cudaEventRecord(h->done, stream));
@@ -951,10 +951,11 @@ extern "C" int pdeb_controls_search_batch(const PdebBatch* in, const int64_t* sa
             double best = 0.0;
             int32_t found = 0;
             PdebTiming tm;
+            memset(&tm, 0, sizeof tm);
             rc = pdeb_controls_search(h, population, generations, elite_frac, lo, hi, seed_s, by, &best, &found, nullptr, nullptr, nullptr,
-                                      (void*)stream, &tm);
+                                      (void*)stream, timing ? &tm : nullptr);           /* two event records less per search */
             if (rc != PDEB_E_OK) break;
-            ms[(size_t)w] += tm.kernel_ms; launches[(size_t)w] += tm.launches;
+            ms[(size_t)w] += tm.kernel_ms; launches[(size_t)w] += timing ? tm.launches : 1 + 2 * generations;
             found_out[s] = found;
             best_out[s] = best;
             if (found) for (int j = 0; j < nk; ++j) knot_y_out[(int64_t)j * st + s] = by[j];

@@ -476,12 +476,14 @@ class BlockPipeline:
 
 
 def search_batch(batch: ProblemBatch, samples=None, population: int = 4096, generations: int = 6, elite_frac: float = 0.02,
-                 bounds=(0.0, 1.0e6, -5.0e3, 5.0e3), seed: int = 0, device: int = 0, conv=None, nthreads: int = 0, knot_y_out=None):
+                 bounds=(0.0, 1.0e6, -5.0e3, 5.0e3), seed: int = 0, device: int = 0, conv=None, nthreads: int = 0, knot_y_out=None,
+                 timing: bool = False):
     """pdeb_controls_search_batch: the device-resident search for many samples of `batch` in one call (host threads inside
     the library, nothing per sample in Python).  The knot times are the batch's (`n_knots`, `knot_t`; a uniform-knots batch:
     linspace(0, T, n_knots)); the values found are written into `knot_y_out` (default: batch.knot_y itself, so the batch
     can be evaluated right away).  -> dict(best f64[n], found bool[n], kernel_ms, launches); entries of samples that were
-    not asked for, or that are outside the controls family, have found False."""
+    not asked for, or that are outside the controls family, have found False.  kernel_ms is the sum of the searches' device
+    times and only measured with timing=True (two more driver calls per search)."""
     n = batch.n
     idx = None if samples is None else np.ascontiguousarray(samples, dtype=np.int64)
     ky = batch.knot_y if knot_y_out is None else knot_y_out
@@ -497,7 +499,7 @@ def search_batch(batch: ProblemBatch, samples=None, population: int = 4096, gene
     _check(lib().pdeb_controls_search_batch(C.addressof(cb), _ptr(idx), n if idx is None else int(idx.size), int(population),
                                             int(generations), float(elite_frac), _ptr(b4), C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF),
                                             int(device), _conv_ptr(conv), int(nthreads), _ptr(ky), _ptr(best), _ptr(found),
-                                            C.addressof(tm)), "pdeb_controls_search_batch")
+                                            C.addressof(tm) if timing else None), "pdeb_controls_search_batch")
     return {"best": best, "found": found.astype(bool), "kernel_ms": float(tm.kernel_ms), "launches": int(tm.launches)}
 
 

@@ -206,7 +206,7 @@ def search_controls(problems: Sequence[Problem], population: int = 4096, generat
             if bounds is not None:
                 b4 = [bounds[0], bounds[1], bounds[0], bounds[1]]
             res = native.search_batch(wide, samples=idx, population=population, generations=generations, elite_frac=elite_frac,
-                                      bounds=b4, seed=_seed64(seed), device=device, conv=conv, nthreads=workers)
+                                      bounds=b4, seed=_seed64(seed), device=device, conv=conv, nthreads=workers, timing=True)
             per = res["kernel_ms"] / idx.size
             for i in idx.tolist():
                 k = int(wide.n_knots[i])
