@@ -547,6 +547,21 @@ def main():
 
     st = out_host["status"]
     n_fail = int((st != 0).sum())
+    # the ONE-SHOT entry (pdeb_eval_batch: a synchronous call with host arrays, what eval_robustness_batch makes): from
+    # ordinary pageable memory and from the page-locked slab, best of 3 -- the cost of not pipelining, next to `e2e`
+    one_shot = {}
+    if rank == 0:
+        for name, hb in (("pageable", src), ("page_locked", host)):
+            native.evaluate_batch(hb, device=dev, precision=args.precision)
+            best = None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                o1 = native.evaluate_batch(hb, device=dev, precision=args.precision)
+                dt_ = time.perf_counter() - t0
+                best = dt_ if best is None else min(best, dt_)
+            if not np.array_equal(o1["robustness"], out_host["robustness"]):
+                raise SystemExit("bench: one-shot results differ from the resident evaluation")
+            one_shot[name] = {"value": src.n / best, "unit": UNIT, "ms_per_call": best * 1e3}
     os.sched_setaffinity(0, all_cpus)
     if world > 1:
         nb_ = torch.tensor([1.0 if numa.get("bound") else 0.0], dtype=torch.float64, device="cuda")
@@ -642,7 +657,8 @@ def main():
             "config": common_config(args, world),
             "detail": {"gather": bool(rob_t is not None), "failed_samples": n_fail,
                        "knots": "uniform (formed on device)" if uk else "explicit", "e2e_block": args.e2e_block,
-                       "e2e_pipeline_depth": E2E_DEPTH, "wall_s_timed_region": wall1 - wall0, "numa": numa},
+                       "e2e_pipeline_depth": E2E_DEPTH, "wall_s_timed_region": wall1 - wall0, "numa": numa,
+                       "one_shot_call": one_shot},
             "e2e": e2e,
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,

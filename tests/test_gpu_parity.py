@@ -393,3 +393,24 @@ def test_uniform_knots_form_matches_explicit(oracle_lib, wl):
     assert np.array_equal(out["robustness"], ga["robustness"])
     check(b, oracle_lib)
 
+
+
+@pytest.mark.gpu
+def test_large_one_shot_call_is_chunked_and_equal_to_the_resident_evaluation():
+    """pdeb_eval_batch above 131,072 samples runs as 65,536-sample chunks on a few host threads (stage / copy / compute of
+    different chunks overlap); a ragged tail, clause outputs at the caller's stride, and the two-device entry go the same way."""
+    n = 3 * 65536 + 1234
+    b = synth.make_batch(n, "mixed", seed=21)
+    res = native.ResidentBatch(b)
+    try:
+        res.eval(64)
+        ref = res.fetch(want_clauses=True)
+    finally:
+        res.close()
+    out = native.evaluate_batch(b, want_clauses=True, timing=True)
+    assert np.array_equal(out["robustness"], ref["robustness"]) and np.array_equal(out["status"], ref["status"])
+    assert np.array_equal(out["clause"][:, :n], ref["clause"][:, :n])
+    assert out["timing"].launches >= 4 and out["timing"].total_ms > 0
+    devs = [0, 1] if native.device_count() >= 2 else [0, 0]
+    two = native.evaluate_batch_multi(b, 2, devices=devs)
+    assert np.array_equal(two["robustness"], ref["robustness"]) and np.array_equal(two["status"], ref["status"])
