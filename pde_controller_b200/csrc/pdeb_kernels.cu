@@ -15,7 +15,11 @@
 #ifdef PDEB_REG_MAXNREG
 #define PDEB_REG_BOUNDS __maxnreg__(PDEB_REG_MAXNREG)
 #else
-#define PDEB_REG_BOUNDS __launch_bounds__(PDEB_REG_THREADS, PDEB_REG_MINBLOCKS)
+/* FP32 mode: half the registers and 544 instead of 904 bytes of shared memory per thread, so a third (fourth) block fits */
+#ifndef PDEB_REG_MINBLOCKS_F32
+#define PDEB_REG_MINBLOCKS_F32 3
+#endif
+#define PDEB_REG_BOUNDS __launch_bounds__(PDEB_REG_THREADS, sizeof(real) == 4 ? PDEB_REG_MINBLOCKS_F32 : PDEB_REG_MINBLOCKS)
 #endif
 
 template <int KIND, int N, typename real>
