@@ -610,7 +610,7 @@ def main():
     configs = {}
     if not args.no_configs and args.workload == "heat":
         for name, wl, nb, steps_c in (("configs[2] wave 65536", "wave", 65536, 5), ("configs[4] mixed 65536 per GPU", "mixed", 65536, 5),
-                                      ("configs[3] refined heat 1024x10000, 4096 per GPU", "heat_refined", 4096, 2)):
+                                      ("configs[3] refined heat 1024x10000, 16384 per GPU", "heat_refined", 16384, 2)):
             bsrc = synth.make_batch(nb, wl, seed=args.seed, start=rank * nb, total=nb * world, uniform_knots=True,
                                     kind_slice=(rank, world) if wl == "mixed" and world > 1 else None)
             r2 = native.ResidentBatch(bsrc, device=dev, stream=stream)
