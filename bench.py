@@ -599,8 +599,20 @@ def main():
         search_leg = {"value": ms_ / secs_s, "unit": "programs/s", "programs": ms_, "candidates_per_program": 4096 * 6,
                       "positive": int(sum(r > 0 for r in rob_s)),
                       "positive_under_the_given_controls": int((out_host["robustness"][:ms_] > 0).sum())}
+        # and with the controls handed over as arrays (control_arrays): what a caller that holds them in bulk pays
+        kmax_ = max(len(c[0]) for c in ctrls)
+        T_, Y_, K_ = np.zeros((m, kmax_)), np.zeros((m, kmax_)), np.zeros(m, dtype=np.int64)
+        for i_, c_ in enumerate(ctrls):
+            K_[i_] = len(c_[0]); T_[i_, : K_[i_]] = c_[0]; Y_[i_, : K_[i_]] = c_[1]
+        es.eval_robustness_batch(texts, control_arrays=(T_, Y_, K_))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            rob_a, _ = es.eval_robustness_batch(texts, control_arrays=(T_, Y_, K_))
+        secs_a = (time.perf_counter() - t0) / reps
+        if not np.array_equal(np.array(rob_a), out_host["robustness"][:m]):
+            raise SystemExit("bench: text-level results (control arrays) differ from the resident evaluation")
         e2e_text = {"value": m / secs, "unit": "programs/s", "programs": m, "cores": os.cpu_count(), "calls_timed": reps,
-                    "search_mode": search_leg,
+                    "control_arrays_value": m / secs_a, "search_mode": search_leg,
                     "first_call_value": m / first,
                     "route": "eval_robustness_batch(program strings, given controls): native template matcher "
                              "(pdeb_parse_programs, host threads; anything else -> Python front-end) -> PdebBatch -> "

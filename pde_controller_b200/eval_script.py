@@ -79,7 +79,7 @@ def eval_robustness_batch(programs: Sequence[str], natural_language: Optional[Se
                           controls=None, device: Optional[int] = None,
                           precision: Optional[int] = None, conventions=None, return_status: bool = False,
                           parse_workers: Optional[int] = None, return_controls: bool = False, search: Optional[dict] = None,
-                          devices: Optional[Sequence[int]] = None):
+                          devices: Optional[Sequence[int]] = None, control_arrays=None):
     """Evaluate many programs in one GPU call (long lists are parsed by worker processes: frontend.parse_many).
 
     controls: a list with one entry per program -- `(knot_times, knot_values)` or None -- or one of the mode strings
@@ -87,6 +87,10 @@ def eval_robustness_batch(programs: Sequence[str], natural_language: Optional[Se
     changed).  An entry that is None is evaluated under the mode: "search" runs the sampling surrogate of the
     reference's control synthesis per program (search.search_controls) and evaluates under the input it found,
     "zero" evaluates under zero input.  `search` overrides the search budget for this call.
+
+    control_arrays: the bulk form of `controls` for callers that hold their inputs as arrays -- `(knot_t [n, kmax],
+    knot_y [n, kmax], n_knots [n])`, n_knots[i] < 0 meaning "no control for program i" (the mode applies); no Python object
+    per program is made.  Give one of `controls` (list form) or `control_arrays`, not both.
 
     -> (robustness list, runtime list[, status array][, controls used]).  A program that does not parse, or a
     simulation that fails, yields robustness -100 (the failure label of simulate_gt.py:59);
@@ -99,6 +103,17 @@ def eval_robustness_batch(programs: Sequence[str], natural_language: Optional[Se
         if controls not in CONTROL_MODES:
             raise ValueError(f"controls must be a list or one of {CONTROL_MODES}")
         mode, controls = controls, None
+    arr = None
+    if control_arrays is not None:
+        if controls is not None:
+            raise ValueError("give controls or control_arrays, not both")
+        at, ay, ak = (np.asarray(a) for a in control_arrays)
+        if at.ndim != 2 or at.shape != ay.shape or at.shape[0] != n or ak.shape != (n,):
+            raise ValueError("control_arrays = (knot_t [n, kmax], knot_y [n, kmax], n_knots [n])")
+        ak = ak.astype(np.int64)
+        if (ak > at.shape[1]).any():
+            raise ValueError("control_arrays: n_knots exceeds the arrays' second dimension")
+        arr = (np.ascontiguousarray(at, dtype=np.float64), np.ascontiguousarray(ay, dtype=np.float64), ak)
     controls = list(controls) if controls is not None else [None] * n
     if len(controls) != n:
         raise ValueError("controls must have one entry per program")
@@ -131,8 +146,11 @@ def eval_robustness_batch(programs: Sequence[str], natural_language: Optional[Se
         pmax = int(max([int(wide.n_pred[accepted].max(initial=1)) if wide is not None else 1] + [len(p.predicates) for _, p in ok_rest] + [1]))
         tmax = int(max([2 * pmax - 1] + [len(p.tree) for _, p in ok_rest]))
         # controls: no per-sample numpy call (a list of n (times, values) pairs goes through two concatenations)
-        given = (np.fromiter((c is not None for c in controls), dtype=bool, count=n) if None in controls
-                 else np.ones(n, dtype=bool))
+        if arr is not None:
+            given = arr[2] >= 0
+        else:
+            given = (np.fromiter((c is not None for c in controls), dtype=bool, count=n) if None in controls
+                     else np.ones(n, dtype=bool))
         need = np.nonzero(~given & live)[0]
         searching = need.size > 0 and mode == "search"
         k_need = np.zeros(0, dtype=np.int64)
@@ -150,7 +168,12 @@ def eval_robustness_batch(programs: Sequence[str], natural_language: Optional[Se
         have = np.nonzero(given)[0]
         cnt = np.zeros(n, dtype=np.int64)
         flat_t = flat_y = None
-        if have.size:
+        if have.size and arr is not None:
+            len_t = len_y = arr[2][have]
+            km_in = np.arange(arr[0].shape[1])[None, :] < len_t[:, None]
+            flat_t, flat_y = arr[0][have][km_in], arr[1][have][km_in]          # sample-major, like the concatenations below
+            cnt[have] = len_t
+        elif have.size:
             sel = controls if have.size == n else [controls[i] for i in have.tolist()]
             ts = list(map(operator.itemgetter(0), sel))
             ys = list(map(operator.itemgetter(1), sel))
@@ -264,6 +287,9 @@ def eval_robustness_batch(programs: Sequence[str], natural_language: Optional[Se
             out = native.evaluate_batch(batch, device=dev, precision=prec, conv=conv)
         rob[live] = out["robustness"][live]
         status[live] = out["status"][live]
+    if return_controls and arr is not None:
+        for i in np.nonzero(arr[2] >= 0)[0].tolist():
+            controls[i] = (arr[0][i, : arr[2][i]].copy(), arr[1][i, : arr[2][i]].copy())
     runtime = (time.perf_counter() - t0) / max(n, 1)
     res = (rob.tolist(), [runtime] * n)
     if return_status:

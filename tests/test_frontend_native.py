@@ -198,3 +198,42 @@ def test_eval_robustness_batch_assembles_controls_without_a_device(monkeypatch):
         es.eval_robustness_batch(texts[:2], controls=[([0.0, 1.0], [1.0]), ([0.0], [1.0, 2.0])])
     with pytest.raises(ValueError):
         es.eval_robustness_batch(texts[:2], controls=[None])
+
+
+def test_control_arrays_form_equals_the_list_form(monkeypatch):
+    """eval_robustness_batch(control_arrays=(T, Y, counts)): the bulk form of the control list (no Python object per program)
+    assembles the same batch; a negative count means "no control" and follows the mode."""
+    from pde_controller_b200 import eval_script as es, native
+
+    src = synth.make_batch(40, "heat", seed=4)
+    probs, ctrls = zip(*(src.get_problem(i) for i in range(40)))
+    texts = [render_program(p) for p in probs]
+    ctrls = list(ctrls)
+    for i in (3, 17):
+        ctrls[i] = None
+    seen = []
+
+    def fake(batch, **kw):
+        seen.append(batch)
+        return {"robustness": np.arange(batch.n, dtype=np.float64), "status": np.zeros(batch.n, np.int32), "clause": None}
+
+    monkeypatch.setattr(native, "evaluate_batch", fake)
+    monkeypatch.setattr(es, "_CONTROL_MODE", "zero")
+    kmax = max(len(c[0]) for c in ctrls if c is not None)
+    T, Y, K = np.zeros((40, kmax + 2)), np.zeros((40, kmax + 2)), np.full(40, -1)
+    for i, c in enumerate(ctrls):
+        if c is not None:
+            K[i] = len(c[0]); T[i, : K[i]] = c[0]; Y[i, : K[i]] = c[1]
+    a = es.eval_robustness_batch(texts, controls=ctrls, return_controls=True)
+    b = es.eval_robustness_batch(texts, control_arrays=(T, Y, K), return_controls=True)
+    ba, bb = seen
+    assert a[0] == b[0] and ba.kmax == bb.kmax
+    for name in ("n_knots", "knot_t", "knot_y", "T", "pred_m", "tree_op"):
+        assert np.array_equal(getattr(ba, name), getattr(bb, name)), name
+    assert b[2][3] is None and np.array_equal(b[2][5][1], ctrls[5][1])
+    with pytest.raises(ValueError):
+        es.eval_robustness_batch(texts, controls=ctrls, control_arrays=(T, Y, K))
+    with pytest.raises(ValueError):
+        es.eval_robustness_batch(texts, control_arrays=(T, Y[:, :3], K))
+    with pytest.raises(ValueError):
+        es.eval_robustness_batch(texts, control_arrays=(T, Y, K + 100))
