@@ -134,7 +134,9 @@ def eval_robustness_batch(programs: Sequence[str], natural_language: Optional[Se
     rest = np.nonzero(~accepted)[0]
     rest_problems: List[Optional[Problem]] = []
     if rest.size:
-        for prob, _msg in parse_many([programs[i] for i in rest], workers=parse_workers):
+        as_text = [programs[i] for i in rest]
+        as_text = [t.decode("utf-8", "replace") if isinstance(t, (bytes, bytearray)) else t for t in as_text]
+        for prob, _msg in parse_many(as_text, workers=parse_workers):
             rest_problems.append(prob)
     bad = [int(i) for i, p in zip(rest, rest_problems) if p is None]
     status[bad] = abi.ST_PARSE

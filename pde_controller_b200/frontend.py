@@ -742,8 +742,16 @@ def parse_native(texts, pmax: int = abi.MAX_PRED, nthreads: int = 0):
     # per-text route below (one bytes object and one ctypes conversion per program) cost more than the parse itself
     blob, lens = None, None
     try:
-        joined = "\0".join(texts)
-        if joined.isascii():
+        if n and isinstance(texts[0], (bytes, bytearray)):
+            # a caller that holds its programs as bytes (a file read in binary mode, a socket): no encode at all
+            lens = np.fromiter(map(len, texts), dtype=np.int64, count=n)
+            blob = b"\0".join(texts)
+            joined = None
+        else:
+            joined = "\0".join(texts)
+        if joined is None:
+            pass
+        elif joined.isascii():
             lens = np.fromiter(map(len, texts), dtype=np.int64, count=n)          # characters == bytes
             if int(lens.sum()) + n - 1 == len(joined):
                 blob = joined.encode("ascii")
@@ -756,7 +764,8 @@ def parse_native(texts, pmax: int = abi.MAX_PRED, nthreads: int = 0):
         table = (starts + base).astype(np.uint64)
         ptrs = table.ctypes.data
     else:
-        enc = [t.encode("utf-8", "surrogatepass") if isinstance(t, str) else b"" for t in texts]
+        enc = [t.encode("utf-8", "surrogatepass") if isinstance(t, str) else (bytes(t) if isinstance(t, (bytes, bytearray)) else b"")
+               for t in texts]
         keep = (C.c_char_p * n)(*enc)
         ptrs = C.cast(keep, C.c_void_p).value
         lens = np.fromiter(map(len, enc), dtype=np.int64, count=n)

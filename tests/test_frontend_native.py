@@ -237,3 +237,15 @@ def test_control_arrays_form_equals_the_list_form(monkeypatch):
         es.eval_robustness_batch(texts, control_arrays=(T, Y[:, :3], K))
     with pytest.raises(ValueError):
         es.eval_robustness_batch(texts, control_arrays=(T, Y, K + 100))
+
+
+def test_programs_as_bytes():
+    """parse_native takes the programs as bytes too (no encode), alone or mixed with str in the per-text route."""
+    src = synth.make_batch(16, "wave", seed=6)
+    texts = [render_program(src.get_problem(i)[0]) for i in range(16)]
+    a, acc_a = parse_native(texts)
+    b, acc_b = parse_native([t.encode() for t in texts])
+    c, acc_c = parse_native([t.encode() if i % 2 else t for i, t in enumerate(texts)] + ["é"])
+    assert acc_a.all() and acc_b.all() and acc_c[:16].all() and not acc_c[16]
+    for name in ("L", "T", "E_in", "pred_b", "pred_thi", "tree_lhs"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)) and np.array_equal(getattr(a, name), getattr(c, name)[..., :16]), name

@@ -358,3 +358,24 @@ def test_drop_in_call_sharded_over_devices_equals_one_device(tmp_path):
     m2 = simulate_gt.main(simulate_gt.build_parser().parse_args(base + ["--devices", ",".join(map(str, devs))]))
     r2 = [json.loads(l)["robustness"] for l in open(str(d) + "_24/test.jsonl")]
     assert r1 == r2 and m1 == m2
+
+
+def test_control_arrays_with_missing_entries_are_searched_like_the_list_form(oracle_lib):
+    from pde_controller_b200 import eval_script as es
+    src = synth.make_batch(48, "heat", seed=17)
+    probs, ctrls = zip(*(src.get_problem(i) for i in range(48)))
+    texts = [render_program(p).encode() for p in probs]                 # programs as bytes, for good measure
+    ctrls = [None if i % 3 == 0 else c for i, c in enumerate(ctrls)]
+    kmax = max(len(c[0]) for c in ctrls if c is not None)
+    T, Y, K = np.zeros((48, kmax)), np.zeros((48, kmax)), np.full(48, -1)
+    for i, c in enumerate(ctrls):
+        if c is not None:
+            K[i] = len(c[0]); T[i, : K[i]] = c[0]; Y[i, : K[i]] = c[1]
+    budget = {"population": 512, "generations": 3, "seed": 9}
+    a = es.eval_robustness_batch(texts, controls=ctrls, return_status=True, return_controls=True, search=budget)
+    b = es.eval_robustness_batch(texts, control_arrays=(T, Y, K), return_status=True, return_controls=True, search=budget)
+    assert a[0] == b[0] and (a[2] == 0).all() and (b[2] == 0).all()
+    assert all(np.array_equal(x[1], y[1]) and np.array_equal(x[0], y[0]) for x, y in zip(a[3], b[3]))
+    batch = ProblemBatch.from_problems(list(probs), b[3])
+    ref, st = oracle_lib.eval_batch(batch)
+    assert (st == 0).all() and rel_err(np.array(b[0]), ref, batch).max() <= TOL_FP64
