@@ -309,7 +309,8 @@ int  pdeb_controls_respec(PdebControls* h, const PdebBatch* spec, int64_t sample
  * control synthesis, eval_robustness_wrapper.py:16): `generations` times { draw `population` candidates
  * y = clip(mean + std z, lo, hi) from a counter-based generator (generation 0: uniform over [lo, hi], plus the zero input
  * and both bounds; the incumbent is always candidate 0) -> their robustness -> the elite_frac best re-centre mean / std }.
- * Two launches per generation (score; rank + next draw), nothing crosses PCIe in between, deterministic for a given seed.
+ * ONE launch per generation (every thread draws and scores its candidate, the last block to finish ranks), nothing crosses
+ * PCIe in between, deterministic for a given seed.
  *   best_y_out [n_knots], best_value_out, found_out (0: no candidate had status 0; then best_value = -100),
  *   history_out [generations] best robustness after each generation (never decreases), mean_out / std_out [n_knots]
  *   the final sampling distribution: all optional.  Synchronises `stream` before returning.
@@ -319,7 +320,7 @@ int  pdeb_controls_search(PdebControls* h, int64_t population, int32_t generatio
                           double* mean_out, double* std_out, void* stream, PdebTiming* timing);
 /*
  * pdeb_controls_search for MANY specifications: samples[0..n_samples) of `in` (NULL = every sample), `nthreads` host threads
- * (<= 0: one per host core, at most 16; never more than 32) with one stream and one controls handle each.  Knot TIMES are the batch's own (n_knots, knot_t;
+ * (<= 0: 8; at most 32), each with three searches in flight with one stream and one controls handle each.  Knot TIMES are the batch's own (n_knots, knot_t;
  * knot_t == NULL: linspace(0, T, n_knots)), the knot VALUES found are written to knot_y_out in the batch's plane-major
  * layout [kmax][stride] (it may BE in->knot_y), best_out [n] / found_out [n] per sample.  bounds = { heat lo, heat hi, wave lo,
  * wave hi }.  Sample s draws from the generator stream mix(seed, s): the result does not depend on the thread count.

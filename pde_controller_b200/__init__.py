@@ -7,7 +7,7 @@ plus the batched forms the GPU path is built for:
 """
 import os as _os
 
-# A sweep of searches (pdeb_controls_search_batch) runs up to 16 host threads with a stream each; with CUDA's default of 8
+# A sweep of searches (pdeb_controls_search_batch) keeps about 24 streams busy from its host threads; with CUDA's default of 8
 # hardware queues their streams alias and serialise.  Only has an effect if this import precedes the first CUDA call of the
 # process, and never overrides the caller's own setting.
 _os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")

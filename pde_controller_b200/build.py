@@ -27,7 +27,9 @@ def build(force=False, verbose=False, defines=(), out=None):
     objs = []
     procs = []
     for s in srcs:
-        o = os.path.splitext(s)[0] + (".o" if out is None else "." + os.path.basename(out) + ".o")
+        # a variant's objects live next to the variant (one directory to delete), the default library's next to the sources
+        o = (os.path.splitext(s)[0] + ".o" if global_so == SO
+             else os.path.join(os.path.dirname(global_so), os.path.basename(os.path.splitext(s)[0]) + "." + os.path.basename(global_so) + ".o"))
         objs.append(o)
         # NVCC_EXTRA: extra compiler flags of an experimental variant (tools/variant_bench.py), e.g. "-Xptxas --opt-level=4"
         cmd = [nvcc] + NVCC_FLAGS + os.environ.get("NVCC_EXTRA", "").split() + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
@@ -40,6 +42,9 @@ def build(force=False, verbose=False, defines=(), out=None):
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", global_so] + objs + ["-lcudart"]
     subprocess.run(link, check=True)
+    if global_so != SO:
+        for o in objs:              # a variant's objects are not reused: 20 MB each would swamp the snapshot sent to the GPU box
+            os.remove(o)
     return global_so
 
 

@@ -351,21 +351,20 @@ __global__ void pdeb_argmax_partial_kernel(const double* __restrict__ r, const i
 /* ---- device-resident cross-entropy search over the candidates of one specification ------------------------------
  * The host-driven search (pde_controller_b200/search.py, round 1) drew every generation with numpy, uploaded it,
  * fetched every robustness and ranked them on the host: ~4 ms of host work per program around ~0.7 ms of kernels.
- * Here a generation is two launches and nothing crosses PCIe until the search is over:
- *   pdeb_cem_sample_kernel   (once) generation 0: candidates uniform over the bounds, plus the zero input and the two
- *                            bounds,
- *   pdeb_controls_kernel     their robustness (the kernel above, unchanged),
- *   pdeb_cem_update_kernel   ONE block: radix select of the elite (largest robustness, ties by lowest index), mean /
- *                            standard deviation of the elite's knot values, incumbent, history; then the candidates of the
- *                            next generation  y = clip(mean + std * z)  from a counter-based generator (the incumbent is
- *                            always candidate 0).
- * A single cooperative launch for the whole search (grid-wide barriers between scoring and ranking) was built and measured:
- * 1.36 ms instead of 0.95 ms per search (one 128-thread block ranks while the grid waits) and concurrent cooperative launches
- * of different streams do not overlap: 2.8e3 programs/s instead of 4.9e3; removed.
+ * Here a generation is ONE launch (pdeb_cem_gen_kernel, below) and nothing crosses PCIe until the search is over: every
+ * thread draws its candidate  y = clip(mean + std * z)  from a counter-based generator (generation 0: uniform over the bounds,
+ * plus the zero input and the two bounds; the incumbent is always candidate 0) and scores it with the body of the controls
+ * kernel; the last block to finish selects the elite by a radix select (largest robustness, ties by lowest index), forms
+ * mean / standard deviation of the elite's knot values, keeps the incumbent and the history.
+ * Measured and removed on the way here: three launches per generation (draw / score / rank: 13 per search, 8.5e3 programs/s
+ * at best and erratic), and a single COOPERATIVE launch for the whole search (grid-wide barriers between scoring and ranking:
+ * 1.36 ms instead of 0.95 ms per search, and cooperative launches of different streams do not overlap: 2.8e3 programs/s).
  * Deterministic for a given seed (fixed reduction trees, no atomics on floating-point values). */
+#ifndef PDEB_SEARCH_DEPTH
+#define PDEB_SEARCH_DEPTH 3      /* searches in flight per host thread of pdeb_controls_search_batch */
+#endif
 #define PDEB_CEM_MAX_GEN 64
 #define PDEB_CEM_MAX_ELITE 8192
-#define PDEB_CEM_THREADS 1024
 struct PdebCemState {
     double mean[PDEB_CTL_KMAX], std[PDEB_CTL_KMAX], best_y[PDEB_CTL_KMAX];
     double history[PDEB_CEM_MAX_GEN];
@@ -406,27 +405,18 @@ __device__ __forceinline__ void pdeb_cem_draw(double* ky, int64_t stride, int nk
     }
 }
 
-/* generation 0 (the draw does not look at the state) and the state's initial values: no host -> device copy per search */
-__global__ void pdeb_cem_sample_kernel(double* __restrict__ ky, int64_t stride, int nk, int64_t P, PdebCemState* __restrict__ st,
-                                       uint64_t seed, double lo, double hi) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < PDEB_CTL_KMAX) { st->mean[i] = 0.5 * (lo + hi); st->std[i] = 0.5 * (hi - lo); st->best_y[i] = 0.0; }
-    if (i < PDEB_CEM_MAX_GEN) st->history[i] = 0.0;
-    if (i == 0) { st->best_r = -INFINITY; st->has_best = 0; st->n_valid_last = 0; }
-    if (i < P) pdeb_cem_draw(ky, stride, nk, i, st, 0, seed, lo, hi);
-}
-
 /* larger robustness <-> larger key; 0 is reserved for candidates that do not count (status != 0, non-finite) */
+template <bool CG>
 __device__ __forceinline__ uint64_t pdeb_cem_key(const double* rob, const int32_t* status, int64_t i) {
-    const double r = rob[i];
-    const int32_t st = status[i];
+    const double r = CG ? __ldcg(rob + i) : rob[i];
+    const int32_t st = CG ? __ldcg(status + i) : status[i];
     if (st != PDEB_OK || !isfinite(r)) return 0ull;
     const uint64_t u = (uint64_t)__double_as_longlong(r);
     return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
 }
 
 /* ONE block of THREADS threads (a multiple of 32, at most 1024): elite, its statistics, the incumbent */
-template <int THREADS>
+template <int THREADS, bool CG = false>
 __device__ __forceinline__ void pdeb_cem_update_body(const double* rob, const int32_t* status, const double* ky, int64_t stride, int64_t P,
                                                      int nk, int n_elite, double std_floor, PdebCemState* st, int gen) {
     constexpr int WARPS = THREADS / 32;
@@ -445,7 +435,7 @@ __device__ __forceinline__ void pdeb_cem_update_body(const double* rob, const in
     unsigned nv_local = 0;
     uint64_t bk = 0ull; int64_t bi = -1;
     for (int64_t i = tid; i < P; i += THREADS) {
-        const uint64_t k = pdeb_cem_key(rob, status, i);
+        const uint64_t k = pdeb_cem_key<CG>(rob, status, i);
         if (k) { ++nv_local; if (k > bk) { bk = k; bi = i; } }        /* ascending i per thread: first of equal keys */
     }
     atomicAdd(&hist[0], nv_local);
@@ -466,7 +456,7 @@ __device__ __forceinline__ void pdeb_cem_update_body(const double* rob, const in
             __syncthreads();
             const uint64_t prefix = s_prefix;
             for (int64_t i = tid; i < P; i += THREADS) {
-                const uint64_t k = pdeb_cem_key(rob, status, i);
+                const uint64_t k = pdeb_cem_key<CG>(rob, status, i);
                 if (k && (b == 7 || (k >> (8 * (b + 1))) == prefix)) atomicAdd(&hist[(unsigned)(k >> (8 * b)) & 255u], 1u);
             }
             __syncthreads();
@@ -485,7 +475,7 @@ __device__ __forceinline__ void pdeb_cem_update_body(const double* rob, const in
         __syncthreads();
         for (int64_t base = 0; base < P; base += THREADS) {
             const int64_t i = base + tid;
-            const uint64_t k = (i < P) ? pdeb_cem_key(rob, status, i) : 0ull;
+            const uint64_t k = (i < P) ? pdeb_cem_key<CG>(rob, status, i) : 0ull;
             const bool eq = k != 0ull && k == thr;
             const unsigned beq = __ballot_sync(0xffffffffu, eq);
             if (lane == 0) s_woff[warp] = __popc(beq);
@@ -518,22 +508,22 @@ __device__ __forceinline__ void pdeb_cem_update_body(const double* rob, const in
         for (int j = warp; j < nk; j += WARPS) {
             const double* col = ky + (int64_t)j * stride;
             double sum = 0.0;
-            for (int q = lane; q < ke; q += 32) sum += col[elist[q]];
+            for (int q = lane; q < ke; q += 32) sum += CG ? __ldcg(col + elist[q]) : col[elist[q]];
             for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
             const double mean = sum / (double)ke;
             double var = 0.0;
-            for (int q = lane; q < ke; q += 32) { const double d = col[elist[q]] - mean; var = fma(d, d, var); }
+            for (int q = lane; q < ke; q += 32) { const double d = (CG ? __ldcg(col + elist[q]) : col[elist[q]]) - mean; var = fma(d, d, var); }
             for (int o = 16; o >= 1; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
             if (lane == 0) { st->mean[j] = mean; st->std[j] = fmax(sqrt(var / (double)ke), std_floor); }
         }
     }
     /* ---- incumbent ---- */
     __syncthreads();
-    const double cand = best_i >= 0 ? rob[best_i] : 0.0;
+    const double cand = best_i >= 0 ? (CG ? __ldcg(rob + best_i) : rob[best_i]) : 0.0;
     const bool better = best_i >= 0 && (gen == 0 || !st->has_best || cand > st->best_r);
     __syncthreads();
     if (better) {
-        for (int j = tid; j < nk; j += THREADS) st->best_y[j] = ky[(int64_t)j * stride + best_i];
+        for (int j = tid; j < nk; j += THREADS) st->best_y[j] = CG ? __ldcg(ky + (int64_t)j * stride + best_i) : ky[(int64_t)j * stride + best_i];
         if (tid == 0) { st->best_r = cand; st->has_best = 1; }
     }
     __syncthreads();
@@ -544,15 +534,35 @@ __device__ __forceinline__ void pdeb_cem_update_body(const double* rob, const in
     }
 }
 
-/* ranks generation `gen` and, unless it was the last, draws generation gen + 1 from the re-centred distribution: two
- * launches per generation (the searches of a sweep are launch-rate bound: ~9e4 launches/s from 16 host threads) */
-__global__ void __launch_bounds__(PDEB_CEM_THREADS)
-pdeb_cem_update_kernel(const double* rob, const int32_t* status, double* ky, int64_t stride, int64_t P, int nk, int n_elite,
-                       double std_floor, PdebCemState* st, int gen, int generations, uint64_t seed, double lo, double hi) {
-    pdeb_cem_update_body<PDEB_CEM_THREADS>(rob, status, ky, stride, P, nk, n_elite, std_floor, st, gen);
-    if (gen + 1 < generations) {
-        __syncthreads();                       /* mean / std / incumbent of this block's own writes */
-        for (int64_t i = threadIdx.x; i < P; i += PDEB_CEM_THREADS) pdeb_cem_draw(ky, stride, nk, i, st, gen + 1, seed, lo, hi);
+/*
+ * ONE launch per generation: every thread draws its own candidate from the distribution the previous launch left, scores
+ * it, and the LAST block to finish (a ticket counter) ranks the generation and re-centres the distribution.  Six launches
+ * per search instead of thirteen: a sweep of searches is bound by the rate at which a process can launch kernels
+ * (~1e5 per second from 16 host threads), not by the device.  What the ranking block reads was written by other blocks
+ * of the same launch: it is read past the L1 (__ldcg) behind a __threadfence on the writers' side.
+ */
+template <int KIND, int N, int PMAX, bool MOM = false>
+__global__ void PDEB_CTL_BOUNDS(KIND, MOM)
+pdeb_cem_gen_kernel(const __grid_constant__ PdebSpecConst<N> sp, double* ky, int64_t P, const __grid_constant__ PdebCtlOut out,
+                    PdebCemState* st, unsigned* ticket, int gen, int n_elite, uint64_t seed, double lo, double hi, double std_floor) {
+    const int64_t t = (int64_t)blockIdx.x * PDEB_CTL_THREADS + threadIdx.x;
+    const int nk = sp.nk;
+    if (gen == 0 && blockIdx.x == 0) {        /* nobody reads the state before the ranking at the end of this launch */
+        if (threadIdx.x < PDEB_CTL_KMAX) { st->mean[threadIdx.x] = 0.5 * (lo + hi); st->std[threadIdx.x] = 0.5 * (hi - lo); st->best_y[threadIdx.x] = 0.0; }
+        if (threadIdx.x < PDEB_CEM_MAX_GEN) st->history[threadIdx.x] = 0.0;
+        if (threadIdx.x == 0) { st->best_r = -INFINITY; st->has_best = 0; st->n_valid_last = 0; }
+    }
+    if (t < P) pdeb_cem_draw(ky, P, nk, t, st, gen, seed, lo, hi);
+    pdeb_controls_body<KIND, N, PMAX, MOM>(sp, ky, P, P, out, t);
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        pdeb_cem_update_body<PDEB_CTL_THREADS, true>(out.robustness, out.status, ky, P, P, nk, n_elite, std_floor, st, gen);
+        if (threadIdx.x == 0) *ticket = 0u;
     }
 }
 
@@ -581,10 +591,12 @@ struct PdebControls {
     double* h_pv = nullptr;       /* pinned */
     int64_t* h_pi = nullptr;
     struct PdebCemState* d_cem = nullptr;   /* state of the device-resident search (pdeb_controls_search) */
+    unsigned* d_ticket = nullptr;           /* "last block ranks" counter of pdeb_cem_gen_kernel (zero between launches) */
     struct PdebCemState* h_cem = nullptr;   /* pinned mirror */
     cudaEvent_t ev[2] = {nullptr, nullptr};
     cudaEvent_t done = nullptr;   /* blocking-sync event (sweeps): a waiting host thread sleeps instead of spinning on the stream */
     bool sleep_on_done = false;
+    int last_launches = 0;        /* kernels the last search_enqueue launched */
 };
 #define PDEB_ARGMAX_BLOCKS 128
 
@@ -670,7 +682,7 @@ extern "C" void pdeb_controls_destroy(PdebControls* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaFree(h->d_y); cudaFree(h->d_rob); cudaFree(h->d_clause); cudaFree(h->d_status); cudaFree(h->d_pv); cudaFree(h->d_pi);
-    cudaFree(h->d_cem);
+    cudaFree(h->d_cem); cudaFree(h->d_ticket);
     if (h->h_pv) cudaFreeHost(h->h_pv);
     if (h->h_pi) cudaFreeHost(h->h_pi);
     if (h->h_cem) cudaFreeHost(h->h_cem);
@@ -718,6 +730,8 @@ extern "C" int pdeb_controls_create(const PdebBatch* spec, int64_t sample, int64
     if (e == cudaSuccess) e = cudaMalloc(&h->d_pv, sizeof(double) * PDEB_ARGMAX_BLOCKS);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_pi, sizeof(int64_t) * PDEB_ARGMAX_BLOCKS);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_cem, sizeof(PdebCemState));
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_ticket, sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemset(h->d_ticket, 0, sizeof(unsigned));
     if (e == cudaSuccess) e = cudaHostAlloc(&h->h_pv, sizeof(double) * PDEB_ARGMAX_BLOCKS, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc(&h->h_pi, sizeof(int64_t) * PDEB_ARGMAX_BLOCKS, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc(&h->h_cem, sizeof(PdebCemState), cudaHostAllocDefault);
@@ -747,6 +761,23 @@ static cudaError_t launch_controls(const PdebSpecConst<N>& sp, int pmax, const d
     }
     if (pmax <= 3) pdeb_controls_kernel<KIND, N, 3><<<blocks, PDEB_CTL_THREADS, 0, stream>>>(sp, ky, stride, m, out);
     else pdeb_controls_kernel<KIND, N, PDEB_MAX_PRED><<<blocks, PDEB_CTL_THREADS, 0, stream>>>(sp, ky, stride, m, out);
+    return cudaGetLastError();
+}
+
+template <int KIND, int N>
+static cudaError_t launch_gen(const PdebSpecConst<N>& sp, int pmax, double* ky, int64_t P, const PdebCtlOut& out, PdebCemState* st,
+                              unsigned* ticket, int gen, int n_elite, uint64_t seed, double lo, double hi, double std_floor,
+                              cudaStream_t stream) {
+    const unsigned blocks = (unsigned)((P + PDEB_CTL_THREADS - 1) / PDEB_CTL_THREADS);
+    if constexpr (KIND == PDEB_KIND_WAVE) {
+        if (sp.momentum) {
+            if (pmax <= 3) pdeb_cem_gen_kernel<KIND, N, 3, true><<<blocks, PDEB_CTL_THREADS, 0, stream>>>(sp, ky, P, out, st, ticket, gen, n_elite, seed, lo, hi, std_floor);
+            else pdeb_cem_gen_kernel<KIND, N, PDEB_MAX_PRED, true><<<blocks, PDEB_CTL_THREADS, 0, stream>>>(sp, ky, P, out, st, ticket, gen, n_elite, seed, lo, hi, std_floor);
+            return cudaGetLastError();
+        }
+    }
+    if (pmax <= 3) pdeb_cem_gen_kernel<KIND, N, 3><<<blocks, PDEB_CTL_THREADS, 0, stream>>>(sp, ky, P, out, st, ticket, gen, n_elite, seed, lo, hi, std_floor);
+    else pdeb_cem_gen_kernel<KIND, N, PDEB_MAX_PRED><<<blocks, PDEB_CTL_THREADS, 0, stream>>>(sp, ky, P, out, st, ticket, gen, n_elite, seed, lo, hi, std_floor);
     return cudaGetLastError();
 }
 
@@ -819,50 +850,52 @@ extern "C" int pdeb_controls_fetch_knots(PdebControls* h, int64_t m, double* kno
     return PDEB_E_OK;
 }
 
-extern "C" int pdeb_controls_search(PdebControls* h, int64_t population, int32_t generations, double elite_frac, double lo, double hi,
-                                    uint64_t seed, double* best_y_out, double* best_value_out, int32_t* found_out, double* history_out,
-                                    double* mean_out, double* std_out, void* stream_, PdebTiming* timing) {
+/* the first half of a search: everything enqueued on `stream`, nothing waited for.  -1 in *skipped: the specification
+ * is unusable and nothing was enqueued */
+static int search_enqueue(PdebControls* h, int64_t population, int32_t generations, double elite_frac, double lo, double hi,
+                          uint64_t seed, cudaStream_t stream, bool timing, bool* skipped) {
+    *skipped = false;
     if (!h || population < 4 || population > h->capacity || generations < 1 || generations > PDEB_CEM_MAX_GEN || !(hi >= lo) ||
         !(elite_frac > 0.0 && elite_frac <= 1.0))
         return cfail(PDEB_E_ARG, "pdeb_controls_search: bad arguments (population 4..capacity, generations 1..64, lo <= hi, 0 < elite_frac <= 1)");
     int64_t n_elite = (int64_t)llround(elite_frac * (double)population);
     if (n_elite < 2) n_elite = 2;
     if (n_elite > PDEB_CEM_MAX_ELITE) return cfail(PDEB_E_ARG, "pdeb_controls_search: more than 8192 elite candidates");
-    cudaStream_t stream = (cudaStream_t)stream_;
     CCK(cudaSetDevice(h->device));
-    if (timing) memset(timing, 0, sizeof *timing);
+    if (h->spec_status != PDEB_OK) { *skipped = true; return PDEB_E_OK; }     /* nothing to search (never raises per sample) */
     const int nk = h->nk;
-    if (h->spec_status != PDEB_OK) {
-        /* the specification itself is unusable: nothing to search (never raises per sample) */
+    PdebCtlOut out{h->d_rob, h->d_clause, h->d_status};
+    const double std_floor = 1e-3 * (hi - lo);
+    if (timing) CCK(cudaEventRecord(h->ev[0], stream));
+    for (int g = 0; g < generations; ++g) {
+        cudaError_t e = (h->kind == PDEB_KIND_HEAT)
+                            ? launch_gen<PDEB_KIND_HEAT, 30>(h->heat, h->pmax, h->d_y, population, out, h->d_cem, h->d_ticket, g, (int)n_elite, seed, lo, hi, std_floor, stream)
+                            : launch_gen<PDEB_KIND_WAVE, 20>(h->wave, h->pmax, h->d_y, population, out, h->d_cem, h->d_ticket, g, (int)n_elite, seed, lo, hi, std_floor, stream);
+        if (e != cudaSuccess) return cfail(PDEB_E_CUDA, "search kernel launch", e);
+    }
+    h->last_launches = generations;
+    if (timing) CCK(cudaEventRecord(h->ev[1], stream));
+    CCK(cudaMemcpyAsync(h->h_cem, h->d_cem, sizeof(PdebCemState), cudaMemcpyDeviceToHost, stream));
+    if (h->sleep_on_done) CCK(cudaEventRecord(h->done, stream));
+    return PDEB_E_OK;
+}
+
+/* the second half: wait for what search_enqueue queued and hand the results out */
+static int search_collect(PdebControls* h, int32_t generations, bool skipped, double* best_y_out, double* best_value_out,
+                          int32_t* found_out, double* history_out, double* mean_out, double* std_out, cudaStream_t stream,
+                          PdebTiming* timing) {
+    if (timing) memset(timing, 0, sizeof *timing);
+    if (skipped) {
         if (found_out) *found_out = 0;
         if (best_value_out) *best_value_out = PDEB_FAILED_ROBUSTNESS;
         if (history_out) for (int g = 0; g < generations; ++g) history_out[g] = PDEB_FAILED_ROBUSTNESS;
         return PDEB_E_OK;
     }
-    PdebCemState* hs = h->h_cem;
-    PdebCtlOut out{h->d_rob, h->d_clause, h->d_status};
-    const double std_floor = 1e-3 * (hi - lo);
-    if (timing) CCK(cudaEventRecord(h->ev[0], stream));
-    pdeb_cem_sample_kernel<<<(unsigned)((population + 255) / 256), 256, 0, stream>>>(h->d_y, population, nk, population, h->d_cem, seed, lo, hi);
-    CCK(cudaGetLastError());
-    for (int g = 0; g < generations; ++g) {
-        cudaError_t e = (h->kind == PDEB_KIND_HEAT)
-                            ? launch_controls<PDEB_KIND_HEAT, 30>(h->heat, h->pmax, h->d_y, population, population, out, stream)
-                            : launch_controls<PDEB_KIND_WAVE, 20>(h->wave, h->pmax, h->d_y, population, population, out, stream);
-        if (e != cudaSuccess) return cfail(PDEB_E_CUDA, "controls kernel launch", e);
-        pdeb_cem_update_kernel<<<1, PDEB_CEM_THREADS, 0, stream>>>(h->d_rob, h->d_status, h->d_y, population, population, nk, (int)n_elite,
-                                                                  std_floor, h->d_cem, g, generations, seed, lo, hi);
-        CCK(cudaGetLastError());
-    }
-    const int launches = 1 + 2 * generations;
-    if (timing) CCK(cudaEventRecord(h->ev[1], stream));
-    CCK(cudaMemcpyAsync(hs, h->d_cem, sizeof *hs, cudaMemcpyDeviceToHost, stream));
-    if (h->sleep_on_done) {
-        CCK(cudaEventRecord(h->done, stream));
-        CCK(cudaEventSynchronize(h->done));
-    } else {
-        CCK(cudaStreamSynchronize(stream));
-    }
+    CCK(cudaSetDevice(h->device));
+    if (h->sleep_on_done) CCK(cudaEventSynchronize(h->done));      /* sleeps: the other threads of a sweep need the cores to launch */
+    else CCK(cudaStreamSynchronize(stream));
+    const PdebCemState* hs = h->h_cem;
+    const int nk = h->nk;
     const bool found = hs->has_best != 0;
     if (found_out) *found_out = found ? 1 : 0;
     if (best_value_out) *best_value_out = found ? hs->best_r : PDEB_FAILED_ROBUSTNESS;
@@ -873,9 +906,19 @@ extern "C" int pdeb_controls_search(PdebControls* h, int64_t population, int32_t
     if (timing) {
         float ms = 0;
         CCK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
-        timing->kernel_ms = ms; timing->total_ms = ms; timing->launches = launches;
+        timing->kernel_ms = ms; timing->total_ms = ms; timing->launches = h->last_launches;
     }
     return PDEB_E_OK;
+}
+
+extern "C" int pdeb_controls_search(PdebControls* h, int64_t population, int32_t generations, double elite_frac, double lo, double hi,
+                                    uint64_t seed, double* best_y_out, double* best_value_out, int32_t* found_out, double* history_out,
+                                    double* mean_out, double* std_out, void* stream_, PdebTiming* timing) {
+    bool skipped = false;
+    int rc = search_enqueue(h, population, generations, elite_frac, lo, hi, seed, (cudaStream_t)stream_, timing != nullptr, &skipped);
+    if (rc != PDEB_E_OK) return rc;
+    return search_collect(h, generations, skipped, best_y_out, best_value_out, found_out, history_out, mean_out, std_out,
+                          (cudaStream_t)stream_, timing);
 }
 
 /*
@@ -899,16 +942,16 @@ extern "C" int pdeb_controls_search_batch(const PdebBatch* in, const int64_t* sa
     if (n_samples == 0) return PDEB_E_OK;
     for (int64_t q = 0; q < n_samples; ++q)
         if (samples && (samples[q] < 0 || samples[q] >= in->n)) return cfail(PDEB_E_ARG, "pdeb_controls_search_batch: sample index out of range");
-    /* default: one thread per host core, at most 16.  Measured on the 16-core B200 box (tools/search_workers_sweep.py): 0.8e3
-     * programs/s with one thread, 4.9e3 with 8, 8e3 with 16, 8-10e3 with 24 -- PROVIDED the process has more than the default 8
-     * hardware queues (CUDA_DEVICE_MAX_CONNECTIONS=32, which the Python package sets before CUDA starts: with 8, streams
-     * alias onto the same queue and 12+ threads run slower than 8) and the waiting threads sleep instead of spinning
-     * (the event below): a search is ~20 driver calls, and 16 spinning threads on 16 cores starve the ones that launch. */
+    /* default: 8 host threads, each with PDEB_SEARCH_DEPTH searches in flight on streams of their own.  Measured on the
+     * 16-core B200 box (tools/search_depth_sweep.py, 4,096 x 6 candidates per program): 3.8e3 programs/s with 2 threads, 6.0e3
+     * with 4, 9.1e3 with 8, no more with 16 -- about 24 searches in flight is what pays.  Needs more than CUDA's default 8
+     * hardware queues (CUDA_DEVICE_MAX_CONNECTIONS=32, set by the Python package before CUDA starts: with 8 the streams alias)
+     * and waiting threads that sleep instead of spinning (the blocking event of the handle). */
     unsigned hw = std::thread::hardware_concurrency();
-    int nt = nthreads > 0 ? nthreads : (hw == 0 ? 8 : (hw > 16 ? 16 : (int)hw));
+    int nt = nthreads > 0 ? nthreads : (hw == 0 || hw >= 8 ? 8 : (int)hw);
     if (nt > 32) nt = 32;
     if ((int64_t)nt > n_samples) nt = (int)n_samples;
-    const bool sleep_wait = nt >= 8;
+    const bool sleep_wait = nt * PDEB_SEARCH_DEPTH >= 8;
     std::atomic<int64_t> next{0};
     std::atomic<int> failed{0};
     std::mutex err_mutex;
@@ -918,55 +961,78 @@ extern "C" int pdeb_controls_search_batch(const PdebBatch* in, const int64_t* sa
     std::vector<int> launches((size_t)nt, 0);
     const int64_t st = in->stride;
 
+    /* every worker keeps PDEB_SEARCH_DEPTH searches in flight, each on a stream and a handle of its own: while the device
+     * runs the 13 kernels of one, the thread is already launching the next (a search is ~1 ms of device time and ~0.1 ms of
+     * launching) */
     auto work = [&](int w) {
-        PdebControls* h = nullptr;
-        cudaStream_t stream = nullptr;
+        struct Slot { PdebControls* h = nullptr; cudaStream_t st = nullptr; int64_t s = -1; int nk = 0; bool busy = false, skipped = false; };
+        Slot slot[PDEB_SEARCH_DEPTH];
         int rc = PDEB_E_OK;
-        if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) {
-            cudaGetLastError();
-            rc = cfail(PDEB_E_CUDA, "pdeb_controls_search_batch: stream");
-        }
+        if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); rc = cfail(PDEB_E_CUDA, "pdeb_controls_search_batch: device"); }
+        for (int q = 0; q < PDEB_SEARCH_DEPTH && rc == PDEB_E_OK; ++q)
+            if (cudaStreamCreateWithFlags(&slot[q].st, cudaStreamNonBlocking) != cudaSuccess) {
+                cudaGetLastError();
+                rc = cfail(PDEB_E_CUDA, "pdeb_controls_search_batch: stream");
+            }
+        auto collect = [&](Slot& sl) {
+            double by[PDEB_CTL_KMAX], best = 0.0;
+            int32_t found = 0;
+            PdebTiming tm;
+            memset(&tm, 0, sizeof tm);
+            const int r2 = search_collect(sl.h, generations, sl.skipped, by, &best, &found, nullptr, nullptr, nullptr, sl.st, timing ? &tm : nullptr);
+            sl.busy = false;
+            if (r2 != PDEB_E_OK) return r2;
+            ms[(size_t)w] += tm.kernel_ms; launches[(size_t)w] += sl.skipped ? 0 : sl.h->last_launches;
+            found_out[sl.s] = found;
+            best_out[sl.s] = best;
+            if (found) for (int j = 0; j < sl.nk; ++j) knot_y_out[(int64_t)j * st + sl.s] = by[j];
+            return (int)PDEB_E_OK;
+        };
+        int cur = 0;
         while (rc == PDEB_E_OK && !failed.load(std::memory_order_relaxed)) {
+            Slot& sl = slot[cur];
+            if (sl.busy) { rc = collect(sl); if (rc != PDEB_E_OK) break; }       /* the oldest search of this thread */
             const int64_t q = next.fetch_add(1);
             if (q >= n_samples) break;
             const int64_t s = samples ? samples[q] : q;
             found_out[s] = 0;
             best_out[s] = PDEB_FAILED_ROBUSTNESS;
             const int kind = in->kind[s], N = in->n_elem[s];
-            int nk = in->n_knots[s];
+            const int nk = in->n_knots[s];
             if (!((kind == PDEB_KIND_HEAT && N == 30) || (kind == PDEB_KIND_WAVE && N == 20)) || nk < 0 || nk > PDEB_CTL_KMAX || nk > in->kmax)
                 continue;                                   /* not this family's: the caller searches it another way */
-            double kt[PDEB_CTL_KMAX], by[PDEB_CTL_KMAX];
+            double kt[PDEB_CTL_KMAX];
             for (int j = 0; j < nk; ++j)
                 kt[j] = in->knot_t ? in->knot_t[(int64_t)j * st + s]
                                    : ((j == nk - 1 && nk > 1) ? in->T[s] : (nk > 1 ? (double)j * (in->T[s] / (double)(nk - 1)) : 0.0));
-            if (!h) {
-                rc = pdeb_controls_create(in, s, population, nk, kt, device, conv, &h);
-                if (rc == PDEB_E_OK) h->sleep_on_done = sleep_wait;
-            } else rc = pdeb_controls_respec(h, in, s, nk, kt, conv);
+            if (!sl.h) {
+                rc = pdeb_controls_create(in, s, population, nk, kt, device, conv, &sl.h);
+                if (rc == PDEB_E_OK) sl.h->sleep_on_done = sleep_wait;
+            } else rc = pdeb_controls_respec(sl.h, in, s, nk, kt, conv);
             if (rc != PDEB_E_OK) break;
             const double lo = bounds[kind == PDEB_KIND_HEAT ? 0 : 2], hi = bounds[kind == PDEB_KIND_HEAT ? 1 : 3];
             /* one generator stream per sample, whatever thread takes it */
             const uint64_t seed_s = pdeb_mix64(seed ^ pdeb_mix64((uint64_t)s));
-            double best = 0.0;
-            int32_t found = 0;
-            PdebTiming tm;
-            memset(&tm, 0, sizeof tm);
-            rc = pdeb_controls_search(h, population, generations, elite_frac, lo, hi, seed_s, by, &best, &found, nullptr, nullptr, nullptr,
-                                      (void*)stream, timing ? &tm : nullptr);           /* two event records less per search */
+            sl.s = s; sl.nk = nk;
+            rc = search_enqueue(sl.h, population, generations, elite_frac, lo, hi, seed_s, sl.st, timing != nullptr, &sl.skipped);
             if (rc != PDEB_E_OK) break;
-            ms[(size_t)w] += tm.kernel_ms; launches[(size_t)w] += timing ? tm.launches : 1 + 2 * generations;
-            found_out[s] = found;
-            best_out[s] = best;
-            if (found) for (int j = 0; j < nk; ++j) knot_y_out[(int64_t)j * st + s] = by[j];
+            sl.busy = true;
+            cur = (cur + 1) % PDEB_SEARCH_DEPTH;
+        }
+        for (int q = 0; q < PDEB_SEARCH_DEPTH; ++q) {                            /* drain, oldest first */
+            Slot& sl = slot[(cur + q) % PDEB_SEARCH_DEPTH];
+            if (sl.busy) { const int r2 = collect(sl); if (rc == PDEB_E_OK) rc = r2; }
         }
         if (rc != PDEB_E_OK) {
             std::lock_guard<std::mutex> lock(err_mutex);
             if (err_code == PDEB_E_OK) { err_code = rc; err_text = pdeb_last_error(); }
             failed.store(1);
         }
-        if (h) pdeb_controls_destroy(h);
-        if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
+        for (int q = 0; q < PDEB_SEARCH_DEPTH; ++q) {
+            if (slot[q].st) cudaStreamSynchronize(slot[q].st);
+            if (slot[q].h) pdeb_controls_destroy(slot[q].h);
+            if (slot[q].st) cudaStreamDestroy(slot[q].st);
+        }
     };
     std::vector<std::thread> pool;
     for (int w = 1; w < nt; ++w) pool.emplace_back(work, w);

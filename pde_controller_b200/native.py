@@ -561,7 +561,7 @@ class ControlsEvaluator:
                "pdeb_controls_respec")
 
     def search(self, population: int, generations: int, elite_frac: float, lo: float, hi: float, seed: int = 0, stream: int = 0):
-        """The whole cross-entropy search on the device (pdeb_controls_search): two launches per generation, nothing
+        """The whole cross-entropy search on the device (pdeb_controls_search): one launch per generation, nothing
         crosses PCIe until it is over.  -> dict(knot_y [n_knots] or None, robustness, history [generations], mean, std,
         kernel_ms, launches)."""
         nk = self.nk

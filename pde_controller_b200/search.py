@@ -100,7 +100,7 @@ def search_control(problem: Problem, knot_t: Optional[np.ndarray] = None, bounds
     Deterministic for a given seed.
 
     engine: "device" (default) runs the whole search in ONE library call (pdeb_controls_search: candidates drawn, scored
-    and ranked on the GPU, two launches per generation); "host" draws and ranks with numpy and calls the device once per
+    and ranked on the GPU, one launch per generation); "host" draws and ranks with numpy and calls the device once per
     generation (the round-1 form; also what meshes outside the controls family use, whatever `engine` says).  The two
     draw different candidates (different generators), so their results differ like two seeds do.
     evaluator: a ControlsEvaluator of capacity >= population to re-target (`respec`) instead of creating one: a sweep over

@@ -229,7 +229,7 @@ def test_device_search_one_generation_equals_numpy_ranking(rec):
     assert np.allclose(res["mean"], mean, rtol=1e-12, atol=0) and np.allclose(res["std"], std, rtol=1e-10, atol=0)
     bi = int(np.argmax(r))
     assert res["robustness"] == r[bi] and np.array_equal(res["knot_y"], y[:, bi]) and res["history"] == [r[bi]]
-    assert res["launches"] == 3                                  # first draw + { score, rank (+ next draw) }
+    assert res["launches"] == 1                                  # draw, score and rank of a generation are ONE launch
     # uniform draws: every knot's sample mean is near the middle of the bounds
     assert np.all(np.abs(y[:, 4:].mean(axis=1) - 0.5 * (lo + hi)) < 0.05 * (hi - lo))
 
