@@ -364,7 +364,8 @@ __global__ void pdeb_argmax_partial_kernel(const double* __restrict__ r, const i
 #define PDEB_SEARCH_DEPTH 3      /* searches in flight per host thread of pdeb_controls_search_batch */
 #endif
 #define PDEB_CEM_MAX_GEN 64
-#define PDEB_CEM_MAX_ELITE 8192
+#define PDEB_CEM_MAX_ELITE 2048      /* elite candidates of a generation (list in shared memory) */
+#define PDEB_CEM_KEY_CACHE 4096      /* populations up to this size are ranked out of shared memory */
 struct PdebCemState {
     double mean[PDEB_CTL_KMAX], std[PDEB_CTL_KMAX], best_y[PDEB_CTL_KMAX];
     double history[PDEB_CEM_MAX_GEN];
@@ -387,7 +388,9 @@ __device__ __forceinline__ double pdeb_cem_uniform(uint64_t seed, int gen, int j
 /* the nk knot values of candidate i of generation `gen` */
 __device__ __forceinline__ void pdeb_cem_draw(double* ky, int64_t stride, int nk, int64_t i, const PdebCemState* st, int gen,
                                               uint64_t seed, double lo, double hi) {
-    const bool has_best = gen > 0 && st->has_best != 0;
+    /* the state was written by the last block of the PREVIOUS launch of this handle: read past the L1 (blocks of other
+     * searches keep this SM busy across the launch boundary) */
+    const bool has_best = gen > 0 && __ldcg(&st->has_best) != 0;
     for (int j = 0; j < nk; ++j) {
         double y;
         if (gen == 0) {
@@ -398,9 +401,9 @@ __device__ __forceinline__ void pdeb_cem_draw(double* ky, int64_t stride, int nk
         } else {
             const double u1 = pdeb_cem_uniform(seed, gen, j, i, 0), u2 = pdeb_cem_uniform(seed, gen, j, i, 1);
             const double z = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
-            y = fmin(fmax(fma(st->std[j], z, st->mean[j]), lo), hi);
+            y = fmin(fmax(fma(__ldcg(&st->std[j]), z, __ldcg(&st->mean[j])), lo), hi);
         }
-        if (i == 0 && has_best) y = st->best_y[j];    /* the incumbent stays in the population */
+        if (i == 0 && has_best) y = __ldcg(&st->best_y[j]);    /* the incumbent stays in the population */
         ky[(int64_t)j * stride + i] = y;
     }
 }
@@ -422,11 +425,27 @@ __device__ __forceinline__ void pdeb_cem_update_body(const double* rob, const in
     constexpr int WARPS = THREADS / 32;
     __shared__ unsigned hist[256];
     __shared__ int32_t elist[PDEB_CEM_MAX_ELITE];
+    __shared__ uint64_t skeys[PDEB_CEM_KEY_CACHE];
     __shared__ uint64_t s_prefix;
     __shared__ unsigned long long s_best;
     __shared__ uint64_t s_bestkey;
     __shared__ int s_need, s_k, s_woff[32], s_eoff, s_goff;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    /* The keys are looked at ten times (count, eight radix passes, compaction).  One block reading them from the L2 each
+     * time, one dependent load per loop iteration, was ~115 us of the ~150-280 us a generation took; a population of up to
+     * PDEB_CEM_KEY_CACHE candidates is read ONCE, eight loads in flight per thread, into shared memory. */
+    const bool cached = P <= PDEB_CEM_KEY_CACHE;
+    if (cached) {
+        for (int64_t base = tid; base < P; base += (int64_t)THREADS * 8) {
+            uint64_t kk[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int64_t i = base + (int64_t)u * THREADS; kk[u] = (i < P) ? pdeb_cem_key<CG>(rob, status, i) : 0ull; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int64_t i = base + (int64_t)u * THREADS; if (i < P) skeys[i] = kk[u]; }
+        }
+        __syncthreads();
+    }
+    auto key_at = [&](int64_t i) -> uint64_t { return cached ? skeys[i] : pdeb_cem_key<CG>(rob, status, i); };
 
     /* ---- how many candidates count, and the best of them (largest key, lowest index) ---- */
     for (int q = tid; q < 256; q += THREADS) hist[q] = 0;
@@ -435,7 +454,7 @@ __device__ __forceinline__ void pdeb_cem_update_body(const double* rob, const in
     unsigned nv_local = 0;
     uint64_t bk = 0ull; int64_t bi = -1;
     for (int64_t i = tid; i < P; i += THREADS) {
-        const uint64_t k = pdeb_cem_key<CG>(rob, status, i);
+        const uint64_t k = key_at(i);
         if (k) { ++nv_local; if (k > bk) { bk = k; bi = i; } }        /* ascending i per thread: first of equal keys */
     }
     atomicAdd(&hist[0], nv_local);
@@ -456,7 +475,7 @@ __device__ __forceinline__ void pdeb_cem_update_body(const double* rob, const in
             __syncthreads();
             const uint64_t prefix = s_prefix;
             for (int64_t i = tid; i < P; i += THREADS) {
-                const uint64_t k = pdeb_cem_key<CG>(rob, status, i);
+                const uint64_t k = key_at(i);
                 if (k && (b == 7 || (k >> (8 * (b + 1))) == prefix)) atomicAdd(&hist[(unsigned)(k >> (8 * b)) & 255u], 1u);
             }
             __syncthreads();
@@ -475,7 +494,7 @@ __device__ __forceinline__ void pdeb_cem_update_body(const double* rob, const in
         __syncthreads();
         for (int64_t base = 0; base < P; base += THREADS) {
             const int64_t i = base + tid;
-            const uint64_t k = (i < P) ? pdeb_cem_key<CG>(rob, status, i) : 0ull;
+            const uint64_t k = (i < P) ? key_at(i) : 0ull;
             const bool eq = k != 0ull && k == thr;
             const unsigned beq = __ballot_sync(0xffffffffu, eq);
             if (lane == 0) s_woff[warp] = __popc(beq);
@@ -555,9 +574,12 @@ pdeb_cem_gen_kernel(const __grid_constant__ PdebSpecConst<N> sp, double* ky, int
     if (t < P) pdeb_cem_draw(ky, P, nk, t, st, gen, seed, lo, hi);
     pdeb_controls_body<KIND, N, PMAX, MOM>(sp, ky, P, P, out, t);
     __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    __threadfence();                     /* this thread's results, device-wide */
+    __syncthreads();                     /* ... and every thread of the block has got that far */
+    if (threadIdx.x == 0) {
+        __threadfence();                 /* cumulative: what the barrier made visible to thread 0 is released with its ticket */
+        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    }
     __syncthreads();
     if (s_last) {
         __threadfence();
@@ -731,7 +753,10 @@ extern "C" int pdeb_controls_create(const PdebBatch* spec, int64_t sample, int64
     if (e == cudaSuccess) e = cudaMalloc(&h->d_pi, sizeof(int64_t) * PDEB_ARGMAX_BLOCKS);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_cem, sizeof(PdebCemState));
     if (e == cudaSuccess) e = cudaMalloc(&h->d_ticket, sizeof(unsigned));
+    /* the ticket must BE zero before the first search, which runs on a non-blocking stream of the caller's: a memset on
+     * the default stream is not ordered against that stream, so it is waited for here (the kernel leaves it zero) */
     if (e == cudaSuccess) e = cudaMemset(h->d_ticket, 0, sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
     if (e == cudaSuccess) e = cudaHostAlloc(&h->h_pv, sizeof(double) * PDEB_ARGMAX_BLOCKS, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc(&h->h_pi, sizeof(int64_t) * PDEB_ARGMAX_BLOCKS, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc(&h->h_cem, sizeof(PdebCemState), cudaHostAllocDefault);
@@ -860,7 +885,7 @@ static int search_enqueue(PdebControls* h, int64_t population, int32_t generatio
         return cfail(PDEB_E_ARG, "pdeb_controls_search: bad arguments (population 4..capacity, generations 1..64, lo <= hi, 0 < elite_frac <= 1)");
     int64_t n_elite = (int64_t)llround(elite_frac * (double)population);
     if (n_elite < 2) n_elite = 2;
-    if (n_elite > PDEB_CEM_MAX_ELITE) return cfail(PDEB_E_ARG, "pdeb_controls_search: more than 8192 elite candidates");
+    if (n_elite > PDEB_CEM_MAX_ELITE) return cfail(PDEB_E_ARG, "pdeb_controls_search: more than 2048 elite candidates");
     CCK(cudaSetDevice(h->device));
     if (h->spec_status != PDEB_OK) { *skipped = true; return PDEB_E_OK; }     /* nothing to search (never raises per sample) */
     const int nk = h->nk;

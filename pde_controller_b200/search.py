@@ -62,7 +62,7 @@ class _BatchScorer:
 
 ENGINES = ("device", "host")
 _MAX_DEVICE_KNOTS = 32          # PDEB_CTL_KMAX
-_MAX_DEVICE_ELITE = 8192        # PDEB_CEM_MAX_ELITE
+_MAX_DEVICE_ELITE = 2048        # PDEB_CEM_MAX_ELITE
 _MAX_DEVICE_GENERATIONS = 64    # PDEB_CEM_MAX_GEN
 
 
