@@ -429,7 +429,7 @@ __device__ __forceinline__ void pdeb_cem_update_body(const double* rob, const in
     __shared__ uint64_t s_prefix;
     __shared__ unsigned long long s_best;
     __shared__ uint64_t s_bestkey;
-    __shared__ int s_need, s_k, s_woff[32], s_eoff, s_goff;
+    __shared__ int s_need, s_k, s_woff[32], s_eoff, s_goff, s_done;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     /* The keys are looked at ten times (count, eight radix passes, compaction).  One block reading them from the L2 each
      * time, one dependent load per loop iteration, was ~115 us of the ~150-280 us a generation took; a population of up to
@@ -467,7 +467,7 @@ __device__ __forceinline__ void pdeb_cem_update_body(const double* rob, const in
     const int k_el = nv < n_elite ? nv : n_elite;
 
     /* ---- radix select of the k_el-th largest key ---- */
-    if (tid == 0) { s_prefix = 0ull; s_need = k_el; }
+    if (tid == 0) { s_prefix = 0ull; s_need = k_el; s_done = 0; }
     __syncthreads();
     if (k_el >= 2) {
         for (int b = 7; b >= 0; --b) {
@@ -479,13 +479,29 @@ __device__ __forceinline__ void pdeb_cem_update_body(const double* rob, const in
                 if (k && (b == 7 || (k >> (8 * (b + 1))) == prefix)) atomicAdd(&hist[(unsigned)(k >> (8 * b)) & 255u], 1u);
             }
             __syncthreads();
-            if (tid == 0) {
-                int need = s_need, bin = 255;
-                for (; bin > 0; --bin) { if ((int)hist[bin] >= need) break; need -= (int)hist[bin]; }
-                s_need = need;                         /* still to take among the keys of this bin */
-                s_prefix = (prefix << 8) | (uint64_t)bin;
+            if (warp == 0) {
+                /* the bin that holds the need-th largest key: lane l owns the bins 255 - 8 l .. 248 - 8 l (descending), a
+                 * shuffle scan gives the keys above each lane's bins (thread 0 walking the bins alone was 2-3 us a pass) */
+                unsigned own = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) own += hist[255 - 8 * lane - q];
+                unsigned above = own;
+                for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, above, o); if (lane >= o) above += v; }
+                above -= own;                                        /* keys in the bins of the lanes before this one */
+                const int need = s_need;
+                const bool mine = (int)above < need && (int)(above + own) >= need;
+                if (mine) {
+                    int rest = need - (int)above, bin = 255 - 8 * lane;
+                    for (int q = 0; q < 8; ++q, --bin) { if ((int)hist[bin] >= rest) break; rest -= (int)hist[bin]; }
+                    /* every key of that bin is wanted: the selection is over, the threshold is the lowest key of the bin */
+                    const bool all = (int)hist[bin] == rest && b > 0;
+                    s_prefix = all ? (((prefix << 8) | (uint64_t)bin) << (8 * b)) : ((prefix << 8) | (uint64_t)bin);
+                    s_need = all ? 0x7fffffff : rest;              /* still to take among the keys equal to the threshold */
+                    s_done = all ? 1 : 0;
+                }
             }
             __syncthreads();
+            if (s_done) break;                                       /* block-uniform */
         }
         /* ---- the elite in index order: every key above the threshold, and the first s_need of those equal to it ---- */
         const uint64_t thr = s_prefix;
