@@ -331,6 +331,8 @@ int  pdeb_controls_search_batch(const PdebBatch* in, const int64_t* samples, int
                                 int32_t generations, double elite_frac, const double* bounds, uint64_t seed, int device,
                                 const PdebConventions* conv, int nthreads, double* knot_y_out, double* best_out,
                                 int32_t* found_out, PdebTiming* timing);
+/* pdeb_controls_search_batch keeps the handles of a finished sweep for the next one (per device); this frees them */
+void pdeb_controls_pool_clear(void);
 /* the candidates currently on the device, host [n_knots][m] plane-major (diagnostics, tests) */
 int  pdeb_controls_fetch_knots(PdebControls* h, int64_t m, double* knot_y_out, void* stream);
 

@@ -183,6 +183,7 @@ EXPORTS = [
     "pdeb_controls_respec",
     "pdeb_controls_search",
     "pdeb_controls_search_batch",
+    "pdeb_controls_pool_clear",
     "pdeb_controls_fetch_knots",
     "pdeb_resident_fetch",
     "pdeb_resident_fetch_async",

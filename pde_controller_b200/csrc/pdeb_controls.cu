@@ -721,9 +721,7 @@ extern "C" void pdeb_controls_destroy(PdebControls* h) {
     cudaSetDevice(h->device);
     cudaFree(h->d_y); cudaFree(h->d_rob); cudaFree(h->d_clause); cudaFree(h->d_status); cudaFree(h->d_pv); cudaFree(h->d_pi);
     cudaFree(h->d_cem); cudaFree(h->d_ticket);
-    if (h->h_pv) cudaFreeHost(h->h_pv);
-    if (h->h_pi) cudaFreeHost(h->h_pi);
-    if (h->h_cem) cudaFreeHost(h->h_cem);
+    if (h->h_pv) cudaFreeHost(h->h_pv);          /* one page-locked block: { partial values | partial indices | search state } */
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->done) cudaEventDestroy(h->done);
     delete h;
@@ -773,9 +771,17 @@ extern "C" int pdeb_controls_create(const PdebBatch* spec, int64_t sample, int64
      * the default stream is not ordered against that stream, so it is waited for here (the kernel leaves it zero) */
     if (e == cudaSuccess) e = cudaMemset(h->d_ticket, 0, sizeof(unsigned));
     if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
-    if (e == cudaSuccess) e = cudaHostAlloc(&h->h_pv, sizeof(double) * PDEB_ARGMAX_BLOCKS, cudaHostAllocDefault);
-    if (e == cudaSuccess) e = cudaHostAlloc(&h->h_pi, sizeof(int64_t) * PDEB_ARGMAX_BLOCKS, cudaHostAllocDefault);
-    if (e == cudaSuccess) e = cudaHostAlloc(&h->h_cem, sizeof(PdebCemState), cudaHostAllocDefault);
+    /* ONE page-locked allocation per handle (cudaHostAlloc is slow and serialised process-wide: three per handle made the
+     * first sweep of a process, which creates 24 handles, run at a seventh of the steady rate) */
+    if (e == cudaSuccess) {
+        unsigned char* hp = nullptr;
+        e = cudaHostAlloc(&hp, 16 * PDEB_ARGMAX_BLOCKS + sizeof(PdebCemState), cudaHostAllocDefault);
+        if (e == cudaSuccess) {
+            h->h_pv = (double*)hp;
+            h->h_pi = (int64_t*)(hp + 8 * PDEB_ARGMAX_BLOCKS);
+            h->h_cem = (PdebCemState*)(hp + 16 * PDEB_ARGMAX_BLOCKS);
+        }
+    }
     for (auto& ev : h->ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->done, cudaEventBlockingSync | cudaEventDisableTiming);
     if (e != cudaSuccess) { pdeb_controls_destroy(h); return cfail(PDEB_E_CUDA, "pdeb_controls_create", e); }
@@ -962,6 +968,39 @@ extern "C" int pdeb_controls_search(PdebControls* h, int64_t population, int32_t
                           (cudaStream_t)stream_, timing);
 }
 
+/* Handles of finished sweeps, kept per device for the next one (creating a handle is seven device allocations, a page-locked
+ * one, events: ~24 of them per sweep were most of a SHORT sweep's time).  pdeb_controls_pool_clear frees them. */
+static std::mutex g_ctl_pool_mu;
+static std::vector<PdebControls*> g_ctl_pool;
+#define PDEB_CTL_POOL_MAX 96
+
+static PdebControls* ctl_pool_take(int device, int64_t capacity) {
+    std::lock_guard<std::mutex> lock(g_ctl_pool_mu);
+    for (size_t i = 0; i < g_ctl_pool.size(); ++i) {
+        PdebControls* h = g_ctl_pool[i];
+        if (h->device == device && h->capacity >= capacity && h->capacity <= 4 * capacity) {
+            g_ctl_pool.erase(g_ctl_pool.begin() + (long)i);
+            return h;
+        }
+    }
+    return nullptr;
+}
+static void ctl_pool_give(PdebControls* h) {
+    {
+        std::lock_guard<std::mutex> lock(g_ctl_pool_mu);
+        if (g_ctl_pool.size() < PDEB_CTL_POOL_MAX) { g_ctl_pool.push_back(h); return; }
+    }
+    pdeb_controls_destroy(h);
+}
+extern "C" void pdeb_controls_pool_clear(void) {
+    std::vector<PdebControls*> dead;
+    {
+        std::lock_guard<std::mutex> lock(g_ctl_pool_mu);
+        dead.swap(g_ctl_pool);
+    }
+    for (PdebControls* h : dead) pdeb_controls_destroy(h);
+}
+
 /*
  * The search for MANY specifications: host threads, each with its own stream and ONE controls handle that it points at
  * sample after sample (no allocation per program, nothing per program in the caller's language).  The knot TIMES are the
@@ -1046,10 +1085,10 @@ extern "C" int pdeb_controls_search_batch(const PdebBatch* in, const int64_t* sa
             for (int j = 0; j < nk; ++j)
                 kt[j] = in->knot_t ? in->knot_t[(int64_t)j * st + s]
                                    : ((j == nk - 1 && nk > 1) ? in->T[s] : (nk > 1 ? (double)j * (in->T[s] / (double)(nk - 1)) : 0.0));
-            if (!sl.h) {
-                rc = pdeb_controls_create(in, s, population, nk, kt, device, conv, &sl.h);
-                if (rc == PDEB_E_OK) sl.h->sleep_on_done = sleep_wait;
-            } else rc = pdeb_controls_respec(sl.h, in, s, nk, kt, conv);
+            if (!sl.h) sl.h = ctl_pool_take(device, population);
+            if (!sl.h) rc = pdeb_controls_create(in, s, population, nk, kt, device, conv, &sl.h);
+            else rc = pdeb_controls_respec(sl.h, in, s, nk, kt, conv);
+            if (rc == PDEB_E_OK) sl.h->sleep_on_done = sleep_wait;
             if (rc != PDEB_E_OK) break;
             const double lo = bounds[kind == PDEB_KIND_HEAT ? 0 : 2], hi = bounds[kind == PDEB_KIND_HEAT ? 1 : 3];
             /* one generator stream per sample, whatever thread takes it */
@@ -1071,7 +1110,7 @@ extern "C" int pdeb_controls_search_batch(const PdebBatch* in, const int64_t* sa
         }
         for (int q = 0; q < PDEB_SEARCH_DEPTH; ++q) {
             if (slot[q].st) cudaStreamSynchronize(slot[q].st);
-            if (slot[q].h) pdeb_controls_destroy(slot[q].h);
+            if (slot[q].h) { if (rc == PDEB_E_OK) ctl_pool_give(slot[q].h); else pdeb_controls_destroy(slot[q].h); }
             if (slot[q].st) cudaStreamDestroy(slot[q].st);
         }
     };

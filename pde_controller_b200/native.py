@@ -103,6 +103,8 @@ def lib():
         L.pdeb_controls_search_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_double, C.c_void_p,
                                                  C.c_uint64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                                  C.c_void_p]
+        L.pdeb_controls_pool_clear.restype = None
+        L.pdeb_controls_pool_clear.argtypes = []
         L.pdeb_controls_fetch_knots.restype = C.c_int
         L.pdeb_controls_fetch_knots.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         if L.pdeb_version() != abi.ABI_VERSION:
@@ -276,6 +278,11 @@ def shard_bounds(batch: ProblemBatch, ndev: int, conv=None) -> np.ndarray:
     out = np.zeros(ndev + 1, dtype=np.int64)
     _check(lib().pdeb_shard_bounds(C.addressof(cb), ndev, _conv_ptr(conv), _ptr(out)), "pdeb_shard_bounds")
     return out
+
+
+def controls_pool_clear():
+    """Free the controls handles finished search sweeps have left for the next one."""
+    lib().pdeb_controls_pool_clear()
 
 
 def cache_clear():
