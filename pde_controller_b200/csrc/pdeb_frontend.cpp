@@ -9,15 +9,19 @@
  * ~85 us of the Python template matcher (pde_controller_b200/frontend.py::_parse_fast, whose regular expression this file
  * restates) and the ~1 ms of the general interpreter.
  *
- * Contract: a text this matcher ACCEPTS is accepted by the Python template matcher with identical values (tests compare
- * them on rendered programs, on the reference's records and under fuzz); a text it declines is not an error: accepted[i]
- * stays 0 and the caller hands that program to the Python front-end, which decides.  Nothing is executed.
+ * Contract: a text this matcher ACCEPTS is accepted by the Python front-end with identical values (tests compare them on
+ * rendered programs, on the reference's records and under fuzz); a text it declines is not an error: accepted[i] stays 0
+ * and the caller hands that program to the Python front-end, which decides.  Nothing is executed.
+ * What may differ from the canonical text is what Python's tokenizer does not care about: runs of blanks and tabs between
+ * tokens (Cursor::lit), and -- in a second attempt on a cleaned copy -- CR LF, blanks at line ends, empty and comment lines,
+ * comments behind statements (normalise).  The cspec / cregions STRINGS are matched byte for byte.
  */
 #include <charconv>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -30,10 +34,32 @@ struct Tok { const char* p; int len; };
 struct Cursor {
     const char* p;
     const char* end;
-    bool lit(const char* s) {
+    /* strict: byte for byte (inside the cspec / cregions strings, whose own grammar is the Python front-end's) */
+    bool lits(const char* s) {
         const size_t n = strlen(s);
         if ((size_t)(end - p) < n || memcmp(p, s, n) != 0) return false;
         p += n;
+        return true;
+    }
+    static bool ident(char c) { return (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || (c >= '0' && c <= '9') || c == '_' || c == '.'; }
+    /* statement level: a blank of the pattern stands for ANY run of blanks and tabs, as Python's tokenizer sees it -- an
+     * empty run too, unless that would fuse two names / numbers / keywords ("lambda x", "137 or", "else 5": a blank with a
+     * name character on both sides, where the text of a number or name in front of / behind the pattern counts as one) */
+    bool lit(const char* s) {
+        const char* q = p;
+        for (const char* c = s; *c; ++c) {
+            if (*c != ' ') {
+                if (q >= end || *q != *c) return false;
+                ++q;
+                continue;
+            }
+            const char prev = (c == s) ? 'x' : c[-1], next = c[1] ? c[1] : 'x';
+            const char* r = q;
+            while (r < end && (*r == ' ' || *r == '\t')) ++r;
+            if (r == q && ident(prev) && ident(next)) return false;
+            q = r;
+        }
+        p = q;
         return true;
     }
     bool newlines() {                       /* \n+ */
@@ -138,42 +164,42 @@ bool value(Cursor& c, double* out) {
 /* one clause of the cspec:  (G_[t0, t1] (A))  with the expected label */
 bool clause(Cursor& c, int j, Parsed* q) {
     Tok a, b;
-    if (!c.lit("(")) return false;
+    if (!c.lits("(")) return false;
     if (c.p >= c.end || (*c.p != 'G' && *c.p != 'F')) return false;
     q->top[j] = (*c.p == 'G') ? PDEB_TOP_G : PDEB_TOP_F;
     ++c.p;
-    if (!c.lit("_[") || !c.num(&a) || !c.lit(", ") || !c.num(&b) || !c.lit("] (")) return false;
+    if (!c.lits("_[") || !c.num(&a) || !c.lits(", ") || !c.num(&b) || !c.lits("] (")) return false;
     if (c.p >= c.end || *c.p != (char)('A' + j)) return false;
     ++c.p;
-    if (!c.lit("))")) return false;
+    if (!c.lits("))")) return false;
     return to_double(a, &q->tlo[j]) && to_double(b, &q->thi[j]);
 }
 
 bool spec_nested(const char* s, const char* e, Parsed* q) {
     Cursor c{s, e};
-    for (int k = 0; k < q->P - 1; ++k) if (!c.lit("(")) return false;
+    for (int k = 0; k < q->P - 1; ++k) if (!c.lits("(")) return false;
     if (!clause(c, 0, q)) return false;
     for (int j = 1; j < q->P; ++j) {
-        if (!c.lit(" ")) return false;
+        if (!c.lits(" ")) return false;
         if (c.p >= c.end || (*c.p != '&' && *c.p != '|')) return false;
         q->op[j] = (*c.p == '&') ? PDEB_TREE_AND : PDEB_TREE_OR;
         ++c.p;
-        if (!c.lit(" ") || !clause(c, j, q) || !c.lit(")")) return false;
+        if (!c.lits(" ") || !clause(c, j, q) || !c.lits(")")) return false;
     }
     return c.p == e;
 }
 
 bool spec_flat(const char* s, const char* e, Parsed* q) {      /* ((A) & (B) & (C)), ((A)) : conjunctions only */
     Cursor c{s, e};
-    if (!c.lit("(") || !clause(c, 0, q)) return false;
+    if (!c.lits("(") || !clause(c, 0, q)) return false;
     for (int j = 1; j < q->P; ++j) {
-        if (!c.lit(" & ") || !clause(c, j, q)) return false;
+        if (!c.lits(" & ") || !clause(c, j, q)) return false;
         q->op[j] = PDEB_TREE_AND;
     }
-    return c.lit(")") && c.p == e;
+    return c.lits(")") && c.p == e;
 }
 
-bool parse_one(const char* text, int64_t len, Parsed* q) {
+bool parse_raw(const char* text, int64_t len, Parsed* q) {
     const char* s = text;
     const char* e = text + len;
     if (memchr(text, 0, (size_t)len)) return false;                         /* NUL bytes: the Python route strips them */
@@ -262,8 +288,8 @@ bool parse_one(const char* text, int64_t len, Parsed* q) {
             char item[16] = "\"A\" : apc0";
             item[1] = (char)('A' + j);
             item[9] = (char)('0' + j);
-            if (j > 0 && !rc.lit(", ")) return false;
-            if (!rc.lit(item)) return false;
+            if (j > 0 && !rc.lits(", ")) return false;
+            if (!rc.lits(item)) return false;
         }
         if (rc.p != r1) return false;
     }
@@ -281,6 +307,49 @@ bool parse_one(const char* text, int64_t len, Parsed* q) {
         if (!std::isfinite(q->xlo[j]) || !std::isfinite(q->xhi[j]) || !std::isfinite(q->m[j]) || !std::isfinite(q->b[j])) return false;
     }
     return true;
+}
+
+/*
+ * What a program may differ in from the canonical text without meaning anything else to Python: CR LF line ends, blanks
+ * at the end of a line, empty lines, comment lines, a comment behind a statement (only where no quote precedes the '#':
+ * a '#' inside a string is not a comment).  The text is first tried as it is; only if that fails is a cleaned copy tried.
+ */
+bool normalise(const char* text, int64_t len, std::string* out) {
+    out->clear();
+    out->reserve((size_t)len);
+    bool changed = false;
+    const char* p = text;
+    const char* e = text + len;
+    /* any other control character decides things this pass does not model (a lone CR ends a line for Python's tokenizer,
+     * also inside a comment; form feeds reset indentation): such a text is left to the Python front-end */
+    for (const char* c = text; c < e; ++c) {
+        const unsigned char u = (unsigned char)*c;
+        if (u < 0x20 && u != '\n' && u != '\t' && !(u == '\r' && c + 1 < e && c[1] == '\n')) return false;
+        if (u == 0x7f) return false;
+    }
+    while (p < e) {
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(e - p));
+        const char* le = nl ? nl : e;
+        const char* q = le;
+        if (q > p && q[-1] == '\r') { --q; changed = true; }
+        const char* hash = nullptr;
+        for (const char* c = p; c < q; ++c) {
+            if (*c == '"' || *c == '\'') break;
+            if (*c == '#') { if (c == p || c[-1] == ' ' || c[-1] == '\t') hash = c; break; }
+        }
+        if (hash) { q = hash; changed = true; }
+        while (q > p && (q[-1] == ' ' || q[-1] == '\t')) { --q; changed = true; }
+        if (q > p) { out->append(p, (size_t)(q - p)); out->push_back('\n'); }
+        else if (hash) changed = true;
+        p = nl ? nl + 1 : e;
+    }
+    return changed;
+}
+
+bool parse_one(const char* text, int64_t len, Parsed* q, std::string* scratch) {
+    if (parse_raw(text, len, q)) return true;
+    if (len > 16384 || !normalise(text, len, scratch)) return false;
+    return parse_raw(scratch->data(), (int64_t)scratch->size(), q);
 }
 
 void store(const Parsed& q, const PdebBatch* out, int64_t s) {
@@ -323,11 +392,12 @@ extern "C" int pdeb_parse_programs(const char* const* texts, const int64_t* leng
                          out->pred_thi, out->pred_rel, out->pred_top, out->n_tree, out->tree_op, out->tree_lhs, out->tree_rhs};
     for (const void* p : req) if (!p) return PDEB_E_ARG;
     auto work = [&](int64_t lo, int64_t hi) {
+        std::string scratch;
         for (int64_t i = lo; i < hi; ++i) {
             Parsed q;
             accepted[i] = 0;
             if (!texts[i] || lengths[i] <= 0) continue;
-            if (!parse_one(texts[i], lengths[i], &q)) continue;
+            if (!parse_one(texts[i], lengths[i], &q, &scratch)) continue;
             if (q.P > out->pmax || 2 * q.P - 1 > out->tmax) continue;           /* does not fit this batch's planes: Python route */
             store(q, out, first + i);
             accepted[i] = 1;
